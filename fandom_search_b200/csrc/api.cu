@@ -1,0 +1,689 @@
+// C ABI of the reuse-search hot path (see include/fandom_search.h).
+#include <cstdarg>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace fs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+constexpr int kTimingRing = 256;
+// Slack of the tensor-core pre-filter: fp16 operand rounding is bounded by
+// 2*2^-11 * sum|f_k s_k| <= 0.00098 |f||s| (Cauchy-Schwarz); fp32 accumulation and
+// fp32 norms add ~1e-5.  Every pair with float64 cos > 1-thr passes cos_fp16 > 1-thr-kEps.
+constexpr double kEps = 2.0e-3;
+
+template <typename T>
+static int dev_alloc(T** p, int64_t count) {
+    *p = nullptr;
+    if (count <= 0) count = 1;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), static_cast<size_t>(count) * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc of %lld bytes failed: %s",
+                  static_cast<long long>(count * static_cast<int64_t>(sizeof(T))),
+                  cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return FS_E_NOMEM;
+    }
+    return FS_OK;
+}
+
+template <typename T>
+static int dev_grow(T** p, int64_t* cap, int64_t need) {
+    if (need <= *cap && *p) return FS_OK;
+    int64_t ncap = *cap > 0 ? *cap : 1;
+    while (ncap < need) ncap += ncap / 2 + 1024;
+    if (*p) {
+        cudaDeviceSynchronize();
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    int r = dev_alloc(p, ncap);
+    if (r != FS_OK) {
+        *cap = 0;
+        return r;
+    }
+    *cap = ncap;
+    return FS_OK;
+}
+
+}  // namespace fs
+
+using namespace fs;
+
+struct fs_index {
+    int device = 0;
+    int sm_count = 148;
+    int32_t dim = 0, dim_pad = 0, window = 6;
+    double threshold = 0.1;
+    float scale = 1.f;
+    int64_t n_base = 0, n_sx = 0;
+
+    float* table32 = nullptr;
+    __half* table16 = nullptr;
+    float* table_sq = nullptr;
+    float* sx32 = nullptr;
+    __half* sx16 = nullptr;
+    float* sx_sq = nullptr;
+
+    int32_t* script_tok = nullptr;
+    int64_t n_script_tok = 0;
+    int64_t* script_off = nullptr;
+    int32_t n_scripts = 0;
+    int64_t n_script_windows = 0;
+    __half* script_emb = nullptr;
+    float* script_tok_sq = nullptr;
+    float* script_norm = nullptr;
+    int32_t tiles_n = 0;
+    CUtensorMap map_script;
+
+    unsigned long long* hash_table = nullptr;
+    uint32_t hash_slots = 0;
+
+    // per-batch workspace
+    int64_t tok_cap = 0;  // rows of fan_emb
+    int64_t emb_cap = 0;  // elements of fan_emb
+    __half* fan_emb = nullptr;
+    int64_t sq_cap = 0;
+    float* fan_tok_sq = nullptr;
+    int64_t thr_cap = 0;
+    float* fan_thr = nullptr;
+    int64_t cand_cap = 0;
+    fs_pair* cand = nullptr;
+    int64_t fx_cap = 0;  // fan extra rows
+    __half* fx16 = nullptr;
+    int64_t fxsq_cap = 0;
+    float* fx_sq = nullptr;
+
+    // staging of the _host entry points
+    cudaStream_t stream = nullptr;
+    int64_t h_tok_cap = 0;
+    int32_t* h_tok = nullptr;
+    int64_t h_off_cap = 0;
+    int64_t* h_off = nullptr;
+    int64_t h_extra_cap = 0;
+    float* h_extra = nullptr;
+    int64_t h_out_cap = 0;
+    fs_match* h_out = nullptr;
+    int64_t h_pair_cap = 0;
+    fs_pair* h_pair = nullptr;
+    unsigned long long* h_counters = nullptr;
+
+    // options
+    int32_t shifts_per_stage = 6;
+    int32_t base_offset_mode = 0;
+    int32_t grid_limit = 0;
+
+    // timing ring
+    cudaEvent_t ev_start[kTimingRing];
+    cudaEvent_t ev_stop[kTimingRing];
+    bool ev_created = false;
+    int64_t ev_count = 0;
+};
+
+static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+extern "C" {
+
+int fs_abi_version(void) { return FS_ABI_VERSION; }
+
+const char* fs_last_error(void) { return g_err; }
+
+int fs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int fs_index_destroy(fs_index* idx) {
+    if (!idx) return FS_OK;
+    cudaSetDevice(idx->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {idx->table32, idx->table16,   idx->table_sq,   idx->sx32,       idx->sx16,
+                    idx->sx_sq,   idx->script_tok, idx->script_off, idx->script_emb, idx->script_tok_sq,
+                    idx->script_norm, idx->hash_table, idx->fan_emb, idx->fan_tok_sq, idx->fan_thr,
+                    idx->cand,    idx->fx16,      idx->fx_sq,      idx->h_tok,      idx->h_off,
+                    idx->h_extra, idx->h_out,     idx->h_pair,     idx->h_counters};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (idx->ev_created) {
+        for (int i = 0; i < kTimingRing; ++i) {
+            cudaEventDestroy(idx->ev_start[i]);
+            cudaEventDestroy(idx->ev_stop[i]);
+        }
+    }
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    delete idx;
+    return FS_OK;
+}
+
+int fs_index_create(fs_index** out, int device, const float* table, int64_t n_rows, int32_t dim,
+                    const float* extra, int64_t n_extra, const int32_t* script_tok,
+                    int64_t n_script_tok, const int64_t* script_off, int64_t n_scripts,
+                    int32_t window, double threshold) {
+    if (!out || !table || n_rows < 0 || dim <= 0 || n_extra < 0 || (n_extra > 0 && !extra) ||
+        n_script_tok < 0 || (n_script_tok > 0 && !script_tok) || !script_off || n_scripts < 1 ||
+        window < 1 || window > 8 || !(threshold > 0.0) || !(threshold < 1.0)) {
+        set_error("fs_index_create: invalid argument");
+        return FS_E_INVALID;
+    }
+    if (n_script_tok >= (1ll << 31) - 1024 || n_rows + n_extra >= (1ll << 31) - 1) {
+        set_error("fs_index_create: sizes exceed int32 positions");
+        return FS_E_INVALID;
+    }
+    if (script_off[0] != 0 || script_off[n_scripts] != n_script_tok) {
+        set_error("fs_index_create: script_off must start at 0 and end at n_script_tok");
+        return FS_E_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        (void)cudaGetLastError();
+        set_error("fs_index_create: CUDA device %d not available (%d visible); this path has no CPU fallback",
+                  device, ndev);
+        return FS_E_NODEVICE;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FS_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("fs_index_create: device %d is sm_%d%d; these kernels are built for sm_100a only",
+                  device, prop.major, prop.minor);
+        return FS_E_NODEVICE;
+    }
+    fs_index* idx = new (std::nothrow) fs_index();
+    if (!idx) return FS_E_NOMEM;
+    idx->device = device;
+    idx->sm_count = prop.multiProcessorCount;
+    idx->dim = dim;
+    idx->dim_pad = static_cast<int32_t>(round_up(dim, kChunkK));
+    idx->window = window;
+    idx->threshold = threshold;
+    idx->n_base = n_rows;
+    idx->n_sx = n_extra;
+    idx->n_script_tok = n_script_tok;
+    idx->n_scripts = static_cast<int32_t>(n_scripts);
+    // largest divisor of window that is <= 6 shifts per stage (halo of the TMA box is 8 rows)
+    idx->shifts_per_stage = window;
+
+#define FS_TRY(expr)                    \
+    do {                                \
+        int _r = (expr);                \
+        if (_r != FS_OK) {              \
+            fs_index_destroy(idx);      \
+            return _r;                  \
+        }                               \
+    } while (0)
+#define FS_TRY_CUDA(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,     \
+                      __LINE__);                                                            \
+            fs_index_destroy(idx);                                                          \
+            return FS_E_CUDA;                                                               \
+        }                                                                                   \
+    } while (0)
+
+    FS_TRY_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
+    cudaStream_t st = idx->stream;
+    for (int i = 0; i < kTimingRing; ++i) {
+        FS_TRY_CUDA(cudaEventCreate(&idx->ev_start[i]));
+        FS_TRY_CUDA(cudaEventCreate(&idx->ev_stop[i]));
+    }
+    idx->ev_created = true;
+
+    FS_TRY(dev_alloc(&idx->h_counters, FS_CNT_COUNT));
+    FS_TRY(dev_alloc(&idx->table32, n_rows * dim));
+    FS_TRY(dev_alloc(&idx->table16, n_rows * idx->dim_pad));
+    FS_TRY(dev_alloc(&idx->table_sq, n_rows));
+    FS_TRY(dev_alloc(&idx->sx32, n_extra * dim));
+    FS_TRY(dev_alloc(&idx->sx16, n_extra * idx->dim_pad));
+    FS_TRY(dev_alloc(&idx->sx_sq, n_extra));
+    if (n_rows)
+        FS_TRY_CUDA(cudaMemcpyAsync(idx->table32, table, sizeof(float) * n_rows * dim,
+                                    cudaMemcpyHostToDevice, st));
+    if (n_extra)
+        FS_TRY_CUDA(cudaMemcpyAsync(idx->sx32, extra, sizeof(float) * n_extra * dim,
+                                    cudaMemcpyHostToDevice, st));
+    // global scale so that fp16 never overflows: 1 / max|x|
+    unsigned int* d_max = reinterpret_cast<unsigned int*>(idx->h_counters);
+    FS_TRY_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned int), st));
+    FS_TRY(launch_absmax(idx->table32, n_rows * dim, d_max, st));
+    FS_TRY(launch_absmax(idx->sx32, n_extra * dim, d_max, st));
+    unsigned int h_max_bits = 0;
+    FS_TRY_CUDA(cudaMemcpyAsync(&h_max_bits, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    FS_TRY_CUDA(cudaStreamSynchronize(st));
+    float h_max;
+    memcpy(&h_max, &h_max_bits, sizeof(float));
+    idx->scale = (h_max > 0.f && std::isfinite(h_max)) ? 1.0f / h_max : 1.0f;
+    FS_TRY(launch_convert_rows(idx->table32, n_rows, dim, idx->dim_pad, idx->scale, idx->table16,
+                               idx->table_sq, st));
+    FS_TRY(launch_convert_rows(idx->sx32, n_extra, dim, idx->dim_pad, idx->scale, idx->sx16,
+                               idx->sx_sq, st));
+
+    // script side: tokens, CSR, embeddings, window norms, tensor map, hash table
+    idx->tiles_n = static_cast<int32_t>((n_script_tok + kBlockN - 1) / kBlockN);
+    const int64_t n_pad = static_cast<int64_t>(idx->tiles_n) * kBlockN;
+    FS_TRY(dev_alloc(&idx->script_tok, n_script_tok + 8));
+    FS_TRY(dev_alloc(&idx->script_off, n_scripts + 1));
+    FS_TRY(dev_alloc(&idx->script_emb, n_script_tok * idx->dim_pad));
+    FS_TRY(dev_alloc(&idx->script_tok_sq, n_script_tok + 8));
+    FS_TRY(dev_alloc(&idx->script_norm, n_pad));
+    FS_TRY_CUDA(cudaMemsetAsync(idx->script_tok, 0xFF, sizeof(int32_t) * (n_script_tok + 8), st));
+    if (n_script_tok)
+        FS_TRY_CUDA(cudaMemcpyAsync(idx->script_tok, script_tok, sizeof(int32_t) * n_script_tok,
+                                    cudaMemcpyHostToDevice, st));
+    FS_TRY_CUDA(cudaMemcpyAsync(idx->script_off, script_off, sizeof(int64_t) * (n_scripts + 1),
+                                cudaMemcpyHostToDevice, st));
+    GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16, idx->sx_sq,
+                      idx->n_sx,    nullptr,       nullptr,     0};
+    FS_TRY(launch_gather(idx->script_tok, n_script_tok, src, idx->dim_pad, idx->script_emb,
+                         idx->script_tok_sq, idx->sm_count, st));
+    unsigned long long* d_cnt = idx->h_counters;
+    FS_TRY_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
+    FS_TRY(launch_window_norm(idx->script_tok_sq, n_script_tok, idx->script_off, idx->n_scripts,
+                              window, 1.0f, idx->script_norm, n_pad, d_cnt + FS_CNT_WINDOWS, st));
+    unsigned long long h_cnt[FS_CNT_COUNT];
+    FS_TRY_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    if (n_script_tok > 0)
+        FS_TRY(make_token_map(&idx->map_script, idx->script_emb, n_script_tok, idx->dim_pad));
+
+    uint32_t slots = 1024;
+    while (slots < 2 * static_cast<uint64_t>(n_script_tok)) slots <<= 1;
+    idx->hash_slots = slots;
+    FS_TRY(dev_alloc(&idx->hash_table, slots));
+    FS_TRY(launch_hash_build(idx->script_tok, n_script_tok, idx->script_off, idx->n_scripts, window,
+                             idx->hash_table, slots, st));
+    FS_TRY_CUDA(cudaStreamSynchronize(st));
+    idx->n_script_windows = static_cast<int64_t>(h_cnt[FS_CNT_WINDOWS]);
+#undef FS_TRY
+#undef FS_TRY_CUDA
+    *out = idx;
+    return FS_OK;
+}
+
+int fs_index_reserve(fs_index* idx, int64_t max_tokens, int64_t max_candidates) {
+    if (!idx || max_tokens < 0 || max_candidates < 0) {
+        set_error("fs_index_reserve: invalid argument");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    int r;
+    if ((r = dev_grow(&idx->fan_emb, &idx->emb_cap, max_tokens * idx->dim_pad)) != FS_OK) return r;
+    idx->tok_cap = idx->emb_cap / idx->dim_pad;
+    if ((r = dev_grow(&idx->fan_tok_sq, &idx->sq_cap, max_tokens + 8)) != FS_OK) return r;
+    if ((r = dev_grow(&idx->fan_thr, &idx->thr_cap, round_up(max_tokens, kBlockM) + kBlockM)) != FS_OK)
+        return r;
+    if ((r = dev_grow(&idx->cand, &idx->cand_cap, max_candidates)) != FS_OK) return r;
+    return FS_OK;
+}
+
+int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
+    if (!idx) return FS_E_INVALID;
+    switch (option) {
+        case FS_OPT_SHIFTS_PER_STAGE:
+            if (value < 1 || value > 8 || idx->window % value != 0) {
+                set_error("shifts per stage must divide the window and be <= 8");
+                return FS_E_INVALID;
+            }
+            idx->shifts_per_stage = static_cast<int32_t>(value);
+            return FS_OK;
+        case FS_OPT_BASE_OFFSET_MODE:
+            idx->base_offset_mode = value ? 1 : 0;
+            return FS_OK;
+        case FS_OPT_GRID_LIMIT:
+            idx->grid_limit = static_cast<int32_t>(value < 0 ? 0 : value);
+            return FS_OK;
+        default:
+            set_error("unknown option %d", option);
+            return FS_E_INVALID;
+    }
+}
+
+int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
+    if (!idx) return -1;
+    switch (what) {
+        case 0: return idx->n_script_windows;
+        case 1: return idx->dim_pad;
+        case 2: return idx->sm_count;
+        case 3: return idx->cand_cap;
+        case 4: return idx->shifts_per_stage;
+        default: return -1;
+    }
+}
+
+float fs_index_scale(const fs_index* idx) { return idx ? idx->scale : 0.f; }
+
+int fs_timing_reset(fs_index* idx) {
+    if (!idx) return FS_E_INVALID;
+    idx->ev_count = 0;
+    return FS_OK;
+}
+
+int fs_timing_read(fs_index* idx, double* total_ms, int64_t* launches) {
+    if (!idx || !total_ms || !launches) return FS_E_INVALID;
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    const int64_t n = idx->ev_count < kTimingRing ? idx->ev_count : kTimingRing;
+    double tot = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        FS_CUDA_CHECK(cudaEventSynchronize(idx->ev_stop[i]));
+        float ms = 0.f;
+        FS_CUDA_CHECK(cudaEventElapsedTime(&ms, idx->ev_start[i], idx->ev_stop[i]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = n;
+    return FS_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// shared pipeline
+// ---------------------------------------------------------------------------
+namespace {
+
+enum class Mode { kSearch, kCandidates, kDots, kEmbed };
+
+struct BatchArgs {
+    const int32_t* tok;
+    int64_t n_tok;
+    const int64_t* off;
+    int64_t n_works;
+    const float* extra;
+    int64_t n_extra;
+};
+
+int check_batch(const fs_index* idx, const BatchArgs& a, const char* who) {
+    if (!idx || a.n_tok < 0 || a.n_works < 0 || (a.n_tok > 0 && !a.tok) || !a.off || a.n_extra < 0 ||
+        (a.n_extra > 0 && !a.extra)) {
+        set_error("%s: invalid argument", who);
+        return FS_E_INVALID;
+    }
+    if (a.n_tok >= (1ll << 31) - 1024 || a.n_works >= (1ll << 31) - 1) {
+        set_error("%s: batch exceeds int32 positions; split it", who);
+        return FS_E_INVALID;
+    }
+    return FS_OK;
+}
+
+// gather + window thresholds of one batch into the index workspace
+int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned long long* counters,
+                __half* emb_out, float* thr_out, int64_t thr_pad) {
+    int r;
+    if (a.n_extra > 0) {
+        if ((r = dev_grow(&idx->fx16, &idx->fx_cap, a.n_extra * idx->dim_pad)) != FS_OK) return r;
+        if ((r = dev_grow(&idx->fx_sq, &idx->fxsq_cap, a.n_extra)) != FS_OK) return r;
+        if ((r = launch_convert_rows(a.extra, a.n_extra, idx->dim, idx->dim_pad, idx->scale, idx->fx16,
+                                     idx->fx_sq, st)) != FS_OK)
+            return r;
+    }
+    GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16,  idx->sx_sq,
+                      idx->n_sx,    idx->fx16,     idx->fx_sq,  a.n_extra};
+    if ((r = launch_gather(a.tok, a.n_tok, src, idx->dim_pad, emb_out, idx->fan_tok_sq, idx->sm_count,
+                           st)) != FS_OK)
+        return r;
+    // zero the halo so the window sums never read stale squares
+    FS_CUDA_CHECK(cudaMemsetAsync(idx->fan_tok_sq + a.n_tok, 0, sizeof(float) * 8, st));
+    const float coef = static_cast<float>(1.0 - idx->threshold - kEps);
+    return launch_window_norm(idx->fan_tok_sq, a.n_tok, a.off, static_cast<int32_t>(a.n_works),
+                              idx->window, coef, thr_out, thr_pad,
+                              counters ? counters + FS_CNT_WINDOWS : nullptr, st);
+}
+
+int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, fs_match* out,
+                 int64_t cap, fs_pair* cand_out, int64_t cand_out_cap, float* dots, int64_t dots_ld,
+                 unsigned long long* counters) {
+    int r;
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    if (counters) FS_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
+    if (a.n_tok == 0 || idx->n_script_tok == 0) return FS_OK;
+    const int32_t tiles_m = static_cast<int32_t>((a.n_tok + kBlockM - 1) / kBlockM);
+    const int64_t thr_pad = static_cast<int64_t>(tiles_m) * kBlockM;
+    int64_t want_cand = idx->cand_cap > 0 ? idx->cand_cap : (1 << 20);
+    if ((r = fs_index_reserve(idx, a.n_tok, want_cand)) != FS_OK) return r;
+    if ((r = embed_batch(idx, st, a, counters, idx->fan_emb, idx->fan_thr, thr_pad)) != FS_OK) return r;
+
+    CUtensorMap map_fan;
+    if ((r = make_token_map(&map_fan, idx->fan_emb, a.n_tok, idx->dim_pad)) != FS_OK) return r;
+    DistParams p{};
+    p.thr_fan = idx->fan_thr;
+    p.norm_script = idx->script_norm;
+    p.n_fan_tok = a.n_tok;
+    p.n_script_tok = idx->n_script_tok;
+    p.chunks = idx->dim_pad / kChunkK;
+    p.window = idx->window;
+    p.shifts_per_stage = idx->shifts_per_stage;
+    p.base_offset_mode = idx->base_offset_mode;
+    p.tiles_m = tiles_m;
+    p.tiles_n = idx->tiles_n;
+    p.cand = (mode == Mode::kCandidates) ? cand_out : idx->cand;
+    p.cand_cap = (mode == Mode::kCandidates) ? cand_out_cap : idx->cand_cap;
+    p.counters = counters;
+    p.dump = (mode == Mode::kDots) ? dots : nullptr;
+    p.dump_ld = dots_ld;
+    const int grid_limit = idx->grid_limit > 0 ? idx->grid_limit : idx->sm_count;
+    const int slot = static_cast<int>(idx->ev_count % kTimingRing);
+    FS_CUDA_CHECK(cudaEventRecord(idx->ev_start[slot], st));
+    if ((r = launch_distance(map_fan, idx->map_script, p, grid_limit, st)) != FS_OK) return r;
+    FS_CUDA_CHECK(cudaEventRecord(idx->ev_stop[slot], st));
+    idx->ev_count++;
+    if (mode != Mode::kSearch) return FS_OK;
+
+    RescoreParams rp{};
+    rp.cand = idx->cand;
+    rp.counters = counters;
+    rp.cand_cap = idx->cand_cap;
+    rp.fan_tok = a.tok;
+    rp.n_fan_tok = a.n_tok;
+    rp.fan_off = a.off;
+    rp.n_works = static_cast<int32_t>(a.n_works);
+    rp.script_tok = idx->script_tok;
+    rp.table = idx->table32;
+    rp.n_base = idx->n_base;
+    rp.script_extra = idx->sx32;
+    rp.n_script_extra = idx->n_sx;
+    rp.fan_extra = a.extra;
+    rp.n_fan_extra = a.n_extra;
+    rp.dim = idx->dim;
+    rp.window = idx->window;
+    rp.threshold = idx->threshold;
+    rp.out = out;
+    rp.out_cap = cap;
+    rp.match_counter = counters + FS_CNT_MATCHES;
+    return launch_rescore(rp, idx->sm_count, st);
+}
+
+// stage a host batch into the index's device staging buffers
+int stage_host_batch(fs_index* idx, const BatchArgs& h, BatchArgs* d) {
+    int r;
+    cudaStream_t st = idx->stream;
+    if ((r = dev_grow(&idx->h_tok, &idx->h_tok_cap, h.n_tok + 8)) != FS_OK) return r;
+    if ((r = dev_grow(&idx->h_off, &idx->h_off_cap, h.n_works + 1)) != FS_OK) return r;
+    if ((r = dev_grow(&idx->h_extra, &idx->h_extra_cap, h.n_extra * idx->dim)) != FS_OK) return r;
+    if (h.n_tok)
+        FS_CUDA_CHECK(cudaMemcpyAsync(idx->h_tok, h.tok, sizeof(int32_t) * h.n_tok,
+                                      cudaMemcpyHostToDevice, st));
+    // ids read past the end of the batch by the last (invalid) windows must stay harmless
+    FS_CUDA_CHECK(cudaMemsetAsync(idx->h_tok + h.n_tok, 0xFF, sizeof(int32_t) * 8, st));
+    FS_CUDA_CHECK(cudaMemcpyAsync(idx->h_off, h.off, sizeof(int64_t) * (h.n_works + 1),
+                                  cudaMemcpyHostToDevice, st));
+    if (h.n_extra)
+        FS_CUDA_CHECK(cudaMemcpyAsync(idx->h_extra, h.extra, sizeof(float) * h.n_extra * idx->dim,
+                                      cudaMemcpyHostToDevice, st));
+    *d = BatchArgs{idx->h_tok, h.n_tok, idx->h_off, h.n_works, idx->h_extra, h.n_extra};
+    return FS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fs_search_csr_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n_tok,
+                      const int64_t* off, int64_t n_works, const float* extra, int64_t n_extra,
+                      fs_match* out, int64_t cap, int64_t* counters) {
+    BatchArgs a{tok, n_tok, off, n_works, extra, n_extra};
+    int r = check_batch(idx, a, "fs_search_csr_dev");
+    if (r != FS_OK) return r;
+    if (!counters || cap < 0 || (cap > 0 && !out)) {
+        set_error("fs_search_csr_dev: invalid output arguments");
+        return FS_E_INVALID;
+    }
+    return run_pipeline(idx, static_cast<cudaStream_t>(stream), a, Mode::kSearch, out, cap, nullptr, 0,
+                        nullptr, 0, reinterpret_cast<unsigned long long*>(counters));
+}
+
+int fs_search_csr_host(fs_index* idx, const int32_t* tok, int64_t n_tok, const int64_t* off,
+                       int64_t n_works, const float* extra, int64_t n_extra, fs_match* out,
+                       int64_t cap, int64_t* counters) {
+    BatchArgs h{tok, n_tok, off, n_works, extra, n_extra};
+    int r = check_batch(idx, h, "fs_search_csr_host");
+    if (r != FS_OK) return r;
+    if (!counters || cap < 0 || (cap > 0 && !out)) {
+        set_error("fs_search_csr_host: invalid output arguments");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    BatchArgs d;
+    if ((r = stage_host_batch(idx, h, &d)) != FS_OK) return r;
+    if ((r = dev_grow(&idx->h_out, &idx->h_out_cap, cap)) != FS_OK) return r;
+    cudaStream_t st = idx->stream;
+    if ((r = run_pipeline(idx, st, d, Mode::kSearch, idx->h_out, cap, nullptr, 0, nullptr, 0,
+                          idx->h_counters)) != FS_OK)
+        return r;
+    FS_CUDA_CHECK(cudaMemcpyAsync(counters, idx->h_counters, sizeof(int64_t) * FS_CNT_COUNT,
+                                  cudaMemcpyDeviceToHost, st));
+    FS_CUDA_CHECK(cudaStreamSynchronize(st));
+    const int64_t n_match = counters[FS_CNT_MATCHES];
+    const int64_t n_copy = n_match < cap ? n_match : cap;
+    if (n_copy > 0) {
+        FS_CUDA_CHECK(cudaMemcpyAsync(out, idx->h_out, sizeof(fs_match) * n_copy,
+                                      cudaMemcpyDeviceToHost, st));
+        FS_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (counters[FS_CNT_CANDIDATES] > idx->cand_cap) {
+        set_error("candidate buffer overflow: %lld candidates, capacity %lld; fs_index_reserve more",
+                  static_cast<long long>(counters[FS_CNT_CANDIDATES]),
+                  static_cast<long long>(idx->cand_cap));
+        return FS_E_OVERFLOW;
+    }
+    if (n_match > cap) {
+        set_error("match buffer overflow: %lld matches, capacity %lld", static_cast<long long>(n_match),
+                  static_cast<long long>(cap));
+        return FS_E_OVERFLOW;
+    }
+    return FS_OK;
+}
+
+int fs_exact_join_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n_tok,
+                      const int64_t* off, int64_t n_works, fs_pair* out, int64_t cap,
+                      int64_t* counters) {
+    BatchArgs a{tok, n_tok, off, n_works, nullptr, 0};
+    int r = check_batch(idx, a, "fs_exact_join_dev");
+    if (r != FS_OK) return r;
+    if (!counters || cap < 0 || (cap > 0 && !out)) {
+        set_error("fs_exact_join_dev: invalid output arguments");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counters);
+    FS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
+    return launch_hash_probe(tok, n_tok, off, static_cast<int32_t>(n_works), idx->script_tok,
+                             idx->window, idx->hash_table, idx->hash_slots, out, cap,
+                             cnt + FS_CNT_EXACT, idx->sm_count, st);
+}
+
+int fs_exact_join_host(fs_index* idx, const int32_t* tok, int64_t n_tok, const int64_t* off,
+                       int64_t n_works, fs_pair* out, int64_t cap, int64_t* counters) {
+    BatchArgs h{tok, n_tok, off, n_works, nullptr, 0};
+    int r = check_batch(idx, h, "fs_exact_join_host");
+    if (r != FS_OK) return r;
+    if (!counters || cap < 0 || (cap > 0 && !out)) {
+        set_error("fs_exact_join_host: invalid output arguments");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    BatchArgs d;
+    if ((r = stage_host_batch(idx, h, &d)) != FS_OK) return r;
+    if ((r = dev_grow(&idx->h_pair, &idx->h_pair_cap, cap)) != FS_OK) return r;
+    cudaStream_t st = idx->stream;
+    if ((r = fs_exact_join_dev(idx, st, d.tok, d.n_tok, d.off, d.n_works, idx->h_pair, cap,
+                               reinterpret_cast<int64_t*>(idx->h_counters))) != FS_OK)
+        return r;
+    FS_CUDA_CHECK(cudaMemcpyAsync(counters, idx->h_counters, sizeof(int64_t) * FS_CNT_COUNT,
+                                  cudaMemcpyDeviceToHost, st));
+    FS_CUDA_CHECK(cudaStreamSynchronize(st));
+    const int64_t n = counters[FS_CNT_EXACT];
+    const int64_t n_copy = n < cap ? n : cap;
+    if (n_copy > 0) {
+        FS_CUDA_CHECK(cudaMemcpyAsync(out, idx->h_pair, sizeof(fs_pair) * n_copy,
+                                      cudaMemcpyDeviceToHost, st));
+        FS_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (n > cap) {
+        set_error("pair buffer overflow: %lld pairs, capacity %lld", static_cast<long long>(n),
+                  static_cast<long long>(cap));
+        return FS_E_OVERFLOW;
+    }
+    return FS_OK;
+}
+
+int fs_stage_embed_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n_tok,
+                       const int64_t* off, int64_t n_works, const float* extra, int64_t n_extra,
+                       void* emb_out, float* thr_out) {
+    BatchArgs a{tok, n_tok, off, n_works, extra, n_extra};
+    int r = check_batch(idx, a, "fs_stage_embed_dev");
+    if (r != FS_OK) return r;
+    if (!emb_out || !thr_out) {
+        set_error("fs_stage_embed_dev: invalid output arguments");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    if ((r = fs_index_reserve(idx, n_tok, idx->cand_cap > 0 ? idx->cand_cap : 1024)) != FS_OK) return r;
+    return embed_batch(idx, static_cast<cudaStream_t>(stream), a, nullptr,
+                       static_cast<__half*>(emb_out), thr_out, n_tok);
+}
+
+int fs_stage_dots_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n_tok,
+                      const int64_t* off, int64_t n_works, const float* extra, int64_t n_extra,
+                      float* dots, int64_t ld) {
+    BatchArgs a{tok, n_tok, off, n_works, extra, n_extra};
+    int r = check_batch(idx, a, "fs_stage_dots_dev");
+    if (r != FS_OK) return r;
+    if (!dots || ld <= 0) {
+        set_error("fs_stage_dots_dev: invalid output arguments");
+        return FS_E_INVALID;
+    }
+    return run_pipeline(idx, static_cast<cudaStream_t>(stream), a, Mode::kDots, nullptr, 0, nullptr, 0,
+                        dots, ld, nullptr);
+}
+
+int fs_stage_candidates_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n_tok,
+                            const int64_t* off, int64_t n_works, const float* extra, int64_t n_extra,
+                            fs_pair* out, int64_t cap, int64_t* counters) {
+    BatchArgs a{tok, n_tok, off, n_works, extra, n_extra};
+    int r = check_batch(idx, a, "fs_stage_candidates_dev");
+    if (r != FS_OK) return r;
+    if (!counters || cap < 0 || (cap > 0 && !out)) {
+        set_error("fs_stage_candidates_dev: invalid output arguments");
+        return FS_E_INVALID;
+    }
+    return run_pipeline(idx, static_cast<cudaStream_t>(stream), a, Mode::kCandidates, nullptr, 0, out,
+                        cap, nullptr, 0, reinterpret_cast<unsigned long long*>(counters));
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+// Shared device/host helpers for the reuse-search kernels (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/fandom_search.h"
+
+namespace fs {
+
+// ---------------------------------------------------------------------------
+// error plumbing (no exceptions cross the C ABI)
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define FS_CUDA_CHECK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            fs::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                          __FILE__, __LINE__);                                           \
+            return FS_E_CUDA;                                                            \
+        }                                                                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// geometry of the distance kernel
+// ---------------------------------------------------------------------------
+constexpr int kBlockM = 128;            // fan windows per tile  (UMMA M, one TMEM lane each)
+constexpr int kBlockN = 256;            // script windows per tile (UMMA N)
+constexpr int kChunkK = 64;             // fp16 elements per smem row = 128 B = one swizzle row
+constexpr int kUmmaK = 16;              // K of one tcgen05.mma.kind::f16
+constexpr int kBoxRows = 136;           // rows per TMA box (128 + 8 halo rows for the shifts)
+constexpr int kStageABytes = kBoxRows * 128;       // 17408 (17 swizzle atoms)
+constexpr int kStageBBytes = 2 * kBoxRows * 128;   // 34816 (272 rows >= 256 + 5)
+constexpr int kStageBytes = kStageABytes + kStageBBytes;  // 52224
+constexpr int kStages = 4;
+constexpr int kAccumStages = 2;         // TMEM double buffer: 2 x 256 columns = all 512
+constexpr int kTmemCols = 512;
+constexpr int kDistThreads = 192;       // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kDistSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct DistParams {
+    const float* thr_fan;     // [Mpad]  (1 - thr - eps) * |fan window|, +inf when invalid
+    const float* norm_script; // [Npad]  |script window|, +inf when invalid
+    int64_t n_fan_tok;        // rows of the fan token matrix (M)
+    int64_t n_script_tok;     // rows of the script token matrix (N)
+    int32_t chunks;           // dim_pad / 64
+    int32_t window;           // 6
+    int32_t shifts_per_stage; // S: 1,2,3,6
+    int32_t base_offset_mode; // how shifted descriptors fill base_offset
+    int32_t tiles_m, tiles_n;
+    fs_pair* cand;            // candidate output
+    int64_t cand_cap;
+    unsigned long long* counters;  // [FS_CNT_COUNT]
+    float* dump;              // optional dense dump [n_fan_tok, dump_ld]
+    int64_t dump_ld;
+};
+
+
+// ---------------------------------------------------------------------------
+// embedding-row sources: ids [0, n_base) -> base table, then the script-side
+// extras (OOV rows registered with the index), then the per-batch fan extras
+// ---------------------------------------------------------------------------
+struct RescoreParams {
+    const fs_pair* cand;
+    const unsigned long long* counters;  // n candidates at FS_CNT_CANDIDATES
+    int64_t cand_cap;
+    const int32_t* fan_tok;
+    int64_t n_fan_tok;
+    const int64_t* fan_off;
+    int32_t n_works;
+    const int32_t* script_tok;
+    const float* table;  // [n_base, dim] fp32
+    int64_t n_base;
+    const float* script_extra;  // [n_script_extra, dim]
+    int64_t n_script_extra;
+    const float* fan_extra;  // [n_fan_extra, dim]
+    int64_t n_fan_extra;
+    int32_t dim;
+    int32_t window;
+    double threshold;
+    fs_match* out;
+    int64_t out_cap;
+    unsigned long long* match_counter;
+};
+
+struct GatherSources {
+    const __half* base16;
+    const float* base_sq;
+    int64_t n_base;
+    const __half* sx16;  // script extras
+    const float* sx_sq;
+    int64_t n_sx;
+    const __half* fx16;  // fan extras of this batch
+    const float* fx_sq;
+    int64_t n_fx;
+};
+
+int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad);
+int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
+                    int grid_limit, cudaStream_t stream);
+int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
+                        __half* dst, float* sq, cudaStream_t stream);
+int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t stream);
+int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,
+                  __half* emb, float* tok_sq, int sm_count, cudaStream_t stream);
+int launch_window_norm(const float* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
+                       int32_t window, float coef, float* out, int64_t n_pad,
+                       unsigned long long* window_counter, cudaStream_t stream);
+int launch_rescore(const RescoreParams& p, int sm_count, cudaStream_t stream);
+int launch_hash_build(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,
+                      int32_t window, unsigned long long* table, uint32_t slots,
+                      cudaStream_t stream);
+int launch_hash_probe(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,
+                      const int32_t* script_tok, int32_t window, const unsigned long long* table,
+                      uint32_t slots, fs_pair* out, int64_t cap, unsigned long long* counter,
+                      int sm_count, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// 2-D tiled TMA load: box of the tensor map at (col, row) -> swizzled smem, completes on mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int32_t col, int32_t row) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(col), "r"(row)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t gets lane (base_lane + t), columns c..c+31
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// K-major, 128-byte-swizzled shared memory operand descriptor (UMMA "matrix descriptor"):
+//   [0,14)  start address >> 4          [16,30) leading byte offset >> 4 (unused for SW128 K-major)
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups
+//   [46,48) descriptor version = 1      [49,52) base offset      [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t base_offset) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(base_offset & 7) << 49;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// instruction descriptor for kind::f16: D=f32, A=B=f16, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+    return (1u << 4)                               // c_format = F32
+           | (0u << 7) | (0u << 10)                // a_format = b_format = F16
+           | (0u << 15) | (0u << 16)               // a_major = b_major = K
+           | (static_cast<uint32_t>(n >> 3) << 17) // n_dim
+           | (static_cast<uint32_t>(m >> 4) << 24);  // m_dim
+}
+
+// first CSR row whose end is > t  (off has n_rows+1 entries, off[0] = 0)
+__device__ __forceinline__ int32_t csr_row_of(const int64_t* __restrict__ off, int32_t n_rows,
+                                              int64_t t) {
+    int32_t lo = 0, hi = n_rows;  // invariant: off[lo] <= t < off[hi]
+    while (hi - lo > 1) {
+        int32_t mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= t)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace fs

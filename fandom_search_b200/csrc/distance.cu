@@ -1,0 +1,282 @@
+// Window-vs-script distance search on tcgen05 tensor cores.
+//
+// Replaces the reference's hot loop (search.py:176-184): for every fan window one
+// engine.neighbours(row) call = cosine distance against script windows, then
+// `distance < distance_threshold`.
+//
+// Formulation.  A window vector is the concatenation of `w` consecutive token rows
+// (search.py:94-95, 170-173), so with E_f [T_f, d_pad] and E_s [T_s, d_pad] (fp16,
+// row-major, zero padded) the window matrices are overlapping strided views and
+//
+//     dot(fanwin_i, scriptwin_j) = sum_{s<w} sum_c  E_f[i+s, c-chunk] . E_s[j+s, c-chunk]
+//
+// One smem stage holds a 64-column chunk of rows [m0+s0, m0+s0+136) of E_f and rows
+// [n0+s0, n0+s0+272) of E_s.  The S shifts served by that stage are plain row offsets
+// of the UMMA shared-memory descriptors (row pitch 128 B inside the 128B-swizzled
+// tile), so every token row is fetched from L2 once per tile instead of `w` times.
+//
+// Roles (192 threads, 1 CTA/SM, persistent over a contiguous range of tiles):
+//   warp 0 lane 0 : TMA producer       (cp.async.bulk.tensor, 4-stage mbarrier ring)
+//   warp 1 lane 0 : tcgen05.mma issuer (128x256x16, fp32 accumulators in TMEM, 2 buffers)
+//   warps 2..5    : epilogue           (tcgen05.ld, norm/threshold compare, compaction)
+//
+// Epilogue.  acc[i][j] > thr_fan[i] * norm_script[j]  <=>  cos > 1 - thr - eps, with
+// thr_fan = (1-thr-eps)*|fanwin_i| (+inf for windows that straddle a work boundary) and
+// norm_script = |scriptwin_j| (+inf for invalid).  Survivors are appended to a global
+// candidate list through an atomic cursor; they are re-scored in float64 afterwards.
+#include "common.cuh"
+
+namespace fs {
+
+template <bool kDump>
+__global__ void __launch_bounds__(kDistThreads, 1)
+distance_kernel(const __grid_constant__ CUtensorMap map_fan,
+                const __grid_constant__ CUtensorMap map_script, const DistParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // layout: [stages x (A | B)] [barriers]
+    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAccumStages + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * kAccumStages);
+    uint32_t* tmem_slot_ptr =
+        reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_fan);
+        tma_prefetch_desc(&map_script);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < kAccumStages; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kTmemCols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    // contiguous range of linearised tiles (n fastest) for this CTA
+    const int64_t total_tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+    const int64_t per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t tile_begin = per_cta * blockIdx.x;
+    const int64_t tile_end = min(total_tiles, tile_begin + per_cta);
+    const int S = p.shifts_per_stage;
+    const int stages_per_tile = p.chunks * (p.window / S);
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------------------------------------ TMA producer
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t t = tile_begin; t < tile_end; ++t) {
+            const int32_t m0 = static_cast<int32_t>(t / p.tiles_n) * kBlockM;
+            const int32_t n0 = static_cast<int32_t>(t % p.tiles_n) * kBlockN;
+            for (int c = 0; c < p.chunks; ++c) {
+                for (int s0 = 0; s0 < p.window; s0 += S) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t a_dst = smem_base + stage * kStageBytes;
+                    const uint32_t b_dst = a_dst + kStageABytes;
+                    mbar_expect_tx(full_bar(stage), kStageBytes);
+                    tma_load_2d(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
+                    tma_load_2d(b_dst, &map_script, full_bar(stage), c * kChunkK, n0 + s0);
+                    tma_load_2d(b_dst + kStageABytes, &map_script, full_bar(stage), c * kChunkK,
+                                n0 + s0 + kBoxRows);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_f16(kBlockM, kBlockN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int64_t t = tile_begin; t < tile_end; ++t) {
+            mbar_wait(tempty_bar(as), aphase ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
+            uint32_t accumulate = 0;
+            for (int it = 0; it < stages_per_tile; ++it) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t a_src = smem_base + stage * kStageBytes;
+                const uint32_t b_src = a_src + kStageABytes;
+                for (int s = 0; s < S; ++s) {
+                    const uint32_t bo = p.base_offset_mode ? static_cast<uint32_t>(s) : 0u;
+#pragma unroll
+                    for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+                        const uint32_t off = static_cast<uint32_t>(s * 128 + k * kUmmaK * 2);
+                        umma_f16(tmem_d, umma_smem_desc(a_src + off, bo),
+                                 umma_smem_desc(b_src + off, bo), idesc, accumulate);
+                        accumulate = 1;
+                    }
+                }
+                umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            umma_commit(tfull_bar(as));  // accumulator tile complete
+            if (++as == kAccumStages) {
+                as = 0;
+                aphase ^= 1u;
+            }
+        }
+    } else if (warp >= 2) {
+        // ------------------------------------------------------------ epilogue
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+        const int row = quarter * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int64_t t = tile_begin; t < tile_end; ++t) {
+            const int32_t m0 = static_cast<int32_t>(t / p.tiles_n) * kBlockM;
+            const int32_t n0 = static_cast<int32_t>(t % p.tiles_n) * kBlockN;
+            const int32_t gi = m0 + row;
+            const float thr = __ldg(p.thr_fan + gi);  // padded to a tile multiple
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>(as * kBlockN);
+#pragma unroll 1
+            for (int ch = 0; ch < kBlockN / 32; ++ch) {
+                uint32_t r[32];
+                __syncwarp();
+                tmem_ld_32x32(taddr + ch * 32, r);
+                tmem_ld_wait();
+                const int32_t gj0 = n0 + ch * 32;
+                if (kDump) {
+                    if (gi < p.n_fan_tok) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            if (gj0 + e < p.dump_ld)
+                                p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + e] =
+                                    __uint_as_float(r[e]);
+                        }
+                    }
+                } else {
+                    const float4* ns4 = reinterpret_cast<const float4*>(p.norm_script + gj0);
+                    bool any = false;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 n4 = __ldg(ns4 + q);
+                        any |= __uint_as_float(r[4 * q + 0]) > thr * n4.x;
+                        any |= __uint_as_float(r[4 * q + 1]) > thr * n4.y;
+                        any |= __uint_as_float(r[4 * q + 2]) > thr * n4.z;
+                        any |= __uint_as_float(r[4 * q + 3]) > thr * n4.w;
+                    }
+                    if (any) {  // rare: hits are sparse
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            if (__uint_as_float(r[e]) > thr * __ldg(p.norm_script + gj0 + e)) {
+                                const unsigned long long slot =
+                                    atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
+                                if (slot < static_cast<unsigned long long>(p.cand_cap)) {
+                                    p.cand[slot].fan_pos = gi;
+                                    p.cand[slot].script_pos = gj0 + e;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (++as == kAccumStages) {
+                as = 0;
+                aphase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    return fn;
+}
+
+// tensor map over a row-major fp16 matrix [rows, dim_pad]; box = 64 columns x 136 rows, SW128
+int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+        return FS_E_NODEVICE;
+    }
+    if (rows < 1) rows = 1;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim_pad), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim_pad) * sizeof(__half)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(kBoxRows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld dim_pad=%d)",
+                  static_cast<int>(r), static_cast<long long>(rows), dim_pad);
+        return FS_E_CUDA;
+    }
+    return FS_OK;
+}
+
+int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
+                    int grid_limit, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kDistSmemBytes));
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kDistSmemBytes));
+        attr_set = true;
+    }
+    const int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+    if (total <= 0) return FS_OK;
+    int grid = static_cast<int>(total < grid_limit ? total : grid_limit);
+    if (p.dump)
+        distance_kernel<true><<<grid, kDistThreads, kDistSmemBytes, stream>>>(map_fan, map_script, p);
+    else
+        distance_kernel<false><<<grid, kDistThreads, kDistSmemBytes, stream>>>(map_fan, map_script, p);
+    FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
+}  // namespace fs

@@ -1,0 +1,153 @@
+// Token gather and window norms.
+//
+// Replaces mk_vectors (search.py:65-84) and the rolling-window build
+// (search.py:94-95, 169-173).  The reference materialises a float64 [T-5, 1800]
+// window matrix per work; here only the per-token matrix E [T, dim_pad] (fp16) is
+// written and a window is the strided view E[i : i+w, :] that the distance kernel's
+// TMA loads address directly.  HBM-bound: 4 B read + dim_pad*2 B written per token
+// (table rows are L2 hits).
+#include "common.cuh"
+
+namespace fs {
+
+// fp32 rows -> scaled fp16 rows padded to dim_pad, plus the squared norm of the scaled row
+// (one warp per row).  Used once for the base table and per batch for OOV extras.
+__global__ void convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int32_t dim,
+                                    int32_t dim_pad, float scale, __half* __restrict__ dst,
+                                    float* __restrict__ sq) {
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const float* s = src + row * dim;
+    __half* d = dst + row * dim_pad;
+    float acc = 0.f;
+    for (int c = lane; c < dim_pad; c += 32) {
+        float v = c < dim ? s[c] * scale : 0.f;
+        const __half h = __float2half_rn(v);
+        d[c] = h;
+        acc = fmaf(v, v, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sq[row] = acc;
+}
+
+// max |x| over a float array (for the global fp16 scale); result via atomicMax on the bit pattern
+__global__ void absmax_kernel(const float* __restrict__ src, int64_t n, unsigned int* out) {
+    float m = 0.f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float v = fabsf(src[i]);
+        if (isfinite(v)) m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+// E[t, :] = rows16[tok[t]]  (one 16-byte chunk per thread, fully coalesced stores)
+__global__ void gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSources src,
+                              int32_t chunks16 /* dim_pad*2/16 */, int4* __restrict__ emb,
+                              float* __restrict__ tok_sq) {
+    const int64_t total = n_tok * chunks16;
+    const int4* base16 = reinterpret_cast<const int4*>(src.base16);
+    const int4* sx16 = reinterpret_cast<const int4*>(src.sx16);
+    const int4* fx16 = reinterpret_cast<const int4*>(src.fx16);
+    for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
+         g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t t = g / chunks16;
+        const int32_t c = static_cast<int32_t>(g - t * chunks16);
+        int64_t id = __ldg(tok + t);
+        int4 v = make_int4(0, 0, 0, 0);  // unknown ids embed as the zero vector
+        float sq = 0.f;
+        if (id >= 0 && id < src.n_base) {
+            v = __ldg(base16 + id * chunks16 + c);
+            if (c == 0) sq = __ldg(src.base_sq + id);
+        } else if ((id -= src.n_base) >= 0 && id < src.n_sx) {
+            v = __ldg(sx16 + id * chunks16 + c);
+            if (c == 0) sq = __ldg(src.sx_sq + id);
+        } else if ((id -= src.n_sx) >= 0 && id < src.n_fx) {
+            v = __ldg(fx16 + id * chunks16 + c);
+            if (c == 0) sq = __ldg(src.fx_sq + id);
+        }
+        emb[g] = v;
+        if (c == 0) tok_sq[t] = sq;
+    }
+}
+
+// Per window start t:  norm = sqrt(sum_{k<w} tok_sq[t+k]) when the window lies inside its
+// CSR row, else +inf.  out[t] = coef * norm  (coef = 1-thr-eps on the fan side, 1 on the
+// script side).  out is padded with +inf up to n_pad.
+__global__ void window_norm_kernel(const float* __restrict__ tok_sq, int64_t n_tok,
+                                   const int64_t* __restrict__ off, int32_t n_rows, int32_t window,
+                                   float coef, float* __restrict__ out, int64_t n_pad,
+                                   unsigned long long* window_counter) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    unsigned int valid = 0;
+    if (t < n_pad) {
+        float r = INFINITY;
+        if (t < n_tok) {
+            const int32_t row = csr_row_of(off, n_rows, t);
+            if (t + window <= __ldg(off + row + 1)) {
+                float s = 0.f;
+                for (int k = 0; k < window; ++k) s += tok_sq[t + k];
+                r = coef * sqrtf(s);
+                valid = 1;
+            }
+        }
+        out[t] = r;
+    }
+    if (window_counter) {
+        const unsigned int n = __reduce_add_sync(0xffffffffu, valid);
+        if ((threadIdx.x & 31) == 0 && n) atomicAdd(window_counter, static_cast<unsigned long long>(n));
+    }
+}
+
+int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
+                        __half* dst, float* sq, cudaStream_t stream) {
+    if (n_rows <= 0) return FS_OK;
+    const int threads = 256;
+    const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
+    convert_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(src, n_rows, dim,
+                                                                              dim_pad, scale, dst, sq);
+    FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
+int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t stream) {
+    if (n <= 0) return FS_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    absmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(src, n, out);
+    FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
+int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,
+                  __half* emb, float* tok_sq, int sm_count, cudaStream_t stream) {
+    if (n_tok <= 0) return FS_OK;
+    const int32_t chunks16 = dim_pad * 2 / 16;
+    const int64_t total = n_tok * chunks16;
+    const int threads = 256;
+    int64_t blocks = (total + threads - 1) / threads;
+    const int64_t max_blocks = static_cast<int64_t>(sm_count) * 16;  // 8 resident + 1 more wave
+    if (blocks > max_blocks) blocks = max_blocks;
+    gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        tok, n_tok, src, chunks16, reinterpret_cast<int4*>(emb), tok_sq);
+    FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
+int launch_window_norm(const float* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
+                       int32_t window, float coef, float* out, int64_t n_pad,
+                       unsigned long long* window_counter, cudaStream_t stream) {
+    if (n_pad <= 0) return FS_OK;
+    const int threads = 256;
+    const int64_t blocks = (n_pad + threads - 1) / threads;
+    window_norm_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+        tok_sq, n_tok, off, n_rows, window, coef, out, n_pad, window_counter);
+    FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
+}  // namespace fs

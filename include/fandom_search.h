@@ -1,0 +1,201 @@
+/*
+ * fandom_search.h -- C ABI of the B200-native reuse-search hot path.
+ *
+ * This is the drop-in boundary for the one step of senderle/fandom-search that
+ * the reference runs as
+ *
+ *     pool.map(multi_search_wrapper, fan_cluster)          (search.py:381-386)
+ *       -> AnnIndexSearch.search(filename)                 (search.py:163-226)
+ *            -> mk_vectors / rolling 6-gram windows        (search.py:65-84,169-173)
+ *            -> engine.neighbours(row) per window          (search.py:176-178)
+ *            -> distance < distance_threshold              (search.py:182-184)
+ *
+ * The reference has no FFI; its seam is that Python call.  The entry points
+ * below are what a ctypes binding of that seam calls (see INTEGRATION.md for
+ * the reference-side stub).  Plain pointers and sizes only; no exceptions and
+ * no C++/torch types cross this boundary.
+ *
+ * Conventions
+ *   - Every function returns FS_OK (0) or a negative fs_status.  A human
+ *     readable message for the last failure on the calling thread is available
+ *     from fs_last_error().
+ *   - "_dev" entry points take DEVICE pointers, enqueue work on `stream`
+ *     (a cudaStream_t passed as void*) and do not synchronise.
+ *     "_host" entry points take HOST pointers, do the H2D/D2H copies
+ *     themselves and return after the stream has drained.
+ *   - The caller owns every buffer it passes in.  An fs_index owns only its
+ *     device copies and workspace.  An fs_index is bound to one device and is
+ *     not thread safe: one per process/GPU, calls issued from one thread.
+ *   - Token positions are indices into the CSR token array of the call
+ *     (all works of the batch concatenated); `work` is the CSR row.
+ */
+#ifndef FANDOM_SEARCH_H_
+#define FANDOM_SEARCH_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_ABI_VERSION 1
+
+typedef enum fs_status {
+    FS_OK = 0,
+    FS_E_INVALID = -1,   /* bad argument                                          */
+    FS_E_CUDA = -2,      /* a CUDA runtime/driver call failed                     */
+    FS_E_OVERFLOW = -3,  /* an output/candidate buffer was too small; counters
+                            hold the required sizes, call again with more room  */
+    FS_E_NOMEM = -4,     /* device or host allocation failed                      */
+    FS_E_NODEVICE = -5   /* no sm_100 device / driver entry point unavailable    */
+} fs_status;
+
+typedef struct fs_index fs_index; /* opaque */
+
+/* One surviving (fan window, script window) pair.
+ * Replaces one element of the list built at search.py:182-184:
+ * (match_ix, match_str, distance) for the fan window fan_ix. */
+typedef struct fs_match {
+    int32_t fan_pos;    /* first token of the fan window, index into the CSR token array */
+    int32_t script_pos; /* first token of the script window (= match_ix, search.py:183)  */
+    double distance;    /* 1.0 - dot(unit(script window), unit(fan window)), float64     */
+    int32_t work;       /* CSR row (fanwork) the window belongs to                       */
+    uint32_t flags;     /* FS_MATCH_* bits                                               */
+} fs_match;
+
+#define FS_MATCH_EXACT 1u /* the six embedding-row ids are identical (distance-0 case,
+                             what ao3.py:353-355 reads as BEST_COMBINED_DISTANCE <= 0) */
+
+/* One exact 6-gram hit of the hash-join kernel. */
+typedef struct fs_pair {
+    int32_t fan_pos;
+    int32_t script_pos;
+} fs_pair;
+
+/* Device-side counters written by the search entry points (all int64). */
+enum {
+    FS_CNT_CANDIDATES = 0, /* pairs that passed the tensor-core pre-filter          */
+    FS_CNT_MATCHES = 1,    /* pairs with float64 distance < threshold                */
+    FS_CNT_EXACT = 2,      /* pairs emitted by the hash-join                         */
+    FS_CNT_WINDOWS = 3,    /* fan windows searched = sum max(T_i - w + 1, 0)         */
+    FS_CNT_COUNT = 4
+};
+
+/* Options for fs_index_set_option. */
+enum {
+    FS_OPT_SHIFTS_PER_STAGE = 1, /* 1, 2, 3 or 6: token-row shifts served by one smem stage */
+    FS_OPT_BASE_OFFSET_MODE = 2, /* 0/1: UMMA descriptor base_offset handling for shifted rows */
+    FS_OPT_GRID_LIMIT = 3        /* max CTAs of the persistent distance kernel (0 = #SMs)  */
+};
+
+int fs_abi_version(void);
+const char* fs_last_error(void);
+int fs_device_count(void);
+
+/*
+ * Build the script-side index (replaces AnnIndexSearch.__init__ +
+ * build_lsh_engine, search.py:131-154, 86-124).
+ *
+ *   table        host  [n_rows, dim] float32   embedding rows (spaCy vectors table)
+ *   extra        host  [n_extra, dim] float32  rows for ids >= n_rows (OOV pseudo
+ *                                              vectors of search.py:79-83); may be NULL
+ *   script_tok   host  [n_script_tok] int32    embedding-row id per script token
+ *   script_off   host  [n_scripts + 1] int64   CSR offsets; windows never straddle scripts
+ *   window       6 in the reference (search.py:337)
+ *   threshold    0.1 in the reference (search.py:340); matches have distance < threshold
+ */
+int fs_index_create(fs_index** out, int device,
+                    const float* table, int64_t n_rows, int32_t dim,
+                    const float* extra, int64_t n_extra,
+                    const int32_t* script_tok, int64_t n_script_tok,
+                    const int64_t* script_off, int64_t n_scripts,
+                    int32_t window, double threshold);
+int fs_index_destroy(fs_index* idx);
+
+/* Pre-size the workspace (token capacity of one batch, candidate capacity).
+ * Optional: search calls grow the workspace on demand (which synchronises). */
+int fs_index_reserve(fs_index* idx, int64_t max_tokens, int64_t max_candidates);
+int fs_index_set_option(fs_index* idx, int32_t option, int64_t value);
+int64_t fs_index_get_info(const fs_index* idx, int32_t what); /* 0: script windows, 1: dim_pad, 2: SM count */
+
+/*
+ * Search one batch of fanworks (replaces the pool.map over one cluster,
+ * search.py:381-386, up to and including the threshold test at :182-184).
+ *
+ *   tok        [n_tok] int32   embedding-row id per fan token, works concatenated
+ *   off        [n_works+1] int64 CSR offsets
+ *   extra      [n_extra, dim] float32 rows for ids >= n_rows + (index extras); may be NULL
+ *   out        [cap] fs_match  in arbitrary order
+ *   counters   [FS_CNT_COUNT] int64
+ *
+ * Returns FS_E_OVERFLOW (host variant only) when counters[FS_CNT_MATCHES] > cap or
+ * the internal candidate buffer overflowed; the first `cap` slots are valid.
+ */
+int fs_search_csr_dev(fs_index* idx, void* stream,
+                      const int32_t* tok, int64_t n_tok,
+                      const int64_t* off, int64_t n_works,
+                      const float* extra, int64_t n_extra,
+                      fs_match* out, int64_t cap, int64_t* counters);
+int fs_search_csr_host(fs_index* idx,
+                       const int32_t* tok, int64_t n_tok,
+                       const int64_t* off, int64_t n_works,
+                       const float* extra, int64_t n_extra,
+                       fs_match* out, int64_t cap, int64_t* counters);
+
+/* Exact 6-gram hash-join only (the distance-0 special case). */
+int fs_exact_join_dev(fs_index* idx, void* stream,
+                      const int32_t* tok, int64_t n_tok,
+                      const int64_t* off, int64_t n_works,
+                      fs_pair* out, int64_t cap, int64_t* counters);
+int fs_exact_join_host(fs_index* idx,
+                       const int32_t* tok, int64_t n_tok,
+                       const int64_t* off, int64_t n_works,
+                       fs_pair* out, int64_t cap, int64_t* counters);
+
+/*
+ * Stage-level entry points used by the parity tests and by bench.py to time
+ * one kernel at a time.  All pointers are DEVICE pointers.
+ */
+/* token gather + window norms: emb_out [n_tok, dim_pad] fp16, thr_out [n_tok] float */
+int fs_stage_embed_dev(fs_index* idx, void* stream,
+                       const int32_t* tok, int64_t n_tok,
+                       const int64_t* off, int64_t n_works,
+                       const float* extra, int64_t n_extra,
+                       void* emb_out, float* thr_out);
+/* tensor-core window-vs-script contraction, dense dump: dots [n_tok, ld] float
+ * (scaled by the index's global scale^2); for small inputs only. */
+int fs_stage_dots_dev(fs_index* idx, void* stream,
+                      const int32_t* tok, int64_t n_tok,
+                      const int64_t* off, int64_t n_works,
+                      const float* extra, int64_t n_extra,
+                      float* dots, int64_t ld);
+/* tensor-core pre-filter only: candidate pairs, no float64 rescoring */
+int fs_stage_candidates_dev(fs_index* idx, void* stream,
+                            const int32_t* tok, int64_t n_tok,
+                            const int64_t* off, int64_t n_works,
+                            const float* extra, int64_t n_extra,
+                            fs_pair* out, int64_t cap, int64_t* counters);
+/* Device time of the distance kernel, measured with CUDA events recorded on the
+ * launching stream around every launch since the last reset (ring of 256 launches).
+ * fs_timing_read synchronises on the recorded events. */
+int fs_timing_reset(fs_index* idx);
+int fs_timing_read(fs_index* idx, double* total_ms, int64_t* launches);
+float fs_index_scale(const fs_index* idx);
+
+/*
+ * Host-side text helpers of the path (native, no GPU).
+ */
+/* Unit-cost edit distance over Unicode code points of two UTF-8 strings
+ * (replaces Levenshtein.distance, search.py:14,190). */
+int32_t fs_levenshtein_utf8(const char* a, int64_t a_len, const char* b, int64_t b_len);
+/* MurmurHash64A(key, len, seed) -- spaCy's 64-bit string id uses seed 1
+ * (FAN_WORK_ORTH_ID / ORIGINAL_SCRIPT_ORTH_ID columns, search.py:195,327). */
+uint64_t fs_murmurhash64a(const void* key, int64_t len, uint64_t seed);
+/* Split UTF-8 text on ASCII whitespace.  Writes up to cap (start,end) byte
+ * offsets; returns the number of tokens found (may exceed cap). */
+int64_t fs_tokenize_ws(const char* text, int64_t len, int64_t* starts, int64_t* ends, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FANDOM_SEARCH_H_ */

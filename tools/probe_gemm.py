@@ -1,0 +1,128 @@
+"""Hardware probe: which UMMA descriptor variants reproduce the window contraction?
+
+Run on a B200:  python tools/probe_gemm.py
+Compares fs_stage_dots_dev (tcgen05 path, dense dump) against a numpy contraction of the
+same fp16-rounded operands for every (shifts_per_stage, base_offset_mode) variant.
+"""
+import sys
+import time
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from fandom_search_b200 import _native as nt
+from fandom_search_b200.engine import DeviceIndex
+
+
+def ref_dots(table, scale, tok_f, tok_s, w):
+    e16 = (table * np.float32(scale)).astype(np.float16).astype(np.float32)
+    ef = np.zeros((len(tok_f) + w, table.shape[1]), np.float32)
+    es = np.zeros((len(tok_s) + w, table.shape[1]), np.float32)
+    ef[:len(tok_f)] = e16[tok_f]
+    es[:len(tok_s)] = e16[tok_s]
+    g = ef @ es.T
+    out = np.zeros((len(tok_f), len(tok_s)), np.float32)
+    for k in range(w):
+        out += g[k:k + len(tok_f), k:k + len(tok_s)]
+    return out
+
+
+def main():
+    rng = np.random.default_rng(0)
+    V, d, w = 3000, 300, 6
+    table = rng.standard_normal((V, d)).astype(np.float32)
+    tok_s = rng.integers(0, V, 700).astype(np.int32)
+    tok_f = rng.integers(0, V, 600).astype(np.int32)
+    off = np.array([0, 200, 203, 600], np.int64)
+    idx = DeviceIndex(table, tok_s, window=w, threshold=0.1)
+    print("scale", idx.scale, "dim_pad", idx.dim_pad, "sms", idx.sm_count, flush=True)
+    ref = ref_dots(table, idx.scale, tok_f, tok_s, w)
+    tok_t, off_t, _ = idx.to_device(tok_f, off)
+    results = {}
+    for S in (1, 2, 3, 6):
+        for bo in (0, 1):
+            if S == 1 and bo == 1:
+                continue
+            idx.set_option(nt.FS_OPT_SHIFTS_PER_STAGE, S)
+            idx.set_option(nt.FS_OPT_BASE_OFFSET_MODE, bo)
+            dots = idx.stage_dots(tok_t, off_t)
+            torch.cuda.synchronize()
+            got = dots.cpu().numpy()
+            err = np.abs(got - ref).max()
+            results[(S, bo)] = float(err)
+            print("variant S=%d base_offset_mode=%d max_abs_err=%.4g (ref absmax %.3g)" %
+                  (S, bo, err, np.abs(ref).max()), flush=True)
+    good = [k for k, v in results.items() if v < 1e-2]
+    print("GOOD_VARIANTS", good, flush=True)
+    if not good:
+        return 1
+    S, bo = max(good)
+    idx.set_option(nt.FS_OPT_SHIFTS_PER_STAGE, S)
+    idx.set_option(nt.FS_OPT_BASE_OFFSET_MODE, bo)
+
+    # full search vs float64 brute force on planted data
+    tok_f2 = tok_f.copy()
+    tok_f2[50:70] = tok_s[100:120]          # verbatim reuse
+    tok_f2[300:312] = tok_s[400:412]
+    m, cnt = idx.search_host(tok_f2, off)
+    t64 = table.astype(np.float64)
+
+    def wins(tok, offs):
+        rows, pos = [], []
+        for a, b in zip(offs[:-1], offs[1:]):
+            for i in range(a, b - w + 1):
+                rows.append(t64[tok[i:i + w]].ravel())
+                pos.append(i)
+        return np.array(rows), np.array(pos)
+    fw, fpos = wins(tok_f2, off)
+    sw, spos = wins(tok_s, np.array([0, len(tok_s)]))
+    fw /= np.linalg.norm(fw, axis=1, keepdims=True)
+    sw /= np.linalg.norm(sw, axis=1, keepdims=True)
+    dist = 1.0 - fw @ sw.T
+    ii, jj = np.nonzero(dist < 0.1)
+    want = set(zip(fpos[ii].tolist(), spos[jj].tolist()))
+    got = set(zip(m["fan_pos"].tolist(), m["script_pos"].tolist()))
+    print("search: want %d got %d missing %d extra %d counters %s" %
+          (len(want), len(got), len(want - got), len(got - want), cnt.tolist()), flush=True)
+    dmap = {(int(fpos[a]), int(spos[b])): dist[a, b] for a, b in zip(ii, jj)}
+    derr = max((abs(dmap[(r["fan_pos"], r["script_pos"])] - r["distance"]) for r in m
+                if (r["fan_pos"], r["script_pos"]) in dmap), default=0.0)
+    print("max |distance - float64 ref| = %.3g" % derr, flush=True)
+
+    # first throughput number: 2.5 M fan tokens vs 25 k script tokens
+    V2 = 50000
+    table2 = rng.standard_normal((V2, d)).astype(np.float32)
+    tok_s2 = rng.integers(0, V2, 25000).astype(np.int32)
+    n_works = 500
+    lens = np.clip(rng.normal(5000, 1000, n_works).round().astype(np.int64), 50, 20000)
+    off2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tok_f3 = rng.integers(0, V2, int(off2[-1])).astype(np.int32)
+    idx2 = DeviceIndex(table2, tok_s2, window=w, threshold=0.1)
+    for (S, bo) in good:
+        idx2.set_option(nt.FS_OPT_SHIFTS_PER_STAGE, S)
+        idx2.set_option(nt.FS_OPT_BASE_OFFSET_MODE, bo)
+        tok_t, off_t, _ = idx2.to_device(tok_f3, off2)
+        out_t = torch.empty(24 << 20, dtype=torch.uint8, device="cuda")
+        cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
+        for it in range(3):
+            if it == 1:
+                idx2.timing_reset()
+                torch.cuda.synchronize()
+                t0 = time.time()
+            idx2.search_dev(tok_t, off_t, None, out_t, cnt_t)
+        torch.cuda.synchronize()
+        dt = (time.time() - t0) / 2
+        ms, n = idx2.timing_read()
+        c = cnt_t.cpu().numpy()
+        nwin = int(c[3])
+        flops = 2.0 * 1800 * idx2.n_script_windows * nwin
+        print("perf S=%d bo=%d: %d windows, step %.1f ms, kernel %.1f ms -> %.2f M win/s, %.0f TFLOP/s dense; counters %s"
+              % (S, bo, nwin, dt * 1e3, ms / n, nwin / (ms / n) / 1e3, flops / (ms / n) / 1e9, c.tolist()),
+              flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
