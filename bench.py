@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the reuse-search hot path (BASELINE.json metric: fanwork 6-gram windows
+searched per second).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+
+Workload (BASELINE.json configs[1], "C2"): synthetic fanworks (~5k tokens each, Zipf text with
+planted reuse) against one feature-length script (25 000 tokens -> 24 995 six-gram windows),
+d = 300, w = 6, threshold 0.1.  One step = one cluster of 500 fanworks (~2.5 M windows), the
+reference's own batch unit (search.py:341,361).  Under torchrun every rank searches its own
+clusters (work-sharded, no data-path collective) -> weak scaling.
+
+Numbers on the JSON line
+  value     windows/s with the cluster's CSR token arrays already resident in HBM, timed with
+            CUDA events over exactly K steps (barrier + synchronize on both sides, max over ranks)
+  e2e       the same K steps through the host-buffer C-ABI call the drop-in search.py makes
+            (fs_search_csr_host): pinned host CSR -> H2D, search, matches -> D2H, every step
+  roofline  distance kernel only: F_dense = 2*(6*300)*24995 flop per window (nominal d, SURVEY
+            8d) x windows per launch / mean launch time from CUDA events recorded on the
+            launching stream inside the timed region; peak = MEASURED_PEAKS.json
+  cpu_baseline  the oracle's port of the reference algorithm (per-window LSH loop over the nearpy
+            stand-in) on a bounded sample of the same workload, on this box's host cores
+"""
+import argparse
+import json
+import multiprocessing
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fanwork 6-gram windows searched/sec"
+UNIT = "windows/s"
+WINDOW = 6
+DIM = 300
+SCRIPT_TOKENS = 25000
+WORKS_PER_STEP = 500
+VOCAB = 50000
+WORKLOAD = ("C2: synthetic fanworks (~5k tokens, Zipf + planted reuse) vs one feature-length script "
+            "(25000 tokens), d=300, w=6, thr=0.1; step = one cluster of 500 fanworks")
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"burst": float(p["bf16_tflops"]), "sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------------------------
+def make_lexicon():
+    from fandom_search_b200 import synth
+    return synth.SynthLexicon(vocab=VOCAB, dim=DIM, oov_frac=0.0, seed=1001)
+
+
+def make_cluster(lex, script, cluster_id):
+    from fandom_search_b200 import synth
+    first = cluster_id * WORKS_PER_STEP
+    words, off = synth.synth_csr_batch(lex, script, range(first, first + WORKS_PER_STEP))
+    return words.astype(np.int32), off
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe) during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's port of the reference algorithm (test infrastructure, timed here
+# only as the reported baseline -- never on the product path)
+# ---------------------------------------------------------------------------------------------
+_CPU_INDEX = None
+_CPU_WORKS = None
+
+
+def _cpu_search_one(k):
+    fan = _CPU_WORKS[k]
+    recs = _CPU_INDEX.search_words(fan, "work%07d.txt" % k)
+    return max(len(fan) - WINDOW + 1, 0), len(recs)
+
+
+class CpuReference:
+    """Reference algorithm (search.py:163-226: per-window nearpy LSH query, 15 tables x 14 bits,
+    threshold, Levenshtein, dedup) over oracle/shims, one process per host core."""
+
+    def __init__(self, lex, script, procs):
+        global _CPU_INDEX
+        from fandom_search_b200 import synth
+        from oracle import reference_search as ora
+        self.lex = lex
+        self.script = script
+        self.procs = procs
+        self.tmp = tempfile.mkdtemp(prefix="fs_cpu_ref_")
+        lex_path = lex.save(os.path.join(self.tmp, "lexicon.npz"))
+        script_path = os.path.join(self.tmp, "script.txt")
+        synth.write_markup_script(lex, script, script_path)
+        t0 = time.perf_counter()
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        _CPU_INDEX = ora.OracleIndex(script_path, ora.OracleLexicon(lex_path), mode="lsh", seed=0,
+                                     engine="nearpy")
+        self.index_build_s = time.perf_counter() - t0
+
+    def run(self, first_work, n_works):
+        """Search n_works synthetic works; returns (windows, seconds)."""
+        global _CPU_WORKS
+        from fandom_search_b200 import synth
+        _CPU_WORKS = {}
+        for k in range(first_work, first_work + n_works):
+            ids, _ = synth.make_fanwork_tokens(self.lex, self.script, k)
+            _CPU_WORKS[k] = self.lex.words[ids].tolist()
+        ctx = multiprocessing.get_context("fork")
+        t0 = time.perf_counter()
+        with ctx.Pool(processes=self.procs) as pool:
+            res = pool.map(_cpu_search_one, sorted(_CPU_WORKS), chunksize=1)
+        dt = time.perf_counter() - t0
+        return sum(r[0] for r in res), dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0") or 0)
+    if rank != 0:
+        return 0
+    procs = max(1, host_cores())
+    lex = make_lexicon()
+    from fandom_search_b200 import synth
+    script = synth.make_script_tokens(lex, SCRIPT_TOKENS)
+    ref = CpuReference(lex, script, procs)
+    works_per_step = procs
+    for w in range(args.warmup):
+        ref.run(10_000_000 + w * works_per_step, works_per_step)
+    windows = 0
+    seconds = 0.0
+    for s in range(args.steps):
+        n, dt = ref.run(s * works_per_step, works_per_step)
+        windows += n
+        seconds += dt
+    value = windows / seconds if seconds > 0 else 0.0
+    sample = ("%d steps x %d synthetic fanworks of the C2 workload (%d windows) vs the 25000-token script; "
+              "oracle port of search.py:163-226 over the nearpy stand-in, seeded LSH 15x14 bits, "
+              "whitespace tokeniser (faster than spaCy), index build %.1f s not timed"
+              % (args.steps, works_per_step, windows, ref.index_build_s))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * seconds / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": "bounded sample: %d fanworks per step" % works_per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------
+def run_native_arm(args):
+    import torch
+    import torch.distributed as dist
+    from fandom_search_b200 import _native as nt
+    from fandom_search_b200 import synth
+    from fandom_search_b200.engine import DeviceIndex
+
+    world = int(os.environ.get("WORLD_SIZE", "1") or 1)
+    rank = int(os.environ.get("RANK", "0") or 0)
+    local = int(os.environ.get("LOCAL_RANK", "0") or 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    lex = make_lexicon()
+    script = synth.make_script_tokens(lex, SCRIPT_TOKENS).astype(np.int32)
+    index = DeviceIndex(lex.table_all, script, window=WINDOW, threshold=0.1, device=local)
+    n_script_windows = index.n_script_windows
+
+    # distinct clusters per rank; a handful are generated and cycled (each step's fp16 token
+    # matrix is 1.6 GB, far larger than the 126 MB L2, so nothing carries over between steps)
+    n_distinct = max(1, min(args.steps + args.warmup, args.distinct))
+    clusters = [make_cluster(lex, script, rank * 1000 + c) for c in range(n_distinct)]
+    max_tok = max(len(t) for t, _ in clusters)
+    index.reserve(max_tok, 1 << 20)
+    cap = 1 << 20
+    dev_in = [index.to_device(t, o) for t, o in clusters]
+    out_t = torch.empty(cap * nt.MATCH_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    cnt_t = torch.zeros((n_distinct, nt.FS_CNT_COUNT), dtype=torch.int64, device=dev)
+    pinned = [(torch.from_numpy(t).pin_memory(), torch.from_numpy(o).pin_memory()) for t, o in clusters]
+    out_host = np.empty(cap, dtype=nt.MATCH_DTYPE)
+    out_host_t = torch.from_numpy(out_host.view(np.uint8)).pin_memory()
+    out_host = out_host_t.numpy().view(nt.MATCH_DTYPE)
+    windows_of = [int(np.maximum(np.diff(o) - (WINDOW - 1), 0).sum()) for _, o in clusters]
+
+    def step_resident(s):
+        c = s % n_distinct
+        tok_t, off_t, _ = dev_in[c]
+        index.search_dev(tok_t, off_t, None, out_t, cnt_t[c])
+
+    def step_host(s):
+        c = s % n_distinct
+        tok_p, off_p = pinned[c]
+        m, counters = index.search_host(tok_p.numpy(), off_p.numpy(), None, cap=cap, out=out_host)
+        return len(m), counters
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------
+    for s in range(args.warmup):
+        step_resident(s)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    index.timing_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for s in range(args.steps):
+        step_resident(args.warmup + s)
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    kernel_ms, launches = index.timing_read()
+    step_windows = sum(windows_of[(args.warmup + s) % n_distinct] for s in range(args.steps))
+    counters = cnt_t.cpu().numpy()
+    for c in range(min(n_distinct, args.steps + args.warmup)):
+        assert counters[c][nt.FS_CNT_WINDOWS] == windows_of[c], "window count mismatch"
+        assert counters[c][nt.FS_CNT_MATCHES] <= cap and counters[c][nt.FS_CNT_CANDIDATES] <= (1 << 20)
+
+    # ---- e2e: host buffers through the C-ABI call of the drop-in --------------------------------
+    for s in range(min(args.warmup, 2)):
+        step_host(s)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for s in range(args.steps):
+        n_match, _ = step_host(args.warmup + s)
+        d2h += n_match * nt.MATCH_DTYPE.itemsize + 8 * nt.FS_CNT_COUNT
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = sum(clusters[(args.warmup + s) % n_distinct][0].nbytes + clusters[(args.warmup + s) % n_distinct][1].nbytes
+              for s in range(args.steps))
+
+    # ---- reduce over ranks: max time, summed windows ------------------------------------------
+    stats = torch.tensor([elapsed_ms, e2e_s * 1e3, float(step_windows)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        elapsed_ms, e2e_ms, total_windows = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        e2e_ms, total_windows = e2e_s * 1e3, float(step_windows)
+
+    peaks = measured_peaks()
+    f_dense = 2.0 * WINDOW * DIM * n_script_windows
+    win_per_launch = step_windows / max(launches, 1)
+    achieved_tflops = f_dense * win_per_launch / (kernel_ms / max(launches, 1) * 1e-3) / 1e12 if launches else 0.0
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "distance_kernel_ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        procs = max(1, host_cores())
+        ref = CpuReference(lex, script, procs)
+        n_works = max(procs, min(4 * procs, 64))
+        n, dt = ref.run(0, n_works)
+        cpu_baseline = {
+            "value": n / dt, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": "%d synthetic fanworks of the same workload (%d windows, %.1f s) vs the 25000-token script; "
+                      "oracle port of search.py:163-226 (seeded 15x14-bit LSH over the nearpy stand-in), "
+                      "index build %.1f s not timed" % (n_works, n, dt, ref.index_build_s)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": total_windows / (elapsed_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "script_windows": n_script_windows,
+                       "windows_per_step_per_gpu": step_windows // max(args.steps, 1),
+                       "parallelism": "work-sharded x%d, script index replicated" % world,
+                       "l2": "inputs larger than L2 (1.6 GB fp16 token matrix per step)",
+                       "precision": "fp16 tcgen05 pre-filter (fp32 accumulate, slack 2e-3) + float64 rescoring"},
+            "clocks": clocks,
+            "e2e": {"value": total_windows / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1)},
+            "gpu_launches": 4 * args.steps * world,
+            "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["sustained"],
+                         "unit": "TFLOP/s", "frac": achieved_tflops / peaks["sustained"],
+                         "traffic": traffic, "peak_kind": "%s sustained bf16 cuBLAS" % peaks["source"],
+                         "frac_of_burst": achieved_tflops / peaks["burst"],
+                         "kernel": "distance_kernel", "kernel_ms_per_launch": kernel_ms / max(launches, 1),
+                         "kernel_share_of_step": kernel_ms / elapsed_ms if elapsed_ms else None,
+                         "flop_per_window": f_dense},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic clusters cycled per rank")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1") or 1)
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_native_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

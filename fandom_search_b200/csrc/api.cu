@@ -40,7 +40,7 @@ static int dev_alloc(T** p, int64_t count) {
 template <typename T>
 static int dev_grow(T** p, int64_t* cap, int64_t need) {
     if (need <= *cap && *p) return FS_OK;
-    int64_t ncap = *cap > 0 ? *cap : 1;
+    int64_t ncap = *cap > 0 ? *cap : need;  // first allocation is exact, growth is geometric
     while (ncap < need) ncap += ncap / 2 + 1024;
     if (*p) {
         cudaDeviceSynchronize();

@@ -1,0 +1,492 @@
+"""Drop-in replacement for the reference's `search.py` call surface, on the B200 path.
+
+`ao3.py` reaches this module at `search.analyze` (ao3.py:519), `search.validate_cmd`
+(ao3.py:511) and `search.load_markup_script` (ao3.py:365,434); names, argument meaning, file
+naming and the CSV schema follow /root/reference/search.py.  What changes is underneath:
+
+  reference (search.py:381-386)                   here
+  ------------------------------------------      -------------------------------------------
+  Pool(4).map(multi_search_wrapper, cluster)  ->  AnnIndexSearch.search_many(cluster):
+    per work: spaCy tokens -> float64 windows       tokens -> CSR row ids -> ONE C-ABI call
+    per window: nearpy LSH neighbours()             (gather + tcgen05 window contraction +
+    threshold, Levenshtein, explode, dedup          float64 rescoring on the GPU), then the
+                                                    same Levenshtein/explode/dedup on the few
+                                                    surviving pairs
+
+The default search is exhaustive (a superset of what the reference's LSH finds; identical for
+identical windows).  FANDOM_SEARCH_MODE=lsh reproduces a seeded random-hyperplane index
+exactly (FANDOM_SEARCH_LSH_SEED), see `lsh.py`.  There is no CPU fallback: without the CUDA
+library or a B200 the search raises.
+
+Environment knobs (the CLI itself is unchanged):
+  FANDOM_SEARCH_LEXICON   path of the lexicon .npz (stand-in for spaCy's en_core_web_md table)
+  FANDOM_SEARCH_MODE      exhaustive (default) | lsh
+  FANDOM_SEARCH_LSH_SEED  int seed of the emulated hyperplanes (mode lsh)
+  FANDOM_SEARCH_DEVICE    CUDA device ordinal (default: LOCAL_RANK or 0)
+  FANDOM_SEARCH_OOV_HASH  python (default: builtin hash, as the reference) | seed0
+"""
+import csv
+import datetime
+import os
+import random
+import re
+import sys
+
+import numpy
+
+from . import _native as nt
+from . import text as _text
+from .lexicon import Lexicon, py_hash_seed0
+
+_SPACY_MODEL = None
+_ANN_INDEX = None
+
+# search.py:20-37 -- the CSV schema is the drop-in contract
+new_record_structure = {
+    'fields': ['FAN_WORK_FILENAME',
+               'FAN_WORK_WORD_INDEX',
+               'FAN_WORK_WORD',
+               'FAN_WORK_ORTH_ID',
+               'ORIGINAL_SCRIPT_WORD_INDEX',
+               'ORIGINAL_SCRIPT_WORD',
+               'ORIGINAL_SCRIPT_ORTH_ID',
+               'ORIGINAL_SCRIPT_CHARACTER',
+               'ORIGINAL_SCRIPT_SCENE',
+               'BEST_MATCH_DISTANCE',
+               'BEST_LEVENSHTEIN_DISTANCE',
+               'BEST_COMBINED_DISTANCE'],
+    'types': [str, int, str, int, int, str, int, str, int, float, int, float],
+}
+
+
+class Token(object):
+    """What the hot path needs of a spaCy Token (search.py:166,194-195,327)."""
+    __slots__ = ('text',)
+
+    def __init__(self, text):
+        self.text = text
+
+    is_space = False
+
+    @property
+    def orth_(self):
+        return self.text
+
+    @property
+    def orth(self):
+        return _text.string_id(self.text)
+
+    @property
+    def lower_(self):
+        return self.text.lower()
+
+    @property
+    def lower(self):
+        return _text.string_id(self.text.lower())
+
+    def __str__(self):
+        return self.text
+
+    __repr__ = __str__
+
+
+class Pipeline(object):
+    """Tokeniser + lexicon; stands where the reference holds the spaCy model."""
+
+    def __init__(self, lexicon, tokenizer=None):
+        self.lexicon = lexicon
+        self.tokenizer = tokenizer or _text.tokenize
+
+    def __call__(self, text):
+        return [Token(w) for w in self.tokenizer(text)]
+
+
+def set_pipeline(pipeline):
+    """Install the tokeniser/lexicon explicitly (instead of FANDOM_SEARCH_LEXICON)."""
+    global _SPACY_MODEL
+    _SPACY_MODEL = pipeline
+
+
+def get_spacy_model():
+    # search.py:40-45 (lazy module-level singleton)
+    global _SPACY_MODEL
+    if _SPACY_MODEL is None:
+        path = os.environ.get('FANDOM_SEARCH_LEXICON')
+        if not path:
+            raise RuntimeError(
+                "no lexicon configured: set FANDOM_SEARCH_LEXICON to a lexicon .npz exported "
+                "from the spaCy vectors table (Lexicon.from_spacy) or call search.set_pipeline()")
+        hash_fn = py_hash_seed0 if os.environ.get('FANDOM_SEARCH_OOV_HASH') == 'seed0' else None
+        _SPACY_MODEL = Pipeline(Lexicon.from_npz(path, hash_fn=hash_fn))
+    return _SPACY_MODEL
+
+
+def sp_parse_chunks(txt, size=100000):
+    # search.py:47-63: texts of 100000+ characters are cut at spaces into <=100k pieces.
+    # (`size` is ignored there too.)  With a whitespace tokeniser the pieces tokenise to the
+    # same stream as the whole text; kept for call-surface parity.
+    model = get_spacy_model()
+    if len(txt) < 100000:
+        yield model(txt)
+        return
+    start = 0
+    while start < len(txt):
+        end = start + 100000
+        if end > len(txt):
+            end = len(txt)
+        else:
+            while txt[end] != ' ':   # IndexError at end == len(txt), as in the reference
+                end -= 1
+        yield model(txt[start:end])
+        start = end + 1
+
+
+def mk_vectors(sp_txt):
+    # search.py:65-84, host restatement for API parity (the search itself gathers on the GPU)
+    lex = get_spacy_model().lexicon
+    rows = len(sp_txt)
+    cols = lex.dim if rows else 0
+    vectors = numpy.empty((rows, cols), dtype=float)
+    for i, word in enumerate(sp_txt):
+        vectors[i] = lex.vector(str(word))
+    return vectors
+
+
+def _device_ordinal():
+    for key in ('FANDOM_SEARCH_DEVICE', 'LOCAL_RANK'):
+        v = os.environ.get(key)
+        if v not in (None, ''):
+            return int(v)
+    return 0
+
+
+class ScriptEngine(object):
+    """Returned by build_lsh_engine: the device-resident script index (replaces the nearpy
+    Engine of search.py:118-123).  The per-window `neighbours(v)` seam of nearpy is replaced
+    by the batched `DeviceIndex.search_host`."""
+
+    def __init__(self, device_index, lsh=None):
+        self.index = device_index
+        self.lsh = lsh
+
+    def neighbours(self, v):
+        raise NotImplementedError(
+            "the per-window nearpy seam (search.py:178) is replaced by the batched GPU search; "
+            "use AnnIndexSearch.search / search_many")
+
+    def store_vector(self, v, data=None):
+        raise NotImplementedError("the script index is immutable once built")
+
+
+def build_lsh_engine(orig, window_size, number_of_hashes, hash_dimensions,
+                     distance_threshold=0.1):
+    # search.py:86-124: script tokens -> device index.  `orig` is the sequence of script
+    # tokens (lower-cased words).
+    from .engine import DeviceIndex
+    lex = get_spacy_model().lexicon
+    words = [str(t) for t in orig]
+    script_tok = lex.row_ids(words)
+    n_sx = lex.n_oov
+    index = DeviceIndex(lex.table, script_tok, extra=lex.oov_rows(0, n_sx), window=window_size,
+                        threshold=distance_threshold, device=_device_ordinal())
+    lsh = None
+    if os.environ.get('FANDOM_SEARCH_MODE', 'exhaustive') == 'lsh':
+        from .lsh import LshEmulation
+        seed = int(os.environ.get('FANDOM_SEARCH_LSH_SEED', '0'))
+        lsh = LshEmulation(number_of_hashes, hash_dimensions, window_size * lex.dim, seed)
+    engine = ScriptEngine(index, lsh)
+    engine.script_tok = script_tok
+    engine.n_script_extra = n_sx
+    return engine
+
+
+def multi_search_wrapper(work):
+    # search.py:126-128
+    result = _ANN_INDEX.search(work)
+    return result
+
+
+class AnnIndexSearch(object):
+    def __init__(self, original_script_filename, window_size,
+                 number_of_hashes, hash_dimensions, distance_threshold):
+        # search.py:131-154
+        orig_csv = load_markup_script(original_script_filename)
+        orig_csv = orig_csv[1:]
+        if orig_csv:
+            (self.word_lowercase, self.orth_id, self.scene, self.character) = zip(*orig_csv)
+        else:
+            self.word_lowercase = self.orth_id = self.scene = self.character = ()
+        self.word_index = tuple(range(len(self.word_lowercase)))
+        self.window_size = window_size
+        self.distance_threshold = distance_threshold
+        self.spacy_model = get_spacy_model()
+        self.engine = build_lsh_engine(self.word_lowercase, window_size, number_of_hashes,
+                                       hash_dimensions, distance_threshold)
+        self.reset_stats()
+
+    def reset_stats(self):
+        self._windows_processed = 0
+
+    @property
+    def windows_processed(self):
+        return self._windows_processed
+
+    # -- host side of one batch --------------------------------------------
+    def _tokenize_file(self, filename):
+        # search.py:164-166.  Returns the token TEXTS (no per-token objects on the fast path).
+        # The reference tokenises >=100k-character texts in pieces cut at spaces
+        # (sp_parse_chunks); a whitespace tokeniser yields the same stream for the whole text.
+        with open(filename, encoding='utf8') as fan_file:
+            fan = fan_file.read()
+        return self.spacy_model.tokenizer(fan)
+
+    def search(self, filename):
+        # search.py:163-226 for one work
+        return self.search_many([filename])[0]
+
+    def search_many(self, filenames):
+        """Record lists (one per file, each sorted) for a cluster of works."""
+        lex = self.spacy_model.lexicon
+        n_fixed = lex.n_rows + self.engine.n_script_extra
+        fans = [self._tokenize_file(fn) for fn in filenames]
+        offs = numpy.zeros(len(fans) + 1, dtype=numpy.int64)
+        for i, fan in enumerate(fans):
+            offs[i + 1] = offs[i] + len(fan)
+        tok = numpy.empty(int(offs[-1]), dtype=numpy.int32)
+        for i, fan in enumerate(fans):
+            tok[offs[i]:offs[i + 1]] = lex.row_ids(fan)
+        # batch-local numbering of the fan-side OOV rows
+        extra = None
+        is_new = tok >= n_fixed
+        if is_new.any():
+            uniq, inv = numpy.unique(tok[is_new], return_inverse=True)
+            tok[is_new] = (n_fixed + inv).astype(numpy.int32)
+            extra = numpy.concatenate(
+                [lex.oov_rows(int(u) - lex.n_rows, int(u) - lex.n_rows + 1) for u in uniq], axis=0)
+        matches, counters = self.engine.index.search_host(tok, offs, extra)
+        self._windows_processed += int(counters[nt.FS_CNT_WINDOWS])
+        if self.engine.lsh is not None and len(matches):
+            keep = self.engine.lsh.shared_bucket_mask(self, lex, tok, extra, n_fixed, matches)
+            matches = matches[keep]
+        return self._records(filenames, fans, offs, matches)
+
+    def _records(self, filenames, fans, offs, matches):
+        w = self.window_size
+        out = [[] for _ in filenames]
+        if len(matches) == 0:
+            return out
+        # neighbours() returns candidates sorted by distance (stable, script order on ties),
+        # at most 10 of them (NearestFilter(10)); windows are visited in ascending order
+        order = numpy.lexsort((matches['script_pos'], matches['distance'], matches['fan_pos']))
+        m = matches[order]
+        fan_pos = m['fan_pos']
+        first = numpy.r_[True, fan_pos[1:] != fan_pos[:-1]]
+        group_start = numpy.maximum.accumulate(numpy.where(first, numpy.arange(len(m)), 0))
+        rank = numpy.arange(len(m)) - group_start
+        m = m[rank < 10]
+        lev_cache = {}
+        per_work = {}
+        for rec in m:
+            per_work.setdefault(int(rec['work']), []).append(rec)
+        for wi, recs in per_work.items():
+            filename = filenames[wi]
+            fan = fans[wi]
+            base = int(offs[wi])
+            best = {}
+            for rec in recs:
+                fan_ix = int(rec['fan_pos']) - base
+                match_ix = int(rec['script_pos'])
+                distance = float(rec['distance'])
+                # search.py:123,189-190: str(Span) vs str(list of Token)
+                match_str = ' '.join(self.word_lowercase[match_ix:match_ix + w])
+                fan_context = '[' + ', '.join(fan[fan_ix:fan_ix + w]) + ']'
+                key = (match_str, fan_context)
+                lev_d = lev_cache.get(key)
+                if lev_d is None:
+                    lev_d = _text.levenshtein(match_str, fan_context)
+                    lev_cache[key] = lev_d
+                combined = distance * lev_d
+                for window_ix in range(w):
+                    fan_word_ix = fan_ix + window_ix
+                    cur = best.get(fan_word_ix)
+                    # min(..., key=itemgetter(11)) keeps the FIRST minimal record
+                    if cur is None or combined < cur[0]:
+                        best[fan_word_ix] = (combined, window_ix, match_ix, distance, lev_d)
+            rows = []
+            for fan_word_ix in sorted(best):
+                combined, window_ix, match_ix, distance, lev_d = best[fan_word_ix]
+                orig_word_ix = match_ix + window_ix
+                fan_word = fan[fan_word_ix]
+                rows.append([filename,
+                             fan_word_ix,
+                             fan_word,                       # orth_
+                             _text.string_id(fan_word),      # orth
+                             orig_word_ix,
+                             self.word_lowercase[orig_word_ix],
+                             self.orth_id[orig_word_ix],
+                             self.character[orig_word_ix],
+                             self.scene[orig_word_ix],
+                             distance,
+                             lev_d,
+                             combined])
+            out[wi] = rows
+        return out
+
+
+def validate_markup_script(filename, interactive=False,
+                           _unbalanced_l=re.compile('<<[^>]*<<'),
+                           _unbalanced_r=re.compile('>>[^<]*>>'),
+                           _tags=re.compile(r'>>\s*([^<]*)\s*<<')):
+    # search.py:228-285 (not on the hot path; kept so `ao3.py validate` keeps working)
+    with open(filename, encoding='utf-8') as ip:
+        script = ip.read()
+    print('Checking script for markup errors.')
+    print()
+    problems = False
+
+    def report(title, rex, group=0, keep=lambda s: True):
+        found = False
+        for m in rex.finditer(script):
+            shown = m.group(group).strip()
+            if not keep(shown):
+                continue
+            if not found:
+                print(title)
+                found = True
+            print('  On line {}'.format(script[:m.start(group) + 1].count('\n') + 1))
+            print('    {}'.format(shown))
+        if found:
+            print()
+        return found
+
+    problems |= report('Unbalanced left tag delimiters:', _unbalanced_l)
+    problems |= report('Unbalanced right tag delimiters:', _unbalanced_r)
+    expected = {'LINE', 'DIRECTION', 'SCENE_NUMBER', 'SCENE_DESCRIPTION', 'CHARACTER_NAME'}
+    problems |= report('Unexpected tag labels:', _tags, 1, lambda s: s not in expected)
+    if not problems:
+        print('No markup errors found.')
+        return True
+    if interactive:
+        print('Errors were found in the script markup. Do you want to continue? (Default is no.)')
+        print()
+        r = ''
+        while r.lower() not in ('y', 'yes', 'n', 'no'):
+            r = input('Enter y for yes or n for no: ')
+            if not r.strip():
+                r = 'n'
+        return r.lower() in ('y', 'yes')
+    return False
+
+
+def validate_cmd(args):
+    return validate_markup_script(args.script)
+
+
+def load_markup_script(filename,
+                       _line_rex=re.compile('LINE<<(?P<line>[^>]*)>>'),
+                       _scene_rex=re.compile('SCENE_NUMBER<<(?P<scene>[^>]*)>>'),
+                       _char_rex=re.compile('CHARACTER_NAME<<(?P<character>[^>]*)>>')):
+    # search.py:290-329: one row [lower_, lower id, scene, character] per LINE token
+    model = get_spacy_model()
+    rows = [['LOWERCASE', 'SPACY_ORTH_ID', 'SCENE', 'CHARACTER']]
+    scene = None
+    scenes_seen = 0
+    scene_fallback = False     # sticky once a scene number fails to parse (search.py:313-317)
+    character = None
+    with open(filename, encoding='utf-8') as ip:
+        for line in ip:
+            m = _scene_rex.search(line)
+            if m:
+                scenes_seen += 1
+                digits = ''.join(c for c in m.group('scene') if c.isdigit())
+                try:
+                    scene = int(digits)
+                except ValueError:
+                    scene_fallback = True
+                    print("Error in Scene markup: {}".format(line))
+                if scene_fallback:
+                    scene = scenes_seen
+                continue
+            m = _char_rex.search(line)
+            if m:
+                character = m.group('character')
+                continue
+            m = _line_rex.search(line)
+            if m:
+                for t in model(m.group('line')):
+                    if not t.is_space:
+                        rows.append([t.lower_, t.lower, scene, character])
+    return rows
+
+
+def write_records(records, filename):
+    # search.py:331-334 (csv default dialect: \r\n, minimal quoting, None -> empty)
+    with open(filename, 'w', encoding='utf-8') as out:
+        wr = csv.writer(out)
+        wr.writerows(records)
+
+
+def _dist_env():
+    world = int(os.environ.get('WORLD_SIZE', '1') or 1)
+    rank = int(os.environ.get('RANK', '0') or 0)
+    return rank, world
+
+
+def analyze(args,
+            window_size=6,
+            number_of_hashes=15,
+            hash_dimensions=14,
+            distance_threshold=0.1,
+            chunk_size=500):
+    # search.py:336-399.  Listing, seeded shuffle, sub-sampling, clustering and file names are
+    # the reference's; the per-cluster pool.map becomes one batched GPU search.  Under
+    # torchrun (WORLD_SIZE > 1) cluster i is searched by rank i % WORLD_SIZE on its own GPU,
+    # each rank writes its own batch files and rank 0 writes the aggregate in cluster order.
+    fan_work_directory = args.fan_works
+    original_script_markup = args.script
+    subsample_start = 0 if args.skip_works < 0 else args.skip_works
+    subsample_end = None if args.num_works < 0 else args.num_works + subsample_start
+
+    fan_works = [os.path.join(fan_work_directory, f) for f in os.listdir(fan_work_directory)]
+    random.seed(4815162342)
+    random.shuffle(fan_works)
+    fan_works = fan_works[subsample_start:subsample_end]
+
+    start = 0
+    fan_clusters = [fan_works[i:i + chunk_size] for i in range(start, len(fan_works), chunk_size)]
+    filename_base = 'match-{}gram{{}}'.format(window_size)
+    batch_filename = filename_base.format('-batch-{}.csv')
+
+    rank, world = _dist_env()
+    ann_index = AnnIndexSearch(original_script_markup, window_size, number_of_hashes,
+                               hash_dimensions, distance_threshold)
+    global _ANN_INDEX
+    _ANN_INDEX = ann_index
+
+    my_records = {}
+    for i, fan_cluster in enumerate(fan_clusters, start=start):
+        if i % world != rank:
+            continue
+        print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
+        record_sets = ann_index.search_many(fan_cluster)
+        records = [r for r_set in record_sets for r in r_set]
+        write_records(records, batch_filename.format(i))
+        my_records[i] = records
+
+    if world > 1:
+        from .parallel import gather_cluster_records
+        my_records = gather_cluster_records(my_records, rank, world)
+        if rank != 0:
+            return
+    accumulated_records = [new_record_structure['fields']]
+    for i in sorted(my_records):
+        accumulated_records.extend(my_records[i])
+
+    i = 0
+    today_str = '-{:%Y%m%d}.csv'.format(datetime.date.today())
+    name_check = filename_base.format(today_str)
+    while os.path.exists(name_check):
+        i += 1
+        today_str = '-{:%Y%m%d}-{}.csv'.format(datetime.date.today(), i)
+        name_check = filename_base.format(today_str)
+    write_records(accumulated_records, name_check)

@@ -1,0 +1,329 @@
+"""GPU parity tests: every CUDA stage, called through the C ABI, against the float64 numpy
+checker (tests/numpy_index.py), the oracle and the golden CSVs of the unmodified reference.
+
+Bar: bit-exact for integer/index work (gather, hash-join, match sets, CSV string/int columns);
+|delta distance| <= 1e-12 for the float64 rescoring (tolerance stated here; the reference's own
+BLAS order is not reproducible bit-for-bit)."""
+import argparse
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from fandom_search_b200 import _native as nt
+from fandom_search_b200 import search, synth
+from fandom_search_b200.lexicon import Lexicon, py_hash_seed0
+from tests.numpy_index import NumpyIndex
+from tests.util import compare_records, normalise, read_csv
+
+pytestmark = pytest.mark.gpu
+
+DIST_TOL = 1e-12
+
+
+def _device_index(*a, **kw):
+    from fandom_search_b200.engine import DeviceIndex
+    return DeviceIndex(*a, **kw)
+
+
+def _case(seed, vocab=800, dim=300, n_script=700, works=(200, 3, 0, 6, 397, 150), n_extra_s=3,
+          n_extra_f=4, plant=True, clustered=True):
+    rng = np.random.default_rng(seed)
+    if clustered:
+        centres = rng.standard_normal((vocab // 8 + 1, dim)).astype(np.float32)
+        table = (0.8 * centres[np.arange(vocab) // 8] + 0.6 * rng.standard_normal((vocab, dim))).astype(np.float32)
+    else:
+        table = rng.standard_normal((vocab, dim)).astype(np.float32)
+    sx = np.zeros((n_extra_s, dim), np.float32)
+    fx = np.zeros((n_extra_f, dim), np.float32)
+    for m in (sx, fx):
+        for r in range(m.shape[0]):
+            m[r, rng.integers(0, dim, 3)] = 1.0
+    script = rng.integers(0, vocab + n_extra_s, n_script).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum(works)]).astype(np.int64)
+    tok = rng.integers(0, vocab + n_extra_s + n_extra_f, int(off[-1])).astype(np.int32)
+    if plant:
+        for w in range(len(works)):
+            a, b = int(off[w]), int(off[w + 1])
+            if b - a >= 40:
+                src = int(rng.integers(0, n_script - 30))
+                ln = int(rng.integers(6, 25))
+                dst = int(rng.integers(a, b - ln))
+                tok[dst:dst + ln] = script[src:src + ln]
+                # near copy: one within-cluster substitution
+                src2 = int(rng.integers(0, n_script - 12))
+                dst2 = int(rng.integers(a, b - 12))
+                tok[dst2:dst2 + 12] = script[src2:src2 + 12]
+                p = dst2 + 3
+                if tok[p] < vocab:
+                    tok[p] = (tok[p] // 8) * 8 + (tok[p] + 1) % 8
+                    tok[p] = min(tok[p], vocab - 1)
+    return table, sx, fx, script, tok, off
+
+
+def _pairs(m):
+    return set(zip(m['fan_pos'].tolist(), m['script_pos'].tolist()))
+
+
+@pytest.mark.parametrize("seed,dim", [(1, 300), (2, 64), (3, 768), (4, 100)])
+def test_search_equals_float64_reference(seed, dim):
+    table, sx, fx, script, tok, off = _case(seed, dim=dim)
+    ref = NumpyIndex(table, script, extra=sx)
+    want, wc = ref.search_host(tok, off, fx)
+    idx = _device_index(table, script, extra=sx)
+    got, gc = idx.search_host(tok, off, fx)
+    assert _pairs(got) == _pairs(want) and len(got) == len(want)
+    assert len(want) > 0
+    wd = {(a, b): (d, w, f) for a, b, d, w, f in zip(want['fan_pos'].tolist(), want['script_pos'].tolist(),
+                                                      want['distance'].tolist(), want['work'].tolist(),
+                                                      want['flags'].tolist())}
+    for a, b, d, w, f in zip(got['fan_pos'].tolist(), got['script_pos'].tolist(), got['distance'].tolist(),
+                             got['work'].tolist(), got['flags'].tolist()):
+        rd, rw, rf = wd[(a, b)]
+        assert abs(d - rd) <= DIST_TOL and w == rw and f == rf
+    assert gc[nt.FS_CNT_WINDOWS] == wc[nt.FS_CNT_WINDOWS]
+    assert gc[nt.FS_CNT_CANDIDATES] >= gc[nt.FS_CNT_MATCHES] == len(want)
+    assert idx.n_script_windows == ref.n_script_windows
+    idx.close()
+
+
+def test_gather_is_bit_exact_and_norms_match():
+    import torch
+    table, sx, fx, script, tok, off = _case(5)
+    idx = _device_index(table, script, extra=sx)
+    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+    emb, thr = idx.stage_embed(tok_t, off_t, fx_t)
+    torch.cuda.synchronize()
+    allrows = np.concatenate([table, sx, fx], axis=0)
+    scale = np.float32(idx.scale)
+    want16 = np.zeros((len(tok), idx.dim_pad), np.float16)
+    want16[:, :table.shape[1]] = (allrows[tok] * scale).astype(np.float16)
+    got16 = emb.cpu().numpy()
+    assert got16.dtype == np.float16 and np.array_equal(got16.view(np.uint16), want16.view(np.uint16))
+    # window thresholds: (1 - thr - eps) * |window| (scaled), +inf where the window leaves its work
+    thr = thr.cpu().numpy()
+    sq = ((allrows[tok].astype(np.float64) * float(scale)) ** 2).sum(axis=1)
+    valid = np.zeros(len(tok), bool)
+    wantn = np.zeros(len(tok))
+    for a, b in zip(off[:-1], off[1:]):
+        for i in range(int(a), int(b) - 5):
+            valid[i] = True
+            wantn[i] = np.sqrt(sq[i:i + 6].sum())
+    assert np.all(np.isinf(thr[~valid])) and np.all(np.isfinite(thr[valid]))
+    coef = 1.0 - 0.1 - 2.0e-3
+    np.testing.assert_allclose(thr[valid], coef * wantn[valid], rtol=2e-6)
+    idx.close()
+
+
+@pytest.mark.parametrize("shifts", [1, 2, 3, 6])
+def test_tensor_core_dots_match_fp16_contraction(shifts):
+    import torch
+    table, sx, fx, script, tok, off = _case(6, plant=False, clustered=False)
+    idx = _device_index(table, script, extra=sx)
+    idx.set_option(nt.FS_OPT_SHIFTS_PER_STAGE, shifts)
+    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+    dots = idx.stage_dots(tok_t, off_t, fx_t).cpu().numpy()
+    allrows = np.concatenate([table, sx, fx], axis=0)
+    e16 = (allrows * np.float32(idx.scale)).astype(np.float16).astype(np.float32)
+    ef = np.zeros((len(tok) + 6, table.shape[1]), np.float32)
+    es = np.zeros((len(script) + 6, table.shape[1]), np.float32)
+    ef[:len(tok)] = e16[tok]
+    es[:len(script)] = e16[script]
+    g = ef.astype(np.float64) @ es.astype(np.float64).T
+    want = sum(g[k:k + len(tok), k:k + len(script)] for k in range(6))
+    # fp32 accumulation of 1800 fp16 products: tolerance 1e-3 of the largest magnitude
+    assert np.abs(dots - want).max() <= 1e-3 * np.abs(want).max()
+    idx.close()
+
+
+def test_candidates_are_a_superset_within_slack():
+    import torch
+    table, sx, fx, script, tok, off = _case(7)
+    ref = NumpyIndex(table, script, extra=sx)
+    d, fpos = ref.distances(tok, off, fx)
+    idx = _device_index(table, script, extra=sx)
+    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+    cand, cnt = idx.stage_candidates(tok_t, off_t, fx_t)
+    n = int(cnt.cpu()[nt.FS_CNT_CANDIDATES])
+    cand = cand.cpu().numpy()[:n]
+    got = set(map(tuple, cand.tolist()))
+    row_of = {int(p): i for i, p in enumerate(fpos)}
+    col_of = {int(p): j for j, p in enumerate(ref.spos)}
+    ii, jj = np.nonzero(d < 0.1)
+    must = set(zip(fpos[ii].tolist(), ref.spos[jj].tolist()))
+    assert must <= got
+    for a, b in got:                      # nothing far from the threshold gets through
+        assert d[row_of[a], col_of[b]] < 0.1 + 2 * 2.0e-3
+    idx.close()
+
+
+def test_hash_join_is_bit_exact():
+    table, sx, fx, script, tok, off = _case(8, n_script=900)
+    script[300:306] = script[100:106]          # duplicate script 6-grams -> several hits per window
+    script[500:506] = script[100:106]
+    tok[20:30] = script[98:108]
+    ref = NumpyIndex(table, script, extra=sx)
+    want, _ = ref.exact_join_host(tok, off)
+    idx = _device_index(table, script, extra=sx)
+    got, cnt = idx.exact_join_host(tok, off)
+    assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
+    assert cnt[nt.FS_CNT_EXACT] == len(want) > 10
+    # every exact pair is also found by the distance path, flagged exact, at distance ~0
+    m, _ = idx.search_host(tok, off, fx)
+    exact = {(a, b) for a, b, f in zip(m['fan_pos'].tolist(), m['script_pos'].tolist(), m['flags'].tolist())
+             if f & nt.FS_MATCH_EXACT}
+    assert exact == set(map(tuple, want.tolist()))
+    assert np.all(np.abs(m['distance'][(m['flags'] & 1) == 1]) < 1e-12)
+    idx.close()
+
+
+def test_ragged_and_empty_batches():
+    table, sx, fx, script, _, _ = _case(9)
+    idx = _device_index(table, script, extra=sx)
+    ref = NumpyIndex(table, script, extra=sx)
+    for works in ([], [0], [5], [6], [0, 0, 7, 0], [5, 5, 5]):
+        off = np.concatenate([[0], np.cumsum(works)]).astype(np.int64)
+        tok = np.resize(script[10:40], int(off[-1])).astype(np.int32)
+        got, gc = idx.search_host(tok, off)
+        want, wc = ref.search_host(tok, off)
+        assert _pairs(got) == _pairs(want)
+        assert gc[nt.FS_CNT_WINDOWS] == wc[nt.FS_CNT_WINDOWS] == sum(max(w - 5, 0) for w in works)
+        pj, _ = idx.exact_join_host(tok, off)
+        wj, _ = ref.exact_join_host(tok, off)
+        assert sorted(map(tuple, pj.tolist())) == sorted(map(tuple, wj.tolist()))
+    idx.close()
+
+
+def test_multiple_scripts_do_not_straddle():
+    table, sx, fx, script, tok, off = _case(10, n_script=600)
+    soff = np.array([0, 200, 203, 600], np.int64)
+    # a fan span copied across the script boundary must NOT match as one window
+    tok[50:62] = script[194:206]
+    ref = NumpyIndex(table, script, script_off=soff, extra=sx)
+    idx = _device_index(table, script, script_off=soff, extra=sx)
+    got, _ = idx.search_host(tok, off, fx)
+    want, _ = ref.search_host(tok, off, fx)
+    assert _pairs(got) == _pairs(want)
+    assert all(not (195 <= b < 200) and not (198 <= b < 203) for _, b in _pairs(got))
+    assert idx.n_script_windows == ref.n_script_windows == 195 + 0 + 392
+    idx.close()
+
+
+def test_overflow_is_reported_and_retried():
+    table, sx, fx, script, tok, off = _case(11)
+    ref = NumpyIndex(table, script, extra=sx)
+    want, _ = ref.search_host(tok, off, fx)
+    idx = _device_index(table, script, extra=sx)
+    out = np.empty(2, dtype=nt.MATCH_DTYPE)
+    cnt = np.zeros(nt.FS_CNT_COUNT, np.int64)
+    st = idx._lib.fs_search_csr_host(idx._h, nt.ptr(tok), len(tok), nt.ptr(off), len(off) - 1,
+                                     nt.ptr(fx), fx.shape[0], nt.ptr(out), 2, nt.ptr(cnt))
+    assert st == nt.FS_E_OVERFLOW and cnt[nt.FS_CNT_MATCHES] == len(want)
+    assert b"overflow" in idx._lib.fs_last_error()
+    idx.close()
+    idx2 = _device_index(table, script, extra=sx)
+    idx2.reserve(len(tok), 4)                       # tiny candidate buffer
+    assert idx2._lib.fs_index_get_info(idx2._h, 3) == 4
+    got, _ = idx2.search_host(tok, off, fx, cap=3)  # wrapper grows both buffers and retries
+    assert _pairs(got) == _pairs(want)
+    idx2.close()
+
+
+def test_device_entry_point_equals_host_entry_point():
+    import torch
+    table, sx, fx, script, tok, off = _case(12)
+    idx = _device_index(table, script, extra=sx)
+    host, hc = idx.search_host(tok, off, fx)
+    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+    out_t = torch.empty(24 * 4096, dtype=torch.uint8, device="cuda")
+    cnt_t = torch.zeros(nt.FS_CNT_COUNT, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        idx.search_dev(tok_t, off_t, fx_t, out_t, cnt_t, stream=stream)
+    stream.synchronize()
+    cnt = cnt_t.cpu().numpy()
+    dev = np.frombuffer(out_t.cpu().numpy().tobytes(), dtype=nt.MATCH_DTYPE)[:cnt[nt.FS_CNT_MATCHES]]
+    assert _pairs(dev) == _pairs(host) and np.array_equal(cnt, hc)
+    ms, n = idx.timing_read()
+    assert n >= 2 and ms > 0
+    idx.close()
+
+
+def test_invalid_arguments_fail_loudly():
+    table, sx, fx, script, tok, off = _case(13)
+    lib = nt.load()
+    import ctypes
+    h = ctypes.c_void_p()
+    bad = lib.fs_index_create(ctypes.byref(h), 0, nt.ptr(table), table.shape[0], table.shape[1], None, 0,
+                              nt.ptr(script), len(script), nt.ptr(np.array([0, 5], np.int64)), 1, 6, 0.1)
+    assert bad == nt.FS_E_INVALID and b"script_off" in lib.fs_last_error()
+    with pytest.raises(nt.NativeError):
+        _device_index(table, script, device=99)
+
+
+def _golden_pipeline(golden_dir):
+    search.set_pipeline(search.Pipeline(
+        Lexicon.from_npz(os.path.join(golden_dir, "lexicon.npz"), hash_fn=py_hash_seed0)))
+
+
+def test_golden_csv_end_to_end(golden_dir, tmp_path, monkeypatch):
+    """ao3.py search equivalent on the committed corpus == CSV of the unmodified reference."""
+    _golden_pipeline(golden_dir)
+    try:
+        listing = open(os.path.join(golden_dir, "listing.txt")).read().split()
+        real_listdir = os.listdir
+        monkeypatch.setattr(os, "listdir", lambda d: list(listing) if str(d) == "fanworks" else real_listdir(d))
+        monkeypatch.chdir(tmp_path)
+        os.symlink(os.path.join(golden_dir, "fanworks"), "fanworks")
+        os.symlink(os.path.join(golden_dir, "script.txt"), "script.txt")
+        args = argparse.Namespace(fan_works="fanworks", script="script.txt", skip_works=-1, num_works=-1)
+        search.analyze(args, chunk_size=16)
+        got = read_csv(glob.glob("match-6gram-2*.csv")[0])
+        want = read_csv(os.path.join(golden_dir, "golden_exhaustive.csv"))
+        ties = compare_records(got, want, tol=DIST_TOL, basename=False)
+        assert ties <= len(want) // 10
+        assert [(r[0], r[1]) for r in got] == [(r[0], r[1]) for r in want]
+        for i in range(3):
+            b = read_csv("match-6gram-batch-%d.csv" % i, header=False)
+            wb = read_csv(os.path.join(golden_dir, "golden_exhaustive.batch%d.csv" % i), header=False)
+            assert [(r[0], r[1]) for r in b] == [(r[0], r[1]) for r in wb]
+    finally:
+        search.set_pipeline(None)
+
+
+def test_full_size_cluster_properties():
+    """One BASELINE-size cluster (500 works x ~5k tokens vs a 25k-token script, d=300):
+    size-independent properties instead of an O(N^2) CPU check."""
+    lex = synth.SynthLexicon(vocab=50000, dim=300, oov_frac=0.0, seed=1001)
+    script = synth.make_script_tokens(lex, 25000).astype(np.int32)
+    words, off = synth.synth_csr_batch(lex, script, range(500))
+    tok = words.astype(np.int32)
+    idx = _device_index(lex.table_all, script)
+    m, cnt = idx.search_host(tok, off, cap=1 << 20)
+    assert cnt[nt.FS_CNT_WINDOWS] == int(np.maximum(np.diff(off) - 5, 0).sum())
+    # (1) every hash-join pair is found by the distance path, flagged exact, |distance| ~ 0
+    pj, _ = idx.exact_join_host(tok, off, cap=1 << 20)
+    exact = set(map(tuple, pj.tolist()))
+    found = {(a, b): (d, f) for a, b, d, f in zip(m['fan_pos'].tolist(), m['script_pos'].tolist(),
+                                                  m['distance'].tolist(), m['flags'].tolist())}
+    assert len(exact) > 1000 and exact <= set(found)
+    assert all(found[p][1] & 1 and abs(found[p][0]) < 1e-12 for p in exact)
+    assert {p for p, v in found.items() if v[1] & 1} == exact
+    # (2) all reported distances are below the threshold, windows lie inside their work
+    assert np.all(m['distance'] < 0.1)
+    assert np.all(m['fan_pos'] + 6 <= off[m['work'] + 1]) and np.all(m['fan_pos'] >= off[m['work']])
+    # (3) spot check 200 reported pairs against a float64 recomputation
+    t64 = lex.table_all.astype(np.float64)
+    rng = np.random.default_rng(0)
+    for k in rng.choice(len(m), 200, replace=False):
+        f = t64[tok[m['fan_pos'][k]:m['fan_pos'][k] + 6]].ravel()
+        s = t64[script[m['script_pos'][k]:m['script_pos'][k] + 6]].ravel()
+        d = 1.0 - (f / np.linalg.norm(f)) @ (s / np.linalg.norm(s))
+        assert abs(d - m['distance'][k]) <= DIST_TOL
+    # (4) idempotence: a second pass returns the identical set (order aside)
+    m2, cnt2 = idx.search_host(tok, off, cap=1 << 20)
+    a = np.sort(m, order=['fan_pos', 'script_pos'])
+    b = np.sort(m2, order=['fan_pos', 'script_pos'])
+    assert a.tobytes() == b.tobytes() and np.array_equal(cnt, cnt2)
+    idx.close()

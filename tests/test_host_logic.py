@@ -1,0 +1,100 @@
+"""CPU tests of the host side of the drop-in search.py (tokenise -> CSR row ids -> OOV
+extras -> records -> CSV) with the device replaced by tests/numpy_index.NumpyIndex.
+The GPU parity tests (tests/test_gpu_parity.py) run the same flow on the real device."""
+import argparse
+import glob
+import os
+
+import pytest
+
+import fandom_search_b200.engine as engine_mod
+from fandom_search_b200 import search
+from fandom_search_b200.lexicon import Lexicon, py_hash_seed0
+from oracle import reference_search as ora
+from tests.numpy_index import NumpyIndex
+from tests.util import compare_records, normalise, read_csv
+
+
+@pytest.fixture()
+def cpu_device(monkeypatch, golden_dir):
+    monkeypatch.setattr(engine_mod, "DeviceIndex", NumpyIndex)
+    search.set_pipeline(search.Pipeline(
+        Lexicon.from_npz(os.path.join(golden_dir, "lexicon.npz"), hash_fn=py_hash_seed0)))
+    yield
+    search.set_pipeline(None)
+
+
+def test_load_markup_script_matches_oracle(cpu_device, golden_dir):
+    rows = search.load_markup_script(os.path.join(golden_dir, "script.txt"))
+    assert rows[0] == ['LOWERCASE', 'SPACY_ORTH_ID', 'SCENE', 'CHARACTER']
+    lex = ora.OracleLexicon(os.path.join(golden_dir, "lexicon.npz"), oov_hash=py_hash_seed0)
+    assert rows[1:] == ora.load_markup_script(os.path.join(golden_dir, "script.txt"), lex)
+    assert rows[-1][2] == 2 and rows[-1][3] == 'LEIA'     # scene-number fallback to the running count
+
+
+def test_search_many_matches_reference_golden(cpu_device, golden_dir):
+    idx = search.AnnIndexSearch(os.path.join(golden_dir, "script.txt"), 6, 15, 14, 0.1)
+    files = sorted(glob.glob(os.path.join(golden_dir, "fanworks", "*.txt")))
+    sets = idx.search_many(files)
+    got = normalise([r for s in sets for r in s])
+    want = read_csv(os.path.join(golden_dir, "golden_exhaustive.csv"))
+    compare_records(got, want, tol=1e-12)
+    assert idx.windows_processed > 0
+    # single-file entry point == the batched one
+    k = files.index(os.path.join(golden_dir, "fanworks", "0000003.txt"))
+    assert normalise(idx.search(files[k])) == normalise(sets[k])
+    # edge cases: 5-token, empty and exactly-6-token works
+    assert sets[files.index(os.path.join(golden_dir, "fanworks", "0000037.txt"))] == []
+    assert sets[files.index(os.path.join(golden_dir, "fanworks", "0000038.txt"))] == []
+    assert len(sets[files.index(os.path.join(golden_dir, "fanworks", "0000039.txt"))]) == 6
+
+
+def test_analyze_writes_reference_files(cpu_device, golden_dir, tmp_path, monkeypatch):
+    listing = open(os.path.join(golden_dir, "listing.txt")).read().split()
+    real_listdir = os.listdir
+    monkeypatch.setattr(os, "listdir", lambda d: list(listing) if str(d) == "fanworks" else real_listdir(d))
+    monkeypatch.chdir(tmp_path)
+    os.symlink(os.path.join(golden_dir, "fanworks"), "fanworks")
+    os.symlink(os.path.join(golden_dir, "script.txt"), "script.txt")
+    args = argparse.Namespace(fan_works="fanworks", script="script.txt", skip_works=-1, num_works=-1)
+    search.analyze(args, chunk_size=16)
+    aggs = glob.glob("match-6gram-2*.csv")
+    assert len(aggs) == 1
+    got = read_csv(aggs[0])
+    want = read_csv(os.path.join(golden_dir, "golden_exhaustive.csv"))
+    compare_records(got, want, tol=1e-12, basename=False)
+    assert [(r[0], r[1]) for r in got] == [(r[0], r[1]) for r in want]      # same row order
+    header = open(aggs[0], newline='').readline()
+    assert header == ",".join(search.new_record_structure['fields']) + "\r\n"
+    for i in range(3):
+        b = read_csv("match-6gram-batch-%d.csv" % i, header=False)
+        wb = read_csv(os.path.join(golden_dir, "golden_exhaustive.batch%d.csv" % i), header=False)
+        assert [(r[0], r[1]) for r in b] == [(r[0], r[1]) for r in wb]
+    # a second run the same day must not overwrite the aggregate (search.py:390-397)
+    search.analyze(args, chunk_size=16)
+    assert len(glob.glob("match-6gram-2*.csv")) == 2
+    # -s / -n sub-sampling (search.py:345-358)
+    args2 = argparse.Namespace(fan_works="fanworks", script="script.txt", skip_works=4, num_works=3)
+    for f in glob.glob("match-6gram-*.csv"):
+        os.remove(f)
+    search.analyze(args2, chunk_size=16)
+    sub = read_csv(glob.glob("match-6gram-2*.csv")[0])
+    import random
+    order = [os.path.join("fanworks", f) for f in listing]
+    random.seed(4815162342)
+    random.shuffle(order)
+    assert {r[0] for r in sub} <= set(order[4:7])
+
+
+def test_mk_vectors_and_chunks(cpu_device):
+    toks = search.get_spacy_model()("w00001 W00001 notaword w00002")
+    v = search.mk_vectors(toks)
+    assert v.shape == (4, 300) and v.dtype == float
+    assert sorted(set(v[2].tolist())) == [0.0, 1.0] and 1 <= v[2].sum() <= 3
+    hot = {py_hash_seed0("notaword") % 300, py_hash_seed0("notaword" * 2) % 300,
+           py_hash_seed0("notaword" * 3) % 300}
+    assert set(v[2].nonzero()[0].tolist()) == hot
+    assert search.mk_vectors([]).shape == (0, 0)
+    long_text = " ".join(["w00001"] * 20000)          # 139999 chars -> two chunks
+    chunks = list(search.sp_parse_chunks(long_text))
+    assert len(chunks) == 2 and sum(len(c) for c in chunks) == 20000
