@@ -29,6 +29,7 @@ FS_OPT_BASE_OFFSET_MODE = 2
 FS_OPT_GRID_LIMIT = 3
 
 FS_MATCH_EXACT = 1
+FS_MATCH_LSH_SHIFT = 8
 
 # struct fs_match {int32 fan_pos; int32 script_pos; double distance; int32 work; uint32 flags;}
 MATCH_DTYPE = np.dtype([("fan_pos", "<i4"), ("script_pos", "<i4"), ("distance", "<f8"),
@@ -49,6 +50,7 @@ SIGNATURES = {
     "fs_index_destroy": (ctypes.c_int, [_vp]),
     "fs_index_reserve": (ctypes.c_int, [_vp, _i64, _i64]),
     "fs_index_set_option": (ctypes.c_int, [_vp, _i32, _i64]),
+    "fs_index_set_lsh": (ctypes.c_int, [_vp, _vp, _i32, _i32]),
     "fs_index_get_info": (_i64, [_vp, _i32]),
     "fs_search_csr_dev": (ctypes.c_int, [_vp, _vp] + _BATCHX + [_vp, _i64, _vp]),
     "fs_search_csr_host": (ctypes.c_int, [_vp] + _BATCHX + [_vp, _i64, _vp]),

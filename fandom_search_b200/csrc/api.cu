@@ -118,6 +118,10 @@ struct fs_index {
     fs_pair* h_pair = nullptr;
     unsigned long long* h_counters = nullptr;
 
+    // LSH emulation (parity mode)
+    double* lsh_normals = nullptr;
+    int32_t lsh_tables = 0, lsh_bits = 0;
+
     // options
     int32_t shifts_per_stage = 6;
     int32_t base_offset_mode = 0;
@@ -155,7 +159,8 @@ int fs_index_destroy(fs_index* idx) {
                     idx->sx_sq,   idx->script_tok, idx->script_off, idx->script_emb, idx->script_tok_sq,
                     idx->script_norm, idx->hash_table, idx->fan_emb, idx->fan_tok_sq, idx->fan_thr,
                     idx->cand,    idx->fx16,      idx->fx_sq,      idx->h_tok,      idx->h_off,
-                    idx->h_extra, idx->h_out,     idx->h_pair,     idx->h_counters};
+                    idx->h_extra, idx->h_out,     idx->h_pair,     idx->h_counters,
+                    idx->lsh_normals};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (idx->ev_created) {
@@ -208,7 +213,7 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     idx->device = device;
     idx->sm_count = prop.multiProcessorCount;
     idx->dim = dim;
-    idx->dim_pad = static_cast<int32_t>(round_up(dim, kChunkK));
+    idx->dim_pad = static_cast<int32_t>(round_up(dim, kUmmaK));  // K granularity of tcgen05.mma.kind::f16
     idx->window = window;
     idx->threshold = threshold;
     idx->n_base = n_rows;
@@ -353,6 +358,26 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
     }
 }
 
+int fs_index_set_lsh(fs_index* idx, const double* normals, int32_t n_tables, int32_t n_bits) {
+    if (!idx || n_tables < 0 || n_tables > 255 || (n_tables > 0 && (!normals || n_bits < 1 || n_bits > 64))) {
+        set_error("fs_index_set_lsh: invalid argument");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    FS_CUDA_CHECK(cudaDeviceSynchronize());
+    if (idx->lsh_normals) cudaFree(idx->lsh_normals);
+    idx->lsh_normals = nullptr;
+    idx->lsh_tables = idx->lsh_bits = 0;
+    if (n_tables == 0) return FS_OK;
+    const int64_t n = static_cast<int64_t>(n_tables) * n_bits * idx->window * idx->dim;
+    int r = dev_alloc(&idx->lsh_normals, n);
+    if (r != FS_OK) return r;
+    FS_CUDA_CHECK(cudaMemcpy(idx->lsh_normals, normals, sizeof(double) * n, cudaMemcpyHostToDevice));
+    idx->lsh_tables = n_tables;
+    idx->lsh_bits = n_bits;
+    return FS_OK;
+}
+
 int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
     if (!idx) return -1;
     switch (what) {
@@ -464,7 +489,8 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.norm_script = idx->script_norm;
     p.n_fan_tok = a.n_tok;
     p.n_script_tok = idx->n_script_tok;
-    p.chunks = idx->dim_pad / kChunkK;
+    p.chunks = (idx->dim_pad + kChunkK - 1) / kChunkK;
+    p.last_chunk_ksteps = (idx->dim_pad - (p.chunks - 1) * kChunkK) / kUmmaK;
     p.window = idx->window;
     p.shifts_per_stage = idx->shifts_per_stage;
     p.base_offset_mode = idx->base_offset_mode;
@@ -504,7 +530,28 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     rp.out = out;
     rp.out_cap = cap;
     rp.match_counter = counters + FS_CNT_MATCHES;
-    return launch_rescore(rp, idx->sm_count, st);
+    if ((r = launch_rescore(rp, idx->sm_count, st)) != FS_OK) return r;
+    if (idx->lsh_tables > 0) {
+        LshParams lp{};
+        lp.matches = out;
+        lp.match_counter = counters + FS_CNT_MATCHES;
+        lp.match_cap = cap;
+        lp.normals = idx->lsh_normals;
+        lp.n_tables = idx->lsh_tables;
+        lp.n_bits = idx->lsh_bits;
+        lp.fan_tok = a.tok;
+        lp.script_tok = idx->script_tok;
+        lp.table = idx->table32;
+        lp.n_base = idx->n_base;
+        lp.script_extra = idx->sx32;
+        lp.n_script_extra = idx->n_sx;
+        lp.fan_extra = a.extra;
+        lp.n_fan_extra = a.n_extra;
+        lp.dim = idx->dim;
+        lp.window = idx->window;
+        return launch_lsh(lp, idx->sm_count, st);
+    }
+    return FS_OK;
 }
 
 // stage a host batch into the index's device staging buffers

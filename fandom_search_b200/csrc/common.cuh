@@ -52,7 +52,8 @@ struct DistParams {
     const float* norm_script; // [Npad]  |script window|, +inf when invalid
     int64_t n_fan_tok;        // rows of the fan token matrix (M)
     int64_t n_script_tok;     // rows of the script token matrix (N)
-    int32_t chunks;           // dim_pad / 64
+    int32_t chunks;           // ceil(dim_pad / 64) 64-column chunks
+    int32_t last_chunk_ksteps;// UMMA K-steps (16 columns) in the last chunk: 1..4
     int32_t window;           // 6
     int32_t shifts_per_stage; // S: 1,2,3,6
     int32_t base_offset_mode; // how shifted descriptors fill base_offset
@@ -92,6 +93,23 @@ struct RescoreParams {
     unsigned long long* match_counter;
 };
 
+struct LshParams {
+    fs_match* matches;
+    const unsigned long long* match_counter;
+    int64_t match_cap;
+    const double* normals;  // [n_tables * n_bits, window * dim]
+    int32_t n_tables, n_bits;
+    const int32_t* fan_tok;
+    const int32_t* script_tok;
+    const float* table;
+    int64_t n_base;
+    const float* script_extra;
+    int64_t n_script_extra;
+    const float* fan_extra;
+    int64_t n_fan_extra;
+    int32_t dim, window;
+};
+
 struct GatherSources {
     const __half* base16;
     const float* base_sq;
@@ -116,6 +134,7 @@ int launch_window_norm(const float* tok_sq, int64_t n_tok, const int64_t* off, i
                        int32_t window, float coef, float* out, int64_t n_pad,
                        unsigned long long* window_counter, cudaStream_t stream);
 int launch_rescore(const RescoreParams& p, int sm_count, cudaStream_t stream);
+int launch_lsh(const LshParams& p, int sm_count, cudaStream_t stream);
 int launch_hash_build(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,
                       int32_t window, unsigned long long* table, uint32_t slots,
                       cudaStream_t stream);
@@ -254,6 +273,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
            | (0u << 15) | (0u << 16)               // a_major = b_major = K
            | (static_cast<uint32_t>(n >> 3) << 17) // n_dim
            | (static_cast<uint32_t>(m >> 4) << 24);  // m_dim
+}
+
+__device__ __forceinline__ const float* lsh_row_ptr(const LshParams& p, int64_t id) {
+    if (id >= 0 && id < p.n_base) return p.table + id * p.dim;
+    id -= p.n_base;
+    if (id >= 0 && id < p.n_script_extra) return p.script_extra + id * p.dim;
+    id -= p.n_script_extra;
+    if (id >= 0 && id < p.n_fan_extra) return p.fan_extra + id * p.dim;
+    return nullptr;
 }
 
 // first CSR row whose end is > t  (off has n_rows+1 entries, off[0] = 0)

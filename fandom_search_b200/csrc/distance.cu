@@ -74,7 +74,8 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     const int64_t tile_begin = per_cta * blockIdx.x;
     const int64_t tile_end = min(total_tiles, tile_begin + per_cta);
     const int S = p.shifts_per_stage;
-    const int stages_per_tile = p.chunks * (p.window / S);
+    const int shift_groups = p.window / S;
+    const int stages_per_tile = p.chunks * shift_groups;
 
     if (warp == 0 && lane == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -117,10 +118,13 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 tc_fence_after();
                 const uint32_t a_src = smem_base + stage * kStageBytes;
                 const uint32_t b_src = a_src + kStageABytes;
+                // the last chunk may hold fewer than 64 real columns (d_pad is a multiple of
+                // 16, not 64): its trailing K-steps are all-zero TMA fill and are skipped
+                const int chunk = it / shift_groups;
+                const int ksteps = (chunk == p.chunks - 1) ? p.last_chunk_ksteps : kChunkK / kUmmaK;
                 for (int s = 0; s < S; ++s) {
                     const uint32_t bo = p.base_offset_mode ? static_cast<uint32_t>(s) : 0u;
-#pragma unroll
-                    for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+                    for (int k = 0; k < ksteps; ++k) {
                         const uint32_t off = static_cast<uint32_t>(s * 128 + k * kUmmaK * 2);
                         umma_f16(tmem_d, umma_smem_desc(a_src + off, bo),
                                  umma_smem_desc(b_src + off, bo), idesc, accumulate);

@@ -70,6 +70,16 @@ class DeviceIndex:
     def set_option(self, option, value):
         nt.check(self._lib.fs_index_set_option(self._h, option, value))
 
+    def set_lsh(self, normals, n_tables, n_bits):
+        """Switch on LSH emulation: normals float64 [n_tables*n_bits, window*dim] (None = off)."""
+        if normals is None or n_tables == 0:
+            nt.check(self._lib.fs_index_set_lsh(self._h, None, 0, 0))
+            return
+        normals = np.ascontiguousarray(normals, dtype=np.float64)
+        if normals.shape != (n_tables * n_bits, self.window * self.dim):
+            raise ValueError("normals must be [n_tables*n_bits, window*dim]")
+        nt.check(self._lib.fs_index_set_lsh(self._h, nt.ptr(normals), n_tables, n_bits))
+
     def reserve(self, max_tokens, max_candidates):
         nt.check(self._lib.fs_index_reserve(self._h, max_tokens, max_candidates))
 

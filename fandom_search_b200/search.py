@@ -194,6 +194,7 @@ def build_lsh_engine(orig, window_size, number_of_hashes, hash_dimensions,
         from .lsh import LshEmulation
         seed = int(os.environ.get('FANDOM_SEARCH_LSH_SEED', '0'))
         lsh = LshEmulation(number_of_hashes, hash_dimensions, window_size * lex.dim, seed)
+        lsh.install(index)
     engine = ScriptEngine(index, lsh)
     engine.script_tok = script_tok
     engine.n_script_extra = n_sx
@@ -265,19 +266,24 @@ class AnnIndexSearch(object):
                 [lex.oov_rows(int(u) - lex.n_rows, int(u) - lex.n_rows + 1) for u in uniq], axis=0)
         matches, counters = self.engine.index.search_host(tok, offs, extra)
         self._windows_processed += int(counters[nt.FS_CNT_WINDOWS])
-        if self.engine.lsh is not None and len(matches):
-            keep = self.engine.lsh.shared_bucket_mask(self, lex, tok, extra, n_fixed, matches)
-            matches = matches[keep]
-        return self._records(filenames, fans, offs, matches)
+        first_table = None
+        if self.engine.lsh is not None:
+            # keep only the pairs the emulated LSH index would have compared (lsh.py)
+            first_table = ((matches['flags'] >> nt.FS_MATCH_LSH_SHIFT) & 0xFF).astype(numpy.int64)
+            keep = first_table > 0
+            matches, first_table = matches[keep], first_table[keep]
+        return self._records(filenames, fans, offs, matches, first_table)
 
-    def _records(self, filenames, fans, offs, matches):
+    def _records(self, filenames, fans, offs, matches, first_table=None):
         w = self.window_size
         out = [[] for _ in filenames]
         if len(matches) == 0:
             return out
         # neighbours() returns candidates sorted by distance (stable, script order on ties),
         # at most 10 of them (NearestFilter(10)); windows are visited in ascending order
-        order = numpy.lexsort((matches['script_pos'], matches['distance'], matches['fan_pos']))
+        # (under LSH emulation ties are ordered by the first table holding the candidate)
+        tie = first_table if first_table is not None else numpy.zeros(len(matches), dtype=numpy.int64)
+        order = numpy.lexsort((matches['script_pos'], tie, matches['distance'], matches['fan_pos']))
         m = matches[order]
         fan_pos = m['fan_pos']
         first = numpy.r_[True, fan_pos[1:] != fan_pos[:-1]]

@@ -66,6 +66,11 @@ typedef struct fs_match {
 #define FS_MATCH_EXACT 1u /* the six embedding-row ids are identical (distance-0 case,
                              what ao3.py:353-355 reads as BEST_COMBINED_DISTANCE <= 0) */
 
+/* LSH-emulation mode (fs_index_set_lsh): bits [8,16) of flags hold 1 + the first hash table in
+ * which the fan and script windows share a bucket key, 0 when they share none (the reference's
+ * nearpy index would never have compared that pair). */
+#define FS_MATCH_LSH_SHIFT 8
+
 /* One exact 6-gram hit of the hash-join kernel. */
 typedef struct fs_pair {
     int32_t fan_pos;
@@ -116,6 +121,12 @@ int fs_index_destroy(fs_index* idx);
  * Optional: search calls grow the workspace on demand (which synchronises). */
 int fs_index_reserve(fs_index* idx, int64_t max_tokens, int64_t max_candidates);
 int fs_index_set_option(fs_index* idx, int32_t option, int64_t value);
+/* Parity mode: emulate a random-binary-projection LSH index with the given hyperplanes
+ * (replaces the nearpy lookup of search.py:112-116,178 for a SEEDED reference run).
+ *   normals  host [n_tables * n_bits, window * dim] float64, table-major
+ * After this call every match carries the first-shared-table field described at
+ * FS_MATCH_LSH_SHIFT.  n_tables = 0 switches the mode off. */
+int fs_index_set_lsh(fs_index* idx, const double* normals, int32_t n_tables, int32_t n_bits);
 int64_t fs_index_get_info(const fs_index* idx, int32_t what); /* 0: script windows, 1: dim_pad, 2: SM count */
 
 /*

@@ -327,3 +327,28 @@ def test_full_size_cluster_properties():
     b = np.sort(m2, order=['fan_pos', 'script_pos'])
     assert a.tobytes() == b.tobytes() and np.array_equal(cnt, cnt2)
     idx.close()
+
+
+def test_lsh_emulation_reproduces_seeded_reference_golden(golden_dir, tmp_path, monkeypatch):
+    """FANDOM_SEARCH_MODE=lsh with the seed of the golden run == CSV of the unmodified reference
+    over a seeded 15x14-bit random-hyperplane index (rows the LSH missed are missing here too)."""
+    _golden_pipeline(golden_dir)
+    monkeypatch.setenv("FANDOM_SEARCH_MODE", "lsh")
+    monkeypatch.setenv("FANDOM_SEARCH_LSH_SEED", "7")
+    try:
+        listing = open(os.path.join(golden_dir, "listing.txt")).read().split()
+        real_listdir = os.listdir
+        monkeypatch.setattr(os, "listdir", lambda d: list(listing) if str(d) == "fanworks" else real_listdir(d))
+        monkeypatch.chdir(tmp_path)
+        os.symlink(os.path.join(golden_dir, "fanworks"), "fanworks")
+        os.symlink(os.path.join(golden_dir, "script.txt"), "script.txt")
+        args = argparse.Namespace(fan_works="fanworks", script="script.txt", skip_works=-1, num_works=-1)
+        search.analyze(args, chunk_size=16)
+        got = read_csv(glob.glob("match-6gram-2*.csv")[0])
+        want = read_csv(os.path.join(golden_dir, "golden_lsh_seed7.csv"))
+        exhaustive = read_csv(os.path.join(golden_dir, "golden_exhaustive.csv"))
+        assert len(want) < len(exhaustive)
+        compare_records(got, want, tol=DIST_TOL, basename=False)
+        assert [(r[0], r[1]) for r in got] == [(r[0], r[1]) for r in want]
+    finally:
+        search.set_pipeline(None)

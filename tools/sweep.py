@@ -1,0 +1,75 @@
+"""Kernel sweep (BASELINE.json configs[4]): fan windows x script windows x embedding dim.
+
+    python tools/sweep.py [--quick] > gpurun_out/sweep.jsonl
+
+Token ids are drawn directly (no text), inputs resident in HBM, the distance kernel is timed
+with CUDA events on its launching stream (fs_timing_read); reports windows/s, TFLOP/s by the
+nominal dense formula 2*(6*d)*Ns and by executed flops (d padded to a multiple of 16)."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from fandom_search_b200 import _native as nt
+from fandom_search_b200.engine import DeviceIndex
+
+
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000):
+    table = rng.standard_normal((vocab, d), dtype=np.float32)
+    script = rng.integers(0, vocab, ns + 5).astype(np.int32)
+    idx = DeviceIndex(table, script, window=6, threshold=0.1)
+    n_works = max(1, nf // works_len)
+    lens = np.full(n_works, (nf + 5 * n_works) // n_works + 1, dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    g = torch.Generator(device="cuda").manual_seed(3000)
+    tok_t = torch.randint(0, vocab, (int(off[-1]),), generator=g, device="cuda", dtype=torch.int32)
+    off_t = torch.from_numpy(off).cuda()
+    out_t = torch.empty(24 << 16, dtype=torch.uint8, device="cuda")
+    cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
+    idx.reserve(int(off[-1]), 1 << 16)
+    idx.search_dev(tok_t, off_t, None, out_t, cnt_t)   # warm-up
+    idx.search_dev(tok_t, off_t, None, out_t, cnt_t)
+    torch.cuda.synchronize()
+    idx.timing_reset()
+    for _ in range(reps):
+        idx.search_dev(tok_t, off_t, None, out_t, cnt_t)
+    torch.cuda.synchronize()
+    ms, n = idx.timing_read()
+    windows = int(cnt_t.cpu()[nt.FS_CNT_WINDOWS])
+    per = ms / n * 1e-3
+    res = {"fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
+           "kernel_ms": ms / n, "windows_per_s": windows / per,
+           "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
+           "tflops_executed": 2.0 * 6 * idx.dim_pad * idx.n_script_windows * windows / per / 1e12}
+    idx.close()
+    del tok_t, out_t
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    rng = np.random.default_rng(0)
+    if args.quick:
+        cases = [(2_500_000, 25000, 300, 3), (2_500_000, 25000, 320, 3), (2_500_000, 25000, 304, 3)]
+    else:
+        cases = []
+        for d in (300, 768):
+            for ns in (1000, 10000, 100000):
+                for nf in (100_000, 1_000_000, 10_000_000):
+                    if nf * ns * d > 3.1e15:
+                        continue
+                    cases.append((nf, ns, d, 2))
+        cases += [(2_500_000, 25000, 300, 3), (2_500_000, 25000, 320, 3), (100_000_000, 1000, 300, 1)]
+    for nf, ns, d, reps in cases:
+        print(json.dumps(run_case(nf, ns, d, reps, rng)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
