@@ -15,7 +15,8 @@ from tests.numpy_index import NumpyIndex  # noqa: E402
 
 def main():
     golden, workdir = sys.argv[1], sys.argv[2]
-    engine_mod.DeviceIndex = NumpyIndex
+    if os.environ.get('FS_TEST_REAL_DEVICE') != '1':
+        engine_mod.DeviceIndex = NumpyIndex
     search.set_pipeline(search.Pipeline(
         Lexicon.from_npz(os.path.join(golden, "lexicon.npz"), hash_fn=py_hash_seed0)))
     listing = open(os.path.join(golden, "listing.txt")).read().split()

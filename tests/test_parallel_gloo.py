@@ -21,15 +21,39 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+def test_sharded_analyze_on_two_gpus(golden_dir, tmp_path):
+    """Same as below on real devices: 2 ranks, one B200 each, NCCL process group."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _run_world(golden_dir, tmp_path, 2, real=True)
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_analyze_equals_single_process_golden(golden_dir, tmp_path, world):
+    _run_world(golden_dir, tmp_path, world, real=False)
+
+
+def _run_world(golden_dir, tmp_path, world, real):
     os.symlink(os.path.join(golden_dir, "fanworks"), tmp_path / "fanworks")
     os.symlink(os.path.join(golden_dir, "script.txt"), tmp_path / "script.txt")
     port = _free_port()
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
-                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES="")
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        if real:
+            env["FS_TEST_REAL_DEVICE"] = "1"
+        else:
+            env["CUDA_VISIBLE_DEVICES"] = ""
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_dist_worker.py"),
                                        golden_dir, str(tmp_path)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
