@@ -65,6 +65,15 @@ SIGNATURES = {
     "fs_levenshtein_utf8": (_i32, [ctypes.c_char_p, _i64, ctypes.c_char_p, _i64]),
     "fs_murmurhash64a": (ctypes.c_uint64, [ctypes.c_char_p, _i64, ctypes.c_uint64]),
     "fs_tokenize_ws": (_i64, [ctypes.c_char_p, _i64, _vp, _vp, _i64]),
+    "fs_vocab_create": (_vp, [ctypes.c_char_p, _vp, _vp, _i64]),
+    "fs_vocab_destroy": (None, [_vp]),
+    "fs_vocab_lookup": (_i32, [_vp, ctypes.c_char_p, _i64]),
+    "fs_batch_encode_files": (_vp, [_vp, ctypes.POINTER(ctypes.c_char_p), _i64, _i32]),
+    "fs_batch_destroy": (None, [_vp]),
+    "fs_batch_info": (_i64, [_vp, _i32]),
+    "fs_batch_array": (_vp, [_vp, _i32]),
+    "fs_records_best": (_i64, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
 }
 
 _lib = None

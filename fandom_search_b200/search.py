@@ -247,15 +247,29 @@ class AnnIndexSearch(object):
 
     def search_many(self, filenames):
         """Record lists (one per file, each sorted) for a cluster of works."""
+        return self.run_prepared(self.prepare(filenames))
+
+    def prepare(self, filenames):
+        """Host stage before the GPU: read + tokenise + row ids -> CSR batch (search.py:164-169).
+        Native and multi-threaded for the default whitespace tokeniser; safe to run in a
+        background thread while the previous cluster is being searched."""
         lex = self.spacy_model.lexicon
         n_fixed = lex.n_rows + self.engine.n_script_extra
-        fans = [self._tokenize_file(fn) for fn in filenames]
-        offs = numpy.zeros(len(fans) + 1, dtype=numpy.int64)
-        for i, fan in enumerate(fans):
-            offs[i + 1] = offs[i] + len(fan)
-        tok = numpy.empty(int(offs[-1]), dtype=numpy.int32)
-        for i, fan in enumerate(fans):
-            tok[offs[i]:offs[i + 1]] = lex.row_ids(fan)
+        if self.spacy_model.tokenizer is _text.tokenize:
+            if getattr(self.spacy_model, '_vocab', None) is None:
+                self.spacy_model._vocab = _text.Vocab(lex)
+            batch = self.spacy_model._vocab.encode_files(filenames)
+            tok = numpy.array(batch.tok, dtype=numpy.int32)        # private copy
+            if len(batch.oov_start):
+                oov_ids = numpy.array([lex.row_id(w) for w in batch.oov_strings()], dtype=numpy.int32)
+                neg = tok < 0
+                tok[neg] = oov_ids[-tok[neg] - 1]
+        else:
+            fans = [self._tokenize_file(fn) for fn in filenames]
+            batch = _text.Batch.from_token_lists(fans)
+            tok = numpy.concatenate([lex.row_ids(f) for f in fans] +
+                                    [numpy.zeros(0, numpy.int32)]).astype(numpy.int32)
+        offs = numpy.array(batch.tok_off, dtype=numpy.int64)
         # batch-local numbering of the fan-side OOV rows
         extra = None
         is_new = tok >= n_fixed
@@ -264,78 +278,59 @@ class AnnIndexSearch(object):
             tok[is_new] = (n_fixed + inv).astype(numpy.int32)
             extra = numpy.concatenate(
                 [lex.oov_rows(int(u) - lex.n_rows, int(u) - lex.n_rows + 1) for u in uniq], axis=0)
-        matches, counters = self.engine.index.search_host(tok, offs, extra)
+        return {'filenames': list(filenames), 'batch': batch, 'tok': tok, 'offs': offs, 'extra': extra}
+
+    def run_prepared(self, prep):
+        matches, counters = self.engine.index.search_host(prep['tok'], prep['offs'], prep['extra'])
         self._windows_processed += int(counters[nt.FS_CNT_WINDOWS])
         first_table = None
         if self.engine.lsh is not None:
             # keep only the pairs the emulated LSH index would have compared (lsh.py)
-            first_table = ((matches['flags'] >> nt.FS_MATCH_LSH_SHIFT) & 0xFF).astype(numpy.int64)
+            first_table = ((matches['flags'] >> nt.FS_MATCH_LSH_SHIFT) & 0xFF).astype(numpy.int32)
             keep = first_table > 0
             matches, first_table = matches[keep], first_table[keep]
-        return self._records(filenames, fans, offs, matches, first_table)
+        return self._records(prep['filenames'], prep['batch'], matches, first_table)
 
-    def _records(self, filenames, fans, offs, matches, first_table=None):
-        w = self.window_size
+    def _script_text(self):
+        if getattr(self, '_script_blob', None) is None:
+            enc = [w.encode('utf-8') for w in self.word_lowercase]
+            off = numpy.zeros(len(enc) + 1, dtype=numpy.int64)
+            numpy.cumsum([len(e) for e in enc], out=off[1:])
+            self._script_blob = b''.join(enc)
+            self._script_off = off
+        return self._script_blob, self._script_off
+
+    def _records(self, filenames, batch, matches, first_table=None):
+        # search.py:182-226 on the surviving pairs: top-10 per window, Levenshtein, six records
+        # per pair, per-word argmin (native, fs_records_best); here only the row formatting.
         out = [[] for _ in filenames]
         if len(matches) == 0:
             return out
-        # neighbours() returns candidates sorted by distance (stable, script order on ties),
-        # at most 10 of them (NearestFilter(10)); windows are visited in ascending order
-        # (under LSH emulation ties are ordered by the first table holding the candidate)
-        tie = first_table if first_table is not None else numpy.zeros(len(matches), dtype=numpy.int64)
-        order = numpy.lexsort((matches['script_pos'], tie, matches['distance'], matches['fan_pos']))
-        m = matches[order]
-        fan_pos = m['fan_pos']
-        first = numpy.r_[True, fan_pos[1:] != fan_pos[:-1]]
-        group_start = numpy.maximum.accumulate(numpy.where(first, numpy.arange(len(m)), 0))
-        rank = numpy.arange(len(m)) - group_start
-        m = m[rank < 10]
-        lev_cache = {}
-        per_work = {}
-        for rec in m:
-            per_work.setdefault(int(rec['work']), []).append(rec)
-        for wi, recs in per_work.items():
-            filename = filenames[wi]
-            fan = fans[wi]
-            base = int(offs[wi])
-            best = {}
-            for rec in recs:
-                fan_ix = int(rec['fan_pos']) - base
-                match_ix = int(rec['script_pos'])
-                distance = float(rec['distance'])
-                # search.py:123,189-190: str(Span) vs str(list of Token)
-                match_str = ' '.join(self.word_lowercase[match_ix:match_ix + w])
-                fan_context = '[' + ', '.join(fan[fan_ix:fan_ix + w]) + ']'
-                key = (match_str, fan_context)
-                lev_d = lev_cache.get(key)
-                if lev_d is None:
-                    lev_d = _text.levenshtein(match_str, fan_context)
-                    lev_cache[key] = lev_d
-                combined = distance * lev_d
-                for window_ix in range(w):
-                    fan_word_ix = fan_ix + window_ix
-                    cur = best.get(fan_word_ix)
-                    # min(..., key=itemgetter(11)) keeps the FIRST minimal record
-                    if cur is None or combined < cur[0]:
-                        best[fan_word_ix] = (combined, window_ix, match_ix, distance, lev_d)
-            rows = []
-            for fan_word_ix in sorted(best):
-                combined, window_ix, match_ix, distance, lev_d = best[fan_word_ix]
-                orig_word_ix = match_ix + window_ix
-                fan_word = fan[fan_word_ix]
-                rows.append([filename,
-                             fan_word_ix,
-                             fan_word,                       # orth_
-                             _text.string_id(fan_word),      # orth
-                             orig_word_ix,
-                             self.word_lowercase[orig_word_ix],
-                             self.orth_id[orig_word_ix],
-                             self.character[orig_word_ix],
-                             self.scene[orig_word_ix],
-                             distance,
-                             lev_d,
-                             combined])
-            out[wi] = rows
+        blob, soff = self._script_text()
+        best = _text.records_best(matches, first_table, self.window_size, 10, batch, blob, soff)
+        tok_off = batch.tok_off
+        work = best['work'].tolist()
+        word = best['word'].tolist()
+        window_ix = best['window_ix'].tolist()
+        match_ix = best['match_ix'].tolist()
+        distance = best['distance'].tolist()
+        lev = best['lev'].tolist()
+        for i in range(len(work)):
+            wi = work[i]
+            fan_word = batch.token_text(int(tok_off[wi]) + word[i])
+            orig_word_ix = match_ix[i] + window_ix[i]
+            out[wi].append([filenames[wi],
+                            word[i],
+                            fan_word,                        # orth_
+                            _text.string_id(fan_word),       # orth
+                            orig_word_ix,
+                            self.word_lowercase[orig_word_ix],
+                            self.orth_id[orig_word_ix],
+                            self.character[orig_word_ix],
+                            self.scene[orig_word_ix],
+                            distance[i],
+                            lev[i],
+                            distance[i] * lev[i]])
         return out
 
 
@@ -469,15 +464,21 @@ def analyze(args,
     global _ANN_INDEX
     _ANN_INDEX = ann_index
 
+    # host preparation (file read + tokenise + encode) of my next cluster overlaps the GPU
+    # search of the current one; ctypes releases the GIL inside the native calls
+    from concurrent.futures import ThreadPoolExecutor
+    mine = [(i, c) for i, c in enumerate(fan_clusters, start=start) if i % world == rank]
     my_records = {}
-    for i, fan_cluster in enumerate(fan_clusters, start=start):
-        if i % world != rank:
-            continue
-        print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
-        record_sets = ann_index.search_many(fan_cluster)
-        records = [r for r_set in record_sets for r in r_set]
-        write_records(records, batch_filename.format(i))
-        my_records[i] = records
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = pool.submit(ann_index.prepare, mine[0][1]) if mine else None
+        for k, (i, fan_cluster) in enumerate(mine):
+            print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
+            prep = pending.result()
+            pending = pool.submit(ann_index.prepare, mine[k + 1][1]) if k + 1 < len(mine) else None
+            record_sets = ann_index.run_prepared(prep)
+            records = [r for r_set in record_sets for r in r_set]
+            write_records(records, batch_filename.format(i))
+            my_records[i] = records
 
     if world > 1:
         from .parallel import gather_cluster_records

@@ -48,3 +48,151 @@ def levenshtein(a, b):
     ab = a.encode("utf-8")
     bb = b.encode("utf-8")
     return int(nt.load().fs_levenshtein_utf8(ab, len(ab), bb, len(bb)))
+
+
+# ---------------------------------------------------------------------------------------------
+# native host pipeline (csrc/host_pipeline.cpp)
+# ---------------------------------------------------------------------------------------------
+import ctypes  # noqa: E402
+import os  # noqa: E402
+
+
+def _view(ptr, count, dtype):
+    if count == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    ctype = {np.dtype(np.int64): ctypes.c_int64, np.dtype(np.int32): ctypes.c_int32,
+             np.dtype(np.uint8): ctypes.c_uint8}[np.dtype(dtype)]
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(count,))
+
+
+class Vocab:
+    """Native key -> embedding-row id map built from a Lexicon."""
+
+    def __init__(self, lexicon):
+        lib = nt.load()
+        keys = list(lexicon.key_to_row)
+        enc = [k.encode("utf-8") for k in keys]
+        off = np.zeros(len(enc) + 1, dtype=np.int64)
+        np.cumsum([len(e) for e in enc], out=off[1:])
+        rows = np.array([lexicon.key_to_row[k] for k in keys], dtype=np.int32)
+        blob = b"".join(enc)
+        self._lib = lib
+        self._h = lib.fs_vocab_create(blob, nt.ptr(off), nt.ptr(rows), len(enc))
+        if not self._h:
+            raise nt.NativeError(nt.FS_E_INVALID, lib.fs_last_error().decode())
+
+    def lookup(self, word):
+        b = word.encode("utf-8")
+        return int(self._lib.fs_vocab_lookup(self._h, b, len(b)))
+
+    def encode_files(self, paths, threads=None):
+        if threads is None:
+            threads = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)
+        arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        h = self._lib.fs_batch_encode_files(self._h, arr, len(paths), threads)
+        if not h:
+            raise nt.NativeError(nt.FS_E_INVALID, self._lib.fs_last_error().decode())
+        return Batch(self._lib, h, list(paths))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.fs_vocab_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class Batch:
+    """One cluster of files, read + tokenised + encoded natively.  Arrays are zero-copy views of
+    native memory and stay valid while this object is alive."""
+
+    def __init__(self, lib, handle, paths):
+        self._lib = lib
+        self._h = handle
+        self.paths = paths
+        n_files = int(lib.fs_batch_info(handle, 0))
+        n_tok = int(lib.fs_batch_info(handle, 1))
+        n_oov = int(lib.fs_batch_info(handle, 2))
+        n_text = int(lib.fs_batch_info(handle, 3))
+        arr = lambda which: lib.fs_batch_array(handle, which)
+        self.text = _view(arr(0), n_text, np.uint8)
+        self.tok_off = _view(arr(2), n_files + 1, np.int64)
+        self.tok = _view(arr(3), n_tok, np.int32)
+        self.tok_start = _view(arr(4), n_tok, np.int64)
+        self.tok_end = _view(arr(5), n_tok, np.int64)
+        self.oov_start = _view(arr(6), n_oov, np.int64)
+        self.oov_end = _view(arr(7), n_oov, np.int64)
+        status = _view(arr(8), n_files, np.int32)
+        bad = np.nonzero(status)[0]
+        if len(bad):
+            raise FileNotFoundError("cannot read %s" % paths[int(bad[0])])
+
+    @classmethod
+    def from_token_lists(cls, lists):
+        """Same structure from already-tokenised works (custom tokeniser path)."""
+        self = cls.__new__(cls)
+        self._lib = None
+        self._h = None
+        enc = [[w.encode("utf-8") for w in ws] for ws in lists]
+        flat = [b for ws in enc for b in ws]
+        lens = np.array([len(b) for b in flat], dtype=np.int64)
+        self.tok_start = np.zeros(len(flat), dtype=np.int64)
+        if len(flat):
+            self.tok_start[1:] = np.cumsum(lens[:-1] + 1)
+        self.tok_end = self.tok_start + lens
+        self.text = np.frombuffer(b" ".join(flat), dtype=np.uint8)
+        self.tok_off = np.zeros(len(lists) + 1, dtype=np.int64)
+        np.cumsum([len(ws) for ws in lists], out=self.tok_off[1:])
+        self.tok = np.full(len(flat), -1, dtype=np.int32)
+        self.oov_start = np.zeros(0, dtype=np.int64)
+        self.oov_end = np.zeros(0, dtype=np.int64)
+        return self
+
+    def token_text(self, pos):
+        return self.text[int(self.tok_start[pos]):int(self.tok_end[pos])].tobytes().decode("utf-8")
+
+    def oov_strings(self):
+        return [self.text[int(s):int(e)].tobytes().decode("utf-8")
+                for s, e in zip(self.oov_start.tolist(), self.oov_end.tolist())]
+
+    def close(self):
+        if self._h:
+            self.text = self.tok = self.tok_start = self.tok_end = self.tok_off = None
+            self._lib.fs_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def records_best(matches, tie, window, topk, batch, script_blob, script_off):
+    """Native search.py:182-226 core.  Returns dict of arrays (work, word, window_ix, match_ix,
+    distance, lev) for the winning record of every matched fan word, sorted by (work, word)."""
+    lib = nt.load()
+    n = len(matches)
+    matches = np.ascontiguousarray(matches)
+    tie_arr = None if tie is None else np.ascontiguousarray(tie, dtype=np.int32)
+    cap = max(64, 6 * n)
+    out = None
+    while True:
+        out = {"work": np.empty(cap, np.int32), "word": np.empty(cap, np.int32),
+               "window_ix": np.empty(cap, np.int32), "match_ix": np.empty(cap, np.int32),
+               "distance": np.empty(cap, np.float64), "lev": np.empty(cap, np.int32)}
+        text = np.ascontiguousarray(batch.text)
+        rows = lib.fs_records_best(
+            nt.ptr(matches) if n else None, nt.ptr(tie_arr) if tie_arr is not None and n else None, n,
+            window, topk, nt.ptr(text) if len(text) else None, nt.ptr(np.ascontiguousarray(batch.tok_start)),
+            nt.ptr(np.ascontiguousarray(batch.tok_end)), nt.ptr(np.ascontiguousarray(batch.tok_off)),
+            len(batch.tok_off) - 1, script_blob, nt.ptr(script_off), len(script_off) - 1,
+            nt.ptr(out["work"]), nt.ptr(out["word"]), nt.ptr(out["window_ix"]), nt.ptr(out["match_ix"]),
+            nt.ptr(out["distance"]), nt.ptr(out["lev"]), cap)
+        if rows < 0 and rows > -(1 << 62):
+            cap = -rows
+            continue
+        if rows < 0:
+            raise nt.NativeError(nt.FS_E_INVALID, lib.fs_last_error().decode())
+        return {k: v[:rows] for k, v in out.items()}

@@ -206,6 +206,43 @@ uint64_t fs_murmurhash64a(const void* key, int64_t len, uint64_t seed);
  * offsets; returns the number of tokens found (may exceed cap). */
 int64_t fs_tokenize_ws(const char* text, int64_t len, int64_t* starts, int64_t* ends, int64_t cap);
 
+/*
+ * Native host stages either side of the GPU search (no GPU needed).
+ */
+typedef struct fs_vocab fs_vocab; /* lexicon key -> embedding-row id (Token.has_vector/.vector keys,
+                                     search.py:74-75) */
+typedef struct fs_batch fs_batch; /* one cluster of files read, tokenised and encoded to CSR */
+
+/* keys_blob: the UTF-8 keys concatenated; key_offsets [n_keys+1]; rows [n_keys]. */
+fs_vocab* fs_vocab_create(const char* keys_blob, const int64_t* key_offsets, const int32_t* rows,
+                          int64_t n_keys);
+void fs_vocab_destroy(fs_vocab* v);
+int32_t fs_vocab_lookup(const fs_vocab* v, const char* key, int64_t len); /* row id or -1 */
+
+/* Read `n_files` files with `n_threads` threads, split on ASCII whitespace, look every token up
+ * (replaces the per-file read + tokenise + mk_vectors lookups of search.py:164-169).
+ * Tokens without a vector get the id -(1+u), u numbering the batch's unique OOV strings in order
+ * of first appearance. */
+fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int64_t n_files,
+                                int32_t n_threads);
+void fs_batch_destroy(fs_batch* b);
+int64_t fs_batch_info(const fs_batch* b, int32_t what);  /* 0 files, 1 tokens, 2 unique OOV, 3 text bytes */
+/* 0 text(char) 1 file_off(i64[files+1]) 2 tok_off(i64[files+1]) 3 tok(i32[T]) 4 tok_start(i64[T])
+ * 5 tok_end(i64[T]) 6 oov_start(i64[U]) 7 oov_end(i64[U]) 8 file_status(i32[files]); valid until destroy */
+void* fs_batch_array(fs_batch* b, int32_t which);
+
+/* Top-k per fan window (NearestFilter(10)), Levenshtein of "[t0, ..., t5]" vs "s0 ... s5"
+ * (search.py:123,189-190), six records per pair and the per-word argmin with first-inserted ties
+ * (search.py:192-225).  Returns the number of winning rows (sorted by work, word), or -(rows needed)
+ * when cap_out is too small. */
+int64_t fs_records_best(const fs_match* matches, const int32_t* tie, int64_t n, int32_t window,
+                        int32_t topk, const char* text, const int64_t* tok_start,
+                        const int64_t* tok_end, const int64_t* tok_off, int64_t n_works,
+                        const char* script_blob, const int64_t* script_word_off,
+                        int64_t n_script_words, int32_t* out_work, int32_t* out_word,
+                        int32_t* out_window_ix, int32_t* out_match_ix, double* out_distance,
+                        int32_t* out_lev, int64_t cap_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,3 +98,43 @@ def test_mk_vectors_and_chunks(cpu_device):
     long_text = " ".join(["w00001"] * 20000)          # 139999 chars -> two chunks
     chunks = list(search.sp_parse_chunks(long_text))
     assert len(chunks) == 2 and sum(len(c) for c in chunks) == 20000
+
+
+def test_custom_tokenizer_path_matches_golden(monkeypatch, golden_dir):
+    """A user-supplied tokeniser (e.g. spaCy's) bypasses the native encoder; same records."""
+    monkeypatch.setattr(engine_mod, "DeviceIndex", NumpyIndex)
+    lex = Lexicon.from_npz(os.path.join(golden_dir, "lexicon.npz"), hash_fn=py_hash_seed0)
+    search.set_pipeline(search.Pipeline(lex, tokenizer=lambda text: text.split()))
+    try:
+        idx = search.AnnIndexSearch(os.path.join(golden_dir, "script.txt"), 6, 15, 14, 0.1)
+        files = sorted(glob.glob(os.path.join(golden_dir, "fanworks", "*.txt")))
+        got = normalise([r for s in idx.search_many(files) for r in s])
+        compare_records(got, read_csv(os.path.join(golden_dir, "golden_exhaustive.csv")), tol=1e-12)
+    finally:
+        search.set_pipeline(None)
+
+
+def test_native_vocab_and_batch(golden_dir, tmp_path):
+    from fandom_search_b200 import text
+    lex = Lexicon.from_npz(os.path.join(golden_dir, "lexicon.npz"), hash_fn=py_hash_seed0)
+    vocab = text.Vocab(lex)
+    for k, r in list(lex.key_to_row.items())[:50]:
+        assert vocab.lookup(k) == r
+    assert vocab.lookup("definitely-not-a-word") == -1 and vocab.lookup("") == -1
+    (tmp_path / "a.txt").write_text("w00001  zzz W00001\nzzz\tqqq é日本", encoding="utf-8")
+    (tmp_path / "b.txt").write_text("", encoding="utf-8")
+    (tmp_path / "c.txt").write_text("qqq", encoding="utf-8")
+    b = vocab.encode_files([str(tmp_path / n) for n in ("a.txt", "b.txt", "c.txt")], threads=3)
+    assert b.tok_off.tolist() == [0, 6, 6, 7]
+    words = [b.token_text(i) for i in range(7)]
+    assert words == ["w00001", "zzz", "W00001", "zzz", "qqq", "é日本", "qqq"]
+    want_oov = []
+    for w in words:
+        if w not in lex.key_to_row and w not in want_oov:
+            want_oov.append(w)
+    assert b.oov_strings() == want_oov and want_oov[0] == "zzz"
+    tok = b.tok.tolist()
+    for w, t in zip(words, tok):
+        assert t == (lex.key_to_row[w] if w in lex.key_to_row else -(1 + want_oov.index(w)))
+    with pytest.raises(FileNotFoundError):
+        vocab.encode_files([str(tmp_path / "missing.txt")])

@@ -1,0 +1,94 @@
+"""End-to-end pipeline benchmark: plaintext fanwork folder + markup script -> match CSVs.
+
+    python tools/pipeline_bench.py --works 2000 [--cpu-works 32]
+
+Runs the drop-in `search.analyze` (file listing -> native read/tokenise/encode -> GPU search ->
+native top-10/Levenshtein/argmin -> CSV) on a synthetic corpus written to a temp dir (BASELINE
+config C1 scaled by --works), reports wall-clock windows/s and per-stage times, and optionally the
+oracle's CPU port of the reference on a sample of the same files for comparison."""
+import argparse
+import glob
+import json
+import os
+import sys
+import tempfile
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+from fandom_search_b200 import search, synth
+from fandom_search_b200.lexicon import Lexicon, py_hash_seed0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--works", type=int, default=2000)
+    ap.add_argument("--script-tokens", type=int, default=10000)
+    ap.add_argument("--oov-frac", type=float, default=0.02)
+    ap.add_argument("--cpu-works", type=int, default=0)
+    args = ap.parse_args()
+    tmp = tempfile.mkdtemp(prefix="fs_pipeline_")
+    lex = synth.SynthLexicon(vocab=50000, dim=300, oov_frac=args.oov_frac, seed=1001)
+    lex_path = lex.save(os.path.join(tmp, "lexicon.npz"))
+    script_ids = synth.make_script_tokens(lex, args.script_tokens)
+    script_path = os.path.join(tmp, "script.txt")
+    synth.write_markup_script(lex, script_ids, script_path)
+    fan_dir = os.path.join(tmp, "fanworks")
+    t0 = time.perf_counter()
+    windows = synth.write_corpus(lex, script_ids, fan_dir, args.works)
+    gen_s = time.perf_counter() - t0
+    nbytes = sum(os.path.getsize(f) for f in glob.glob(os.path.join(fan_dir, "*.txt")))
+
+    search.set_pipeline(search.Pipeline(Lexicon.from_npz(lex_path, hash_fn=py_hash_seed0)))
+    cwd = os.getcwd()
+    out_dir = os.path.join(tmp, "out")
+    os.makedirs(out_dir)
+    os.chdir(out_dir)
+    ns = argparse.Namespace(fan_works=fan_dir, script=script_path, skip_works=-1, num_works=-1)
+    # instrument the stages
+    stage = {"prepare": 0.0, "gpu": 0.0, "records": 0.0}
+    A = search.AnnIndexSearch
+    orig_prepare, orig_run, orig_records = A.prepare, A.run_prepared, A._records
+
+    def timed(name, fn):
+        def wrapper(*a, **kw):
+            t = time.perf_counter()
+            try:
+                return fn(*a, **kw)
+            finally:
+                stage[name] += time.perf_counter() - t
+        return wrapper
+    A.prepare = timed("prepare", orig_prepare)
+    A._records = timed("records", orig_records)
+    A.run_prepared = timed("gpu", orig_run)          # includes records; subtracted below
+    t0 = time.perf_counter()
+    search.analyze(ns)
+    total_s = time.perf_counter() - t0
+    os.chdir(cwd)
+    rows = sum(1 for _ in open(glob.glob(os.path.join(out_dir, "match-6gram-2*.csv"))[0])) - 1
+    res = {"works": args.works, "windows": windows, "corpus_mb": nbytes / 1e6, "script_tokens": args.script_tokens,
+           "total_s": total_s, "pipeline_windows_per_s": windows / total_s,
+           "stage_s": {"prepare(read+tokenise+encode, overlapped)": stage["prepare"],
+                       "gpu search (C-ABI host call)": stage["gpu"] - stage["records"],
+                       "records (top10+lev+argmin+rows)": stage["records"]},
+           "csv_rows": rows, "corpus_generation_s": gen_s}
+    if args.cpu_works:
+        from oracle import reference_search as ora
+        files = sorted(glob.glob(os.path.join(fan_dir, "*.txt")))[:args.cpu_works]
+        t0 = time.perf_counter()
+        oidx = ora.OracleIndex(script_path, ora.OracleLexicon(lex_path, oov_hash=py_hash_seed0), mode="lsh",
+                               seed=0, engine="nearpy")
+        build_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for f in files:
+            oidx.search(f)
+        cpu_s = time.perf_counter() - t0
+        res["cpu_port_single_process"] = {"works": len(files), "windows": oidx.windows_processed,
+                                          "index_build_s": build_s, "search_s": cpu_s,
+                                          "windows_per_s": oidx.windows_processed / cpu_s}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
