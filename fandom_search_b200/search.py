@@ -281,6 +281,10 @@ class AnnIndexSearch(object):
         return {'filenames': list(filenames), 'batch': batch, 'tok': tok, 'offs': offs, 'extra': extra}
 
     def run_prepared(self, prep):
+        return self.records_prepared(prep, *self.search_prepared(prep))
+
+    def search_prepared(self, prep):
+        """GPU stage: one C-ABI call for the cluster (search.py:169-184 for every work)."""
         matches, counters = self.engine.index.search_host(prep['tok'], prep['offs'], prep['extra'])
         self._windows_processed += int(counters[nt.FS_CNT_WINDOWS])
         first_table = None
@@ -289,6 +293,10 @@ class AnnIndexSearch(object):
             first_table = ((matches['flags'] >> nt.FS_MATCH_LSH_SHIFT) & 0xFF).astype(numpy.int32)
             keep = first_table > 0
             matches, first_table = matches[keep], first_table[keep]
+        return matches, first_table
+
+    def records_prepared(self, prep, matches, first_table=None):
+        """Host stage after the GPU (search.py:188-226)."""
         return self._records(prep['filenames'], prep['batch'], matches, first_table)
 
     def _script_text(self):
@@ -464,20 +472,30 @@ def analyze(args,
     global _ANN_INDEX
     _ANN_INDEX = ann_index
 
-    # host preparation (file read + tokenise + encode) of my next cluster overlaps the GPU
-    # search of the current one; ctypes releases the GIL inside the native calls
+    # Three overlapped stages per cluster: (1) native read + tokenise + encode of the NEXT
+    # cluster, (2) the GPU search of this one, (3) records + batch CSV of the PREVIOUS one.
+    # ctypes releases the GIL inside the native calls, so plain threads are enough.
     from concurrent.futures import ThreadPoolExecutor
     mine = [(i, c) for i, c in enumerate(fan_clusters, start=start) if i % world == rank]
     my_records = {}
-    with ThreadPoolExecutor(max_workers=1) as pool:
-        pending = pool.submit(ann_index.prepare, mine[0][1]) if mine else None
+
+    def finish(i, prep, found):
+        record_sets = ann_index.records_prepared(prep, *found)
+        records = [r for r_set in record_sets for r in r_set]
+        write_records(records, batch_filename.format(i))
+        return i, records
+
+    with ThreadPoolExecutor(max_workers=1) as prep_pool, ThreadPoolExecutor(max_workers=1) as post_pool:
+        pending = prep_pool.submit(ann_index.prepare, mine[0][1]) if mine else None
+        finishing = []
         for k, (i, fan_cluster) in enumerate(mine):
             print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
             prep = pending.result()
-            pending = pool.submit(ann_index.prepare, mine[k + 1][1]) if k + 1 < len(mine) else None
-            record_sets = ann_index.run_prepared(prep)
-            records = [r for r_set in record_sets for r in r_set]
-            write_records(records, batch_filename.format(i))
+            pending = prep_pool.submit(ann_index.prepare, mine[k + 1][1]) if k + 1 < len(mine) else None
+            found = ann_index.search_prepared(prep)
+            finishing.append(post_pool.submit(finish, i, prep, found))
+        for fut in finishing:
+            i, records = fut.result()
             my_records[i] = records
 
     if world > 1:
