@@ -45,33 +45,63 @@ __global__ void absmax_kernel(const float* __restrict__ src, int64_t n, unsigned
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
-// E[t, :] = rows16[tok[t]]  (one 16-byte chunk per thread, fully coalesced stores)
-__global__ void gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSources src,
-                              int32_t chunks16 /* dim_pad*2/16 */, int4* __restrict__ emb,
-                              float* __restrict__ tok_sq) {
+// E[t, :] = rows16[tok[t]].  One 16-byte chunk per thread and per unrolled step, fully
+// coalesced stores; kGatherUnroll independent row loads are in flight per thread so that the
+// kernel is bound by HBM write bandwidth rather than by L2 read latency.
+constexpr int kGatherUnroll = 4;
+
+__device__ __forceinline__ int4 gather_chunk(const GatherSources& src, const int4* base16,
+                                             const int4* sx16, const int4* fx16, int64_t id,
+                                             int32_t chunks16, int32_t c, float* sq) {
+    int4 v = make_int4(0, 0, 0, 0);  // unknown ids embed as the zero vector
+    *sq = 0.f;
+    if (id >= 0 && id < src.n_base) {
+        v = __ldg(base16 + id * chunks16 + c);
+        if (c == 0) *sq = __ldg(src.base_sq + id);
+    } else if ((id -= src.n_base) >= 0 && id < src.n_sx) {
+        v = __ldg(sx16 + id * chunks16 + c);
+        if (c == 0) *sq = __ldg(src.sx_sq + id);
+    } else if ((id -= src.n_sx) >= 0 && id < src.n_fx) {
+        v = __ldg(fx16 + id * chunks16 + c);
+        if (c == 0) *sq = __ldg(src.fx_sq + id);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSources src,
+              int32_t chunks16 /* dim_pad*2/16 */, int4* __restrict__ emb,
+              float* __restrict__ tok_sq) {
     const int64_t total = n_tok * chunks16;
     const int4* base16 = reinterpret_cast<const int4*>(src.base16);
     const int4* sx16 = reinterpret_cast<const int4*>(src.sx16);
     const int4* fx16 = reinterpret_cast<const int4*>(src.fx16);
-    for (int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
-         g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t t = g / chunks16;
-        const int32_t c = static_cast<int32_t>(g - t * chunks16);
-        int64_t id = __ldg(tok + t);
-        int4 v = make_int4(0, 0, 0, 0);  // unknown ids embed as the zero vector
-        float sq = 0.f;
-        if (id >= 0 && id < src.n_base) {
-            v = __ldg(base16 + id * chunks16 + c);
-            if (c == 0) sq = __ldg(src.base_sq + id);
-        } else if ((id -= src.n_base) >= 0 && id < src.n_sx) {
-            v = __ldg(sx16 + id * chunks16 + c);
-            if (c == 0) sq = __ldg(src.sx_sq + id);
-        } else if ((id -= src.n_sx) >= 0 && id < src.n_fx) {
-            v = __ldg(fx16 + id * chunks16 + c);
-            if (c == 0) sq = __ldg(src.fx_sq + id);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t g0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g0 < total;
+         g0 += stride * kGatherUnroll) {
+        int4 v[kGatherUnroll];
+        float sq[kGatherUnroll];
+        int64_t t[kGatherUnroll];
+        int32_t c[kGatherUnroll];
+        int64_t id[kGatherUnroll];
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            const int64_t g = g0 + u * stride;
+            t[u] = g / chunks16;
+            c[u] = static_cast<int32_t>(g - t[u] * chunks16);
+            id[u] = g < total ? __ldg(tok + t[u]) : -1;
         }
-        emb[g] = v;
-        if (c == 0) tok_sq[t] = sq;
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u)
+            v[u] = gather_chunk(src, base16, sx16, fx16, id[u], chunks16, c[u], &sq[u]);
+#pragma unroll
+        for (int u = 0; u < kGatherUnroll; ++u) {
+            const int64_t g = g0 + u * stride;
+            if (g < total) {
+                emb[g] = v[u];
+                if (c[u] == 0) tok_sq[t[u]] = sq[u];
+            }
+        }
     }
 }
 
@@ -82,12 +112,16 @@ __global__ void window_norm_kernel(const float* __restrict__ tok_sq, int64_t n_t
                                    const int64_t* __restrict__ off, int32_t n_rows, int32_t window,
                                    float coef, float* __restrict__ out, int64_t n_pad,
                                    unsigned long long* window_counter) {
-    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    __shared__ int32_t row_hint;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x;
+    if (threadIdx.x == 0) row_hint = t0 < n_tok ? csr_row_of(off, n_rows, t0) : 0;
+    __syncthreads();
+    const int64_t t = t0 + threadIdx.x;
     unsigned int valid = 0;
     if (t < n_pad) {
         float r = INFINITY;
         if (t < n_tok) {
-            const int32_t row = csr_row_of(off, n_rows, t);
+            const int32_t row = csr_row_from_hint(off, n_rows, t, row_hint);
             if (t + window <= __ldg(off + row + 1)) {
                 float s = 0.f;
                 for (int k = 0; k < window; ++k) s += tok_sq[t + k];
@@ -130,7 +164,7 @@ int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, i
     const int64_t total = n_tok * chunks16;
     const int threads = 256;
     int64_t blocks = (total + threads - 1) / threads;
-    const int64_t max_blocks = static_cast<int64_t>(sm_count) * 16;  // 8 resident + 1 more wave
+    const int64_t max_blocks = static_cast<int64_t>(sm_count) * 8;  // one resident wave, grid-stride
     if (blocks > max_blocks) blocks = max_blocks;
     gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         tok, n_tok, src, chunks16, reinterpret_cast<int4*>(emb), tok_sq);

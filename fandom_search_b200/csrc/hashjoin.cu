@@ -26,9 +26,11 @@ __device__ __forceinline__ uint64_t mix64(uint64_t h) {
 
 __device__ __forceinline__ uint64_t window_hash(const int32_t* __restrict__ tok, int32_t window) {
     uint64_t h = 0x9E3779B97F4A7C15ULL;
-    for (int k = 0; k < window; ++k)
-        h = mix64(h ^ static_cast<uint64_t>(static_cast<uint32_t>(__ldg(tok + k))));
-    return h;
+    for (int k = 0; k < window; ++k) {
+        h = (h ^ static_cast<uint64_t>(static_cast<uint32_t>(__ldg(tok + k)))) * 0xff51afd7ed558ccdULL;
+        h ^= h >> 29;
+    }
+    return mix64(h);
 }
 
 __global__ void hash_build_kernel(const int32_t* __restrict__ tok, int64_t n_tok,
@@ -48,15 +50,20 @@ __global__ void hash_build_kernel(const int32_t* __restrict__ tok, int64_t n_tok
     }
 }
 
-__global__ void hash_probe_kernel(const int32_t* __restrict__ tok, int64_t n_tok,
-                                  const int64_t* __restrict__ off, int32_t n_rows,
-                                  const int32_t* __restrict__ script_tok, int32_t window,
-                                  const unsigned long long* __restrict__ table, uint32_t mask,
-                                  fs_pair* __restrict__ out, int64_t cap,
-                                  unsigned long long* counter) {
-    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n_tok;
-         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int32_t row = csr_row_of(off, n_rows, t);
+__global__ void __launch_bounds__(256)
+hash_probe_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const int64_t* __restrict__ off,
+                  int32_t n_rows, const int32_t* __restrict__ script_tok, int32_t window,
+                  const unsigned long long* __restrict__ table, uint32_t mask,
+                  fs_pair* __restrict__ out, int64_t cap, unsigned long long* counter) {
+    __shared__ int32_t row_hint;
+    for (int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x; t0 < n_tok;
+         t0 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) row_hint = csr_row_of(off, n_rows, t0);
+        __syncthreads();
+        const int64_t t = t0 + threadIdx.x;
+        if (t >= n_tok) continue;
+        const int32_t row = csr_row_from_hint(off, n_rows, t, row_hint);
         if (t + window > __ldg(off + row + 1)) continue;
         const uint64_t h = window_hash(tok + t, window);
         const uint32_t tag = static_cast<uint32_t>(h >> 32);
