@@ -76,9 +76,15 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
     const int4* base16 = reinterpret_cast<const int4*>(src.base16);
     const int4* sx16 = reinterpret_cast<const int4*>(src.sx16);
     const int4* fx16 = reinterpret_cast<const int4*>(src.fx16);
+    // (token, chunk) of a flat chunk index advances by a constant step per unrolled slot; the
+    // 64-bit division is done once per thread, then replaced by add-with-carry
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t g0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; g0 < total;
-         g0 += stride * kGatherUnroll) {
+    const int64_t stride_t = stride / chunks16;
+    const int32_t stride_c = static_cast<int32_t>(stride - stride_t * chunks16);
+    int64_t g0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int64_t t0 = g0 / chunks16;
+    int32_t c0 = static_cast<int32_t>(g0 - t0 * chunks16);
+    while (g0 < total) {
         int4 v[kGatherUnroll];
         float sq[kGatherUnroll];
         int64_t t[kGatherUnroll];
@@ -86,10 +92,15 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
         int64_t id[kGatherUnroll];
 #pragma unroll
         for (int u = 0; u < kGatherUnroll; ++u) {
-            const int64_t g = g0 + u * stride;
-            t[u] = g / chunks16;
-            c[u] = static_cast<int32_t>(g - t[u] * chunks16);
-            id[u] = g < total ? __ldg(tok + t[u]) : -1;
+            t[u] = t0;
+            c[u] = c0;
+            id[u] = (g0 + u * stride) < total ? __ldg(tok + t0) : -1;
+            t0 += stride_t;
+            c0 += stride_c;
+            if (c0 >= chunks16) {
+                c0 -= chunks16;
+                ++t0;
+            }
         }
 #pragma unroll
         for (int u = 0; u < kGatherUnroll; ++u)
@@ -102,6 +113,7 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
                 if (c[u] == 0) tok_sq[t[u]] = sq[u];
             }
         }
+        g0 += stride * kGatherUnroll;
     }
 }
 

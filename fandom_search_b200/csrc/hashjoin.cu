@@ -50,41 +50,67 @@ __global__ void hash_build_kernel(const int32_t* __restrict__ tok, int64_t n_tok
     }
 }
 
+// One block walks segments of kProbeSeg consecutive tokens; the CSR row of the segment start
+// is searched once, every thread then handles kProbeSeg/256 windows with independent loads in
+// flight (ids -> hash -> table slot), so the L2 latencies of different windows overlap.
+constexpr int kProbeSeg = 2048;
+constexpr int kProbePerThread = kProbeSeg / 256;
+
 __global__ void __launch_bounds__(256)
 hash_probe_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const int64_t* __restrict__ off,
                   int32_t n_rows, const int32_t* __restrict__ script_tok, int32_t window,
                   const unsigned long long* __restrict__ table, uint32_t mask,
                   fs_pair* __restrict__ out, int64_t cap, unsigned long long* counter) {
     __shared__ int32_t row_hint;
-    for (int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x; t0 < n_tok;
-         t0 += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    for (int64_t seg = static_cast<int64_t>(blockIdx.x) * kProbeSeg; seg < n_tok;
+         seg += static_cast<int64_t>(gridDim.x) * kProbeSeg) {
         __syncthreads();
-        if (threadIdx.x == 0) row_hint = csr_row_of(off, n_rows, t0);
+        if (threadIdx.x == 0) row_hint = csr_row_of(off, n_rows, seg);
         __syncthreads();
-        const int64_t t = t0 + threadIdx.x;
-        if (t >= n_tok) continue;
-        const int32_t row = csr_row_from_hint(off, n_rows, t, row_hint);
-        if (t + window > __ldg(off + row + 1)) continue;
-        const uint64_t h = window_hash(tok + t, window);
-        const uint32_t tag = static_cast<uint32_t>(h >> 32);
-        uint32_t slot = static_cast<uint32_t>(h) & mask;
-        while (true) {
-            const unsigned long long e = __ldg(table + slot);
-            if (e == kEmptySlot) break;
-            if (static_cast<uint32_t>(e >> 32) == tag) {
-                const int32_t j = static_cast<int32_t>(static_cast<uint32_t>(e));
-                bool same = true;
-                for (int k = 0; k < window; ++k)
-                    same = same && (__ldg(tok + t + k) == __ldg(script_tok + j + k));
-                if (same) {
-                    const unsigned long long s = atomicAdd(counter, 1ull);
-                    if (s < static_cast<unsigned long long>(cap)) {
-                        out[s].fan_pos = static_cast<int32_t>(t);
-                        out[s].script_pos = j;
-                    }
+        uint64_t h[kProbePerThread];
+        bool valid[kProbePerThread];
+        int32_t row = row_hint;
+#pragma unroll
+        for (int u = 0; u < kProbePerThread; ++u) {
+            const int64_t t = seg + u * 256 + threadIdx.x;
+            valid[u] = false;
+            h[u] = 0;
+            if (t < n_tok) {
+                row = csr_row_from_hint(off, n_rows, t, row);
+                if (t + window <= __ldg(off + row + 1)) {
+                    valid[u] = true;
+                    h[u] = window_hash(tok + t, window);
                 }
             }
-            slot = (slot + 1) & mask;
+        }
+        unsigned long long e[kProbePerThread];
+#pragma unroll
+        for (int u = 0; u < kProbePerThread; ++u)
+            e[u] = valid[u] ? __ldg(table + (static_cast<uint32_t>(h[u]) & mask)) : kEmptySlot;
+#pragma unroll
+        for (int u = 0; u < kProbePerThread; ++u) {
+            if (e[u] == kEmptySlot) continue;  // the common case: no script window hashes here
+            const int64_t t = seg + u * 256 + threadIdx.x;
+            const uint32_t tag = static_cast<uint32_t>(h[u] >> 32);
+            uint32_t slot = static_cast<uint32_t>(h[u]) & mask;
+            unsigned long long cur = e[u];
+            while (cur != kEmptySlot) {
+                if (static_cast<uint32_t>(cur >> 32) == tag) {
+                    const int32_t j = static_cast<int32_t>(static_cast<uint32_t>(cur));
+                    bool same = true;
+                    for (int k = 0; k < window; ++k)
+                        same = same && (__ldg(tok + t + k) == __ldg(script_tok + j + k));
+                    if (same) {
+                        const unsigned long long s = atomicAdd(counter, 1ull);
+                        if (s < static_cast<unsigned long long>(cap)) {
+                            out[s].fan_pos = static_cast<int32_t>(t);
+                            out[s].script_pos = j;
+                        }
+                    }
+                }
+                slot = (slot + 1) & mask;
+                cur = __ldg(table + slot);
+            }
         }
     }
 }
@@ -108,8 +134,8 @@ int launch_hash_probe(const int32_t* tok, int64_t n_tok, const int64_t* off, int
                       int sm_count, cudaStream_t stream) {
     if (n_tok <= 0) return FS_OK;
     const int threads = 256;
-    int64_t blocks = (n_tok + threads - 1) / threads;
-    const int64_t max_blocks = static_cast<int64_t>(sm_count) * 16;
+    int64_t blocks = (n_tok + kProbeSeg - 1) / kProbeSeg;
+    const int64_t max_blocks = static_cast<int64_t>(sm_count) * 8;
     if (blocks > max_blocks) blocks = max_blocks;
     hash_probe_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         tok, n_tok, off, n_rows, script_tok, window, table, slots - 1, out, cap, counter);

@@ -61,6 +61,11 @@ def main():
     res["embed"] = {"ms": ms, "algorithmic_gbs": bytes_alg / ms / 1e6, "frac_of_hbm_peak": bytes_alg / ms / 1e6 / peaks["hbm_gbs"],
                     "tokens_per_s": args.tokens / ms * 1e3, "note": "gather + window norms + torch.empty of outputs"}
 
+    # write-only reference: how fast can this GPU stream zeros into a buffer of the same size?
+    buf = torch.empty(args.tokens * idx.dim_pad, dtype=torch.float16, device="cuda")
+    ms = timeit(lambda: buf.zero_())
+    res["memset_same_bytes"] = {"ms": ms, "gbs": buf.numel() * 2 / ms / 1e6}
+    del buf
     out_t = torch.empty((1 << 22, 2), dtype=torch.int32, device="cuda")
     cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
     ms = timeit(lambda: idx.exact_join_dev(tok_t, off_t, out_t, cnt_t))
