@@ -123,7 +123,8 @@ struct fs_index {
     int32_t lsh_tables = 0, lsh_bits = 0;
 
     // options
-    int32_t shifts_per_stage = 6;
+    int32_t diag = 1;              // diagonal-sum factor E of the distance kernel
+    int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
     int32_t base_offset_mode = 0;
     int32_t grid_limit = 0;
 
@@ -220,8 +221,6 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     idx->n_sx = n_extra;
     idx->n_script_tok = n_script_tok;
     idx->n_scripts = static_cast<int32_t>(n_scripts);
-    // largest divisor of window that is <= 6 shifts per stage (halo of the TMA box is 8 rows)
-    idx->shifts_per_stage = window;
 
 #define FS_TRY(expr)                    \
     do {                                \
@@ -280,7 +279,8 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
                                idx->sx_sq, st));
 
     // script side: tokens, CSR, embeddings, window norms, tensor map, hash table
-    idx->tiles_n = static_cast<int32_t>((n_script_tok + kBlockN - 1) / kBlockN);
+    // padded so that any tile stepping (256 - (E-1) columns, E <= 3) stays in bounds
+    idx->tiles_n = static_cast<int32_t>((n_script_tok + kBlockN - 8 - 1) / (kBlockN - 8)) + 1;
     const int64_t n_pad = static_cast<int64_t>(idx->tiles_n) * kBlockN;
     FS_TRY(dev_alloc(&idx->script_tok, n_script_tok + 8));
     FS_TRY(dev_alloc(&idx->script_off, n_scripts + 1));
@@ -330,7 +330,8 @@ int fs_index_reserve(fs_index* idx, int64_t max_tokens, int64_t max_candidates) 
     if ((r = dev_grow(&idx->fan_emb, &idx->emb_cap, max_tokens * idx->dim_pad)) != FS_OK) return r;
     idx->tok_cap = idx->emb_cap / idx->dim_pad;
     if ((r = dev_grow(&idx->fan_tok_sq, &idx->sq_cap, max_tokens + 8)) != FS_OK) return r;
-    if ((r = dev_grow(&idx->fan_thr, &idx->thr_cap, round_up(max_tokens, kBlockM) + kBlockM)) != FS_OK)
+    // tiles step by 128 - (E-1) rows but always read 128 thresholds
+    if ((r = dev_grow(&idx->fan_thr, &idx->thr_cap, (max_tokens / (kBlockM - 8) + 2) * kBlockM)) != FS_OK)
         return r;
     if ((r = dev_grow(&idx->cand, &idx->cand_cap, max_candidates)) != FS_OK) return r;
     return FS_OK;
@@ -340,11 +341,19 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
     if (!idx) return FS_E_INVALID;
     switch (option) {
         case FS_OPT_SHIFTS_PER_STAGE:
-            if (value < 1 || value > 8 || idx->window % value != 0) {
-                set_error("shifts per stage must divide the window and be <= 8");
+            if (value < 0 || value > 8 || (value > 0 && (idx->window / idx->diag) % value != 0)) {
+                set_error("shifts per stage must divide window/diag and be <= 8 (0 = all)");
                 return FS_E_INVALID;
             }
             idx->shifts_per_stage = static_cast<int32_t>(value);
+            return FS_OK;
+        case FS_OPT_DIAG:
+            if (value < 1 || value > 3 || idx->window % value != 0) {
+                set_error("diagonal factor must be 1, 2 or 3 and divide the window");
+                return FS_E_INVALID;
+            }
+            idx->diag = static_cast<int32_t>(value);
+            idx->shifts_per_stage = 0;
             return FS_OK;
         case FS_OPT_BASE_OFFSET_MODE:
             idx->base_offset_mode = value ? 1 : 0;
@@ -386,6 +395,7 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
         case 2: return idx->sm_count;
         case 3: return idx->cand_cap;
         case 4: return idx->shifts_per_stage;
+        case 5: return idx->diag;
         default: return -1;
     }
 }
@@ -476,7 +486,9 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     if (counters) FS_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
     if (a.n_tok == 0 || idx->n_script_tok == 0) return FS_OK;
-    const int32_t tiles_m = static_cast<int32_t>((a.n_tok + kBlockM - 1) / kBlockM);
+    const int32_t m_step = kBlockM - (idx->diag - 1), n_step = kBlockN - (idx->diag - 1);
+    const int32_t tiles_m = static_cast<int32_t>((a.n_tok + m_step - 1) / m_step);
+    const int32_t tiles_n = static_cast<int32_t>((idx->n_script_tok + n_step - 1) / n_step);
     const int64_t thr_pad = static_cast<int64_t>(tiles_m) * kBlockM;
     int64_t want_cand = idx->cand_cap > 0 ? idx->cand_cap : (1 << 20);
     if ((r = fs_index_reserve(idx, a.n_tok, want_cand)) != FS_OK) return r;
@@ -492,10 +504,11 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.chunks = (idx->dim_pad + kChunkK - 1) / kChunkK;
     p.last_chunk_ksteps = (idx->dim_pad - (p.chunks - 1) * kChunkK) / kUmmaK;
     p.window = idx->window;
-    p.shifts_per_stage = idx->shifts_per_stage;
+    p.diag = idx->diag;
+    p.shifts_per_stage = idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag;
     p.base_offset_mode = idx->base_offset_mode;
     p.tiles_m = tiles_m;
-    p.tiles_n = idx->tiles_n;
+    p.tiles_n = tiles_n;
     p.cand = (mode == Mode::kCandidates) ? cand_out : idx->cand;
     p.cand_cap = (mode == Mode::kCandidates) ? cand_out_cap : idx->cand_cap;
     p.counters = counters;

@@ -44,8 +44,13 @@ constexpr int kStageBytes = kStageABytes + kStageBBytes;  // 52224
 constexpr int kStages = 4;
 constexpr int kAccumStages = 2;         // TMEM double buffer: 2 x 256 columns = all 512
 constexpr int kTmemCols = 512;
-constexpr int kDistThreads = 192;       // warp0 TMA, warp1 MMA, warps2-5 epilogue
-constexpr int kDistSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kEpiWarps = 8;            // two per TMEM lane quarter (one per 128-column half)
+constexpr int kDistThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warps2-9 epilogue
+constexpr int kHaloRows = 2;            // rows handed to the previous lane quarter (diag <= 3)
+constexpr int kHaloCols = kBlockN + 8;
+constexpr int kHaloBytes = kAccumStages * 4 * kHaloRows * kHaloCols * 4;  // 16896
+constexpr int kDistSmemBytes =
+    kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kHaloBytes;
 
 struct DistParams {
     const float* thr_fan;     // [Mpad]  (1 - thr - eps) * |fan window|, +inf when invalid
@@ -55,7 +60,8 @@ struct DistParams {
     int32_t chunks;           // ceil(dim_pad / 64) 64-column chunks
     int32_t last_chunk_ksteps;// UMMA K-steps (16 columns) in the last chunk: 1..4
     int32_t window;           // 6
-    int32_t shifts_per_stage; // S: 1,2,3,6
+    int32_t diag;             // E: epilogue adds E diagonal neighbours, MMAs do window/E shifts
+    int32_t shifts_per_stage; // S: MMA shifts served by one smem stage (divides window/E)
     int32_t base_offset_mode; // how shifted descriptors fill base_offset
     int32_t tiles_m, tiles_n;
     fs_pair* cand;            // candidate output
@@ -232,6 +238,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      bar)
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");

@@ -28,13 +28,18 @@
 
 namespace fs {
 
-template <bool kDump>
+// kDiag = E: the MMAs accumulate only the shifts {0, E, 2E, ...} (w/E of them) and the epilogue
+// adds E diagonal neighbours, out[i][j] = sum_{d<E} acc[i+d][j+d].  E = 1 is the plain dense
+// contraction.  E > 1 re-uses every partial sum for E windows (w/E times fewer tensor-core
+// flops for bit-for-bit the same set of products, summed in fp32); tiles then overlap by E-1
+// rows/columns (step 128-(E-1) x 256-(E-1)).
+template <int kDiag, bool kDump>
 __global__ void __launch_bounds__(kDistThreads, 1)
 distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 const __grid_constant__ CUtensorMap map_script, const DistParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    // layout: [stages x (A | B)] [barriers]
+    // layout: [stages x (A | B)] [barriers] [halo rows]
     const uint32_t bar_base = smem_base + kStages * kStageBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -43,6 +48,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * kAccumStages);
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -56,7 +62,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         }
         for (int s = 0; s < kAccumStages; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 4);
+            mbar_init(tempty_bar(s), kEpiWarps);
         }
         mbar_fence_init();
     }
@@ -73,8 +79,10 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     const int64_t per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
     const int64_t tile_begin = per_cta * blockIdx.x;
     const int64_t tile_end = min(total_tiles, tile_begin + per_cta);
-    const int S = p.shifts_per_stage;
-    const int shift_groups = p.window / S;
+    constexpr int kMStep = kBlockM - (kDiag - 1);
+    constexpr int kNStep = kBlockN - (kDiag - 1);
+    const int S = p.shifts_per_stage;                 // MMA shifts served by one smem stage
+    const int shift_groups = (p.window / kDiag) / S;  // stages per 64-column chunk
     const int stages_per_tile = p.chunks * shift_groups;
 
     if (warp == 0 && lane == 0) {
@@ -82,10 +90,11 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         int stage = 0;
         uint32_t phase = 0;
         for (int64_t t = tile_begin; t < tile_end; ++t) {
-            const int32_t m0 = static_cast<int32_t>(t / p.tiles_n) * kBlockM;
-            const int32_t n0 = static_cast<int32_t>(t % p.tiles_n) * kBlockN;
+            const int32_t m0 = static_cast<int32_t>(t / p.tiles_n) * kMStep;
+            const int32_t n0 = static_cast<int32_t>(t % p.tiles_n) * kNStep;
             for (int c = 0; c < p.chunks; ++c) {
-                for (int s0 = 0; s0 < p.window; s0 += S) {
+                for (int g = 0; g < shift_groups; ++g) {
+                    const int32_t s0 = g * S * kDiag;  // first token-row shift of this stage
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t a_dst = smem_base + stage * kStageBytes;
                     const uint32_t b_dst = a_dst + kStageABytes;
@@ -123,9 +132,13 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 const int chunk = it / shift_groups;
                 const int ksteps = (chunk == p.chunks - 1) ? p.last_chunk_ksteps : kChunkK / kUmmaK;
                 for (int s = 0; s < S; ++s) {
-                    const uint32_t bo = p.base_offset_mode ? static_cast<uint32_t>(s) : 0u;
+                    // row shift inside the stage = s * kDiag rows of 128 B: a plain offset of
+                    // the descriptor start address (swizzle is a function of the absolute
+                    // address, so base_offset stays 0)
+                    const uint32_t row_off = static_cast<uint32_t>(s * kDiag * 128);
+                    const uint32_t bo = p.base_offset_mode ? static_cast<uint32_t>(s * kDiag) & 7u : 0u;
                     for (int k = 0; k < ksteps; ++k) {
-                        const uint32_t off = static_cast<uint32_t>(s * 128 + k * kUmmaK * 2);
+                        const uint32_t off = row_off + static_cast<uint32_t>(k * kUmmaK * 2);
                         umma_f16(tmem_d, umma_smem_desc(a_src + off, bo),
                                  umma_smem_desc(b_src + off, bo), idesc, accumulate);
                         accumulate = 1;
@@ -144,56 +157,108 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             }
         }
     } else if (warp >= 2) {
-        // ------------------------------------------------------------ epilogue
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+        // ------------------------------------------------------------ epilogue (8 warps)
+        // warp -> TMEM lane quarter (warp & 3, a hardware restriction) x column half
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
+        auto halo_at = [&](int as_, int q, int d, int col) -> float* {
+            return halo + (((as_ * 4 + q) * kHaloRows + d) * kHaloCols + col);
+        };
         int as = 0;
         uint32_t aphase = 0;
         for (int64_t t = tile_begin; t < tile_end; ++t) {
-            const int32_t m0 = static_cast<int32_t>(t / p.tiles_n) * kBlockM;
-            const int32_t n0 = static_cast<int32_t>(t % p.tiles_n) * kBlockN;
+            const int32_t m0 = static_cast<int32_t>(t / p.tiles_n) * kMStep;
+            const int32_t n0 = static_cast<int32_t>(t % p.tiles_n) * kNStep;
             const int32_t gi = m0 + row;
-            const float thr = __ldg(p.thr_fan + gi);  // padded to a tile multiple
+            const bool row_ok = row < kMStep;
+            const float thr = row_ok ? __ldg(p.thr_fan + gi) : INFINITY;  // padded to a tile multiple
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                   static_cast<uint32_t>(as * kBlockN);
+                                   static_cast<uint32_t>(as * kBlockN + half * (kBlockN / 2));
+            if (kDiag > 1) {
+                // pass 1: publish this warp's first kDiag-1 rows; the warp owning the previous
+                // lane quarter needs them for its last rows (row i+d lives in lane+d)
 #pragma unroll 1
-            for (int ch = 0; ch < kBlockN / 32; ++ch) {
-                uint32_t r[32];
-                __syncwarp();
-                tmem_ld_32x32(taddr + ch * 32, r);
-                tmem_ld_wait();
-                const int32_t gj0 = n0 + ch * 32;
-                if (kDump) {
-                    if (gi < p.n_fan_tok) {
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    tmem_ld_32x32(taddr + ch * 32, r);
+                    tmem_ld_wait();
+                    if (lane < kDiag - 1) {
+                        float* dst = halo_at(as, quarter, lane, half * (kBlockN / 2) + ch * 32);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            if (gj0 + e < p.dump_ld)
-                                p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + e] =
-                                    __uint_as_float(r[e]);
+                        for (int x = 0; x < 32; ++x) dst[x] = __uint_as_float(r[x]);
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            }
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int c0 = half * (kBlockN / 2) + ch * 32;  // first column inside the tile
+                uint32_t r[40];
+                __syncwarp();
+                tmem_ld_32x32(taddr + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+                if (kDiag > 1) {
+                    if (c0 + 32 < kBlockN) {
+                        tmem_ld_32x8(taddr + ch * 32 + 32, *reinterpret_cast<uint32_t(*)[8]>(&r[32]));
+                    } else {
+#pragma unroll
+                        for (int x = 32; x < 40; ++x) r[x] = 0u;
+                    }
+                }
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int x = 0; x < 32; ++x) {
+                    float acc = __uint_as_float(r[x]);
+#pragma unroll
+                    for (int d = 1; d < kDiag; ++d) {
+                        float o = __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + d]), d);
+                        if (lane + d >= 32)
+                            o = quarter < 3 ? *halo_at(as, quarter + 1, lane + d - 32, c0 + x + d) : 0.f;
+                        acc += o;
+                    }
+                    v[x] = acc;
+                }
+                const int32_t gj0 = n0 + c0;
+                if (kDump) {
+                    if (row_ok && gi < p.n_fan_tok) {
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) {
+                            if (c0 + x < kNStep && gj0 + x < p.dump_ld)
+                                p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + x] = v[x];
                         }
                     }
                 } else {
-                    const float4* ns4 = reinterpret_cast<const float4*>(p.norm_script + gj0);
                     bool any = false;
+                    if (kDiag == 1) {
+                        const float4* ns4 = reinterpret_cast<const float4*>(p.norm_script + gj0);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 n4 = __ldg(ns4 + q);
-                        any |= __uint_as_float(r[4 * q + 0]) > thr * n4.x;
-                        any |= __uint_as_float(r[4 * q + 1]) > thr * n4.y;
-                        any |= __uint_as_float(r[4 * q + 2]) > thr * n4.z;
-                        any |= __uint_as_float(r[4 * q + 3]) > thr * n4.w;
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 n4 = __ldg(ns4 + q);
+                            any |= v[4 * q + 0] > thr * n4.x;
+                            any |= v[4 * q + 1] > thr * n4.y;
+                            any |= v[4 * q + 2] > thr * n4.z;
+                            any |= v[4 * q + 3] > thr * n4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int x = 0; x < 32; ++x) {
+                            const float nsv = (c0 + x < kNStep) ? __ldg(p.norm_script + gj0 + x) : INFINITY;
+                            any |= v[x] > thr * nsv;
+                        }
                     }
                     if (any) {  // rare: hits are sparse
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            if (__uint_as_float(r[e]) > thr * __ldg(p.norm_script + gj0 + e)) {
+                        for (int x = 0; x < 32; ++x) {
+                            if (c0 + x < kNStep && v[x] > thr * __ldg(p.norm_script + gj0 + x)) {
                                 const unsigned long long slot =
                                     atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                                 if (slot < static_cast<unsigned long long>(p.cand_cap)) {
                                     p.cand[slot].fan_pos = gi;
-                                    p.cand[slot].script_pos = gj0 + e;
+                                    p.cand[slot].script_pos = gj0 + x;
                                 }
                             }
                         }
@@ -260,27 +325,40 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
     return FS_OK;
 }
 
-int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
-                    int grid_limit, cudaStream_t stream) {
+template <int kDiag>
+static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_script,
+                             const DistParams& p, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<false>,
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kDistSmemBytes));
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<true>,
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kDistSmemBytes));
         attr_set = true;
     }
-    const int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
-    if (total <= 0) return FS_OK;
-    int grid = static_cast<int>(total < grid_limit ? total : grid_limit);
     if (p.dump)
-        distance_kernel<true><<<grid, kDistThreads, kDistSmemBytes, stream>>>(map_fan, map_script, p);
+        distance_kernel<kDiag, true><<<grid, kDistThreads, kDistSmemBytes, stream>>>(map_fan, map_script, p);
     else
-        distance_kernel<false><<<grid, kDistThreads, kDistSmemBytes, stream>>>(map_fan, map_script, p);
+        distance_kernel<kDiag, false><<<grid, kDistThreads, kDistSmemBytes, stream>>>(map_fan, map_script, p);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
+}
+
+int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
+                    int grid_limit, cudaStream_t stream) {
+    const int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+    if (total <= 0) return FS_OK;
+    const int grid = static_cast<int>(total < grid_limit ? total : grid_limit);
+    switch (p.diag) {
+        case 1: return launch_distance_t<1>(map_fan, map_script, p, grid, stream);
+        case 2: return launch_distance_t<2>(map_fan, map_script, p, grid, stream);
+        case 3: return launch_distance_t<3>(map_fan, map_script, p, grid, stream);
+        default:
+            set_error("unsupported diagonal factor %d", p.diag);
+            return FS_E_INVALID;
+    }
 }
 
 }  // namespace fs

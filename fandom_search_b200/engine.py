@@ -6,6 +6,7 @@ Replaces, for one cluster of fanworks, the reference's
 (/root/reference search.py:381-386 -> :163-184).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -53,6 +54,9 @@ class DeviceIndex:
         self.n_script_windows = int(lib.fs_index_get_info(h, 0))
         self.sm_count = int(lib.fs_index_get_info(h, 2))
         self.scale = float(lib.fs_index_scale(h))
+        diag = os.environ.get("FANDOM_SEARCH_DIAG")
+        if diag:
+            self.set_option(nt.FS_OPT_DIAG, int(diag))
 
     # -- lifetime ---------------------------------------------------------
     def close(self):

@@ -18,10 +18,11 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1):
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
+    idx.set_option(nt.FS_OPT_DIAG, diag)
     n_works = max(1, nf // works_len)
     lens = np.full(n_works, (nf + 5 * n_works) // n_works + 1, dtype=np.int64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
@@ -41,10 +42,11 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000):
     ms, n = idx.timing_read()
     windows = int(cnt_t.cpu()[nt.FS_CNT_WINDOWS])
     per = ms / n * 1e-3
-    res = {"fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
+    res = {"diag": diag, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
            "kernel_ms": ms / n, "windows_per_s": windows / per,
            "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
-           "tflops_executed": 2.0 * 6 * idx.dim_pad * idx.n_script_windows * windows / per / 1e12}
+           "tflops_executed": 2.0 * (6 // diag) * idx.dim_pad * idx.n_script_windows * windows / per / 1e12
+           * (128.0 * 256.0) / ((129 - diag) * (257 - diag))}
     idx.close()
     del tok_t, out_t
     torch.cuda.empty_cache()
@@ -54,8 +56,14 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--diag", action="store_true", help="compare the diagonal-sum factors at C2 size")
     args = ap.parse_args()
     rng = np.random.default_rng(0)
+    if args.diag:
+        for diag in (1, 2, 3):
+            for (nf, ns, d) in ((2_500_000, 25000, 300), (2_500_000, 25000, 768), (1_000_000, 100000, 300)):
+                print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag)), flush=True)
+        return
     if args.quick:
         cases = [(2_500_000, 25000, 300, 3), (2_500_000, 25000, 320, 3), (2_500_000, 25000, 304, 3)]
     else:
