@@ -49,8 +49,11 @@ constexpr int kDistThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warp
 constexpr int kHaloRows = 2;            // rows handed to the previous lane quarter (diag <= 3)
 constexpr int kHaloCols = kBlockN + 8;
 constexpr int kHaloBytes = kAccumStages * 4 * kHaloRows * kHaloCols * 4;  // 16896
-constexpr int kDistSmemBytes =
-    kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kHaloBytes;
+constexpr int kZeroRowBytes = kHaloCols * 4;                               // 1056
+constexpr int kNormTileBytes = kAccumStages * kHaloCols * 4;               // 2112
+constexpr int kDistSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                               kHaloBytes + kZeroRowBytes + kNormTileBytes;
+static_assert(kDistSmemBytes <= 232448, "distance kernel exceeds the 227 KB shared memory limit");
 
 struct DistParams {
     const float* thr_fan;     // [Mpad]  (1 - thr - eps) * |fan window|, +inf when invalid
@@ -176,11 +179,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in HW, do not spin
         : "memory");
     return ok != 0;
 }

@@ -49,6 +49,9 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+    float* zero_row = halo + kHaloBytes / 4;
+    float* norm_tile = zero_row + kZeroRowBytes / 4;
+    for (int i = threadIdx.x; i < kHaloCols; i += blockDim.x) zero_row[i] = 0.f;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -162,9 +165,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
-        auto halo_at = [&](int as_, int q, int d, int col) -> float* {
-            return halo + (((as_ * 4 + q) * kHaloRows + d) * kHaloCols + col);
-        };
+        const int epi_tid = (warp - 2) * 32 + lane;  // 0..255
         int as = 0;
         uint32_t aphase = 0;
         for (int64_t t = tile_begin; t < tile_end; ++t) {
@@ -173,27 +174,30 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             const int32_t gi = m0 + row;
             const bool row_ok = row < kMStep;
             const float thr = row_ok ? __ldg(p.thr_fan + gi) : INFINITY;  // padded to a tile multiple
+            // E > 1: script-window norms of this tile staged once in smem, +inf baked in for the
+            // E-1 columns that belong to the next tile (published by the first chunk barrier)
+            float* ns_tile = norm_tile + as * kHaloCols;
+            if (kDiag > 1) {
+                ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.norm_script + n0 + epi_tid) : INFINITY;
+                if (epi_tid < kHaloCols - kBlockN) ns_tile[kBlockN + epi_tid] = INFINITY;
+            }
+            // rows i+d of the last lanes live in the NEXT lane quarter: its warps publish their
+            // first E-1 rows chunk by chunk (quarter 3 has no successor inside the tile; those
+            // outputs belong to the next tile and read a row of zeros)
+            float* pub_row = halo + (((as * 4 + quarter) * kHaloRows + lane) * kHaloCols);
+            const float* edge_row[kDiag];  // [d]: row (lane + d - 32) of the next quarter
+            bool edge[kDiag];
+#pragma unroll
+            for (int d = 1; d < kDiag; ++d) {
+                edge[d] = lane + d >= 32;
+                edge_row[d] = (quarter < 3 && edge[d])
+                                  ? halo + (((as * 4 + quarter + 1) * kHaloRows + (lane + d - 32)) * kHaloCols)
+                                  : zero_row;
+            }
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(as * kBlockN + half * (kBlockN / 2));
-            if (kDiag > 1) {
-                // pass 1: publish this warp's first kDiag-1 rows; the warp owning the previous
-                // lane quarter needs them for its last rows (row i+d lives in lane+d)
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t r[32];
-                    __syncwarp();
-                    tmem_ld_32x32(taddr + ch * 32, r);
-                    tmem_ld_wait();
-                    if (lane < kDiag - 1) {
-                        float* dst = halo_at(as, quarter, lane, half * (kBlockN / 2) + ch * 32);
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) dst[x] = __uint_as_float(r[x]);
-                    }
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-            }
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 const int c0 = half * (kBlockN / 2) + ch * 32;  // first column inside the tile
@@ -210,17 +214,43 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 }
                 tmem_ld_wait();
                 float v[32];
+                if (kDiag > 1) {
+                    if (lane < kDiag - 1) {
+                        uint4* dst = reinterpret_cast<uint4*>(pub_row + c0);
 #pragma unroll
-                for (int x = 0; x < 32; ++x) {
-                    float acc = __uint_as_float(r[x]);
+                        for (int q = 0; q < 10; ++q)
+                            dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+                    float h[kDiag][40];  // [d]: the 40 columns of the successor row, edge lanes only
 #pragma unroll
                     for (int d = 1; d < kDiag; ++d) {
-                        float o = __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + d]), d);
-                        if (lane + d >= 32)
-                            o = quarter < 3 ? *halo_at(as, quarter + 1, lane + d - 32, c0 + x + d) : 0.f;
-                        acc += o;
+                        if (edge[d]) {
+                            const float4* src = reinterpret_cast<const float4*>(edge_row[d] + c0);
+#pragma unroll
+                            for (int q = 0; q < 10; ++q) {
+                                const float4 f = src[q];
+                                h[d][4 * q] = f.x;
+                                h[d][4 * q + 1] = f.y;
+                                h[d][4 * q + 2] = f.z;
+                                h[d][4 * q + 3] = f.w;
+                            }
+                        }
                     }
-                    v[x] = acc;
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) {
+                        float acc = __uint_as_float(r[x]);
+#pragma unroll
+                        for (int d = 1; d < kDiag; ++d) {
+                            float o = __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + d]), d);
+                            if (edge[d]) o = h[d][x + d];
+                            acc += o;
+                        }
+                        v[x] = acc;
+                    }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) v[x] = __uint_as_float(r[x]);
                 }
                 const int32_t gj0 = n0 + c0;
                 if (kDump) {
@@ -233,27 +263,22 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     }
                 } else {
                     bool any = false;
-                    if (kDiag == 1) {
-                        const float4* ns4 = reinterpret_cast<const float4*>(p.norm_script + gj0);
+                    const float4* ns4 = (kDiag == 1)
+                                            ? reinterpret_cast<const float4*>(p.norm_script + gj0)
+                                            : reinterpret_cast<const float4*>(ns_tile + c0);
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 n4 = __ldg(ns4 + q);
-                            any |= v[4 * q + 0] > thr * n4.x;
-                            any |= v[4 * q + 1] > thr * n4.y;
-                            any |= v[4 * q + 2] > thr * n4.z;
-                            any |= v[4 * q + 3] > thr * n4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) {
-                            const float nsv = (c0 + x < kNStep) ? __ldg(p.norm_script + gj0 + x) : INFINITY;
-                            any |= v[x] > thr * nsv;
-                        }
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 n4 = (kDiag == 1) ? __ldg(ns4 + q) : ns4[q];
+                        any |= v[4 * q + 0] > thr * n4.x;
+                        any |= v[4 * q + 1] > thr * n4.y;
+                        any |= v[4 * q + 2] > thr * n4.z;
+                        any |= v[4 * q + 3] > thr * n4.w;
                     }
                     if (any) {  // rare: hits are sparse
 #pragma unroll
                         for (int x = 0; x < 32; ++x) {
-                            if (c0 + x < kNStep && v[x] > thr * __ldg(p.norm_script + gj0 + x)) {
+                            const float nsv = (kDiag == 1) ? __ldg(p.norm_script + gj0 + x) : ns_tile[c0 + x];
+                            if (v[x] > thr * nsv) {
                                 const unsigned long long slot =
                                     atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                                 if (slot < static_cast<unsigned long long>(p.cand_cap)) {

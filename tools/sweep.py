@@ -57,8 +57,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--diag", action="store_true", help="compare the diagonal-sum factors at C2 size")
+    ap.add_argument("--one", type=int, nargs=4, metavar=("DIAG", "NF", "NS", "D"), help="run a single case")
     args = ap.parse_args()
     rng = np.random.default_rng(0)
+    if args.one:
+        diag, nf, ns, d = args.one
+        print(json.dumps(run_case(nf, ns, d, 2, rng, diag=diag)), flush=True)
+        return
     if args.diag:
         for diag in (1, 2, 3):
             for (nf, ns, d) in ((2_500_000, 25000, 300), (2_500_000, 25000, 768), (1_000_000, 100000, 300)):
