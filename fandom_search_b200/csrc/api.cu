@@ -124,6 +124,7 @@ struct fs_index {
 
     // options
     int32_t diag = 1;              // diagonal-sum factor E of the distance kernel
+    int32_t pair = 0;              // CTA-pair (cta_group::2) kernel
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
     int32_t base_offset_mode = 0;
     int32_t grid_limit = 0;
@@ -331,7 +332,7 @@ int fs_index_reserve(fs_index* idx, int64_t max_tokens, int64_t max_candidates) 
     idx->tok_cap = idx->emb_cap / idx->dim_pad;
     if ((r = dev_grow(&idx->fan_tok_sq, &idx->sq_cap, max_tokens + 8)) != FS_OK) return r;
     // tiles step by 128 - (E-1) rows but always read 128 thresholds
-    if ((r = dev_grow(&idx->fan_thr, &idx->thr_cap, (max_tokens / (kBlockM - 8) + 2) * kBlockM)) != FS_OK)
+    if ((r = dev_grow(&idx->fan_thr, &idx->thr_cap, (max_tokens / (kBlockM - 8) + 3) * kBlockM)) != FS_OK)
         return r;
     if ((r = dev_grow(&idx->cand, &idx->cand_cap, max_candidates)) != FS_OK) return r;
     return FS_OK;
@@ -346,6 +347,9 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
                 return FS_E_INVALID;
             }
             idx->shifts_per_stage = static_cast<int32_t>(value);
+            return FS_OK;
+        case FS_OPT_CTA_PAIR:
+            idx->pair = value ? 1 : 0;
             return FS_OK;
         case FS_OPT_DIAG:
             if (value < 1 || value > 3 || idx->window % value != 0) {
@@ -396,6 +400,7 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
         case 3: return idx->cand_cap;
         case 4: return idx->shifts_per_stage;
         case 5: return idx->diag;
+        case 6: return idx->pair;
         default: return -1;
     }
 }
@@ -489,7 +494,8 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     const int32_t m_step = kBlockM - (idx->diag - 1), n_step = kBlockN - (idx->diag - 1);
     const int32_t tiles_m = static_cast<int32_t>((a.n_tok + m_step - 1) / m_step);
     const int32_t tiles_n = static_cast<int32_t>((idx->n_script_tok + n_step - 1) / n_step);
-    const int64_t thr_pad = static_cast<int64_t>(tiles_m) * kBlockM;
+    // (+1 tile: in pair mode an odd tile count is rounded up to a full pair)
+    const int64_t thr_pad = static_cast<int64_t>(tiles_m + 1) * kBlockM;
     int64_t want_cand = idx->cand_cap > 0 ? idx->cand_cap : (1 << 20);
     if ((r = fs_index_reserve(idx, a.n_tok, want_cand)) != FS_OK) return r;
     if ((r = embed_batch(idx, st, a, counters, idx->fan_emb, idx->fan_thr, thr_pad)) != FS_OK) return r;
@@ -505,6 +511,7 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.last_chunk_ksteps = (idx->dim_pad - (p.chunks - 1) * kChunkK) / kUmmaK;
     p.window = idx->window;
     p.diag = idx->diag;
+    p.pair = idx->pair;
     p.shifts_per_stage = idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag;
     p.base_offset_mode = idx->base_offset_mode;
     p.tiles_m = tiles_m;

@@ -42,6 +42,8 @@ constexpr int kStageABytes = kBoxRows * 128;       // 17408 (17 swizzle atoms)
 constexpr int kStageBBytes = 2 * kBoxRows * 128;   // 34816 (272 rows >= 256 + 5)
 constexpr int kStageBytes = kStageABytes + kStageBBytes;  // 52224
 constexpr int kStages = 4;
+constexpr int kPairStageBytes = 2 * kStageABytes;  // CTA-pair mode: A box + this CTA's half of B
+constexpr int kPairStages = 6;                     // 6 x 34816 = 4 x 52224
 constexpr int kAccumStages = 2;         // TMEM double buffer: 2 x 256 columns = all 512
 constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 8;            // two per TMEM lane quarter (one per 128-column half)
@@ -64,6 +66,7 @@ struct DistParams {
     int32_t last_chunk_ksteps;// UMMA K-steps (16 columns) in the last chunk: 1..4
     int32_t window;           // 6
     int32_t diag;             // E: epilogue adds E diagonal neighbours, MMAs do window/E shifts
+    int32_t pair;             // 1: CTA-pair kernel (cta_group::2, M = 2 x 128 fan tiles)
     int32_t shifts_per_stage; // S: MMA shifts served by one smem stage (divides window/E)
     int32_t base_offset_mode; // how shifted descriptors fill base_offset
     int32_t tiles_m, tiles_n;
@@ -242,6 +245,70 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                      bar)
                  : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants ------------------------------------------------
+// In a 2-CTA cluster the shared::cluster address of the odd CTA has bit 24 set; clearing it
+// addresses the same offset in the even ("leader") CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in the leader CTA (cluster rank 0)
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(0u));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader CTA's copy
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+// TMA load issued by either CTA of the pair; bytes are accounted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                                 int32_t col, int32_t row) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_addr(bar)), "r"(col), "r"(row)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+                 : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T with M = 256 split over the CTA pair, issued by the leader
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs once the leader's MMAs retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

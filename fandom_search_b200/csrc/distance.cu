@@ -33,19 +33,29 @@ namespace fs {
 // contraction.  E > 1 re-uses every partial sum for E windows (w/E times fewer tensor-core
 // flops for bit-for-bit the same set of products, summed in fp32); tiles then overlap by E-1
 // rows/columns (step 128-(E-1) x 256-(E-1)).
-template <int kDiag, bool kDump>
+//
+// kPair: two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA
+// owns its own 128-window fan tile (and the TMEM accumulator for it) but stages only HALF of
+// the script tile, so shared-memory operand reads drop from 96 to 64 B/clk/SM and the smem fill
+// from 52 to 35 KB per stage -- the shared-memory pipe, not the tensor pipe, is what saturates
+// first once E > 1.  The leader CTA (cluster rank 0) issues the MMAs; TMA bytes of both CTAs are
+// accounted on the leader's `full` barrier; tcgen05.commit multicasts to both CTAs' barriers.
+template <int kDiag, bool kDump, bool kPair>
 __global__ void __launch_bounds__(kDistThreads, 1)
 distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 const __grid_constant__ CUtensorMap map_script, const DistParams p) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int kNumStages = kPair ? kPairStages : kStages;
+    constexpr int kStageSz = kPair ? kPairStageBytes : kStageBytes;
+    static_assert(kNumStages * kStageSz == kStages * kStageBytes, "stage ring must fill the same smem");
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    // layout: [stages x (A | B)] [barriers] [halo rows]
-    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    // layout: [stages x (A | B)] [barriers] [halo rows] [zero row] [norm tile]
+    const uint32_t bar_base = smem_base + kNumStages * kStageSz;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAccumStages + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * kAccumStages);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kNumStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kNumStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kNumStages + kAccumStages + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kNumStages + 2 * kAccumStages);
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
@@ -55,35 +65,52 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_fan);
         tma_prefetch_desc(&map_script);
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kNumStages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < kAccumStages; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), kEpiWarps);
+            mbar_init(tempty_bar(s), kPair ? 2 * kEpiWarps : kEpiWarps);
         }
         mbar_fence_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, kTmemCols);
+        if (kPair)
+            tmem_alloc_pair(tmem_slot, kTmemCols);
+        else
+            tmem_alloc(tmem_slot, kTmemCols);
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair)
+        cluster_sync_all();
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    // contiguous range of linearised tiles (n fastest) for this CTA
-    const int64_t total_tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
-    const int64_t per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-    const int64_t tile_begin = per_cta * blockIdx.x;
-    const int64_t tile_end = min(total_tiles, tile_begin + per_cta);
+    // Work units: a contiguous range of linearised (m, n) tiles (n fastest) per CTA; in pair
+    // mode per cluster, the unit being (pair of consecutive m tiles, n).
     constexpr int kMStep = kBlockM - (kDiag - 1);
     constexpr int kNStep = kBlockN - (kDiag - 1);
+    const int64_t units_m = kPair ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    const int64_t total_tiles = units_m * p.tiles_n;
+    const int64_t n_workers = kPair ? gridDim.x / 2 : gridDim.x;
+    const int64_t worker = kPair ? blockIdx.x / 2 : blockIdx.x;
+    const int64_t per_cta = (total_tiles + n_workers - 1) / n_workers;
+    const int64_t tile_begin = per_cta * worker;
+    const int64_t tile_end = min(total_tiles, tile_begin + per_cta);
+    auto tile_m0 = [&](int64_t t) {
+        const int64_t um = t / p.tiles_n;
+        return static_cast<int32_t>((kPair ? 2 * um + cta_rank : um) * kMStep);
+    };
+    auto tile_n0 = [&](int64_t t) { return static_cast<int32_t>(t % p.tiles_n) * kNStep; };
     const int S = p.shifts_per_stage;                 // MMA shifts served by one smem stage
     const int shift_groups = (p.window / kDiag) / S;  // stages per 64-column chunk
     const int stages_per_tile = p.chunks * shift_groups;
@@ -93,29 +120,37 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         int stage = 0;
         uint32_t phase = 0;
         for (int64_t t = tile_begin; t < tile_end; ++t) {
-            const int32_t m0 = static_cast<int32_t>(t / p.tiles_n) * kMStep;
-            const int32_t n0 = static_cast<int32_t>(t % p.tiles_n) * kNStep;
+            const int32_t m0 = tile_m0(t);
+            const int32_t n0 = tile_n0(t);
             for (int c = 0; c < p.chunks; ++c) {
                 for (int g = 0; g < shift_groups; ++g) {
                     const int32_t s0 = g * S * kDiag;  // first token-row shift of this stage
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t a_dst = smem_base + stage * kStageBytes;
+                    const uint32_t a_dst = smem_base + stage * kStageSz;
                     const uint32_t b_dst = a_dst + kStageABytes;
-                    mbar_expect_tx(full_bar(stage), kStageBytes);
-                    tma_load_2d(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
-                    tma_load_2d(b_dst, &map_script, full_bar(stage), c * kChunkK, n0 + s0);
-                    tma_load_2d(b_dst + kStageABytes, &map_script, full_bar(stage), c * kChunkK,
-                                n0 + s0 + kBoxRows);
-                    if (++stage == kStages) {
+                    if (kPair) {
+                        // this CTA stages its own fan rows and script rows [128 r, 128 r + 136)
+                        if (leader) mbar_expect_tx(full_bar(stage), 2 * kPairStageBytes);
+                        tma_load_2d_pair(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
+                        tma_load_2d_pair(b_dst, &map_script, full_bar(stage), c * kChunkK,
+                                         n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
+                    } else {
+                        mbar_expect_tx(full_bar(stage), kStageBytes);
+                        tma_load_2d(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
+                        tma_load_2d(b_dst, &map_script, full_bar(stage), c * kChunkK, n0 + s0);
+                        tma_load_2d(b_dst + kStageABytes, &map_script, full_bar(stage), c * kChunkK,
+                                    n0 + s0 + kBoxRows);
+                    }
+                    if (++stage == kNumStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && lane == 0 && leader) {
         // ------------------------------------------------------------ MMA issuer
-        constexpr uint32_t idesc = umma_idesc_f16(kBlockM, kBlockN);
+        constexpr uint32_t idesc = umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, kBlockN);
         int stage = 0;
         uint32_t phase = 0;
         int as = 0;
@@ -128,7 +163,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             for (int it = 0; it < stages_per_tile; ++it) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t a_src = smem_base + stage * kStageBytes;
+                const uint32_t a_src = smem_base + stage * kStageSz;
                 const uint32_t b_src = a_src + kStageABytes;
                 // the last chunk may hold fewer than 64 real columns (d_pad is a multiple of
                 // 16, not 64): its trailing K-steps are all-zero TMA fill and are skipped
@@ -142,18 +177,30 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     const uint32_t bo = p.base_offset_mode ? static_cast<uint32_t>(s * kDiag) & 7u : 0u;
                     for (int k = 0; k < ksteps; ++k) {
                         const uint32_t off = row_off + static_cast<uint32_t>(k * kUmmaK * 2);
-                        umma_f16(tmem_d, umma_smem_desc(a_src + off, bo),
-                                 umma_smem_desc(b_src + off, bo), idesc, accumulate);
+                        if (kPair)
+                            umma_f16_pair(tmem_d, umma_smem_desc(a_src + off, bo),
+                                          umma_smem_desc(b_src + off, bo), idesc, accumulate);
+                        else
+                            umma_f16(tmem_d, umma_smem_desc(a_src + off, bo),
+                                     umma_smem_desc(b_src + off, bo), idesc, accumulate);
                         accumulate = 1;
                     }
                 }
-                umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
-                if (++stage == kStages) {
+                // frees the smem stage (in both CTAs) when these MMAs retire
+                if (kPair)
+                    umma_commit_pair(empty_bar(stage));
+                else
+                    umma_commit(empty_bar(stage));
+                if (++stage == kNumStages) {
                     stage = 0;
                     phase ^= 1u;
                 }
             }
-            umma_commit(tfull_bar(as));  // accumulator tile complete
+            // accumulator tile complete (in both CTAs)
+            if (kPair)
+                umma_commit_pair(tfull_bar(as));
+            else
+                umma_commit(tfull_bar(as));
             if (++as == kAccumStages) {
                 as = 0;
                 aphase ^= 1u;
@@ -169,8 +216,8 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         int as = 0;
         uint32_t aphase = 0;
         for (int64_t t = tile_begin; t < tile_end; ++t) {
-            const int32_t m0 = static_cast<int32_t>(t / p.tiles_n) * kMStep;
-            const int32_t n0 = static_cast<int32_t>(t % p.tiles_n) * kNStep;
+            const int32_t m0 = tile_m0(t);
+            const int32_t n0 = tile_n0(t);
             const int32_t gi = m0 + row;
             const bool row_ok = row < kMStep;
             const float thr = row_ok ? __ldg(p.thr_fan + gi) : INFINITY;  // padded to a tile multiple
@@ -292,7 +339,12 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+                if (kPair)
+                    mbar_arrive_leader(tempty_bar(as));  // the leader's MMA waits for both CTAs
+                else
+                    mbar_arrive(tempty_bar(as));
+            }
             if (++as == kAccumStages) {
                 as = 0;
                 aphase ^= 1u;
@@ -301,10 +353,16 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (kPair)
+        cluster_sync_all();  // the peer may still arrive on / multicast into this CTA
+    else
+        __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (kPair)
+            tmem_dealloc_pair(tmem_base, kTmemCols);
+        else
+            tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -350,36 +408,58 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
     return FS_OK;
 }
 
-template <int kDiag>
+template <int kDiag, bool kPair>
 static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_script,
                              const DistParams& p, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false>,
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kDistSmemBytes));
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true>,
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kDistSmemBytes));
         attr_set = true;
     }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kDistThreads);
+    cfg.dynamicSmemBytes = kDistSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kPair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (p.dump)
-        distance_kernel<kDiag, true><<<grid, kDistThreads, kDistSmemBytes, stream>>>(map_fan, map_script, p);
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair>, map_fan, map_script, p));
     else
-        distance_kernel<kDiag, false><<<grid, kDistThreads, kDistSmemBytes, stream>>>(map_fan, map_script, p);
-    FS_CUDA_CHECK(cudaGetLastError());
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair>, map_fan, map_script, p));
     return FS_OK;
 }
 
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
                     int grid_limit, cudaStream_t stream) {
-    const int64_t total = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+    const int64_t units_m = p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
+    const int64_t total = units_m * p.tiles_n;
     if (total <= 0) return FS_OK;
-    const int grid = static_cast<int>(total < grid_limit ? total : grid_limit);
-    switch (p.diag) {
-        case 1: return launch_distance_t<1>(map_fan, map_script, p, grid, stream);
-        case 2: return launch_distance_t<2>(map_fan, map_script, p, grid, stream);
-        case 3: return launch_distance_t<3>(map_fan, map_script, p, grid, stream);
+    int grid;
+    if (p.pair) {
+        const int64_t clusters = grid_limit / 2 > 0 ? grid_limit / 2 : 1;
+        grid = 2 * static_cast<int>(total < clusters ? total : clusters);
+    } else {
+        grid = static_cast<int>(total < grid_limit ? total : grid_limit);
+    }
+    const int key = p.diag * 2 + (p.pair ? 1 : 0);
+    switch (key) {
+        case 2: return launch_distance_t<1, false>(map_fan, map_script, p, grid, stream);
+        case 3: return launch_distance_t<1, true>(map_fan, map_script, p, grid, stream);
+        case 4: return launch_distance_t<2, false>(map_fan, map_script, p, grid, stream);
+        case 5: return launch_distance_t<2, true>(map_fan, map_script, p, grid, stream);
+        case 6: return launch_distance_t<3, false>(map_fan, map_script, p, grid, stream);
+        case 7: return launch_distance_t<3, true>(map_fan, map_script, p, grid, stream);
         default:
             set_error("unsupported diagonal factor %d", p.diag);
             return FS_E_INVALID;

@@ -18,11 +18,12 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0):
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
     idx.set_option(nt.FS_OPT_DIAG, diag)
+    idx.set_option(nt.FS_OPT_CTA_PAIR, pair)
     n_works = max(1, nf // works_len)
     lens = np.full(n_works, (nf + 5 * n_works) // n_works + 1, dtype=np.int64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
@@ -42,7 +43,7 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1):
     ms, n = idx.timing_read()
     windows = int(cnt_t.cpu()[nt.FS_CNT_WINDOWS])
     per = ms / n * 1e-3
-    res = {"diag": diag, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
+    res = {"diag": diag, "pair": pair, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
            "kernel_ms": ms / n, "windows_per_s": windows / per,
            "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
            "tflops_executed": 2.0 * (6 // diag) * idx.dim_pad * idx.n_script_windows * windows / per / 1e12
@@ -65,9 +66,10 @@ def main():
         print(json.dumps(run_case(nf, ns, d, 2, rng, diag=diag)), flush=True)
         return
     if args.diag:
-        for diag in (1, 2, 3):
-            for (nf, ns, d) in ((2_500_000, 25000, 300), (2_500_000, 25000, 768), (1_000_000, 100000, 300)):
-                print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag)), flush=True)
+        for pair in (0, 1):
+            for diag in (1, 2, 3):
+                for (nf, ns, d) in ((2_500_000, 25000, 300), (2_500_000, 25000, 768)):
+                    print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag, pair=pair)), flush=True)
         return
     if args.quick:
         cases = [(2_500_000, 25000, 300, 3), (2_500_000, 25000, 320, 3), (2_500_000, 25000, 304, 3)]
