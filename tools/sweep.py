@@ -59,11 +59,12 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--diag", action="store_true", help="compare the diagonal-sum factors at C2 size")
     ap.add_argument("--one", type=int, nargs=4, metavar=("DIAG", "NF", "NS", "D"), help="run a single case")
+    ap.add_argument("--pair", type=int, default=0)
     args = ap.parse_args()
     rng = np.random.default_rng(0)
     if args.one:
         diag, nf, ns, d = args.one
-        print(json.dumps(run_case(nf, ns, d, 2, rng, diag=diag)), flush=True)
+        print(json.dumps(run_case(nf, ns, d, 2, rng, diag=diag, pair=args.pair)), flush=True)
         return
     if args.diag:
         for pair in (0, 1):
