@@ -83,6 +83,7 @@ struct fs_index {
     __half* script_emb = nullptr;
     float* script_tok_sq = nullptr;
     float* script_norm = nullptr;
+    float* script_norm_min = nullptr;
     int32_t tiles_n = 0;
     CUtensorMap map_script;
 
@@ -162,7 +163,7 @@ int fs_index_destroy(fs_index* idx) {
                     idx->script_norm, idx->hash_table, idx->fan_emb, idx->fan_tok_sq, idx->fan_thr,
                     idx->cand,    idx->fx16,      idx->fx_sq,      idx->h_tok,      idx->h_off,
                     idx->h_extra, idx->h_out,     idx->h_pair,     idx->h_counters,
-                    idx->lsh_normals};
+                    idx->lsh_normals, idx->script_norm_min};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (idx->ev_created) {
@@ -222,6 +223,10 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     idx->n_sx = n_extra;
     idx->n_script_tok = n_script_tok;
     idx->n_scripts = static_cast<int32_t>(n_scripts);
+    // defaults of the distance kernel: the largest diagonal factor that divides the window
+    // (6-gram windows: 2 MMA shifts + 3-term epilogue sum) on CTA pairs
+    idx->diag = window % 3 == 0 ? 3 : (window % 2 == 0 ? 2 : 1);
+    idx->pair = 1;
 
 #define FS_TRY(expr)                    \
     do {                                \
@@ -288,6 +293,7 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     FS_TRY(dev_alloc(&idx->script_emb, n_script_tok * idx->dim_pad));
     FS_TRY(dev_alloc(&idx->script_tok_sq, n_script_tok + 8));
     FS_TRY(dev_alloc(&idx->script_norm, n_pad));
+    FS_TRY(dev_alloc(&idx->script_norm_min, n_pad));
     FS_TRY_CUDA(cudaMemsetAsync(idx->script_tok, 0xFF, sizeof(int32_t) * (n_script_tok + 8), st));
     if (n_script_tok)
         FS_TRY_CUDA(cudaMemcpyAsync(idx->script_tok, script_tok, sizeof(int32_t) * n_script_tok,
@@ -302,6 +308,7 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     FS_TRY_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
     FS_TRY(launch_window_norm(idx->script_tok_sq, n_script_tok, idx->script_off, idx->n_scripts,
                               window, 1.0f, idx->script_norm, n_pad, d_cnt + FS_CNT_WINDOWS, st));
+    FS_TRY(launch_sliding_min32(idx->script_norm, idx->script_norm_min, n_pad, st));
     unsigned long long h_cnt[FS_CNT_COUNT];
     FS_TRY_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     if (n_script_tok > 0)
@@ -505,6 +512,7 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     DistParams p{};
     p.thr_fan = idx->fan_thr;
     p.norm_script = idx->script_norm;
+    p.norm_min32 = idx->script_norm_min;
     p.n_fan_tok = a.n_tok;
     p.n_script_tok = idx->n_script_tok;
     p.chunks = (idx->dim_pad + kChunkK - 1) / kChunkK;

@@ -46,20 +46,24 @@ constexpr int kPairStageBytes = 2 * kStageABytes;  // CTA-pair mode: A box + thi
 constexpr int kPairStages = 6;                     // 6 x 34816 = 4 x 52224
 constexpr int kAccumStages = 2;         // TMEM double buffer: 2 x 256 columns = all 512
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 8;            // two per TMEM lane quarter (one per 128-column half)
-constexpr int kDistThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warps2-9 epilogue
-constexpr int kHaloRows = 2;            // rows handed to the previous lane quarter (diag <= 3)
+constexpr int kEpiWarps = 16;           // 4 TMEM lane quarters x 4 column groups of 64
+constexpr int kEpiColGroups = kEpiWarps / 4;
+constexpr int kEpiCols = kBlockN / kEpiColGroups;      // 64 columns = 2 chunks of 32 per warp
+constexpr int kProducerWarp = kEpiWarps;               // single-thread roles get the highest
+constexpr int kMmaWarp = kEpiWarps + 1;                // warp ids (scheduler priority)
+constexpr int kDistThreads = 32 * (kEpiWarps + 2);     // 576
 constexpr int kHaloCols = kBlockN + 8;
-constexpr int kHaloBytes = kAccumStages * 4 * kHaloRows * kHaloCols * 4;  // 16896
-constexpr int kZeroRowBytes = kHaloCols * 4;                               // 1056
+constexpr int kPubSlots = 4;            // published boundary rows per lane quarter (E <= 3)
+constexpr int kHaloBytes = 4 * kPubSlots * kHaloCols * 4;                  // 16896
 constexpr int kNormTileBytes = kAccumStages * kHaloCols * 4;               // 2112
 constexpr int kDistSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                               kHaloBytes + kZeroRowBytes + kNormTileBytes;
+                               kHaloBytes + kNormTileBytes;
 static_assert(kDistSmemBytes <= 232448, "distance kernel exceeds the 227 KB shared memory limit");
 
 struct DistParams {
     const float* thr_fan;     // [Mpad]  (1 - thr - eps) * |fan window|, +inf when invalid
     const float* norm_script; // [Npad]  |script window|, +inf when invalid
+    const float* norm_min32;  // [Npad]  min(norm_script[j .. j+31])
     int64_t n_fan_tok;        // rows of the fan token matrix (M)
     int64_t n_script_tok;     // rows of the script token matrix (N)
     int32_t chunks;           // ceil(dim_pad / 64) 64-column chunks
@@ -145,6 +149,7 @@ int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, i
 int launch_window_norm(const float* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
                        int32_t window, float coef, float* out, int64_t n_pad,
                        unsigned long long* window_counter, cudaStream_t stream);
+int launch_sliding_min32(const float* src, float* dst, int64_t n, cudaStream_t stream);
 int launch_rescore(const RescoreParams& p, int sm_count, cudaStream_t stream);
 int launch_lsh(const LshParams& p, int sm_count, cudaStream_t stream);
 int launch_hash_build(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,
@@ -193,6 +198,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
+}
+
+// one elected lane of a converged warp (the same lane every time: lowest active)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, px;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // 2-D tiled TMA load: box of the tensor map at (col, row) -> swizzled smem, completes on mbarrier

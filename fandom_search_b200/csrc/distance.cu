@@ -15,10 +15,10 @@
 // of the UMMA shared-memory descriptors (row pitch 128 B inside the 128B-swizzled
 // tile), so every token row is fetched from L2 once per tile instead of `w` times.
 //
-// Roles (320 threads, 1 CTA/SM, persistent over a contiguous range of tiles):
-//   warps 0..7    : epilogue           (tcgen05.ld, diagonal sum, norm/threshold compare, compaction)
-//   warp 8 lane 0 : TMA producer       (cp.async.bulk.tensor, mbarrier stage ring)
-//   warp 9 lane 0 : tcgen05.mma issuer (128x256x16, fp32 accumulators in TMEM, 2 buffers)
+// Roles (576 threads, 1 CTA/SM, persistent over a contiguous range of tiles):
+//   warps 0..15    : epilogue           (tcgen05.ld, diagonal sum, norm/threshold compare, compaction)
+//   warp 16 lane 0 : TMA producer       (cp.async.bulk.tensor, mbarrier stage ring)
+//   warp 17 lane 0 : tcgen05.mma issuer (128x256x16, fp32 accumulators in TMEM, 2 buffers)
 //
 // Epilogue.  acc[i][j] > thr_fan[i] * norm_script[j]  <=>  cos > 1 - thr - eps, with
 // thr_fan = (1-thr-eps)*|fanwin_i| (+inf for windows that straddle a work boundary) and
@@ -59,9 +59,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
-    float* zero_row = halo + kHaloBytes / 4;
-    float* norm_tile = zero_row + kZeroRowBytes / 4;
-    for (int i = threadIdx.x; i < kHaloCols; i += blockDim.x) zero_row[i] = 0.f;
+    float* norm_tile = halo + kHaloBytes / 4;
 
     // Warp roles.  The warp scheduler prefers the HIGHEST warp id among eligible warps, so the
     // two single-thread roles that everything else waits for get the two highest ids: with
@@ -69,8 +67,6 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     // epilogue is busy, and tile t+1's MMAs no longer overlap tile t's epilogue.
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    constexpr int kProducerWarp = kEpiWarps;      // 8
-    constexpr int kMmaWarp = kEpiWarps + 1;       // 9
     const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
 
@@ -121,7 +117,11 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     const int shift_groups = (p.window / kDiag) / S;  // stages per 64-column chunk
     const int stages_per_tile = p.chunks * shift_groups;
 
-    if (warp == kProducerWarp && lane == 0) {
+    // The two control roles run as WHOLE warps (all lanes converged, one elected lane issues):
+    // addresses and descriptors then stay warp-uniform and live in uniform registers.  Run by a
+    // single diverged lane, every tcgen05.mma costs a ~25-instruction R2UR/ELECT "waterfall",
+    // and the issue thread -- not the tensor pipe -- bounds the kernel once E > 1.
+    if (warp == kProducerWarp) {
         // ------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
@@ -134,19 +134,22 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t a_dst = smem_base + stage * kStageSz;
                     const uint32_t b_dst = a_dst + kStageABytes;
-                    if (kPair) {
-                        // this CTA stages its own fan rows and script rows [128 r, 128 r + 136)
-                        if (leader) mbar_expect_tx(full_bar(stage), 2 * kPairStageBytes);
-                        tma_load_2d_pair(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
-                        tma_load_2d_pair(b_dst, &map_script, full_bar(stage), c * kChunkK,
-                                         n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
-                    } else {
-                        mbar_expect_tx(full_bar(stage), kStageBytes);
-                        tma_load_2d(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
-                        tma_load_2d(b_dst, &map_script, full_bar(stage), c * kChunkK, n0 + s0);
-                        tma_load_2d(b_dst + kStageABytes, &map_script, full_bar(stage), c * kChunkK,
-                                    n0 + s0 + kBoxRows);
+                    if (elect_one()) {
+                        if (kPair) {
+                            // this CTA stages its own fan rows and script rows [128 r, 128 r + 136)
+                            if (leader) mbar_expect_tx(full_bar(stage), 2 * kPairStageBytes);
+                            tma_load_2d_pair(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
+                            tma_load_2d_pair(b_dst, &map_script, full_bar(stage), c * kChunkK,
+                                             n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
+                        } else {
+                            mbar_expect_tx(full_bar(stage), kStageBytes);
+                            tma_load_2d(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
+                            tma_load_2d(b_dst, &map_script, full_bar(stage), c * kChunkK, n0 + s0);
+                            tma_load_2d(b_dst + kStageABytes, &map_script, full_bar(stage),
+                                        c * kChunkK, n0 + s0 + kBoxRows);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == kNumStages) {
                         stage = 0;
                         phase ^= 1u;
@@ -154,7 +157,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 }
             }
         }
-    } else if (warp == kMmaWarp && lane == 0 && leader) {
+    } else if (warp == kMmaWarp && leader) {
         // ------------------------------------------------------------ MMA issuer
         constexpr uint32_t idesc = umma_idesc_f16(kPair ? 2 * kBlockM : kBlockM, kBlockN);
         int stage = 0;
@@ -166,59 +169,81 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
             uint32_t accumulate = 0;
-            for (int it = 0; it < stages_per_tile; ++it) {
-                mbar_wait(full_bar(stage), phase);
-                tc_fence_after();
-                const uint32_t a_src = smem_base + stage * kStageSz;
-                const uint32_t b_src = a_src + kStageABytes;
+            for (int c = 0; c < p.chunks; ++c) {
                 // the last chunk may hold fewer than 64 real columns (d_pad is a multiple of
                 // 16, not 64): its trailing K-steps are all-zero TMA fill and are skipped
-                const int chunk = it / shift_groups;
-                const int ksteps = (chunk == p.chunks - 1) ? p.last_chunk_ksteps : kChunkK / kUmmaK;
-                for (int s = 0; s < S; ++s) {
-                    // row shift inside the stage = s * kDiag rows of 128 B: a plain offset of
-                    // the descriptor start address (swizzle is a function of the absolute
-                    // address, so base_offset stays 0)
-                    const uint32_t row_off = static_cast<uint32_t>(s * kDiag * 128);
-                    const uint32_t bo = p.base_offset_mode ? static_cast<uint32_t>(s * kDiag) & 7u : 0u;
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint32_t off = row_off + static_cast<uint32_t>(k * kUmmaK * 2);
+                const int ksteps = (c == p.chunks - 1) ? p.last_chunk_ksteps : kChunkK / kUmmaK;
+                for (int g = 0; g < shift_groups; ++g) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_src = smem_base + stage * kStageSz;
+                    // descriptors of (shift 0, k-step 0); every other operand of the stage is
+                    // this plus a byte offset >> 4 in the 14-bit start-address field
+                    const uint64_t adesc0 = umma_smem_desc(a_src, 0);
+                    const uint64_t bdesc0 = umma_smem_desc(a_src + kStageABytes, 0);
+                    if (elect_one()) {
+                        for (int s = 0; s < S; ++s) {
+                            // row shift inside the stage = s * kDiag rows of 128 B: a plain offset
+                            // of the descriptor start address (the 128B swizzle is a function of
+                            // the absolute smem address, so base_offset stays 0)
+                            const uint32_t row_off = static_cast<uint32_t>(s * kDiag * 128) >> 4;
+#pragma unroll 4
+                            for (int k = 0; k < ksteps; ++k) {
+                                const uint64_t off = row_off + static_cast<uint32_t>(k * kUmmaK * 2 >> 4);
+                                if (kPair)
+                                    umma_f16_pair(tmem_d, adesc0 + off, bdesc0 + off, idesc, accumulate);
+                                else
+                                    umma_f16(tmem_d, adesc0 + off, bdesc0 + off, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        // frees the smem stage (in both CTAs) when these MMAs retire
                         if (kPair)
-                            umma_f16_pair(tmem_d, umma_smem_desc(a_src + off, bo),
-                                          umma_smem_desc(b_src + off, bo), idesc, accumulate);
+                            umma_commit_pair(empty_bar(stage));
                         else
-                            umma_f16(tmem_d, umma_smem_desc(a_src + off, bo),
-                                     umma_smem_desc(b_src + off, bo), idesc, accumulate);
-                        accumulate = 1;
+                            umma_commit(empty_bar(stage));
                     }
-                }
-                // frees the smem stage (in both CTAs) when these MMAs retire
-                if (kPair)
-                    umma_commit_pair(empty_bar(stage));
-                else
-                    umma_commit(empty_bar(stage));
-                if (++stage == kNumStages) {
-                    stage = 0;
-                    phase ^= 1u;
+                    __syncwarp();
+                    accumulate = 1;
+                    if (++stage == kNumStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
             }
             // accumulator tile complete (in both CTAs)
-            if (kPair)
-                umma_commit_pair(tfull_bar(as));
-            else
-                umma_commit(tfull_bar(as));
+            if (elect_one()) {
+                if (kPair)
+                    umma_commit_pair(tfull_bar(as));
+                else
+                    umma_commit(tfull_bar(as));
+            }
+            __syncwarp();
             if (++as == kAccumStages) {
                 as = 0;
                 aphase ^= 1u;
             }
         }
     } else if (warp < kEpiWarps) {
-        // ------------------------------------------------------------ epilogue (8 warps)
-        // warp -> TMEM lane quarter (warp & 3, a hardware restriction) x column half
+        // ------------------------------------------------------------ epilogue (16 warps)
+        // warp -> TMEM lane quarter (warp & 3, a hardware restriction) x group of 64 columns.
+        //
+        // E > 1: out[i][j] = sum_{d<E} acc[i+d][j+d].  The column shift is a register index; the
+        // row shift is a warp shuffle for lanes < 32-(E-1).  The last E-1 rows of a quarter need
+        // rows of the NEXT quarter (another warp): every warp publishes its first and last E-1
+        // rows to shared memory while it streams its chunks, and after one barrier per tile those
+        // few boundary rows (3(E-1) of 128) are summed from shared memory, one column per lane.
+        constexpr int kEdge = kDiag - 1;            // boundary rows per side
+        constexpr int kTail0 = 32 - kEdge;          // first lane of the tail rows
         const int quarter = warp & 3;
-        const int half = warp >> 2;
+        const int group = warp >> 2;
         const int row = quarter * 32 + lane;
-        const int epi_tid = warp * 32 + lane;  // 0..255
+        const int epi_tid = warp * 32 + lane;  // 0..511
+        // publish slot of this lane: head rows 0..E-2 -> slots 0..E-2, tail rows -> E-1..2E-3
+        const int pub_slot = lane < kEdge ? lane : (lane >= kTail0 ? kEdge + lane - kTail0 : -1);
+        auto pub_at = [&](int q, int slot) -> float* {
+            return halo + (q * kPubSlots + slot) * kHaloCols;
+        };
         int as = 0;
         uint32_t aphase = 0;
         for (int64_t t = tile_begin; t < tile_end; ++t) {
@@ -227,33 +252,20 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             const int32_t gi = m0 + row;
             const bool row_ok = row < kMStep;
             const float thr = row_ok ? __ldg(p.thr_fan + gi) : INFINITY;  // padded to a tile multiple
+            // rows whose sum needs another warp's rows are finished in the boundary pass
+            const float thr_main = (kDiag > 1 && lane >= kTail0) ? INFINITY : thr;
             // E > 1: script-window norms of this tile staged once in smem, +inf baked in for the
-            // E-1 columns that belong to the next tile (published by the first chunk barrier)
+            // E-1 columns that belong to the next tile
             float* ns_tile = norm_tile + as * kHaloCols;
-            if (kDiag > 1) {
+            if (kDiag > 1 && epi_tid < kHaloCols)
                 ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.norm_script + n0 + epi_tid) : INFINITY;
-                if (epi_tid < kHaloCols - kBlockN) ns_tile[kBlockN + epi_tid] = INFINITY;
-            }
-            // rows i+d of the last lanes live in the NEXT lane quarter: its warps publish their
-            // first E-1 rows chunk by chunk (quarter 3 has no successor inside the tile; those
-            // outputs belong to the next tile and read a row of zeros)
-            float* pub_row = halo + (((as * 4 + quarter) * kHaloRows + lane) * kHaloCols);
-            const float* edge_row[kDiag];  // [d]: row (lane + d - 32) of the next quarter
-            bool edge[kDiag];
-#pragma unroll
-            for (int d = 1; d < kDiag; ++d) {
-                edge[d] = lane + d >= 32;
-                edge_row[d] = (quarter < 3 && edge[d])
-                                  ? halo + (((as * 4 + quarter + 1) * kHaloRows + (lane + d - 32)) * kHaloCols)
-                                  : zero_row;
-            }
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                   static_cast<uint32_t>(as * kBlockN + half * (kBlockN / 2));
+                                   static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                const int c0 = half * (kBlockN / 2) + ch * 32;  // first column inside the tile
+            for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+                const int c0 = group * kEpiCols + ch * 32;  // first column inside the tile
                 uint32_t r[40];
                 __syncwarp();
                 tmem_ld_32x32(taddr + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
@@ -266,72 +278,42 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     }
                 }
                 tmem_ld_wait();
-                float v[32];
-                if (kDiag > 1) {
-                    if (lane < kDiag - 1) {
-                        uint4* dst = reinterpret_cast<uint4*>(pub_row + c0);
+                if (kDiag > 1 && pub_slot >= 0) {
+                    uint4* dst = reinterpret_cast<uint4*>(pub_at(quarter, pub_slot) + c0);
 #pragma unroll
-                        for (int q = 0; q < 10; ++q)
-                            dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-                    float h[kDiag][40];  // [d]: the 40 columns of the successor row, edge lanes only
-#pragma unroll
-                    for (int d = 1; d < kDiag; ++d) {
-                        if (edge[d]) {
-                            const float4* src = reinterpret_cast<const float4*>(edge_row[d] + c0);
-#pragma unroll
-                            for (int q = 0; q < 10; ++q) {
-                                const float4 f = src[q];
-                                h[d][4 * q] = f.x;
-                                h[d][4 * q + 1] = f.y;
-                                h[d][4 * q + 2] = f.z;
-                                h[d][4 * q + 3] = f.w;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int x = 0; x < 32; ++x) {
-                        float acc = __uint_as_float(r[x]);
-#pragma unroll
-                        for (int d = 1; d < kDiag; ++d) {
-                            float o = __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + d]), d);
-                            if (edge[d]) o = h[d][x + d];
-                            acc += o;
-                        }
-                        v[x] = acc;
-                    }
-                } else {
-#pragma unroll
-                    for (int x = 0; x < 32; ++x) v[x] = __uint_as_float(r[x]);
+                    for (int q = 0; q < 10; ++q)
+                        dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
                 }
+                auto out_at = [&](int x) {
+                    float acc = __uint_as_float(r[x]);
+#pragma unroll
+                    for (int d = 1; d < kDiag; ++d)
+                        acc += __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + d]), d);
+                    return acc;
+                };
                 const int32_t gj0 = n0 + c0;
                 if (kDump) {
-                    if (row_ok && gi < p.n_fan_tok) {
 #pragma unroll
-                        for (int x = 0; x < 32; ++x) {
-                            if (c0 + x < kNStep && gj0 + x < p.dump_ld)
-                                p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + x] = v[x];
-                        }
+                    for (int x = 0; x < 32; ++x) {
+                        const float v = out_at(x);
+                        if (row_ok && (kDiag == 1 || lane < kTail0) && gi < p.n_fan_tok &&
+                            c0 + x < kNStep && gj0 + x < p.dump_ld)
+                            p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + x] = v;
                     }
                 } else {
-                    bool any = false;
-                    const float4* ns4 = (kDiag == 1)
-                                            ? reinterpret_cast<const float4*>(p.norm_script + gj0)
-                                            : reinterpret_cast<const float4*>(ns_tile + c0);
+                    // one max over the chunk against thr * (smallest norm of the chunk) rejects
+                    // the chunk; the exact per-element test runs only on the rare survivor
+                    float mx = -INFINITY;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 n4 = (kDiag == 1) ? __ldg(ns4 + q) : ns4[q];
-                        any |= v[4 * q + 0] > thr * n4.x;
-                        any |= v[4 * q + 1] > thr * n4.y;
-                        any |= v[4 * q + 2] > thr * n4.z;
-                        any |= v[4 * q + 3] > thr * n4.w;
-                    }
-                    if (any) {  // rare: hits are sparse
+                    for (int x = 0; x < 32; ++x) mx = fmaxf(mx, out_at(x));
+                    const float nmin = __ldg(p.norm_min32 + gj0);
+                    // warp-uniform branch: out_at() shuffles need every lane
+                    if (__any_sync(0xffffffffu, mx > thr_main * nmin)) {
 #pragma unroll
                         for (int x = 0; x < 32; ++x) {
-                            const float nsv = (kDiag == 1) ? __ldg(p.norm_script + gj0 + x) : ns_tile[c0 + x];
-                            if (v[x] > thr * nsv) {
+                            const float v = out_at(x);
+                            const float nsv = (c0 + x < kNStep) ? __ldg(p.norm_script + gj0 + x) : INFINITY;
+                            if (v > thr_main * nsv) {
                                 const unsigned long long slot =
                                     atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                                 if (slot < static_cast<unsigned long long>(p.cand_cap)) {
@@ -342,6 +324,43 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                         }
                     }
                 }
+            }
+            if (kDiag > 1) {
+                // boundary rows: tail rows of quarters 0..2 (quarter 3's belong to the next tile)
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+#pragma unroll
+                for (int tr = 0; tr < kEdge; ++tr) {
+                    const int L = kTail0 + tr;
+                    const float thr_l = __shfl_sync(0xffffffffu, thr, L);
+                    if (quarter < 3) {
+#pragma unroll
+                        for (int it = 0; it < kEpiCols / 32; ++it) {
+                            const int c = group * kEpiCols + it * 32 + lane;
+                            float v = 0.f;
+#pragma unroll
+                            for (int d = 0; d < kDiag; ++d) {
+                                const int lp = L + d;  // row inside this quarter, or lp-32 of the next
+                                const float* src = lp < 32 ? pub_at(quarter, kEdge + lp - kTail0)
+                                                           : pub_at(quarter + 1, lp - 32);
+                                v += src[c + d];
+                            }
+                            const int32_t gr = m0 + quarter * 32 + L;
+                            if (kDump) {
+                                if (gr < p.n_fan_tok && c < kNStep && n0 + c < p.dump_ld)
+                                    p.dump[static_cast<int64_t>(gr) * p.dump_ld + n0 + c] = v;
+                            } else if (v > thr_l * ns_tile[c]) {
+                                const unsigned long long slot =
+                                    atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
+                                if (slot < static_cast<unsigned long long>(p.cand_cap)) {
+                                    p.cand[slot].fan_pos = gr;
+                                    p.cand[slot].script_pos = n0 + c;
+                                }
+                            }
+                        }
+                    }
+                }
+                // the next tile's chunks overwrite the published rows
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
             }
             tc_fence_before();
             __syncwarp();

@@ -149,6 +149,23 @@ __global__ void window_norm_kernel(const float* __restrict__ tok_sq, int64_t n_t
     }
 }
 
+// dst[j] = min(src[j .. j+31]) (clamped at n): lets the distance epilogue reject a whole
+// 32-column chunk with one compare of its largest accumulator
+__global__ void sliding_min32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float m = INFINITY;
+    for (int k = 0; k < 32 && j + k < n; ++k) m = fminf(m, src[j + k]);
+    dst[j] = m;
+}
+
+int launch_sliding_min32(const float* src, float* dst, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return FS_OK;
+    sliding_min32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+    FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
 int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
                         __half* dst, float* sq, cudaStream_t stream) {
     if (n_rows <= 0) return FS_OK;
