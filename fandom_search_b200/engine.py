@@ -74,6 +74,15 @@ class DeviceIndex:
     def set_option(self, option, value):
         nt.check(self._lib.fs_index_set_option(self._h, option, value))
 
+    @property
+    def diag(self):
+        """Diagonal-sum factor E of the distance kernel (tensor cores do window/E shifts)."""
+        return int(self._lib.fs_index_get_info(self._h, 5))
+
+    @property
+    def cta_pair(self):
+        return int(self._lib.fs_index_get_info(self._h, 6))
+
     def set_lsh(self, normals, n_tables, n_bits):
         """Switch on LSH emulation: normals float64 [n_tables*n_bits, window*dim] (None = off)."""
         if normals is None or n_tables == 0:

@@ -92,6 +92,23 @@ def test_search_equals_float64_reference(seed, dim, diag, pair):
     idx.close()
 
 
+@pytest.mark.parametrize("window", [3, 4, 5, 7, 8])
+def test_other_window_sizes(window):
+    """window_size is a keyword of analyze (search.py:337); the kernel picks E = 3, 2 or 1."""
+    table, sx, fx, script, tok, off = _case(20 + window, dim=100)
+    ref = NumpyIndex(table, script, extra=sx, window=window)
+    want, wc = ref.search_host(tok, off, fx)
+    idx = _device_index(table, script, extra=sx, window=window)
+    assert idx.diag == (3 if window % 3 == 0 else 2 if window % 2 == 0 else 1)
+    got, gc = idx.search_host(tok, off, fx)
+    assert _pairs(got) == _pairs(want) and len(want) > 0
+    assert gc[nt.FS_CNT_WINDOWS] == wc[nt.FS_CNT_WINDOWS]
+    pj, _ = idx.exact_join_host(tok, off)
+    wj, _ = ref.exact_join_host(tok, off)
+    assert sorted(map(tuple, pj.tolist())) == sorted(map(tuple, wj.tolist()))
+    idx.close()
+
+
 def test_gather_is_bit_exact_and_norms_match():
     import torch
     table, sx, fx, script, tok, off = _case(5)
@@ -117,6 +134,7 @@ def test_gather_is_bit_exact_and_norms_match():
     assert np.all(np.isinf(thr[~valid])) and np.all(np.isfinite(thr[valid]))
     coef = 1.0 - 0.1 - 2.0e-3
     np.testing.assert_allclose(thr[valid], coef * wantn[valid], rtol=2e-6)
+    assert idx.diag == 3 and idx.cta_pair == 1      # defaults for 6-gram windows
     idx.close()
 
 
