@@ -61,6 +61,7 @@ SIGNATURES = {
     "fs_stage_embed_dev": (ctypes.c_int, [_vp, _vp] + _BATCHX + [_vp, _vp]),
     "fs_stage_dots_dev": (ctypes.c_int, [_vp, _vp] + _BATCHX + [_vp, _i64]),
     "fs_stage_candidates_dev": (ctypes.c_int, [_vp, _vp] + _BATCHX + [_vp, _i64, _vp]),
+    "fs_reuse_histogram_dev": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _i64, _vp]),
     "fs_timing_reset": (ctypes.c_int, [_vp]),
     "fs_timing_read": (ctypes.c_int, [_vp, ctypes.POINTER(_f64), ctypes.POINTER(_i64)]),
     "fs_index_scale": (ctypes.c_float, [_vp]),

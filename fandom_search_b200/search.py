@@ -179,16 +179,17 @@ class ScriptEngine(object):
 
 
 def build_lsh_engine(orig, window_size, number_of_hashes, hash_dimensions,
-                     distance_threshold=0.1):
+                     distance_threshold=0.1, script_offsets=None):
     # search.py:86-124: script tokens -> device index.  `orig` is the sequence of script
-    # tokens (lower-cased words).
+    # tokens (lower-cased words); `script_offsets` (optional) are the CSR boundaries when several
+    # scripts are indexed together -- windows never straddle a boundary.
     from .engine import DeviceIndex
     lex = get_spacy_model().lexicon
     words = [str(t) for t in orig]
     script_tok = lex.row_ids(words)
     n_sx = lex.n_oov
-    index = DeviceIndex(lex.table, script_tok, extra=lex.oov_rows(0, n_sx), window=window_size,
-                        threshold=distance_threshold, device=_device_ordinal())
+    index = DeviceIndex(lex.table, script_tok, script_off=script_offsets, extra=lex.oov_rows(0, n_sx),
+                        window=window_size, threshold=distance_threshold, device=_device_ordinal())
     lsh = None
     if os.environ.get('FANDOM_SEARCH_MODE', 'exhaustive') == 'lsh':
         from .lsh import LshEmulation
@@ -210,19 +211,28 @@ def multi_search_wrapper(work):
 class AnnIndexSearch(object):
     def __init__(self, original_script_filename, window_size,
                  number_of_hashes, hash_dimensions, distance_threshold):
-        # search.py:131-154
-        orig_csv = load_markup_script(original_script_filename)
-        orig_csv = orig_csv[1:]
-        if orig_csv:
-            (self.word_lowercase, self.orth_id, self.scene, self.character) = zip(*orig_csv)
+        # search.py:131-154.  `original_script_filename` may also be a LIST of markup scripts
+        # (SURVEY 8f row N4): they are indexed side by side (one wider script matrix, windows
+        # never straddle scripts) and the corpus is searched against all of them in one pass;
+        # see search_many_scripts / analyze_scripts.
+        multi = not isinstance(original_script_filename, (str, bytes, os.PathLike))
+        self.script_filenames = list(original_script_filename) if multi else [original_script_filename]
+        rows, offsets = [], [0]
+        for fn in self.script_filenames:
+            rows.extend(load_markup_script(fn)[1:])
+            offsets.append(len(rows))
+        if rows:
+            (self.word_lowercase, self.orth_id, self.scene, self.character) = zip(*rows)
         else:
             self.word_lowercase = self.orth_id = self.scene = self.character = ()
+        self.script_offsets = numpy.array(offsets, dtype=numpy.int64)
         self.word_index = tuple(range(len(self.word_lowercase)))
         self.window_size = window_size
         self.distance_threshold = distance_threshold
         self.spacy_model = get_spacy_model()
         self.engine = build_lsh_engine(self.word_lowercase, window_size, number_of_hashes,
-                                       hash_dimensions, distance_threshold)
+                                       hash_dimensions, distance_threshold,
+                                       script_offsets=self.script_offsets)
         self.reset_stats()
 
     def reset_stats(self):
@@ -297,7 +307,25 @@ class AnnIndexSearch(object):
 
     def records_prepared(self, prep, matches, first_table=None):
         """Host stage after the GPU (search.py:188-226)."""
+        if len(self.script_filenames) != 1:
+            raise ValueError("several scripts are indexed: use records_prepared_scripts")
         return self._records(prep['filenames'], prep['batch'], matches, first_table)
+
+    def records_prepared_scripts(self, prep, matches, first_table=None):
+        """One record-set list per indexed script: what separate reference runs, one per script,
+        would each have produced for these works (top-10, argmin and word indices are per script)."""
+        sid = numpy.searchsorted(self.script_offsets, matches['script_pos'], side='right') - 1
+        out = []
+        for k in range(len(self.script_filenames)):
+            sel = sid == k
+            out.append(self._records(prep['filenames'], prep['batch'], matches[sel],
+                                     None if first_table is None else first_table[sel],
+                                     word_base=int(self.script_offsets[k])))
+        return out
+
+    def search_many_scripts(self, filenames):
+        prep = self.prepare(filenames)
+        return self.records_prepared_scripts(prep, *self.search_prepared(prep))
 
     def _script_text(self):
         if getattr(self, '_script_blob', None) is None:
@@ -308,7 +336,7 @@ class AnnIndexSearch(object):
             self._script_off = off
         return self._script_blob, self._script_off
 
-    def _records(self, filenames, batch, matches, first_table=None):
+    def _records(self, filenames, batch, matches, first_table=None, word_base=0):
         # search.py:182-226 on the surviving pairs: top-10 per window, Levenshtein, six records
         # per pair, per-word argmin (native, fs_records_best); here only the row formatting.
         out = [[] for _ in filenames]
@@ -331,7 +359,7 @@ class AnnIndexSearch(object):
                             word[i],
                             fan_word,                        # orth_
                             _text.string_id(fan_word),       # orth
-                            orig_word_ix,
+                            orig_word_ix - word_base,        # index inside its own script
                             self.word_lowercase[orig_word_ix],
                             self.orth_id[orig_word_ix],
                             self.character[orig_word_ix],
@@ -433,6 +461,52 @@ def write_records(records, filename):
     with open(filename, 'w', encoding='utf-8') as out:
         wr = csv.writer(out)
         wr.writerows(records)
+
+
+def analyze_scripts(args, scripts, window_size=6, number_of_hashes=15, hash_dimensions=14,
+                    distance_threshold=0.1, chunk_size=500):
+    """One pass over the fanwork folder for SEVERAL markup scripts (the
+    reference runs `ao3.py search` once per film, workflow/*.py).  Writes, per script, the files
+    a separate run would have written, with the script's file stem in the name:
+    match-{w}gram-{stem}-batch-{i}.csv and match-{w}gram-{stem}-YYYYMMDD[-k].csv."""
+    fan_work_directory = args.fan_works
+    subsample_start = 0 if args.skip_works < 0 else args.skip_works
+    subsample_end = None if args.num_works < 0 else args.num_works + subsample_start
+    fan_works = [os.path.join(fan_work_directory, f) for f in os.listdir(fan_work_directory)]
+    random.seed(4815162342)
+    random.shuffle(fan_works)
+    fan_works = fan_works[subsample_start:subsample_end]
+    fan_clusters = [fan_works[i:i + chunk_size] for i in range(0, len(fan_works), chunk_size)]
+    stems = [os.path.splitext(os.path.basename(sc))[0] for sc in scripts]
+    if len(set(stems)) != len(stems):
+        raise ValueError("script file stems must be distinct: %s" % stems)
+    rank, world = _dist_env()
+    ann_index = AnnIndexSearch(list(scripts), window_size, number_of_hashes, hash_dimensions,
+                               distance_threshold)
+    per_script = [dict() for _ in scripts]
+    for i, fan_cluster in enumerate(fan_clusters):
+        if i % world != rank:
+            continue
+        print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
+        for k, record_sets in enumerate(ann_index.search_many_scripts(fan_cluster)):
+            records = [r for r_set in record_sets for r in r_set]
+            write_records(records, 'match-{}gram-{}-batch-{}.csv'.format(window_size, stems[k], i))
+            per_script[k][i] = records
+    if world > 1:
+        from .parallel import gather_cluster_records
+        per_script = [gather_cluster_records(d, rank, world) for d in per_script]
+        if rank != 0:
+            return
+    for k, stem in enumerate(stems):
+        accumulated = [new_record_structure['fields']]
+        for i in sorted(per_script[k]):
+            accumulated.extend(per_script[k][i])
+        n = 0
+        name = 'match-{}gram-{}-{:%Y%m%d}.csv'.format(window_size, stem, datetime.date.today())
+        while os.path.exists(name):
+            n += 1
+            name = 'match-{}gram-{}-{:%Y%m%d}-{}.csv'.format(window_size, stem, datetime.date.today(), n)
+        write_records(accumulated, name)
 
 
 def _dist_env():

@@ -212,6 +212,15 @@ uint64_t fs_murmurhash64a(const void* key, int64_t len, uint64_t seed);
 int64_t fs_tokenize_ws(const char* text, int64_t len, int64_t* starts, int64_t* ends, int64_t cap);
 
 /*
+ * Per-script-word reuse histogram (the aggregation ao3.py format_data does on the match CSV,
+ * ao3.py:351-363,407-411): counts[word * n_thr + k] += (combined[i] <= thresholds[k]) for
+ * every winning record i with ORIGINAL_SCRIPT_WORD_INDEX word_ix[i].  All DEVICE pointers;
+ * counts [n_words, n_thr] int64 is accumulated into (zero it before the first cluster).
+ */
+int fs_reuse_histogram_dev(void* stream, const int32_t* word_ix, const double* combined, int64_t n,
+                           const double* thresholds, int32_t n_thr, int64_t n_words, int64_t* counts);
+
+/*
  * Native host stages either side of the GPU search (no GPU needed).
  */
 typedef struct fs_vocab fs_vocab; /* lexicon key -> embedding-row id (Token.has_vector/.vector keys,

@@ -382,3 +382,44 @@ def test_lsh_emulation_reproduces_seeded_reference_golden(golden_dir, tmp_path, 
         assert [(r[0], r[1]) for r in got] == [(r[0], r[1]) for r in want]
     finally:
         search.set_pipeline(None)
+
+
+def test_reuse_histogram_matches_format_groupby(golden_dir):
+    """fs_reuse_histogram_dev == the thresholded group-by of ao3.py format_data (ao3.py:351-363,
+    407-411) applied to the reference's golden match CSV."""
+    from fandom_search_b200.aggregate import THRESHOLDS, ReuseHistogram
+    rows = read_csv(os.path.join(golden_dir, "golden_exhaustive.csv"))
+    n_words = 1 + max(r[4] for r in rows)
+    want = np.zeros((n_words, len(THRESHOLDS)), np.int64)
+    for r in rows:                                   # matches.BEST_COMBINED_DISTANCE <= t, summed per word
+        for k, t in enumerate(THRESHOLDS):
+            want[r[4], k] += r[11] <= t
+    hist = ReuseHistogram(n_words)
+    half = len(rows) // 2
+    hist.add_records(rows[:half])
+    hist.add_records(rows[half:])
+    got = hist.result()
+    assert np.array_equal(got, want) and got.sum() > 0
+    assert np.all(np.diff(got, axis=1) >= 0)         # cumulative in the threshold
+
+
+def test_multi_script_pass_on_device(golden_dir, tmp_path):
+    """N4 on the GPU: two scripts indexed side by side == two single-script searches."""
+    _golden_pipeline(golden_dir)
+    try:
+        lines = open(os.path.join(golden_dir, "script.txt"), encoding="utf-8").read().splitlines()
+        cut = len(lines) // 2
+        a, b = tmp_path / "alpha.txt", tmp_path / "beta.txt"
+        a.write_text("\n".join(lines[:cut]) + "\n", encoding="utf-8")
+        b.write_text("\n".join(lines[cut:]) + "\n", encoding="utf-8")
+        files = sorted(glob.glob(os.path.join(golden_dir, "fanworks", "*.txt")))
+        both = search.AnnIndexSearch([str(a), str(b)], 6, 15, 14, 0.1)
+        multi = both.search_many_scripts(files)
+        for k, path in enumerate((a, b)):
+            single = search.AnnIndexSearch(str(path), 6, 15, 14, 0.1)
+            want = normalise([r for s in single.search_many(files) for r in s])
+            got = normalise([r for s in multi[k] for r in s])
+            assert len(want) > 0
+            compare_records(got, want, tol=DIST_TOL)
+    finally:
+        search.set_pipeline(None)

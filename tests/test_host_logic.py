@@ -138,3 +138,31 @@ def test_native_vocab_and_batch(golden_dir, tmp_path):
         assert t == (lex.key_to_row[w] if w in lex.key_to_row else -(1 + want_oov.index(w)))
     with pytest.raises(FileNotFoundError):
         vocab.encode_files([str(tmp_path / "missing.txt")])
+
+
+def test_multi_script_pass_equals_separate_runs(cpu_device, golden_dir, tmp_path, monkeypatch):
+    """N4: indexing two scripts side by side and searching once == two single-script runs."""
+    lines = open(os.path.join(golden_dir, "script.txt"), encoding="utf-8").read().splitlines()
+    cut = len(lines) // 2
+    a, b = tmp_path / "alpha.txt", tmp_path / "beta.txt"
+    a.write_text("\n".join(lines[:cut]) + "\n", encoding="utf-8")
+    b.write_text("\n".join(lines[cut:]) + "\n", encoding="utf-8")
+    files = sorted(glob.glob(os.path.join(golden_dir, "fanworks", "*.txt")))
+    both = search.AnnIndexSearch([str(a), str(b)], 6, 15, 14, 0.1)
+    multi = both.search_many_scripts(files)
+    for k, path in enumerate((a, b)):
+        single = search.AnnIndexSearch(str(path), 6, 15, 14, 0.1)
+        want = normalise([r for s in single.search_many(files) for r in s])
+        got = normalise([r for s in multi[k] for r in s])
+        assert len(want) > 0
+        compare_records(got, want, tol=1e-12)
+    # the driver writes one set of files per script
+    monkeypatch.chdir(tmp_path)
+    args = argparse.Namespace(fan_works=os.path.join(golden_dir, "fanworks"), script=None,
+                              skip_works=-1, num_works=-1)
+    search.analyze_scripts(args, [str(a), str(b)], chunk_size=16)
+    assert len(glob.glob("match-6gram-alpha-batch-*.csv")) == 3
+    assert len(glob.glob("match-6gram-beta-2*.csv")) == 1
+    agg = read_csv(glob.glob("match-6gram-alpha-2*.csv")[0])
+    single = search.AnnIndexSearch(str(a), 6, 15, 14, 0.1)
+    compare_records(agg, normalise([r for s in single.search_many(files) for r in s]), tol=1e-12)
