@@ -359,8 +359,8 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             idx->pair = value ? 1 : 0;
             return FS_OK;
         case FS_OPT_DIAG:
-            if (value < 1 || value > 3 || idx->window % value != 0) {
-                set_error("diagonal factor must be 1, 2 or 3 and divide the window");
+            if (!(value == 1 || value == 2 || value == 3 || value == 6) || idx->window % value != 0) {
+                set_error("diagonal factor must be 1, 2, 3 or 6 and divide the window");
                 return FS_E_INVALID;
             }
             idx->diag = static_cast<int32_t>(value);

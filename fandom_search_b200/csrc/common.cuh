@@ -41,9 +41,7 @@ constexpr int kBoxRows = 136;           // rows per TMA box (128 + 8 halo rows f
 constexpr int kStageABytes = kBoxRows * 128;       // 17408 (17 swizzle atoms)
 constexpr int kStageBBytes = 2 * kBoxRows * 128;   // 34816 (272 rows >= 256 + 5)
 constexpr int kStageBytes = kStageABytes + kStageBBytes;  // 52224
-constexpr int kStages = 4;
 constexpr int kPairStageBytes = 2 * kStageABytes;  // CTA-pair mode: A box + this CTA's half of B
-constexpr int kPairStages = 6;                     // 6 x 34816 = 4 x 52224
 constexpr int kAccumStages = 2;         // TMEM double buffer: 2 x 256 columns = all 512
 constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 16;           // 4 TMEM lane quarters x 4 column groups of 64
@@ -53,12 +51,22 @@ constexpr int kProducerWarp = kEpiWarps;               // single-thread roles ge
 constexpr int kMmaWarp = kEpiWarps + 1;                // warp ids (scheduler priority)
 constexpr int kDistThreads = 32 * (kEpiWarps + 2);     // 576
 constexpr int kHaloCols = kBlockN + 8;
-constexpr int kPubSlots = 4;            // published boundary rows per lane quarter (E <= 3)
-constexpr int kHaloBytes = 4 * kPubSlots * kHaloCols * 4;                  // 16896
 constexpr int kNormTileBytes = kAccumStages * kHaloCols * 4;               // 2112
-constexpr int kDistSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                               kHaloBytes + kNormTileBytes;
-static_assert(kDistSmemBytes <= 232448, "distance kernel exceeds the 227 KB shared memory limit");
+// shared-memory budget of distance_kernel<E, ., pair>: the stage ring shrinks by one stage at
+// E = 6, whose epilogue publishes 10 boundary rows per lane quarter instead of <= 4
+__host__ __device__ constexpr int dist_pub_slots(int diag) { return diag > 1 ? 2 * (diag - 1) : 1; }
+__host__ __device__ constexpr int dist_pub_bytes(int diag) { return 4 * dist_pub_slots(diag) * kHaloCols * 4; }
+__host__ __device__ constexpr int dist_stage_bytes(bool pair) { return pair ? 2 * kStageABytes : kStageBytes; }
+__host__ __device__ constexpr int dist_stages(int diag, bool pair) {
+    return pair ? (diag == 6 ? 5 : 6) : (diag == 6 ? 3 : 4);
+}
+__host__ __device__ constexpr int dist_smem_bytes(int diag, bool pair) {
+    return dist_stages(diag, pair) * dist_stage_bytes(pair) + 1024 /*align slack*/ + 256 /*barriers*/ +
+           dist_pub_bytes(diag) + kNormTileBytes;
+}
+static_assert(dist_smem_bytes(1, false) <= 232448 && dist_smem_bytes(3, true) <= 232448 &&
+                  dist_smem_bytes(6, true) <= 232448 && dist_smem_bytes(6, false) <= 232448,
+              "distance kernel exceeds the 227 KB shared memory limit");
 
 struct DistParams {
     const float* thr_fan;     // [Mpad]  (1 - thr - eps) * |fan window|, +inf when invalid

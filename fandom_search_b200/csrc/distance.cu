@@ -45,9 +45,9 @@ __global__ void __launch_bounds__(kDistThreads, 1)
 distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 const __grid_constant__ CUtensorMap map_script, const DistParams p) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int kNumStages = kPair ? kPairStages : kStages;
-    constexpr int kStageSz = kPair ? kPairStageBytes : kStageBytes;
-    static_assert(kNumStages * kStageSz == kStages * kStageBytes, "stage ring must fill the same smem");
+    constexpr int kNumStages = dist_stages(kDiag, kPair);
+    constexpr int kStageSz = dist_stage_bytes(kPair);
+    constexpr int kPubSlots = dist_pub_slots(kDiag);
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     // layout: [stages x (A | B)] [barriers] [halo rows] [zero row] [norm tile]
     const uint32_t bar_base = smem_base + kNumStages * kStageSz;
@@ -59,7 +59,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
-    float* norm_tile = halo + kHaloBytes / 4;
+    float* norm_tile = halo + dist_pub_bytes(kDiag) / 4;
 
     // Warp roles.  The warp scheduler prefers the HIGHEST warp id among eligible warps, so the
     // two single-thread roles that everything else waits for get the two highest ids: with
@@ -284,11 +284,25 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     for (int q = 0; q < 10; ++q)
                         dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
                 }
+                if (kDiag == 6) {
+                    // pairwise pre-sum in place: r[x] <- acc[i][x] + acc[i+1][x+1]; the six-term
+                    // diagonal sum is then three shuffled pair sums (3.1 instead of 5 shuffles
+                    // per output)
+#pragma unroll
+                    for (int x = 0; x < 36; ++x)
+                        r[x] = __float_as_uint(__uint_as_float(r[x]) +
+                                               __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + 1]), 1));
+                }
                 auto out_at = [&](int x) {
                     float acc = __uint_as_float(r[x]);
+                    if (kDiag == 6) {
+                        acc += __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + 2]), 2);
+                        acc += __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + 4]), 4);
+                    } else {
 #pragma unroll
-                    for (int d = 1; d < kDiag; ++d)
-                        acc += __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + d]), d);
+                        for (int d = 1; d < kDiag; ++d)
+                            acc += __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + d]), d);
+                    }
                     return acc;
                 };
                 const int32_t gj0 = n0 + c0;
@@ -440,16 +454,16 @@ static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_
     if (!attr_set) {
         FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kDistSmemBytes));
+                                           dist_smem_bytes(kDiag, kPair)));
         FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kDistSmemBytes));
+                                           dist_smem_bytes(kDiag, kPair)));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(kDistThreads);
-    cfg.dynamicSmemBytes = kDistSmemBytes;
+    cfg.dynamicSmemBytes = dist_smem_bytes(kDiag, kPair);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -485,6 +499,8 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         case 5: return launch_distance_t<2, true>(map_fan, map_script, p, grid, stream);
         case 6: return launch_distance_t<3, false>(map_fan, map_script, p, grid, stream);
         case 7: return launch_distance_t<3, true>(map_fan, map_script, p, grid, stream);
+        case 12: return launch_distance_t<6, false>(map_fan, map_script, p, grid, stream);
+        case 13: return launch_distance_t<6, true>(map_fan, map_script, p, grid, stream);
         default:
             set_error("unsupported diagonal factor %d", p.diag);
             return FS_E_INVALID;

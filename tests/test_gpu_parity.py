@@ -67,7 +67,7 @@ def _pairs(m):
 
 
 @pytest.mark.parametrize("pair", [0, 1])
-@pytest.mark.parametrize("diag", [1, 2, 3])
+@pytest.mark.parametrize("diag", [1, 2, 3, 6])
 @pytest.mark.parametrize("seed,dim", [(1, 300), (2, 64), (3, 768), (4, 100)])
 def test_search_equals_float64_reference(seed, dim, diag, pair):
     table, sx, fx, script, tok, off = _case(seed, dim=dim)
@@ -139,7 +139,7 @@ def test_gather_is_bit_exact_and_norms_match():
 
 
 @pytest.mark.parametrize("pair", [0, 1])
-@pytest.mark.parametrize("diag,shifts", [(1, 1), (1, 2), (1, 3), (1, 6), (2, 1), (2, 3), (3, 1), (3, 2)])
+@pytest.mark.parametrize("diag,shifts", [(1, 1), (1, 2), (1, 3), (1, 6), (2, 1), (2, 3), (3, 1), (3, 2), (6, 1)])
 def test_tensor_core_dots_match_fp16_contraction(diag, shifts, pair):
     import torch
     table, sx, fx, script, tok, off = _case(6, plant=False, clustered=False)
@@ -163,7 +163,7 @@ def test_tensor_core_dots_match_fp16_contraction(diag, shifts, pair):
 
 
 @pytest.mark.parametrize("pair", [0, 1])
-@pytest.mark.parametrize("diag", [1, 2, 3])
+@pytest.mark.parametrize("diag", [1, 2, 3, 6])
 def test_candidates_are_a_superset_within_slack(diag, pair):
     import torch
     table, sx, fx, script, tok, off = _case(7)

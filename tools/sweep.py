@@ -67,8 +67,8 @@ def main():
         print(json.dumps(run_case(nf, ns, d, 2, rng, diag=diag, pair=args.pair)), flush=True)
         return
     if args.diag:
-        for pair in (0, 1):
-            for diag in (1, 2, 3):
+        for pair in (1,):
+            for diag in (1, 2, 3, 6):
                 for (nf, ns, d) in ((2_500_000, 25000, 300), (2_500_000, 25000, 768)):
                     print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag, pair=pair)), flush=True)
         return
