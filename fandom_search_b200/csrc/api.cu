@@ -126,6 +126,8 @@ struct fs_index {
     // options
     int32_t diag = 1;              // diagonal-sum factor E of the distance kernel
     int32_t pair = 0;              // CTA-pair (cta_group::2) kernel
+    int32_t debug = 0;
+    int32_t ares = 0;              // A-resident variant of the pair kernel
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
     int32_t base_offset_mode = 0;
     int32_t grid_limit = 0;
@@ -355,6 +357,12 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             }
             idx->shifts_per_stage = static_cast<int32_t>(value);
             return FS_OK;
+        case 99:  // timing experiments (results invalid)
+            idx->debug = static_cast<int32_t>(value);
+            return FS_OK;
+        case FS_OPT_A_RESIDENT:
+            idx->ares = value ? 1 : 0;
+            return FS_OK;
         case FS_OPT_CTA_PAIR:
             idx->pair = value ? 1 : 0;
             return FS_OK;
@@ -408,6 +416,7 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
         case 4: return idx->shifts_per_stage;
         case 5: return idx->diag;
         case 6: return idx->pair;
+        case 7: return idx->ares;
         default: return -1;
     }
 }
@@ -520,6 +529,8 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.window = idx->window;
     p.diag = idx->diag;
     p.pair = idx->pair;
+    p.debug = idx->debug;
+    p.ares = idx->ares;
     p.shifts_per_stage = idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag;
     p.base_offset_mode = idx->base_offset_mode;
     p.tiles_m = tiles_m;

@@ -56,16 +56,25 @@ constexpr int kNormTileBytes = kAccumStages * kHaloCols * 4;               // 21
 // E = 6, whose epilogue publishes 10 boundary rows per lane quarter instead of <= 4
 __host__ __device__ constexpr int dist_pub_slots(int diag) { return diag > 1 ? 2 * (diag - 1) : 1; }
 __host__ __device__ constexpr int dist_pub_bytes(int diag) { return 4 * dist_pub_slots(diag) * kHaloCols * 4; }
-__host__ __device__ constexpr int dist_stage_bytes(bool pair) { return pair ? 2 * kStageABytes : kStageBytes; }
-__host__ __device__ constexpr int dist_stages(int diag, bool pair) {
-    return pair ? (diag == 6 ? 5 : 6) : (diag == 6 ? 3 : 4);
+// A-resident mode (CTA pairs, d_pad <= 320): the fan tile (all kAResChunks 64-column chunks,
+// 87 KB) stays in shared memory for the whole sweep over the script tiles; only this CTA's half
+// of the script tile streams through the stage ring (17 KB per stage).
+constexpr int kAResChunks = 5;
+constexpr int kAResBytes = kAResChunks * kStageABytes;  // 87040
+__host__ __device__ constexpr int dist_stage_bytes(bool pair, bool ares) {
+    return ares ? kStageABytes : (pair ? 2 * kStageABytes : kStageBytes);
 }
-__host__ __device__ constexpr int dist_smem_bytes(int diag, bool pair) {
-    return dist_stages(diag, pair) * dist_stage_bytes(pair) + 1024 /*align slack*/ + 256 /*barriers*/ +
-           dist_pub_bytes(diag) + kNormTileBytes;
+__host__ __device__ constexpr int dist_stages(int diag, bool pair, bool ares) {
+    return ares ? (diag == 6 ? 5 : 7) : (pair ? (diag == 6 ? 5 : 6) : (diag == 6 ? 3 : 4));
 }
-static_assert(dist_smem_bytes(1, false) <= 232448 && dist_smem_bytes(3, true) <= 232448 &&
-                  dist_smem_bytes(6, true) <= 232448 && dist_smem_bytes(6, false) <= 232448,
+__host__ __device__ constexpr int dist_smem_bytes(int diag, bool pair, bool ares) {
+    return (ares ? kAResBytes : 0) + dist_stages(diag, pair, ares) * dist_stage_bytes(pair, ares) +
+           1024 /*align slack*/ + 256 /*barriers*/ + dist_pub_bytes(diag) + kNormTileBytes;
+}
+static_assert(dist_smem_bytes(1, false, false) <= 232448 && dist_smem_bytes(3, true, false) <= 232448 &&
+                  dist_smem_bytes(6, true, false) <= 232448 && dist_smem_bytes(6, false, false) <= 232448 &&
+                  dist_smem_bytes(3, true, true) <= 232448 && dist_smem_bytes(6, true, true) <= 232448 &&
+                  dist_smem_bytes(1, true, true) <= 232448,
               "distance kernel exceeds the 227 KB shared memory limit");
 
 struct DistParams {
@@ -78,6 +87,8 @@ struct DistParams {
     int32_t last_chunk_ksteps;// UMMA K-steps (16 columns) in the last chunk: 1..4
     int32_t window;           // 6
     int32_t diag;             // E: epilogue adds E diagonal neighbours, MMAs do window/E shifts
+    int32_t debug;            // timing experiments only: 1 = skip epilogue math, 2 = skip TMEM loads
+    int32_t ares;             // 1: A-resident variant (pair mode, chunks <= kAResChunks)
     int32_t pair;             // 1: CTA-pair kernel (cta_group::2, M = 2 x 128 fan tiles)
     int32_t shifts_per_stage; // S: MMA shifts served by one smem stage (divides window/E)
     int32_t base_offset_mode; // how shifted descriptors fill base_offset

@@ -40,22 +40,31 @@ namespace fs {
 // from 52 to 35 KB per stage -- the shared-memory pipe, not the tensor pipe, is what saturates
 // first once E > 1.  The leader CTA (cluster rank 0) issues the MMAs; TMA bytes of both CTAs are
 // accounted on the leader's `full` barrier; tcgen05.commit multicasts to both CTAs' barriers.
-template <int kDiag, bool kDump, bool kPair>
+//
+// kARes (pair mode, d_pad <= 320): the fan tile stays RESIDENT in shared memory while the CTA
+// sweeps the script tiles, so only the script half-tile streams (87 instead of 174 KB per
+// tile).  With E >= 3 the L2 -> SM traffic (~6 TB/s chip-wide), not the tensor pipe, is the
+// wall otherwise.
+template <int kDiag, bool kDump, bool kPair, bool kARes>
 __global__ void __launch_bounds__(kDistThreads, 1)
 distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 const __grid_constant__ CUtensorMap map_script, const DistParams p) {
+    static_assert(!kARes || kPair, "the A-resident variant exists for CTA pairs only");
     extern __shared__ uint8_t smem_raw[];
-    constexpr int kNumStages = dist_stages(kDiag, kPair);
-    constexpr int kStageSz = dist_stage_bytes(kPair);
+    constexpr int kNumStages = dist_stages(kDiag, kPair, kARes);
+    constexpr int kStageSz = dist_stage_bytes(kPair, kARes);
     constexpr int kPubSlots = dist_pub_slots(kDiag);
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    // layout: [stages x (A | B)] [barriers] [halo rows] [zero row] [norm tile]
+    const uint32_t smem_a_res = (smem_u32(smem_raw) + 1023u) & ~1023u;  // resident fan tile (kARes)
+    const uint32_t smem_base = smem_a_res + (kARes ? kAResBytes : 0);
+    // layout: [resident A] [stages x (A | B)] [barriers] [boundary rows] [norm tile]
     const uint32_t bar_base = smem_base + kNumStages * kStageSz;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kNumStages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kNumStages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kNumStages + kAccumStages + s); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kNumStages + 2 * kAccumStages);
+    const uint32_t afull_bar = bar_base + 8u * (2 * kNumStages + 2 * kAccumStages);
+    const uint32_t aempty_bar = afull_bar + 8u;
+    const uint32_t tmem_slot = aempty_bar + 8u;
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
@@ -81,6 +90,8 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             mbar_init(tfull_bar(s), 1);
             mbar_init(tempty_bar(s), kPair ? 2 * kEpiWarps : kEpiWarps);
         }
+        mbar_init(afull_bar, 1);
+        mbar_init(aempty_bar, 1);
         mbar_fence_init();
     }
     if (warp == kMmaWarp) {
@@ -125,17 +136,35 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         // ------------------------------------------------------------ TMA producer
         int stage = 0;
         uint32_t phase = 0;
+        uint32_t a_phase = 0;
         for (int64_t t = tile_begin; t < tile_end; ++t) {
             const int32_t m0 = tile_m0(t);
             const int32_t n0 = tile_n0(t);
+            if (kARes && (t == tile_begin || t % p.tiles_n == 0)) {
+                // new fan tile: wait until every MMA that read the previous one has retired
+                mbar_wait(aempty_bar, a_phase ^ 1u);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(afull_bar, 2 * p.chunks * kStageABytes);
+                    for (int c = 0; c < p.chunks; ++c)
+                        tma_load_2d_pair(smem_a_res + c * kStageABytes, &map_fan, afull_bar,
+                                         c * kChunkK, m0);
+                }
+                __syncwarp();
+                a_phase ^= 1u;
+            }
             for (int c = 0; c < p.chunks; ++c) {
                 for (int g = 0; g < shift_groups; ++g) {
                     const int32_t s0 = g * S * kDiag;  // first token-row shift of this stage
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t a_dst = smem_base + stage * kStageSz;
-                    const uint32_t b_dst = a_dst + kStageABytes;
+                    const uint32_t b_dst = kARes ? a_dst : a_dst + kStageABytes;
                     if (elect_one()) {
-                        if (kPair) {
+                        if (kARes) {
+                            // only this CTA's half of the script tile streams
+                            if (leader) mbar_expect_tx(full_bar(stage), 2 * kStageABytes);
+                            tma_load_2d_pair(b_dst, &map_script, full_bar(stage), c * kChunkK,
+                                             n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
+                        } else if (kPair) {
                             // this CTA stages its own fan rows and script rows [128 r, 128 r + 136)
                             if (leader) mbar_expect_tx(full_bar(stage), 2 * kPairStageBytes);
                             tma_load_2d_pair(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
@@ -164,7 +193,12 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         uint32_t phase = 0;
         int as = 0;
         uint32_t aphase = 0;
+        uint32_t a_phase = 0;
         for (int64_t t = tile_begin; t < tile_end; ++t) {
+            if (kARes && (t == tile_begin || t % p.tiles_n == 0)) {
+                mbar_wait(afull_bar, a_phase);  // the resident fan tile has landed (both CTAs)
+                a_phase ^= 1u;
+            }
             mbar_wait(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
@@ -176,11 +210,17 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 for (int g = 0; g < shift_groups; ++g) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t a_src = smem_base + stage * kStageSz;
+                    const uint32_t st_src = smem_base + stage * kStageSz;
+                    // resident mode: the fan chunk sits in the resident tile and the stage holds
+                    // only script rows; the stage's first shift is then an offset into the tile
+                    const uint32_t a_src = kARes ? smem_a_res + c * kStageABytes +
+                                                       static_cast<uint32_t>(g * S * kDiag * 128)
+                                                 : st_src;
+                    const uint32_t b_src = kARes ? st_src : st_src + kStageABytes;
                     // descriptors of (shift 0, k-step 0); every other operand of the stage is
                     // this plus a byte offset >> 4 in the 14-bit start-address field
                     const uint64_t adesc0 = umma_smem_desc(a_src, 0);
-                    const uint64_t bdesc0 = umma_smem_desc(a_src + kStageABytes, 0);
+                    const uint64_t bdesc0 = umma_smem_desc(b_src, 0);
                     if (elect_one()) {
                         for (int s = 0; s < S; ++s) {
                             // row shift inside the stage = s * kDiag rows of 128 B: a plain offset
@@ -217,6 +257,9 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     umma_commit_pair(tfull_bar(as));
                 else
                     umma_commit(tfull_bar(as));
+                // last script tile of this fan tile: the resident tile may be replaced once
+                // these MMAs have retired
+                if (kARes && (t + 1 == tile_end || (t + 1) % p.tiles_n == 0)) umma_commit_pair(aempty_bar);
             }
             __syncwarp();
             if (++as == kAccumStages) {
@@ -268,16 +311,25 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 const int c0 = group * kEpiCols + ch * 32;  // first column inside the tile
                 uint32_t r[40];
                 __syncwarp();
-                tmem_ld_32x32(taddr + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-                if (kDiag > 1) {
-                    if (c0 + 32 < kBlockN) {
-                        tmem_ld_32x8(taddr + ch * 32 + 32, *reinterpret_cast<uint32_t(*)[8]>(&r[32]));
-                    } else {
+                if (p.debug & 2) {
 #pragma unroll
-                        for (int x = 32; x < 40; ++x) r[x] = 0u;
+                    for (int x = 0; x < 40; ++x) r[x] = 0u;
+                } else {
+                    tmem_ld_32x32(taddr + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+                    if (kDiag > 1) {
+                        if (c0 + 32 < kBlockN) {
+                            tmem_ld_32x8(taddr + ch * 32 + 32, *reinterpret_cast<uint32_t(*)[8]>(&r[32]));
+                        } else {
+#pragma unroll
+                            for (int x = 32; x < 40; ++x) r[x] = 0u;
+                        }
                     }
+                    tmem_ld_wait();
                 }
-                tmem_ld_wait();
+                if (p.debug & 1) {
+                    if (__uint_as_float(r[0]) == 1.2345e-30f) p.counters[0] = 1;  // keep the loads alive
+                    continue;
+                }
                 if (kDiag > 1 && pub_slot >= 0) {
                     uint4* dst = reinterpret_cast<uint4*>(pub_at(quarter, pub_slot) + c0);
 #pragma unroll
@@ -447,23 +499,23 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
     return FS_OK;
 }
 
-template <int kDiag, bool kPair>
+template <int kDiag, bool kPair, bool kARes = false>
 static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_script,
                              const DistParams& p, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair>,
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair, kARes>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           dist_smem_bytes(kDiag, kPair)));
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair>,
+                                           dist_smem_bytes(kDiag, kPair, kARes)));
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair, kARes>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           dist_smem_bytes(kDiag, kPair)));
+                                           dist_smem_bytes(kDiag, kPair, kARes)));
         attr_set = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(kDistThreads);
-    cfg.dynamicSmemBytes = dist_smem_bytes(kDiag, kPair);
+    cfg.dynamicSmemBytes = dist_smem_bytes(kDiag, kPair, kARes);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -473,9 +525,9 @@ static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (p.dump)
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair>, map_fan, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair, kARes>, map_fan, map_script, p));
     else
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair>, map_fan, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair, kARes>, map_fan, map_script, p));
     return FS_OK;
 }
 
@@ -490,6 +542,15 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         grid = 2 * static_cast<int>(total < clusters ? total : clusters);
     } else {
         grid = static_cast<int>(total < grid_limit ? total : grid_limit);
+    }
+    if (p.pair && p.ares && p.chunks <= kAResChunks) {
+        switch (p.diag) {
+            case 1: return launch_distance_t<1, true, true>(map_fan, map_script, p, grid, stream);
+            case 2: return launch_distance_t<2, true, true>(map_fan, map_script, p, grid, stream);
+            case 3: return launch_distance_t<3, true, true>(map_fan, map_script, p, grid, stream);
+            case 6: return launch_distance_t<6, true, true>(map_fan, map_script, p, grid, stream);
+            default: break;
+        }
     }
     const int key = p.diag * 2 + (p.pair ? 1 : 0);
     switch (key) {

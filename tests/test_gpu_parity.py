@@ -66,7 +66,7 @@ def _pairs(m):
     return set(zip(m['fan_pos'].tolist(), m['script_pos'].tolist()))
 
 
-@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("pair", [0, 1, 2])          # 2 = CTA pair + resident fan tile
 @pytest.mark.parametrize("diag", [1, 2, 3, 6])
 @pytest.mark.parametrize("seed,dim", [(1, 300), (2, 64), (3, 768), (4, 100)])
 def test_search_equals_float64_reference(seed, dim, diag, pair):
@@ -75,7 +75,8 @@ def test_search_equals_float64_reference(seed, dim, diag, pair):
     want, wc = ref.search_host(tok, off, fx)
     idx = _device_index(table, script, extra=sx)
     idx.set_option(nt.FS_OPT_DIAG, diag)
-    idx.set_option(nt.FS_OPT_CTA_PAIR, pair)
+    idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
+    idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
     got, gc = idx.search_host(tok, off, fx)
     assert _pairs(got) == _pairs(want) and len(got) == len(want)
     assert len(want) > 0
@@ -138,14 +139,15 @@ def test_gather_is_bit_exact_and_norms_match():
     idx.close()
 
 
-@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("pair", [0, 1, 2])
 @pytest.mark.parametrize("diag,shifts", [(1, 1), (1, 2), (1, 3), (1, 6), (2, 1), (2, 3), (3, 1), (3, 2), (6, 1)])
 def test_tensor_core_dots_match_fp16_contraction(diag, shifts, pair):
     import torch
     table, sx, fx, script, tok, off = _case(6, plant=False, clustered=False)
     idx = _device_index(table, script, extra=sx)
     idx.set_option(nt.FS_OPT_DIAG, diag)
-    idx.set_option(nt.FS_OPT_CTA_PAIR, pair)
+    idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
+    idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
     idx.set_option(nt.FS_OPT_SHIFTS_PER_STAGE, shifts)
     tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
     dots = idx.stage_dots(tok_t, off_t, fx_t).cpu().numpy()
@@ -162,7 +164,7 @@ def test_tensor_core_dots_match_fp16_contraction(diag, shifts, pair):
     idx.close()
 
 
-@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("pair", [0, 1, 2])
 @pytest.mark.parametrize("diag", [1, 2, 3, 6])
 def test_candidates_are_a_superset_within_slack(diag, pair):
     import torch
@@ -171,7 +173,8 @@ def test_candidates_are_a_superset_within_slack(diag, pair):
     d, fpos = ref.distances(tok, off, fx)
     idx = _device_index(table, script, extra=sx)
     idx.set_option(nt.FS_OPT_DIAG, diag)
-    idx.set_option(nt.FS_OPT_CTA_PAIR, pair)
+    idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
+    idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
     tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
     cand, cnt = idx.stage_candidates(tok_t, off_t, fx_t)
     n = int(cnt.cpu()[nt.FS_CNT_CANDIDATES])

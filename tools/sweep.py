@@ -18,12 +18,15 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, debug=0):
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
     idx.set_option(nt.FS_OPT_DIAG, diag)
-    idx.set_option(nt.FS_OPT_CTA_PAIR, pair)
+    idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
+    idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
+    if debug:
+        idx.set_option(99, debug)
     n_works = max(1, nf // works_len)
     lens = np.full(n_works, (nf + 5 * n_works) // n_works + 1, dtype=np.int64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
@@ -43,7 +46,7 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0):
     ms, n = idx.timing_read()
     windows = int(cnt_t.cpu()[nt.FS_CNT_WINDOWS])
     per = ms / n * 1e-3
-    res = {"diag": diag, "pair": pair, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
+    res = {"diag": diag, "pair": pair, "debug": debug, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
            "kernel_ms": ms / n, "windows_per_s": windows / per,
            "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
            "tflops_executed": 2.0 * (6 // diag) * idx.dim_pad * idx.n_script_windows * windows / per / 1e12
@@ -60,16 +63,22 @@ def main():
     ap.add_argument("--diag", action="store_true", help="compare the diagonal-sum factors at C2 size")
     ap.add_argument("--one", type=int, nargs=4, metavar=("DIAG", "NF", "NS", "D"), help="run a single case")
     ap.add_argument("--pair", type=int, default=0)
+    ap.add_argument("--debug-exp", action="store_true", help="epilogue timing experiments (invalid results)")
     args = ap.parse_args()
     rng = np.random.default_rng(0)
+    if args.debug_exp:
+        for diag in (3, 6):
+            for debug in (0, 1, 2, 3):
+                print(json.dumps(run_case(2_500_000, 25000, 300, 3, rng, diag=diag, pair=1, debug=debug)), flush=True)
+        return
     if args.one:
         diag, nf, ns, d = args.one
         print(json.dumps(run_case(nf, ns, d, 2, rng, diag=diag, pair=args.pair)), flush=True)
         return
     if args.diag:
-        for pair in (1,):
+        for pair in (1, 2):
             for diag in (1, 2, 3, 6):
-                for (nf, ns, d) in ((2_500_000, 25000, 300), (2_500_000, 25000, 768)):
+                for (nf, ns, d) in ((2_500_000, 25000, 300),) + (((2_500_000, 25000, 768),) if pair == 1 else ()):
                     print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag, pair=pair)), flush=True)
         return
     if args.quick:
