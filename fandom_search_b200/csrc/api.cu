@@ -225,9 +225,15 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     idx->n_sx = n_extra;
     idx->n_script_tok = n_script_tok;
     idx->n_scripts = static_cast<int32_t>(n_scripts);
-    // defaults of the distance kernel: the largest diagonal factor that divides the window
-    // (6-gram windows: 2 MMA shifts + 3-term epilogue sum) on CTA pairs
-    idx->diag = window % 3 == 0 ? 3 : (window % 2 == 0 ? 2 : 1);
+    // Defaults of the distance kernel (all variants are parity-tested and selectable):
+    // CTA pairs, and the diagonal factor that balances the tensor pipe against the warp-shuffle
+    // pipe (measured ~0.5 warp-shuffles/clk/SM): E = 3 costs 2 shuffles per accumulator element
+    // against 2*ksteps MMAs per tile, E = 6 costs 3.1 against ksteps -- E = 6 only pays once the
+    // embedding is wide (d_pad >= 416: 26 M vs 18 M windows/s at d = 768).
+    if (window % 6 == 0 && idx->dim_pad >= 416)
+        idx->diag = 6;
+    else
+        idx->diag = window % 3 == 0 ? 3 : (window % 2 == 0 ? 2 : 1);
     idx->pair = 1;
 
 #define FS_TRY(expr)                    \
