@@ -8,12 +8,18 @@
 //                (search.py:182-226), leaving only string formatting to Python
 //
 // No GPU code here; everything is exposed through the same C ABI.
+#include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <atomic>
+#include <memory>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -58,17 +64,58 @@ struct fs_vocab {
 // ---------------------------------------------------------------------------------------
 // encoded batch of files
 // ---------------------------------------------------------------------------------------
+template <typename T>
+struct RawArray {  // uninitialised storage (no zero fill, no page touching before the writers)
+    std::unique_ptr<T[]> p;
+    size_t n = 0;
+    void alloc(size_t count) {
+        p.reset(new T[count > 0 ? count : 1]);
+        n = count;
+    }
+    T* data() { return p.get(); }
+    const T* data() const { return p.get(); }
+    size_t size() const { return n; }
+};
+
 struct fs_batch {
-    std::vector<char> text;           // all file bytes concatenated
+    RawArray<char> text;              // all file bytes concatenated
     std::vector<int64_t> file_off;    // [n_files+1] byte offsets into text
     std::vector<int64_t> tok_off;     // [n_files+1] CSR offsets (tokens)
-    std::vector<int32_t> tok;         // [T] row id, or -(1+u) for the u-th unique OOV string
-    std::vector<int64_t> tok_start;   // [T] byte offsets into text
-    std::vector<int64_t> tok_end;     // [T]
+    RawArray<int32_t> tok;            // [T] row id, or -(1+u) for the u-th unique OOV string
+    RawArray<int64_t> tok_start;      // [T] byte offsets into text
+    RawArray<int64_t> tok_end;        // [T]
     std::vector<int64_t> oov_start;   // [U] one representative span per unique OOV string
     std::vector<int64_t> oov_end;     // [U]
     std::vector<int32_t> file_status; // [n_files] 0 ok, 1 unreadable
 };
+
+namespace {
+
+template <typename F>
+void parallel_for(int64_t n, int n_threads, F&& body) {
+    std::atomic<int64_t> next(0);
+    auto work = [&]() {
+        int64_t k;
+        while ((k = next.fetch_add(1)) < n) body(k);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
+
+inline int64_t count_tokens(const char* text, int64_t len) {
+    int64_t n = 0;
+    bool in_tok = false;
+    for (int64_t i = 0; i < len; ++i) {
+        const bool ws = is_ws(static_cast<unsigned char>(text[i]));
+        n += (!ws && !in_tok);
+        in_tok = !ws;
+    }
+    return n;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -113,27 +160,22 @@ int32_t fs_vocab_lookup(const fs_vocab* v, const char* key, int64_t len) {
     return v->find(key, len);
 }
 
-static void encode_one(const fs_vocab* v, const char* text, int64_t len, int64_t base,
-                       std::vector<int32_t>& tok, std::vector<int64_t>& st, std::vector<int64_t>& en) {
-    int64_t i = 0;
-    while (i < len) {
-        while (i < len && is_ws(static_cast<unsigned char>(text[i]))) ++i;
-        if (i >= len) break;
-        const int64_t s = i;
-        while (i < len && !is_ws(static_cast<unsigned char>(text[i]))) ++i;
-        tok.push_back(v->find(text + s, i - s));  // -1 = OOV for now
-        st.push_back(base + s);
-        en.push_back(base + i);
-    }
-}
-
-// Read, tokenise and encode `n_files` files with `n_threads` threads.
+// Read, tokenise and encode `n_files` files with `n_threads` threads.  Two passes over the
+// text (count, then encode straight into the final arrays): no per-file vectors, no copies.
 fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int64_t n_files,
                                 int32_t n_threads) {
     if (!v || n_files < 0 || (n_files > 0 && !paths)) {
         fs::set_error("fs_batch_encode_files: invalid argument");
         return nullptr;
     }
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!getenv("FS_PROFILE_HOST")) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fs_batch_encode_files] %s %.1f ms\n", what,
+                std::chrono::duration<double, std::milli>(t - T0).count());
+        T0 = t;
+    };
     fs_batch* b = new fs_batch();
     b->file_off.assign(n_files + 1, 0);
     b->tok_off.assign(n_files + 1, 0);
@@ -141,86 +183,84 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
     if (n_threads < 1) n_threads = 1;
     if (n_threads > n_files) n_threads = static_cast<int32_t>(n_files > 0 ? n_files : 1);
 
-    // pass 1: read files (parallel)
-    std::vector<std::string> contents(n_files);
-    {
-        std::atomic<int64_t> next(0);
-        auto work = [&]() {
-            int64_t k;
-            while ((k = next.fetch_add(1)) < n_files) {
-                FILE* f = fopen(paths[k], "rb");
-                if (!f) {
-                    b->file_status[k] = 1;
-                    continue;
-                }
-                std::string& c = contents[k];
-                char buf[1 << 16];
-                size_t got;
-                while ((got = fread(buf, 1, sizeof(buf), f)) > 0) c.append(buf, got);
-                fclose(f);
-            }
-        };
-        std::vector<std::thread> th;
-        for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
-        work();
-        for (auto& t : th) t.join();
-    }
-    for (int64_t k = 0; k < n_files; ++k)
-        b->file_off[k + 1] = b->file_off[k] + static_cast<int64_t>(contents[k].size());
-    b->text.resize(static_cast<size_t>(b->file_off[n_files]));
-
-    // pass 2: tokenise + lookup (parallel), per-file vectors
-    std::vector<std::vector<int32_t>> ftok(n_files);
-    std::vector<std::vector<int64_t>> fst(n_files), fen(n_files);
-    {
-        std::atomic<int64_t> next(0);
-        auto work = [&]() {
-            int64_t k;
-            while ((k = next.fetch_add(1)) < n_files) {
-                const std::string& c = contents[k];
-                if (!c.empty()) memcpy(b->text.data() + b->file_off[k], c.data(), c.size());
-                ftok[k].reserve(c.size() / 5 + 8);
-                fst[k].reserve(c.size() / 5 + 8);
-                fen[k].reserve(c.size() / 5 + 8);
-                encode_one(v, c.data(), static_cast<int64_t>(c.size()), b->file_off[k], ftok[k], fst[k],
-                           fen[k]);
-            }
-        };
-        std::vector<std::thread> th;
-        for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
-        work();
-        for (auto& t : th) t.join();
-    }
-    for (int64_t k = 0; k < n_files; ++k)
-        b->tok_off[k + 1] = b->tok_off[k] + static_cast<int64_t>(ftok[k].size());
+    // sizes, then every file is read straight into its slot of the text buffer
+    std::vector<int64_t> sizes(n_files, 0);
+    parallel_for(n_files, n_threads, [&](int64_t k) {
+        struct stat st;
+        if (stat(paths[k], &st) != 0 || !S_ISREG(st.st_mode)) {
+            b->file_status[k] = 1;
+            return;
+        }
+        sizes[k] = static_cast<int64_t>(st.st_size);
+    });
+    for (int64_t k = 0; k < n_files; ++k) b->file_off[k + 1] = b->file_off[k] + sizes[k];
+    b->text.alloc(static_cast<size_t>(b->file_off[n_files]));
+    std::vector<int64_t> counts(n_files, 0);
+    parallel_for(n_files, n_threads, [&](int64_t k) {
+        if (b->file_status[k] || sizes[k] == 0) return;
+        const int fd = open(paths[k], O_RDONLY);
+        if (fd < 0) {
+            b->file_status[k] = 1;
+            return;
+        }
+        char* dst = b->text.data() + b->file_off[k];
+        int64_t got = 0;
+        while (got < sizes[k]) {
+            const ssize_t r = read(fd, dst + got, static_cast<size_t>(sizes[k] - got));
+            if (r <= 0) break;
+            got += r;
+        }
+        close(fd);
+        if (got != sizes[k])  // file changed under us: pad with spaces
+            memset(dst + got, ' ', static_cast<size_t>(sizes[k] - got));
+        counts[k] = count_tokens(dst, sizes[k]);
+    });
+    lap("read+count");
+    for (int64_t k = 0; k < n_files; ++k) b->tok_off[k + 1] = b->tok_off[k] + counts[k];
     const int64_t T = b->tok_off[n_files];
-    b->tok.resize(static_cast<size_t>(T));
-    b->tok_start.resize(static_cast<size_t>(T));
-    b->tok_end.resize(static_cast<size_t>(T));
-    for (int64_t k = 0; k < n_files; ++k) {
-        const size_t n = ftok[k].size();
-        if (!n) continue;
-        memcpy(b->tok.data() + b->tok_off[k], ftok[k].data(), n * sizeof(int32_t));
-        memcpy(b->tok_start.data() + b->tok_off[k], fst[k].data(), n * sizeof(int64_t));
-        memcpy(b->tok_end.data() + b->tok_off[k], fen[k].data(), n * sizeof(int64_t));
-    }
-    // pass 3 (serial, OOV tokens only): number the unique OOV strings in order of appearance
+    b->tok.alloc(static_cast<size_t>(T));
+    b->tok_start.alloc(static_cast<size_t>(T));
+    b->tok_end.alloc(static_cast<size_t>(T));
+    parallel_for(n_files, n_threads, [&](int64_t k) {
+        const char* text = b->text.data() + b->file_off[k];
+        const int64_t len = sizes[k], base = b->file_off[k];
+        int64_t o = b->tok_off[k];
+        int32_t* tok = b->tok.data();
+        int64_t* st = b->tok_start.data();
+        int64_t* en = b->tok_end.data();
+        int64_t i = 0;
+        while (i < len) {
+            while (i < len && is_ws(static_cast<unsigned char>(text[i]))) ++i;
+            if (i >= len) break;
+            const int64_t s = i;
+            while (i < len && !is_ws(static_cast<unsigned char>(text[i]))) ++i;
+            tok[o] = v->find(text + s, i - s);  // -1 = OOV for now
+            st[o] = base + s;
+            en[o] = base + i;
+            ++o;
+        }
+    });
+    lap("tokenise+lookup");
+    // serial pass over the OOV tokens only: number the unique strings in order of appearance
     std::unordered_map<std::string, int32_t> uniq;
+    const char* text = b->text.data();
     for (int64_t t = 0; t < T; ++t) {
-        if (b->tok[t] >= 0) continue;
-        std::string key(b->text.data() + b->tok_start[t], static_cast<size_t>(b->tok_end[t] - b->tok_start[t]));
+        if (b->tok.data()[t] >= 0) continue;
+        const int64_t s = b->tok_start.data()[t], e = b->tok_end.data()[t];
+        std::string key(text + s, static_cast<size_t>(e - s));
         auto it = uniq.find(key);
         int32_t u;
         if (it == uniq.end()) {
             u = static_cast<int32_t>(uniq.size());
             uniq.emplace(std::move(key), u);
-            b->oov_start.push_back(b->tok_start[t]);
-            b->oov_end.push_back(b->tok_end[t]);
+            b->oov_start.push_back(s);
+            b->oov_end.push_back(e);
         } else {
             u = it->second;
         }
-        b->tok[t] = -(1 + u);
+        b->tok.data()[t] = -(1 + u);
     }
+    lap("oov");
     return b;
 }
 

@@ -27,6 +27,7 @@ Environment knobs (the CLI itself is unchanged):
 """
 import csv
 import datetime
+import io
 import os
 import random
 import re
@@ -463,6 +464,18 @@ def write_records(records, filename):
         wr.writerows(records)
 
 
+def format_records(records):
+    """The exact text write_records would put in the file (rows end in \\r\\n)."""
+    buf = io.StringIO(newline='')
+    csv.writer(buf).writerows(records)
+    return buf.getvalue()
+
+
+def _write_text(text, filename):
+    with open(filename, 'w', encoding='utf-8', newline='') as out:
+        out.write(text)
+
+
 def analyze_scripts(args, scripts, window_size=6, number_of_hashes=15, hash_dimensions=14,
                     distance_threshold=0.1, chunk_size=500):
     """One pass over the fanwork folder for SEVERAL markup scripts (the
@@ -554,10 +567,11 @@ def analyze(args,
     my_records = {}
 
     def finish(i, prep, found):
+        # rows are formatted ONCE: the batch file and the aggregate share the same text
         record_sets = ann_index.records_prepared(prep, *found)
-        records = [r for r_set in record_sets for r in r_set]
-        write_records(records, batch_filename.format(i))
-        return i, records
+        text = format_records([r for r_set in record_sets for r in r_set])
+        _write_text(text, batch_filename.format(i))
+        return i, text
 
     with ThreadPoolExecutor(max_workers=1) as prep_pool, ThreadPoolExecutor(max_workers=1) as post_pool:
         pending = prep_pool.submit(ann_index.prepare, mine[0][1]) if mine else None
@@ -569,17 +583,17 @@ def analyze(args,
             found = ann_index.search_prepared(prep)
             finishing.append(post_pool.submit(finish, i, prep, found))
         for fut in finishing:
-            i, records = fut.result()
-            my_records[i] = records
+            i, text = fut.result()
+            my_records[i] = text
 
     if world > 1:
         from .parallel import gather_cluster_records
         my_records = gather_cluster_records(my_records, rank, world)
         if rank != 0:
             return
-    accumulated_records = [new_record_structure['fields']]
-    for i in sorted(my_records):
-        accumulated_records.extend(my_records[i])
+    # header row (search.py:367) + the rows of every cluster in cluster order (search.py:388)
+    aggregate = format_records([new_record_structure['fields']]) + ''.join(
+        my_records[i] for i in sorted(my_records))
 
     i = 0
     today_str = '-{:%Y%m%d}.csv'.format(datetime.date.today())
@@ -588,4 +602,4 @@ def analyze(args,
         i += 1
         today_str = '-{:%Y%m%d}-{}.csv'.format(datetime.date.today(), i)
         name_check = filename_base.format(today_str)
-    write_records(accumulated_records, name_check)
+    _write_text(aggregate, name_check)
