@@ -30,6 +30,7 @@ FS_OPT_GRID_LIMIT = 3
 FS_OPT_DIAG = 4
 FS_OPT_CTA_PAIR = 5
 FS_OPT_A_RESIDENT = 6
+FS_OPT_PACKED_SHUFFLE = 7
 
 FS_MATCH_EXACT = 1
 FS_MATCH_LSH_SHIFT = 8

@@ -88,6 +88,7 @@ struct DistParams {
     int32_t window;           // 6
     int32_t diag;             // E: epilogue adds E diagonal neighbours, MMAs do window/E shifts
     int32_t debug;            // timing experiments only: 1 = skip epilogue math, 2 = skip TMEM loads
+    int32_t pack;             // 1: fp16x2-packed epilogue shuffles (E = 3, 6)
     int32_t ares;             // 1: A-resident variant (pair mode, chunks <= kAResChunks)
     int32_t pair;             // 1: CTA-pair kernel (cta_group::2, M = 2 x 128 fan tiles)
     int32_t shifts_per_stage; // S: MMA shifts served by one smem stage (divides window/E)

@@ -28,6 +28,92 @@
 
 namespace fs {
 
+// ---------------------------------------------------------------------------------------------
+// Diagonal sum of one 32-column chunk, in place: on return r[x] (x < 32) holds
+//   out[lane][x] = sum_{d<E} acc[lane+d][x+d]
+// for lanes < 32-(E-1) (the other lanes' values are unused; their rows are finished from shared
+// memory).  r[0..39] holds acc[lane][c0 .. c0+39] on entry.  Row shifts are warp shuffles, the
+// scarce resource of this epilogue (~0.5 warp-shuffles/clk/SM measured): with kPack two
+// neighbouring partial sums travel as one fp16x2 word, halving the shuffles.  A shuffled partial
+// sum is then rounded to fp16 once: |error| <= 2^-11 * (sum of the magnitudes of the shuffled
+// terms) <= 2^-10 |f||s| in the worst case, which the pre-filter slack (kEpsPacked) covers --
+// the decision itself is always re-made in float64.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float h2_lo(uint32_t u) {
+    return __low2float(*reinterpret_cast<const __half2*>(&u));
+}
+__device__ __forceinline__ float h2_hi(uint32_t u) {
+    return __high2float(*reinterpret_cast<const __half2*>(&u));
+}
+
+template <int kDiag, bool kPack>
+__device__ __forceinline__ void diag_sum_inplace(uint32_t (&r)[40]) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    auto f = [&](int x) { return __uint_as_float(r[x]); };
+    if (kDiag == 1) return;
+    if (kDiag == 6) {
+        if (kPack) {
+            // stage 1: D2[x] = a[x] + a[x+1]@(lane+1) for x < 36
+#pragma unroll
+            for (int k = 0; k < 18; ++k) {
+                const uint32_t s1 = __shfl_down_sync(kFull, pack_h2(f(2 * k + 1), f(2 * k + 2)), 1);
+                r[2 * k] = __float_as_uint(f(2 * k) + h2_lo(s1));
+                r[2 * k + 1] = __float_as_uint(f(2 * k + 1) + h2_hi(s1));
+            }
+            // stage 2: out[x] = D2[x] + D2[x+2]@(lane+2) + D2[x+4]@(lane+4)
+            uint32_t t2[18], t4[18];
+#pragma unroll
+            for (int k = 1; k < 18; ++k) {
+                const uint32_t q = pack_h2(f(2 * k), f(2 * k + 1));
+                if (k <= 16) t2[k] = __shfl_down_sync(kFull, q, 2);
+                if (k >= 2) t4[k] = __shfl_down_sync(kFull, q, 4);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                r[2 * k] = __float_as_uint(f(2 * k) + h2_lo(t2[k + 1]) + h2_lo(t4[k + 2]));
+                r[2 * k + 1] = __float_as_uint(f(2 * k + 1) + h2_hi(t2[k + 1]) + h2_hi(t4[k + 2]));
+            }
+        } else {
+#pragma unroll
+            for (int x = 0; x < 36; ++x)
+                r[x] = __float_as_uint(f(x) + __shfl_down_sync(kFull, f(x + 1), 1));
+#pragma unroll
+            for (int x = 0; x < 32; ++x)
+                r[x] = __float_as_uint(f(x) + __shfl_down_sync(kFull, f(x + 2), 2) +
+                                       __shfl_down_sync(kFull, f(x + 4), 4));
+        }
+        return;
+    }
+    if (kDiag == 3 && kPack) {
+        uint32_t s1[16], s2[17];
+#pragma unroll
+        for (int k = 0; k < 17; ++k) {
+            const uint32_t q = pack_h2(f(2 * k + 1), f(2 * k + 2));
+            if (k < 16) s1[k] = __shfl_down_sync(kFull, q, 1);
+            s2[k] = __shfl_down_sync(kFull, q, 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            // out[2k]   = a[2k]   + a[2k+1]@+1 + a[2k+2]@+2 ; out[2k+1] = a[2k+1] + a[2k+2]@+1 + a[2k+3]@+2
+            r[2 * k] = __float_as_uint(f(2 * k) + h2_lo(s1[k]) + h2_hi(s2[k]));
+            r[2 * k + 1] = __float_as_uint(f(2 * k + 1) + h2_hi(s1[k]) + h2_lo(s2[k + 1]));
+        }
+        return;
+    }
+    // generic: E-1 full-precision shuffles per output
+#pragma unroll
+    for (int x = 0; x < 32; ++x) {
+        float acc = f(x);
+#pragma unroll
+        for (int d = 1; d < kDiag; ++d) acc += __shfl_down_sync(kFull, f(x + d), d);
+        r[x] = __float_as_uint(acc);
+    }
+}
+
 // kDiag = E: the MMAs accumulate only the shifts {0, E, 2E, ...} (w/E of them) and the epilogue
 // adds E diagonal neighbours, out[i][j] = sum_{d<E} acc[i+d][j+d].  E = 1 is the plain dense
 // contraction.  E > 1 re-uses every partial sum for E windows (w/E times fewer tensor-core
@@ -45,7 +131,7 @@ namespace fs {
 // sweeps the script tiles, so only the script half-tile streams (87 instead of 174 KB per
 // tile).  With E >= 3 the L2 -> SM traffic (~6 TB/s chip-wide), not the tensor pipe, is the
 // wall otherwise.
-template <int kDiag, bool kDump, bool kPair, bool kARes>
+template <int kDiag, bool kDump, bool kPair, bool kARes, bool kPack>
 __global__ void __launch_bounds__(kDistThreads, 1)
 distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 const __grid_constant__ CUtensorMap map_script, const DistParams p) {
@@ -336,50 +422,27 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     for (int q = 0; q < 10; ++q)
                         dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
                 }
-                if (kDiag == 6) {
-                    // pairwise pre-sum in place: r[x] <- acc[i][x] + acc[i+1][x+1]; the six-term
-                    // diagonal sum is then three shuffled pair sums (3.1 instead of 5 shuffles
-                    // per output)
-#pragma unroll
-                    for (int x = 0; x < 36; ++x)
-                        r[x] = __float_as_uint(__uint_as_float(r[x]) +
-                                               __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + 1]), 1));
-                }
-                auto out_at = [&](int x) {
-                    float acc = __uint_as_float(r[x]);
-                    if (kDiag == 6) {
-                        acc += __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + 2]), 2);
-                        acc += __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + 4]), 4);
-                    } else {
-#pragma unroll
-                        for (int d = 1; d < kDiag; ++d)
-                            acc += __shfl_down_sync(0xffffffffu, __uint_as_float(r[x + d]), d);
-                    }
-                    return acc;
-                };
+                diag_sum_inplace<kDiag, kPack>(r);  // r[x] <- out[lane][c0 + x]
                 const int32_t gj0 = n0 + c0;
                 if (kDump) {
 #pragma unroll
                     for (int x = 0; x < 32; ++x) {
-                        const float v = out_at(x);
                         if (row_ok && (kDiag == 1 || lane < kTail0) && gi < p.n_fan_tok &&
                             c0 + x < kNStep && gj0 + x < p.dump_ld)
-                            p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + x] = v;
+                            p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + x] = __uint_as_float(r[x]);
                     }
                 } else {
                     // one max over the chunk against thr * (smallest norm of the chunk) rejects
                     // the chunk; the exact per-element test runs only on the rare survivor
                     float mx = -INFINITY;
 #pragma unroll
-                    for (int x = 0; x < 32; ++x) mx = fmaxf(mx, out_at(x));
+                    for (int x = 0; x < 32; ++x) mx = fmaxf(mx, __uint_as_float(r[x]));
                     const float nmin = __ldg(p.norm_min32 + gj0);
-                    // warp-uniform branch: out_at() shuffles need every lane
-                    if (__any_sync(0xffffffffu, mx > thr_main * nmin)) {
+                    if (mx > thr_main * nmin) {
 #pragma unroll
                         for (int x = 0; x < 32; ++x) {
-                            const float v = out_at(x);
                             const float nsv = (c0 + x < kNStep) ? __ldg(p.norm_script + gj0 + x) : INFINITY;
-                            if (v > thr_main * nsv) {
+                            if (__uint_as_float(r[x]) > thr_main * nsv) {
                                 const unsigned long long slot =
                                     atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                                 if (slot < static_cast<unsigned long long>(p.cand_cap)) {
@@ -499,15 +562,15 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
     return FS_OK;
 }
 
-template <int kDiag, bool kPair, bool kARes = false>
+template <int kDiag, bool kPair, bool kARes, bool kPack>
 static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_script,
                              const DistParams& p, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair, kARes>,
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair, kARes, kPack>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            dist_smem_bytes(kDiag, kPair, kARes)));
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair, kARes>,
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair, kARes, kPack>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            dist_smem_bytes(kDiag, kPair, kARes)));
         attr_set = true;
@@ -525,9 +588,9 @@ static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (p.dump)
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair, kARes>, map_fan, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair, kARes, kPack>, map_fan, map_script, p));
     else
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair, kARes>, map_fan, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair, kARes, kPack>, map_fan, map_script, p));
     return FS_OK;
 }
 
@@ -543,29 +606,39 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
     } else {
         grid = static_cast<int>(total < grid_limit ? total : grid_limit);
     }
-    if (p.pair && p.ares && p.chunks <= kAResChunks) {
-        switch (p.diag) {
-            case 1: return launch_distance_t<1, true, true>(map_fan, map_script, p, grid, stream);
-            case 2: return launch_distance_t<2, true, true>(map_fan, map_script, p, grid, stream);
-            case 3: return launch_distance_t<3, true, true>(map_fan, map_script, p, grid, stream);
-            case 6: return launch_distance_t<6, true, true>(map_fan, map_script, p, grid, stream);
-            default: break;
-        }
-    }
-    const int key = p.diag * 2 + (p.pair ? 1 : 0);
-    switch (key) {
-        case 2: return launch_distance_t<1, false>(map_fan, map_script, p, grid, stream);
-        case 3: return launch_distance_t<1, true>(map_fan, map_script, p, grid, stream);
-        case 4: return launch_distance_t<2, false>(map_fan, map_script, p, grid, stream);
-        case 5: return launch_distance_t<2, true>(map_fan, map_script, p, grid, stream);
-        case 6: return launch_distance_t<3, false>(map_fan, map_script, p, grid, stream);
-        case 7: return launch_distance_t<3, true>(map_fan, map_script, p, grid, stream);
-        case 12: return launch_distance_t<6, false>(map_fan, map_script, p, grid, stream);
-        case 13: return launch_distance_t<6, true>(map_fan, map_script, p, grid, stream);
+    const bool ares = p.pair && p.ares && p.chunks <= kAResChunks;
+    const bool pack = p.pack && (p.diag == 3 || p.diag == 6);
+#define FS_LAUNCH(E, PAIR, ARES, PACK) \
+    return launch_distance_t<E, PAIR, ARES, PACK>(map_fan, map_script, p, grid, stream)
+#define FS_LAUNCH_PACK(E, PAIR, ARES) \
+    do {                              \
+        if (pack) FS_LAUNCH(E, PAIR, ARES, true); \
+        FS_LAUNCH(E, PAIR, ARES, false);          \
+    } while (0)
+#define FS_LAUNCH_MODE(E)                          \
+    do {                                           \
+        if (ares) FS_LAUNCH_PACK(E, true, true);   \
+        if (p.pair) FS_LAUNCH_PACK(E, true, false); \
+        FS_LAUNCH_PACK(E, false, false);           \
+    } while (0)
+    switch (p.diag) {
+        case 1:
+            if (ares) FS_LAUNCH(1, true, true, false);
+            if (p.pair) FS_LAUNCH(1, true, false, false);
+            FS_LAUNCH(1, false, false, false);
+        case 2:
+            if (ares) FS_LAUNCH(2, true, true, false);
+            if (p.pair) FS_LAUNCH(2, true, false, false);
+            FS_LAUNCH(2, false, false, false);
+        case 3: FS_LAUNCH_MODE(3);
+        case 6: FS_LAUNCH_MODE(6);
         default:
             set_error("unsupported diagonal factor %d", p.diag);
             return FS_E_INVALID;
     }
+#undef FS_LAUNCH
+#undef FS_LAUNCH_PACK
+#undef FS_LAUNCH_MODE
 }
 
 }  // namespace fs

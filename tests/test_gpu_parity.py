@@ -133,7 +133,7 @@ def test_gather_is_bit_exact_and_norms_match():
             valid[i] = True
             wantn[i] = np.sqrt(sq[i:i + 6].sum())
     assert np.all(np.isinf(thr[~valid])) and np.all(np.isfinite(thr[valid]))
-    coef = 1.0 - 0.1 - 2.0e-3
+    coef = 1.0 - 0.1 - 3.0e-3
     np.testing.assert_allclose(thr[valid], coef * wantn[valid], rtol=2e-6)
     assert idx.diag == 3 and idx.cta_pair == 1      # defaults for 6-gram windows
     idx.close()
@@ -187,7 +187,7 @@ def test_candidates_are_a_superset_within_slack(diag, pair):
     must = set(zip(fpos[ii].tolist(), ref.spos[jj].tolist()))
     assert must <= got
     for a, b in got:                      # nothing far from the threshold gets through
-        assert d[row_of[a], col_of[b]] < 0.1 + 2 * 2.0e-3
+        assert d[row_of[a], col_of[b]] < 0.1 + 2 * 3.0e-3
     idx.close()
 
 
