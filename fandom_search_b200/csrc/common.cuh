@@ -207,11 +207,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in HW, do not spin
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
