@@ -377,7 +377,7 @@ def run_native_arm(args):
                        "windows_per_step_per_gpu": step_windows // max(args.steps, 1),
                        "parallelism": "work-sharded x%d, script index replicated" % world,
                        "l2": "inputs larger than L2 (1.6 GB fp16 token matrix per step)",
-                       "precision": "fp16 tcgen05 pre-filter (fp32 accumulate, slack 2e-3) + float64 rescoring",
+                       "precision": "fp16 tcgen05 pre-filter (fp32 accumulate, slack 3e-3) + float64 rescoring",
                        "kernel": "diagonal factor E=%d, cta_group::%d" % (diag, 2 if index.cta_pair else 1)},
             "clocks": clocks,
             "e2e": {"value": total_windows / (e2e_ms * 1e-3), "unit": UNIT,
