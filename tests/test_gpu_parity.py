@@ -110,6 +110,22 @@ def test_other_window_sizes(window):
     idx.close()
 
 
+@pytest.mark.parametrize("diag", [3, 6])
+def test_unpacked_shuffles_give_the_same_matches(diag):
+    """FS_OPT_PACKED_SHUFFLE=0 (full fp32 row shuffles) and the default fp16x2-packed shuffles
+    must end in the same float64-decided match set."""
+    table, sx, fx, script, tok, off = _case(31)
+    ref = NumpyIndex(table, script, extra=sx)
+    want, _ = ref.search_host(tok, off, fx)
+    for pack in (0, 1):
+        idx = _device_index(table, script, extra=sx)
+        idx.set_option(nt.FS_OPT_DIAG, diag)
+        idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
+        got, _ = idx.search_host(tok, off, fx)
+        assert _pairs(got) == _pairs(want)
+        idx.close()
+
+
 def test_gather_is_bit_exact_and_norms_match():
     import torch
     table, sx, fx, script, tok, off = _case(5)
