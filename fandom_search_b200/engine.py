@@ -54,9 +54,13 @@ class DeviceIndex:
         self.n_script_windows = int(lib.fs_index_get_info(h, 0))
         self.sm_count = int(lib.fs_index_get_info(h, 2))
         self.scale = float(lib.fs_index_scale(h))
-        diag = os.environ.get("FANDOM_SEARCH_DIAG")
-        if diag:
-            self.set_option(nt.FS_OPT_DIAG, int(diag))
+        # experiment knobs (the defaults are chosen by the library, see csrc/api.cu)
+        for env, opt in (("FANDOM_SEARCH_DIAG", nt.FS_OPT_DIAG), ("FANDOM_SEARCH_CTA_PAIR", nt.FS_OPT_CTA_PAIR),
+                         ("FANDOM_SEARCH_A_RESIDENT", nt.FS_OPT_A_RESIDENT),
+                         ("FANDOM_SEARCH_PACKED_SHUFFLE", nt.FS_OPT_PACKED_SHUFFLE)):
+            v = os.environ.get(env)
+            if v not in (None, ""):
+                self.set_option(opt, int(v))
 
     # -- lifetime ---------------------------------------------------------
     def close(self):
