@@ -93,7 +93,8 @@ enum {
     FS_OPT_GRID_LIMIT = 3,       /* max CTAs of the persistent distance kernel (0 = #SMs)  */
     FS_OPT_CTA_PAIR = 5,         /* 1: two CTAs of a cluster share one tcgen05.mma.cta_group::2
                                     (M = 2 x 128 fan windows, each CTA stages half the script tile) */
-    FS_OPT_PACKED_SHUFFLE = 7,   /* 1 (default): epilogue row shifts of E = 3, 6 move fp16x2 pairs */
+    FS_OPT_PACKED_SHUFFLE = 7,   /* 0: fp32 epilogue shuffles; 1: row shifts of E = 3, 6 move fp16x2
+                                    pairs; 2: E = 6 sums the diagonal entirely in fp16x2 arithmetic */
     FS_OPT_A_RESIDENT = 6,       /* 1: (CTA pairs, dim <= 320) the fan tile stays resident in shared
                                     memory while the script tiles stream                         */
     FS_OPT_DIAG = 4              /* 1 (dense), 2, 3 or 6: the tensor cores accumulate window/E shifts

@@ -117,7 +117,7 @@ def test_unpacked_shuffles_give_the_same_matches(diag):
     table, sx, fx, script, tok, off = _case(31)
     ref = NumpyIndex(table, script, extra=sx)
     want, _ = ref.search_host(tok, off, fx)
-    for pack in (0, 1):
+    for pack in (0, 1, 2):
         idx = _device_index(table, script, extra=sx)
         idx.set_option(nt.FS_OPT_DIAG, diag)
         idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
@@ -149,7 +149,7 @@ def test_gather_is_bit_exact_and_norms_match():
             valid[i] = True
             wantn[i] = np.sqrt(sq[i:i + 6].sum())
     assert np.all(np.isinf(thr[~valid])) and np.all(np.isfinite(thr[valid]))
-    coef = 1.0 - 0.1 - 3.0e-3
+    coef = 1.0 - 0.1 - 4.0e-3
     np.testing.assert_allclose(thr[valid], coef * wantn[valid], rtol=2e-6)
     assert idx.diag == 3 and idx.cta_pair == 1      # defaults for 6-gram windows
     idx.close()
@@ -175,13 +175,57 @@ def test_tensor_core_dots_match_fp16_contraction(diag, shifts, pair):
     es[:len(script)] = e16[script]
     g = ef.astype(np.float64) @ es.astype(np.float64).T
     want = sum(g[k:k + len(tok), k:k + len(script)] for k in range(6))
-    # fp32 accumulation of 1800 fp16 products: tolerance 1e-3 of the largest magnitude
-    assert np.abs(dots - want).max() <= 1e-3 * np.abs(want).max()
+    # fp32 accumulation of 1800 fp16 products (+ fp16-packed shuffles for E = 3, 6): tolerance
+    # 2e-3 of the largest magnitude
+    assert np.abs(dots - want).max() <= 2e-3 * np.abs(want).max()
     idx.close()
 
 
 @pytest.mark.parametrize("pair", [0, 1, 2])
 @pytest.mark.parametrize("diag", [1, 2, 3, 6])
+def test_half_precision_epilogue_dots(pair=2):
+    """E = 6 with the diagonal summed in fp16x2 arithmetic (pack level 2): looser tolerance,
+    bounded by 2^-9 * sum of the six partial-dot magnitudes."""
+    import torch
+    table, sx, fx, script, tok, off = _case(6, plant=False, clustered=False)
+    for pair in (0, 1, 2):
+        idx = _device_index(table, script, extra=sx)
+        idx.set_option(nt.FS_OPT_DIAG, 6)
+        idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, 2)
+        idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
+        idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
+        tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+        dots = idx.stage_dots(tok_t, off_t, fx_t).cpu().numpy()
+        allrows = np.concatenate([table, sx, fx], axis=0)
+        e16 = (allrows * np.float32(idx.scale)).astype(np.float16).astype(np.float64)
+        ef = np.zeros((len(tok) + 6, table.shape[1])); ef[:len(tok)] = e16[tok]
+        es = np.zeros((len(script) + 6, table.shape[1])); es[:len(script)] = e16[script]
+        g = ef @ es.T
+        parts = [g[k:k + len(tok), k:k + len(script)] for k in range(6)]
+        want = sum(parts)
+        bound = 2.0 ** -9 * sum(np.abs(q) for q in parts) + 1e-4 * np.abs(want).max()
+        # rows whose window leaves the tile grid are not dumped (zeros): compare where dumped
+        mask = dots != 0
+        assert mask.mean() > 0.9 and np.all(np.abs(dots - want)[mask] <= bound[mask])
+        idx.close()
+
+
+@pytest.mark.parametrize("pack", [1, 2])
+def test_half_precision_epilogue_search(pack):
+    for seed, dim in ((1, 300), (2, 64), (4, 100)):
+        table, sx, fx, script, tok, off = _case(seed, dim=dim)
+        want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
+        for pair in (0, 1, 2):
+            idx = _device_index(table, script, extra=sx)
+            idx.set_option(nt.FS_OPT_DIAG, 6)
+            idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
+            idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
+            idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
+            got, _ = idx.search_host(tok, off, fx)
+            assert _pairs(got) == _pairs(want)
+            idx.close()
+
+
 def test_candidates_are_a_superset_within_slack(diag, pair):
     import torch
     table, sx, fx, script, tok, off = _case(7)
@@ -203,7 +247,7 @@ def test_candidates_are_a_superset_within_slack(diag, pair):
     must = set(zip(fpos[ii].tolist(), ref.spos[jj].tolist()))
     assert must <= got
     for a, b in got:                      # nothing far from the threshold gets through
-        assert d[row_of[a], col_of[b]] < 0.1 + 2 * 3.0e-3
+        assert d[row_of[a], col_of[b]] < 0.1 + 2 * 4.0e-3
     idx.close()
 
 

@@ -18,7 +18,7 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, debug=0):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, debug=0, pack=None):
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
@@ -27,6 +27,8 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
     if debug:
         idx.set_option(99, debug)
+    if pack is not None:
+        idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
     n_works = max(1, nf // works_len)
     lens = np.full(n_works, (nf + 5 * n_works) // n_works + 1, dtype=np.int64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
@@ -46,7 +48,7 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     ms, n = idx.timing_read()
     windows = int(cnt_t.cpu()[nt.FS_CNT_WINDOWS])
     per = ms / n * 1e-3
-    res = {"diag": diag, "pair": pair, "debug": debug, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
+    res = {"diag": diag, "pair": pair, "debug": debug, "pack": pack, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
            "kernel_ms": ms / n, "windows_per_s": windows / per,
            "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
            "tflops_executed": 2.0 * (6 // diag) * idx.dim_pad * idx.n_script_windows * windows / per / 1e12
@@ -63,6 +65,7 @@ def main():
     ap.add_argument("--diag", action="store_true", help="compare the diagonal-sum factors at C2 size")
     ap.add_argument("--one", type=int, nargs=4, metavar=("DIAG", "NF", "NS", "D"), help="run a single case")
     ap.add_argument("--pair", type=int, default=0)
+    ap.add_argument("--pack", type=int, default=None)
     ap.add_argument("--debug-exp", action="store_true", help="epilogue timing experiments (invalid results)")
     args = ap.parse_args()
     rng = np.random.default_rng(0)
@@ -73,7 +76,7 @@ def main():
         return
     if args.one:
         diag, nf, ns, d = args.one
-        print(json.dumps(run_case(nf, ns, d, 2, rng, diag=diag, pair=args.pair)), flush=True)
+        print(json.dumps(run_case(nf, ns, d, 2, rng, diag=diag, pair=args.pair, pack=args.pack)), flush=True)
         return
     if args.diag:
         for pair in (1, 2):
