@@ -219,6 +219,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Whole-warp wait with ONE polling lane (18 warps x 32 lanes spinning on try_wait is needless
+// pressure on the barrier unit): one lane polls (optionally backing off), the warp re-converges,
+// and every lane then performs one try_wait that succeeds immediately (its own acquire).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, uint32_t backoff_ns) {
+    if ((threadIdx.x & 31) == 0) {
+        while (!mbar_try_wait(bar, parity)) {
+            if (backoff_ns) __nanosleep(backoff_ns);
+        }
+    }
+    __syncwarp();
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
 
 // one elected lane of a converged warp (the same lane every time: lowest active)
 __device__ __forceinline__ bool elect_one() {

@@ -258,7 +258,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             const int32_t n0 = tile_n0(t);
             if (kARes && (t == tile_begin || t % p.tiles_n == 0)) {
                 // new fan tile: wait until every MMA that read the previous one has retired
-                mbar_wait(aempty_bar, a_phase ^ 1u);
+                mbar_wait_warp(aempty_bar, a_phase ^ 1u, 64);
                 if (elect_one()) {
                     if (leader) mbar_expect_tx(afull_bar, 2 * p.chunks * kStageABytes);
                     for (int c = 0; c < p.chunks; ++c)
@@ -271,7 +271,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             for (int c = 0; c < p.chunks; ++c) {
                 for (int g = 0; g < shift_groups; ++g) {
                     const int32_t s0 = g * S * kDiag;  // first token-row shift of this stage
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_wait_warp(empty_bar(stage), phase ^ 1u, 32);
                     const uint32_t a_dst = smem_base + stage * kStageSz;
                     const uint32_t b_dst = kARes ? a_dst : a_dst + kStageABytes;
                     if (elect_one()) {
@@ -312,10 +312,10 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         uint32_t a_phase = 0;
         for (int64_t t = tile_begin; t < tile_end; ++t) {
             if (kARes && (t == tile_begin || t % p.tiles_n == 0)) {
-                mbar_wait(afull_bar, a_phase);  // the resident fan tile has landed (both CTAs)
+                mbar_wait_warp(afull_bar, a_phase, 0);  // the resident fan tile has landed (both CTAs)
                 a_phase ^= 1u;
             }
-            mbar_wait(tempty_bar(as), aphase ^ 1u);
+            mbar_wait_warp(tempty_bar(as), aphase ^ 1u, 0);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
             uint32_t accumulate = 0;
@@ -324,7 +324,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 // 16, not 64): its trailing K-steps are all-zero TMA fill and are skipped
                 const int ksteps = (c == p.chunks - 1) ? p.last_chunk_ksteps : kChunkK / kUmmaK;
                 for (int g = 0; g < shift_groups; ++g) {
-                    mbar_wait(full_bar(stage), phase);
+                    mbar_wait_warp(full_bar(stage), phase, 0);
                     tc_fence_after();
                     const uint32_t st_src = smem_base + stage * kStageSz;
                     // resident mode: the fan chunk sits in the resident tile and the stage holds
@@ -418,7 +418,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             float* ns_tile = norm_tile + as * kHaloCols;
             if (kDiag > 1 && epi_tid < kHaloCols)
                 ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.norm_script + n0 + epi_tid) : INFINITY;
-            mbar_wait(tfull_bar(as), aphase);
+            mbar_wait_warp(tfull_bar(as), aphase, 0);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(as * kBlockN + group * kEpiCols);

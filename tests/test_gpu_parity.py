@@ -181,9 +181,7 @@ def test_tensor_core_dots_match_fp16_contraction(diag, shifts, pair):
     idx.close()
 
 
-@pytest.mark.parametrize("pair", [0, 1, 2])
-@pytest.mark.parametrize("diag", [1, 2, 3, 6])
-def test_half_precision_epilogue_dots(pair=2):
+def test_half_precision_epilogue_dots():
     """E = 6 with the diagonal summed in fp16x2 arithmetic (pack level 2): looser tolerance,
     bounded by 2^-9 * sum of the six partial-dot magnitudes."""
     import torch
@@ -226,6 +224,8 @@ def test_half_precision_epilogue_search(pack):
             idx.close()
 
 
+@pytest.mark.parametrize("pair", [0, 1, 2])
+@pytest.mark.parametrize("diag", [1, 2, 3, 6])
 def test_candidates_are_a_superset_within_slack(diag, pair):
     import torch
     table, sx, fx, script, tok, off = _case(7)

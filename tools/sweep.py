@@ -70,9 +70,10 @@ def main():
     args = ap.parse_args()
     rng = np.random.default_rng(0)
     if args.debug_exp:
-        for diag in (3, 6):
+        for diag, pair, pack in ((6, 2, 2), (6, 1, 2), (3, 2, 1)):
             for debug in (0, 1, 2, 3):
-                print(json.dumps(run_case(2_500_000, 25000, 300, 3, rng, diag=diag, pair=1, debug=debug)), flush=True)
+                print(json.dumps(run_case(2_500_000, 25000, 300, 3, rng, diag=diag, pair=pair, debug=debug,
+                                          pack=pack)), flush=True)
         return
     if args.one:
         diag, nf, ns, d = args.one
