@@ -77,6 +77,11 @@ SIGNATURES = {
     "fs_batch_destroy": (None, [_vp]),
     "fs_batch_info": (_i64, [_vp, _i32]),
     "fs_batch_array": (_vp, [_vp, _i32]),
+    "fs_records_format_csv": (_i64, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_char_p, _vp, _vp, _vp, _vp,
+                                     _vp, ctypes.c_char_p, _vp, _vp, ctypes.c_char_p, _vp, _vp, _vp, _vp, _i64,
+                                     ctypes.POINTER(_vp)]),
+    "fs_free": (None, [_vp]),
+    "fs_format_py_float": (_i64, [_f64, ctypes.c_char_p, _i64]),
     "fs_records_best": (_i64, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64,
                                _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
 }

@@ -17,8 +17,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <atomic>
+#include <charconv>
 #include <memory>
 #include <string>
 #include <thread>
@@ -392,6 +394,200 @@ int64_t fs_records_best(const fs_match* matches, const int32_t* tie, int64_t n, 
         out_lev[i] = bb.lev;
     }
     return rows;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// CSV text of the winning records (search.py:206-217 rows through csv.writer, search.py:331-334)
+// ---------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// repr(float) of CPython ("short" float repr: shortest round-trip digits; exponent form iff
+// decpt <= -4 or decpt > 16; exponent with sign and at least two digits)
+void append_py_float(std::string& out, double x) {
+    if (x != x) {
+        out += "nan";
+        return;
+    }
+    if (x == 1.0 / 0.0 || x == -1.0 / 0.0) {
+        out += x > 0 ? "inf" : "-inf";
+        return;
+    }
+    if (x == 0.0) {
+        out += std::signbit(x) ? "-0.0" : "0.0";
+        return;
+    }
+    char buf[64];
+    auto res = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);
+    const char* p = buf;
+    const char* end = res.ptr;
+    if (*p == '-') {
+        out.push_back('-');
+        ++p;
+    }
+    char digits[32];
+    int nd = 0;
+    while (p < end && *p != 'e') {
+        if (*p != '.') digits[nd++] = *p;
+        ++p;
+    }
+    int exp10 = 0;
+    if (p < end && *p == 'e') {
+        ++p;
+        bool neg = false;
+        if (*p == '+' || *p == '-') neg = *p++ == '-';
+        while (p < end) exp10 = exp10 * 10 + (*p++ - '0');
+        if (neg) exp10 = -exp10;
+    }
+    const int decpt = exp10 + 1;
+    if (decpt <= -4 || decpt > 16) {
+        out.push_back(digits[0]);
+        if (nd > 1) {
+            out.push_back('.');
+            out.append(digits + 1, static_cast<size_t>(nd - 1));
+        }
+        out.push_back('e');
+        const int e = decpt - 1;
+        out.push_back(e < 0 ? '-' : '+');
+        char eb[8];
+        const int ae = e < 0 ? -e : e;
+        auto r2 = std::to_chars(eb, eb + sizeof(eb), ae);
+        if (r2.ptr - eb < 2) out.push_back('0');
+        out.append(eb, static_cast<size_t>(r2.ptr - eb));
+    } else if (decpt <= 0) {
+        out += "0.";
+        out.append(static_cast<size_t>(-decpt), '0');
+        out.append(digits, static_cast<size_t>(nd));
+    } else if (decpt >= nd) {
+        out.append(digits, static_cast<size_t>(nd));
+        out.append(static_cast<size_t>(decpt - nd), '0');
+        out += ".0";
+    } else {
+        out.append(digits, static_cast<size_t>(decpt));
+        out.push_back('.');
+        out.append(digits + decpt, static_cast<size_t>(nd - decpt));
+    }
+}
+
+template <typename I>
+void append_int(std::string& out, I v) {
+    char buf[32];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v);
+    out.append(buf, static_cast<size_t>(r.ptr - buf));
+}
+
+// csv.writer, excel dialect, QUOTE_MINIMAL: quote a field that contains the delimiter, the quote
+// character or a line-terminator character; double embedded quotes
+void append_csv_field(std::string& out, const char* s, size_t n) {
+    bool quote = false;
+    for (size_t i = 0; i < n; ++i) {
+        const char c = s[i];
+        if (c == ',' || c == '"' || c == '\r' || c == '\n') {
+            quote = true;
+            break;
+        }
+    }
+    if (!quote) {
+        out.append(s, n);
+        return;
+    }
+    out.push_back('"');
+    for (size_t i = 0; i < n; ++i) {
+        if (s[i] == '"') out.push_back('"');
+        out.push_back(s[i]);
+    }
+    out.push_back('"');
+}
+
+}  // namespace
+
+extern "C" {
+
+// Formats `rows` winning records (arrays as returned by fs_records_best) as CSV text.
+//   names_blob/names_off [n_works+1]     FAN_WORK_FILENAME per work
+//   text/tok_start/tok_end/tok_off       fan tokens (as in fs_batch)
+//   script_blob/script_word_off          ORIGINAL_SCRIPT_WORD (lower-cased), global word index
+//   script_orth [n_script_words] u64     ORIGINAL_SCRIPT_ORTH_ID
+//   char_blob/char_off [n_script_words+1], char_none [n_script_words] u8 (1 = None -> empty field)
+//   scene [n_script_words] i64, scene_none [n_script_words] u8
+//   word_base                            first global word index of the script (ORIGINAL_SCRIPT_WORD_INDEX
+//                                        is local to its script)
+// Returns a malloc'ed buffer in *out_text (free with fs_free) and its length, or a negative status.
+int64_t fs_records_format_csv(int64_t rows, const int32_t* work, const int32_t* word,
+                              const int32_t* window_ix, const int32_t* match_ix, const double* distance,
+                              const int32_t* lev, const char* names_blob, const int64_t* names_off,
+                              const char* text, const int64_t* tok_start, const int64_t* tok_end,
+                              const int64_t* tok_off, const char* script_blob,
+                              const int64_t* script_word_off, const uint64_t* script_orth,
+                              const char* char_blob, const int64_t* char_off, const uint8_t* char_none,
+                              const int64_t* scene, const uint8_t* scene_none, int64_t word_base,
+                              char** out_text) {
+    if (rows < 0 || !out_text || (rows > 0 && (!work || !word || !window_ix || !match_ix || !distance ||
+                                               !lev || !names_blob || !names_off || !text || !tok_start ||
+                                               !tok_end || !tok_off || !script_blob || !script_word_off ||
+                                               !script_orth || !char_off || !char_none || !scene ||
+                                               !scene_none))) {
+        fs::set_error("fs_records_format_csv: invalid argument");
+        return FS_E_INVALID;
+    }
+    std::string out;
+    out.reserve(static_cast<size_t>(rows) * 160 + 16);
+    for (int64_t i = 0; i < rows; ++i) {
+        const int32_t w = work[i];
+        const int64_t tpos = tok_off[w] + word[i];
+        const int64_t g = static_cast<int64_t>(match_ix[i]) + window_ix[i];  // global script word
+        append_csv_field(out, names_blob + names_off[w], static_cast<size_t>(names_off[w + 1] - names_off[w]));
+        out.push_back(',');
+        append_int(out, word[i]);
+        out.push_back(',');
+        const char* fw = text + tok_start[tpos];
+        const size_t fn = static_cast<size_t>(tok_end[tpos] - tok_start[tpos]);
+        append_csv_field(out, fw, fn);
+        out.push_back(',');
+        append_int(out, fs_murmurhash64a(fw, static_cast<int64_t>(fn), 1));
+        out.push_back(',');
+        append_int(out, g - word_base);
+        out.push_back(',');
+        append_csv_field(out, script_blob + script_word_off[g],
+                         static_cast<size_t>(script_word_off[g + 1] - script_word_off[g]));
+        out.push_back(',');
+        append_int(out, script_orth[g]);
+        out.push_back(',');
+        if (!char_none[g])
+            append_csv_field(out, char_blob + char_off[g], static_cast<size_t>(char_off[g + 1] - char_off[g]));
+        out.push_back(',');
+        if (!scene_none[g]) append_int(out, scene[g]);
+        out.push_back(',');
+        append_py_float(out, distance[i]);
+        out.push_back(',');
+        append_int(out, lev[i]);
+        out.push_back(',');
+        append_py_float(out, distance[i] * static_cast<double>(lev[i]));
+        out += "\r\n";
+    }
+    char* buf = static_cast<char*>(malloc(out.size() + 1));
+    if (!buf) {
+        fs::set_error("fs_records_format_csv: out of memory");
+        return FS_E_NOMEM;
+    }
+    memcpy(buf, out.data(), out.size());
+    buf[out.size()] = 0;
+    *out_text = buf;
+    return static_cast<int64_t>(out.size());
+}
+
+void fs_free(void* p) { free(p); }
+
+// repr(float) as CPython prints it (exposed for tests of the CSV formatter)
+int64_t fs_format_py_float(double x, char* buf, int64_t cap) {
+    std::string s;
+    append_py_float(s, x);
+    if (static_cast<int64_t>(s.size()) + 1 > cap) return -static_cast<int64_t>(s.size());
+    memcpy(buf, s.data(), s.size());
+    buf[s.size()] = 0;
+    return static_cast<int64_t>(s.size());
 }
 
 }  // extern "C"

@@ -337,6 +337,33 @@ class AnnIndexSearch(object):
             self._script_off = off
         return self._script_blob, self._script_off
 
+    def _script_columns(self):
+        # script-side CSV columns as flat arrays for fs_records_format_csv
+        if getattr(self, '_script_cols', None) is None:
+            n = len(self.word_lowercase)
+            orth = numpy.array(self.orth_id, dtype=numpy.uint64) if n else numpy.zeros(0, numpy.uint64)
+            enc = [b'' if c is None else str(c).encode('utf-8') for c in self.character]
+            coff = numpy.zeros(n + 1, dtype=numpy.int64)
+            numpy.cumsum([len(e) for e in enc], out=coff[1:])
+            cnone = numpy.array([c is None for c in self.character], dtype=numpy.uint8)
+            snone = numpy.array([sc is None for sc in self.scene], dtype=numpy.uint8)
+            scene = numpy.array([0 if sc is None else sc for sc in self.scene], dtype=numpy.int64)
+            self._script_cols = (orth, b''.join(enc), coff, cnone, scene, snone)
+        return self._script_cols
+
+    def records_text_prepared(self, prep, matches, first_table=None, word_base=0):
+        """CSV text (utf-8 bytes) of the cluster's records: byte for byte what
+        write_records(records_prepared(...)) puts in the batch file, formatted natively
+        (fs_records_format_csv) without building per-row Python objects."""
+        filenames, batch = prep['filenames'], prep['batch']
+        if len(matches) == 0:
+            return b''
+        blob, soff = self._script_text()
+        best = _text.records_best(matches, first_table, self.window_size, 10, batch, blob, soff)
+        orth, cblob, coff, cnone, scene, snone = self._script_columns()
+        return _text.records_format_csv(best, filenames, batch, blob, soff, orth, cblob, coff, cnone,
+                                        scene, snone, word_base)
+
     def _records(self, filenames, batch, matches, first_table=None, word_base=0):
         # search.py:182-226 on the surviving pairs: top-10 per window, Levenshtein, six records
         # per pair, per-word argmin (native, fs_records_best); here only the row formatting.
@@ -472,7 +499,9 @@ def format_records(records):
 
 
 def _write_text(text, filename):
-    with open(filename, 'w', encoding='utf-8', newline='') as out:
+    if isinstance(text, str):
+        text = text.encode('utf-8')
+    with open(filename, 'wb') as out:
         out.write(text)
 
 
@@ -568,8 +597,7 @@ def analyze(args,
 
     def finish(i, prep, found):
         # rows are formatted ONCE: the batch file and the aggregate share the same text
-        record_sets = ann_index.records_prepared(prep, *found)
-        text = format_records([r for r_set in record_sets for r in r_set])
+        text = ann_index.records_text_prepared(prep, *found)
         _write_text(text, batch_filename.format(i))
         return i, text
 
@@ -592,7 +620,7 @@ def analyze(args,
         if rank != 0:
             return
     # header row (search.py:367) + the rows of every cluster in cluster order (search.py:388)
-    aggregate = format_records([new_record_structure['fields']]) + ''.join(
+    aggregate = format_records([new_record_structure['fields']]).encode('utf-8') + b''.join(
         my_records[i] for i in sorted(my_records))
 
     i = 0

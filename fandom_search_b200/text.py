@@ -196,3 +196,38 @@ def records_best(matches, tie, window, topk, batch, script_blob, script_off):
         if rows < 0:
             raise nt.NativeError(nt.FS_E_INVALID, lib.fs_last_error().decode())
         return {k: v[:rows] for k, v in out.items()}
+
+
+def records_format_csv(best, filenames, batch, script_blob, script_off, script_orth, char_blob, char_off,
+                       char_none, scene, scene_none, word_base=0):
+    """CSV text (bytes) of the records in `best` (records_best output): search.py:206-217 rows as
+    csv.writer writes them (search.py:331-334)."""
+    lib = nt.load()
+    rows = len(best["work"])
+    if rows == 0:
+        return b""
+    names = [os.fspath(f).encode("utf-8") if not isinstance(f, bytes) else f for f in filenames]
+    noff = np.zeros(len(names) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in names], out=noff[1:])
+    text = np.ascontiguousarray(batch.text)
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    arrs = [c(best["work"], np.int32), c(best["word"], np.int32), c(best["window_ix"], np.int32),
+            c(best["match_ix"], np.int32), c(best["distance"], np.float64), c(best["lev"], np.int32)]
+    tok_start, tok_end, tok_off = (c(batch.tok_start, np.int64), c(batch.tok_end, np.int64),
+                                   c(batch.tok_off, np.int64))
+    script_off = c(script_off, np.int64)
+    script_orth = c(script_orth, np.uint64)
+    char_off, char_none = c(char_off, np.int64), c(char_none, np.uint8)
+    scene, scene_none = c(scene, np.int64), c(scene_none, np.uint8)
+    out = ctypes.c_void_p()
+    n = lib.fs_records_format_csv(rows, *[nt.ptr(a) for a in arrs], b"".join(names), nt.ptr(noff),
+                                  nt.ptr(text), nt.ptr(tok_start),
+                                  nt.ptr(tok_end), nt.ptr(tok_off), script_blob, nt.ptr(script_off),
+                                  nt.ptr(script_orth), char_blob, nt.ptr(char_off), nt.ptr(char_none),
+                                  nt.ptr(scene), nt.ptr(scene_none), word_base, ctypes.byref(out))
+    if n < 0:
+        raise nt.NativeError(int(n), lib.fs_last_error().decode())
+    try:
+        return ctypes.string_at(out, n)
+    finally:
+        lib.fs_free(out)

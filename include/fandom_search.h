@@ -261,6 +261,25 @@ int64_t fs_records_best(const fs_match* matches, const int32_t* tie, int64_t n, 
                         int32_t* out_window_ix, int32_t* out_match_ix, double* out_distance,
                         int32_t* out_lev, int64_t cap_out);
 
+/* CSV text of the winning records (arrays as returned by fs_records_best): the rows of
+ * search.py:206-217 exactly as csv.writer(...).writerows writes them (search.py:331-334: excel
+ * dialect, minimal quoting, "\r\n", None -> empty, floats as repr()).  names_*: FAN_WORK_FILENAME
+ * per work; script_*: lower-cased script words by GLOBAL word index, their orth ids, character
+ * (char_none = 1 -> None) and scene (scene_none = 1 -> None); word_base: first global word index
+ * of the script the rows belong to.  *out_text is malloc'ed (release with fs_free); returns its
+ * length or a negative fs_status. */
+int64_t fs_records_format_csv(int64_t rows, const int32_t* work, const int32_t* word,
+                              const int32_t* window_ix, const int32_t* match_ix, const double* distance,
+                              const int32_t* lev, const char* names_blob, const int64_t* names_off,
+                              const char* text, const int64_t* tok_start, const int64_t* tok_end,
+                              const int64_t* tok_off, const char* script_blob,
+                              const int64_t* script_word_off, const uint64_t* script_orth,
+                              const char* char_blob, const int64_t* char_off, const uint8_t* char_none,
+                              const int64_t* scene, const uint8_t* scene_none, int64_t word_base,
+                              char** out_text);
+void fs_free(void* p);
+int64_t fs_format_py_float(double x, char* buf, int64_t cap); /* CPython repr(float) */
+
 #ifdef __cplusplus
 }
 #endif

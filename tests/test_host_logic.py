@@ -166,3 +166,59 @@ def test_multi_script_pass_equals_separate_runs(cpu_device, golden_dir, tmp_path
     agg = read_csv(glob.glob("match-6gram-alpha-2*.csv")[0])
     single = search.AnnIndexSearch(str(a), 6, 15, 14, 0.1)
     compare_records(agg, normalise([r for s in single.search_many(files) for r in s]), tol=1e-12)
+
+
+def test_native_csv_rows_match_python_csv_writer():
+    """fs_records_format_csv == csv.writer(...).writerows on the same records (search.py:331-334),
+    with quoting, None fields, unicode and float repr corner cases."""
+    import numpy as np
+    from fandom_search_b200 import text as T, search as S
+    words = ['plain', 'com,ma', 'quo"te', '"', ',', 'üñí', 'a"b"c', "it's", 'semi;colon', '日本語', 'x']
+    lists = [[words[(i*3+j) % len(words)] for j in range(9)] for i in range(4)]
+    batch = T.Batch.from_token_lists(lists)
+    filenames = ['dir/a,b.txt', 'dir/"q".txt', 'dir/ü.txt', 'plain.txt']
+    script_words = ['may', 'the', 'fo,rce', 'be', '"with"', 'you', 'always', 'ok']
+    enc = [w.encode() for w in script_words]
+    soff = np.zeros(len(enc)+1, np.int64); np.cumsum([len(e) for e in enc], out=soff[1:])
+    blob = b''.join(enc)
+    orth = np.array([T.string_id(w) for w in script_words], np.uint64)
+    chars = ['LUKE', None, 'HAN, SOLO', 'C"3PO', None, 'LEIA', 'OBI\nWAN', 'R2']
+    scenes = [1, None, 3, 40000000000, None, 6, 7, 8]
+    cenc = [b'' if c is None else c.encode() for c in chars]
+    coff = np.zeros(len(cenc)+1, np.int64); np.cumsum([len(e) for e in cenc], out=coff[1:])
+    cnone = np.array([c is None for c in chars], np.uint8)
+    snone = np.array([s is None for s in scenes], np.uint8)
+    scene = np.array([0 if s is None else s for s in scenes], np.int64)
+    rng = np.random.default_rng(0)
+    rows = 30
+    best = {'work': np.sort(rng.integers(0, 4, rows)).astype(np.int32), 'word': rng.integers(0, 9, rows).astype(np.int32),
+            'window_ix': rng.integers(0, 3, rows).astype(np.int32), 'match_ix': rng.integers(0, 6, rows).astype(np.int32),
+            'distance': np.concatenate([[0.0, 1e-17, 2.220446049250313e-16, 0.1], rng.random(rows-4)*0.1]), 'lev': rng.integers(0, 40, rows).astype(np.int32)}
+    got = T.records_format_csv(best, filenames, batch, blob, soff, orth, b''.join(cenc), coff, cnone, scene, snone, 0)
+    recs = []
+    for i in range(rows):
+        w = int(best['work'][i]); g = int(best['match_ix'][i] + best['window_ix'][i])
+        fw = lists[w][int(best['word'][i])]
+        d = float(best['distance'][i]); l = int(best['lev'][i])
+        recs.append([filenames[w], int(best['word'][i]), fw, T.string_id(fw), g, script_words[g], int(orth[g]), chars[g], scenes[g], d, l, d*l])
+    want = S.format_records(recs).encode()
+    assert got == want
+
+def test_native_float_repr_matches_python():
+    import ctypes, random, struct
+    from fandom_search_b200 import _native as nt
+    lib = nt.load()
+    buf = ctypes.create_string_buffer(64)
+    random.seed(5)
+    cases = [0.0, -0.0, 1.0, 0.1, 1e-4, 1e-5, 9.999e-5, 1e15, 1e16, 1e17, 123456789012345678.0, 5e-324,
+             2.2250738585072014e-308, 1.7976931348623157e308, -2.220446049250313e-16,
+             0.05000000000000004, 1e22, 1e23, float('inf'), float('-inf')]
+    for _ in range(20000):
+        cases.append(struct.unpack('d', struct.pack('Q', random.getrandbits(64)))[0])
+        cases.append(random.uniform(0, 0.1) * random.randint(0, 60))
+    for x in cases:
+        if x != x:
+            continue
+        n = lib.fs_format_py_float(x, buf, 64)
+        assert buf.value.decode() == repr(x), (repr(x), buf.value)
+        assert n == len(repr(x))
