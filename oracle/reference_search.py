@@ -146,6 +146,32 @@ def unit_rows(m):
     return m / safe[:, None]
 
 
+def exhaustive_gemm_pairs(script_vectors, fan_vectors, w=6, threshold=0.1, dtype=numpy.float32,
+                          block=2048):
+    """The "best honest CPU" comparator of SURVEY 8(d): the author's own exhaustive formula
+    (_deprecated.py:1-26, 1 - (A@B)/(|A||B|)) as one BLAS GEMM per block of fan windows, in
+    `dtype`.  Returns (fan window, script window) index arrays of the pairs under the threshold."""
+    def fast_windows(v):
+        v = numpy.ascontiguousarray(v, dtype=dtype)
+        if v.shape[0] < w:
+            return numpy.zeros((0, w * v.shape[1]), dtype=dtype)
+        view = numpy.lib.stride_tricks.sliding_window_view(v, (w, v.shape[1]))
+        return unit_rows(view.reshape(v.shape[0] - w + 1, w * v.shape[1])).astype(dtype)
+
+    sw = script_vectors if getattr(script_vectors, 'ndim', 0) == 2 and script_vectors.shape[1] == \
+        w * fan_vectors.shape[1] else fast_windows(script_vectors)
+    fw = fast_windows(fan_vectors)
+    fi, si = [], []
+    for b in range(0, fw.shape[0], block):
+        d = 1.0 - fw[b:b + block] @ sw.T
+        i, j = numpy.nonzero(d < threshold)
+        fi.append(i + b)
+        si.append(j)
+    if not fi:
+        return numpy.zeros(0, numpy.int64), numpy.zeros(0, numpy.int64)
+    return numpy.concatenate(fi), numpy.concatenate(si)
+
+
 def lsh_seed(base, hash_name):
     return (int(base) + zlib.crc32(hash_name.encode('utf-8'))) % (2 ** 32)
 
