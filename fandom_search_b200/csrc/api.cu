@@ -24,6 +24,10 @@ constexpr int kTimingRing = 256;
 // norms add ~1e-5.  Every pair with float64 cos > 1-thr passes
 // cos_approx > 1-thr-kEps.
 constexpr double kEps = 4.0e-3;
+// fp8 operands: the operand rounding is measured per window; this slack covers what is left (fp32
+// accumulation order in the tensor core, fp16x2-packed epilogue sums <= 2^-9)
+constexpr double kEpsAccum = 3.0e-3;
+constexpr float kF8RowNorm = 96.0f;  // largest scaled row norm of an fp8 table
 
 template <typename T>
 static int dev_alloc(T** p, int64_t count) {
@@ -66,17 +70,22 @@ using namespace fs;
 struct fs_index {
     int device = 0;
     int sm_count = 148;
-    int32_t dim = 0, dim_pad = 0, window = 6;
+    int32_t dim = 0, window = 6;
+    int32_t dim_pad = 0;        // operand row length in 2-byte units (fp16 elements, or fp8 elements / 2)
+    int32_t dim_pad_elems = 0;  // operand row length in elements
+    int32_t operand_bits = 16;  // 16: fp16 operands, 8: fp8 e4m3 operands
+    float rho_script = 0.f;     // fp8: largest relative rounding error of a script window
+    int64_t n_extra_rows = 0;
     double threshold = 0.1;
     float scale = 1.f;
     int64_t n_base = 0, n_sx = 0;
 
     float* table32 = nullptr;
     __half* table16 = nullptr;
-    float* table_sq = nullptr;
+    float2* table_sq = nullptr;
     float* sx32 = nullptr;
     __half* sx16 = nullptr;
-    float* sx_sq = nullptr;
+    float2* sx_sq = nullptr;
 
     int32_t* script_tok = nullptr;
     int64_t n_script_tok = 0;
@@ -84,7 +93,7 @@ struct fs_index {
     int32_t n_scripts = 0;
     int64_t n_script_windows = 0;
     __half* script_emb = nullptr;
-    float* script_tok_sq = nullptr;
+    float2* script_tok_sq = nullptr;
     float* script_norm = nullptr;
     float* script_norm_min = nullptr;
     int32_t tiles_n = 0;
@@ -98,7 +107,7 @@ struct fs_index {
     int64_t emb_cap = 0;  // elements of fan_emb
     __half* fan_emb = nullptr;
     int64_t sq_cap = 0;
-    float* fan_tok_sq = nullptr;
+    float2* fan_tok_sq = nullptr;
     int64_t thr_cap = 0;
     float* fan_thr = nullptr;
     int64_t cand_cap = 0;
@@ -106,7 +115,7 @@ struct fs_index {
     int64_t fx_cap = 0;  // fan extra rows
     __half* fx16 = nullptr;
     int64_t fxsq_cap = 0;
-    float* fx_sq = nullptr;
+    float2* fx_sq = nullptr;
 
     // staging of the _host entry points
     cudaStream_t stream = nullptr;
@@ -133,6 +142,8 @@ struct fs_index {
     int32_t ares = 0;              // A-resident variant of the pair kernel
     int32_t pack = 1;              // fp16x2-packed epilogue shuffles
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
+    int64_t last_row0_6 = 0;
+    int32_t mix_pattern = 0x5;     // diag == kDiagMix: bit i = kind of tile i mod 4 (1 -> E = 6)
     int32_t base_offset_mode = 0;
     int32_t grid_limit = 0;
 
@@ -180,6 +191,79 @@ int fs_index_destroy(fs_index* idx) {
     }
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
+    return FS_OK;
+}
+
+// (Re)builds everything that depends on the operand type: the converted table and script
+// extras, the script token matrix, its window norms and tensor map.  fp16: one global scale
+// 1/max|x|; the fixed slack kEps covers the operand rounding.  fp8 e4m3: scale 96/max|row| (so
+// that six token dots, |sum| <= 6 * 96^2, still fit the fp16 range of the packed epilogue), the
+// rounding error of every row is MEASURED and enters the pre-filter threshold per window
+// (run_pipeline / window_norm_kernel), which keeps the candidate set a guaranteed superset.
+static int prepare_operands(fs_index* idx) {
+    cudaStream_t st = idx->stream;
+    const bool f8 = idx->operand_bits == 8;
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    FS_CUDA_CHECK(cudaDeviceSynchronize());
+    idx->dim_pad_elems = static_cast<int32_t>(round_up(idx->dim, f8 ? 2 * kUmmaK : kUmmaK));  // K of one tcgen05.mma
+    idx->dim_pad = f8 ? idx->dim_pad_elems / 2 : idx->dim_pad_elems;
+    void* stale[] = {idx->table16, idx->sx16, idx->script_emb, idx->fan_emb, idx->fx16};
+    for (void* q : stale)
+        if (q) cudaFree(q);
+    idx->table16 = idx->sx16 = idx->script_emb = idx->fan_emb = idx->fx16 = nullptr;
+    idx->emb_cap = idx->tok_cap = idx->fx_cap = 0;
+    int r;
+    if ((r = dev_alloc(&idx->table16, idx->n_base * idx->dim_pad)) != FS_OK) return r;
+    if ((r = dev_alloc(&idx->sx16, idx->n_sx * idx->dim_pad)) != FS_OK) return r;
+    if ((r = dev_alloc(&idx->script_emb, idx->n_script_tok * idx->dim_pad)) != FS_OK) return r;
+    unsigned int* d_max = reinterpret_cast<unsigned int*>(idx->h_counters);
+    FS_CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
+    if (f8) {
+        if ((r = launch_rownorm_max(idx->table32, idx->n_base, idx->dim, d_max, st)) != FS_OK) return r;
+        if ((r = launch_rownorm_max(idx->sx32, idx->n_sx, idx->dim, d_max, st)) != FS_OK) return r;
+    } else {
+        if ((r = launch_absmax(idx->table32, idx->n_base * idx->dim, d_max, st)) != FS_OK) return r;
+        if ((r = launch_absmax(idx->sx32, idx->n_sx * idx->dim, d_max, st)) != FS_OK) return r;
+    }
+    unsigned int h_max_bits = 0;
+    FS_CUDA_CHECK(cudaMemcpyAsync(&h_max_bits, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    FS_CUDA_CHECK(cudaStreamSynchronize(st));
+    float h_max;
+    memcpy(&h_max, &h_max_bits, sizeof(float));
+    if (!(h_max > 0.f && std::isfinite(h_max)))
+        idx->scale = 1.0f;
+    else
+        idx->scale = f8 ? kF8RowNorm / std::sqrt(h_max) : 1.0f / h_max;
+    if ((r = launch_convert_rows(idx->table32, idx->n_base, idx->dim, idx->dim_pad, idx->scale, f8,
+                                 idx->table16, idx->table_sq, st)) != FS_OK)
+        return r;
+    if ((r = launch_convert_rows(idx->sx32, idx->n_sx, idx->dim, idx->dim_pad, idx->scale, f8, idx->sx16,
+                                 idx->sx_sq, st)) != FS_OK)
+        return r;
+    const int64_t n_pad = static_cast<int64_t>(idx->tiles_n) * kBlockN;
+    GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16, idx->sx_sq,
+                      idx->n_sx,    nullptr,       nullptr,     0};
+    if ((r = launch_gather(idx->script_tok, idx->n_script_tok, src, idx->dim_pad, idx->script_emb,
+                           idx->script_tok_sq, idx->sm_count, st)) != FS_OK)
+        return r;
+    FS_CUDA_CHECK(cudaMemsetAsync(idx->script_tok_sq + idx->n_script_tok, 0, sizeof(float2) * 8, st));
+    unsigned long long* d_cnt = idx->h_counters;
+    FS_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
+    unsigned int* d_rho = reinterpret_cast<unsigned int*>(d_cnt);  // slot 0 (candidates) is unused here
+    if ((r = launch_window_norm(idx->script_tok_sq, idx->n_script_tok, idx->script_off, idx->n_scripts,
+                                idx->window, 1.0f, 0.0f, idx->script_norm, n_pad, d_cnt + FS_CNT_WINDOWS,
+                                d_rho, st)) != FS_OK)
+        return r;
+    if ((r = launch_sliding_min32(idx->script_norm, idx->script_norm_min, n_pad, st)) != FS_OK) return r;
+    unsigned long long h_cnt[FS_CNT_COUNT];
+    FS_CUDA_CHECK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    if (idx->n_script_tok > 0)
+        if ((r = make_token_map(&idx->map_script, idx->script_emb, idx->n_script_tok, idx->dim_pad)) != FS_OK)
+            return r;
+    FS_CUDA_CHECK(cudaStreamSynchronize(st));
+    idx->n_script_windows = static_cast<int64_t>(h_cnt[FS_CNT_WINDOWS]);
+    const unsigned int rho_bits = static_cast<unsigned int>(h_cnt[0] & 0xffffffffull);
+    memcpy(&idx->rho_script, &rho_bits, sizeof(float));
     return FS_OK;
 }
 
@@ -269,10 +353,8 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
 
     FS_TRY(dev_alloc(&idx->h_counters, FS_CNT_COUNT));
     FS_TRY(dev_alloc(&idx->table32, n_rows * dim));
-    FS_TRY(dev_alloc(&idx->table16, n_rows * idx->dim_pad));
-    FS_TRY(dev_alloc(&idx->table_sq, n_rows));
     FS_TRY(dev_alloc(&idx->sx32, n_extra * dim));
-    FS_TRY(dev_alloc(&idx->sx16, n_extra * idx->dim_pad));
+    FS_TRY(dev_alloc(&idx->table_sq, n_rows));
     FS_TRY(dev_alloc(&idx->sx_sq, n_extra));
     if (n_rows)
         FS_TRY_CUDA(cudaMemcpyAsync(idx->table32, table, sizeof(float) * n_rows * dim,
@@ -280,29 +362,11 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     if (n_extra)
         FS_TRY_CUDA(cudaMemcpyAsync(idx->sx32, extra, sizeof(float) * n_extra * dim,
                                     cudaMemcpyHostToDevice, st));
-    // global scale so that fp16 never overflows: 1 / max|x|
-    unsigned int* d_max = reinterpret_cast<unsigned int*>(idx->h_counters);
-    FS_TRY_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned int), st));
-    FS_TRY(launch_absmax(idx->table32, n_rows * dim, d_max, st));
-    FS_TRY(launch_absmax(idx->sx32, n_extra * dim, d_max, st));
-    unsigned int h_max_bits = 0;
-    FS_TRY_CUDA(cudaMemcpyAsync(&h_max_bits, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    FS_TRY_CUDA(cudaStreamSynchronize(st));
-    float h_max;
-    memcpy(&h_max, &h_max_bits, sizeof(float));
-    idx->scale = (h_max > 0.f && std::isfinite(h_max)) ? 1.0f / h_max : 1.0f;
-    FS_TRY(launch_convert_rows(idx->table32, n_rows, dim, idx->dim_pad, idx->scale, idx->table16,
-                               idx->table_sq, st));
-    FS_TRY(launch_convert_rows(idx->sx32, n_extra, dim, idx->dim_pad, idx->scale, idx->sx16,
-                               idx->sx_sq, st));
-
-    // script side: tokens, CSR, embeddings, window norms, tensor map, hash table
-    // padded so that any tile stepping (256 - (E-1) columns, E <= 3) stays in bounds
+    // script side: tokens, CSR; padded so that any tile stepping (256 - (E-1) columns) stays in bounds
     idx->tiles_n = static_cast<int32_t>((n_script_tok + kBlockN - 8 - 1) / (kBlockN - 8)) + 1;
     const int64_t n_pad = static_cast<int64_t>(idx->tiles_n) * kBlockN;
     FS_TRY(dev_alloc(&idx->script_tok, n_script_tok + 8));
     FS_TRY(dev_alloc(&idx->script_off, n_scripts + 1));
-    FS_TRY(dev_alloc(&idx->script_emb, n_script_tok * idx->dim_pad));
     FS_TRY(dev_alloc(&idx->script_tok_sq, n_script_tok + 8));
     FS_TRY(dev_alloc(&idx->script_norm, n_pad));
     FS_TRY(dev_alloc(&idx->script_norm_min, n_pad));
@@ -312,19 +376,8 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
                                     cudaMemcpyHostToDevice, st));
     FS_TRY_CUDA(cudaMemcpyAsync(idx->script_off, script_off, sizeof(int64_t) * (n_scripts + 1),
                                 cudaMemcpyHostToDevice, st));
-    GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16, idx->sx_sq,
-                      idx->n_sx,    nullptr,       nullptr,     0};
-    FS_TRY(launch_gather(idx->script_tok, n_script_tok, src, idx->dim_pad, idx->script_emb,
-                         idx->script_tok_sq, idx->sm_count, st));
-    unsigned long long* d_cnt = idx->h_counters;
-    FS_TRY_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
-    FS_TRY(launch_window_norm(idx->script_tok_sq, n_script_tok, idx->script_off, idx->n_scripts,
-                              window, 1.0f, idx->script_norm, n_pad, d_cnt + FS_CNT_WINDOWS, st));
-    FS_TRY(launch_sliding_min32(idx->script_norm, idx->script_norm_min, n_pad, st));
-    unsigned long long h_cnt[FS_CNT_COUNT];
-    FS_TRY_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
-    if (n_script_tok > 0)
-        FS_TRY(make_token_map(&idx->map_script, idx->script_emb, n_script_tok, idx->dim_pad));
+    // operand rows (table, script extras, script token matrix), window norms, tensor map
+    FS_TRY(prepare_operands(idx));
 
     uint32_t slots = 1024;
     while (slots < 2 * static_cast<uint64_t>(n_script_tok)) slots <<= 1;
@@ -333,7 +386,6 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     FS_TRY(launch_hash_build(idx->script_tok, n_script_tok, idx->script_off, idx->n_scripts, window,
                              idx->hash_table, slots, st));
     FS_TRY_CUDA(cudaStreamSynchronize(st));
-    idx->n_script_windows = static_cast<int64_t>(h_cnt[FS_CNT_WINDOWS]);
 #undef FS_TRY
 #undef FS_TRY_CUDA
     *out = idx;
@@ -361,6 +413,10 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
     if (!idx) return FS_E_INVALID;
     switch (option) {
         case FS_OPT_SHIFTS_PER_STAGE:
+            if (idx->diag == kDiagMix) {
+                set_error("the mixed schedule fixes the shifts per stage");
+                return FS_E_INVALID;
+            }
             if (value < 0 || value > 8 || (value > 0 && (idx->window / idx->diag) % value != 0)) {
                 set_error("shifts per stage must divide window/diag and be <= 8 (0 = all)");
                 return FS_E_INVALID;
@@ -380,12 +436,33 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             idx->pair = value ? 1 : 0;
             return FS_OK;
         case FS_OPT_DIAG:
+            if (value == kDiagMix && idx->window == 6) {
+                idx->diag = kDiagMix;  // alternate E = 3 and E = 6 tiles
+                idx->shifts_per_stage = 0;
+                return FS_OK;
+            }
             if (!(value == 1 || value == 2 || value == 3 || value == 6) || idx->window % value != 0) {
-                set_error("diagonal factor must be 1, 2, 3 or 6 and divide the window");
+                set_error("diagonal factor must be 1, 2, 3 or 6 and divide the window (36 = mixed 3/6, window 6)");
                 return FS_E_INVALID;
             }
             idx->diag = static_cast<int32_t>(value);
             idx->shifts_per_stage = 0;
+            return FS_OK;
+        case FS_OPT_OPERAND_BITS: {
+            if (value != 8 && value != 16) {
+                set_error("operand bits must be 16 (fp16) or 8 (fp8 e4m3)");
+                return FS_E_INVALID;
+            }
+            if (idx->operand_bits == value) return FS_OK;
+            idx->operand_bits = static_cast<int32_t>(value);
+            return prepare_operands(idx);
+        }
+        case FS_OPT_MIX_PATTERN:
+            if (value < 0 || value > 15) {
+                set_error("mix pattern is a 4-bit mask (bit i: tile i mod 4 is of the E = 6 kind)");
+                return FS_E_INVALID;
+            }
+            idx->mix_pattern = static_cast<int32_t>(value);
             return FS_OK;
         case FS_OPT_BASE_OFFSET_MODE:
             idx->base_offset_mode = value ? 1 : 0;
@@ -423,7 +500,7 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
     if (!idx) return -1;
     switch (what) {
         case 0: return idx->n_script_windows;
-        case 1: return idx->dim_pad;
+        case 1: return idx->dim_pad_elems;
         case 2: return idx->sm_count;
         case 3: return idx->cand_cap;
         case 4: return idx->shifts_per_stage;
@@ -431,6 +508,9 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
         case 6: return idx->pair;
         case 7: return idx->ares;
         case 8: return idx->pack;
+        case 9: return idx->mix_pattern;
+        case 11: return idx->operand_bits;
+        case 10: return idx->last_row0_6;  // mixed schedule: first fan row of the E = 6 region (last launch)
         default: return -1;
     }
 }
@@ -497,8 +577,8 @@ int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned lon
     if (a.n_extra > 0) {
         if ((r = dev_grow(&idx->fx16, &idx->fx_cap, a.n_extra * idx->dim_pad)) != FS_OK) return r;
         if ((r = dev_grow(&idx->fx_sq, &idx->fxsq_cap, a.n_extra)) != FS_OK) return r;
-        if ((r = launch_convert_rows(a.extra, a.n_extra, idx->dim, idx->dim_pad, idx->scale, idx->fx16,
-                                     idx->fx_sq, st)) != FS_OK)
+        if ((r = launch_convert_rows(a.extra, a.n_extra, idx->dim, idx->dim_pad, idx->scale,
+                                     idx->operand_bits == 8, idx->fx16, idx->fx_sq, st)) != FS_OK)
             return r;
     }
     GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16,  idx->sx_sq,
@@ -507,11 +587,18 @@ int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned lon
                            st)) != FS_OK)
         return r;
     // zero the halo so the window sums never read stale squares
-    FS_CUDA_CHECK(cudaMemsetAsync(idx->fan_tok_sq + a.n_tok, 0, sizeof(float) * 8, st));
-    const float coef = static_cast<float>(1.0 - idx->threshold - kEps);
+    FS_CUDA_CHECK(cudaMemsetAsync(idx->fan_tok_sq + a.n_tok, 0, sizeof(float2) * 8, st));
+    // fp16: fixed slack.  fp8: with qf, qs the rounded windows, errF = |f - qf|, errS = |s - qs| <=
+    // rho |s| and |qs| <= (1 + rho) |s| (rho = rho_script):
+    //   qf.qs >= f.s - errF |qs| - |f| errS,
+    // so every pair with f.s > (1 - thr) |f||s| has  qf.qs > [(1 - thr - rho) |f| - (1 + rho) errF] |s|.
+    const bool f8 = idx->operand_bits == 8;
+    const float coef = static_cast<float>(f8 ? 1.0 - idx->threshold - kEpsAccum - idx->rho_script
+                                             : 1.0 - idx->threshold - kEps);
+    const float kappa = f8 ? 1.0f + idx->rho_script : 0.0f;
     return launch_window_norm(idx->fan_tok_sq, a.n_tok, a.off, static_cast<int32_t>(a.n_works),
-                              idx->window, coef, thr_out, thr_pad,
-                              counters ? counters + FS_CNT_WINDOWS : nullptr, st);
+                              idx->window, coef, kappa, thr_out, thr_pad,
+                              counters ? counters + FS_CNT_WINDOWS : nullptr, nullptr, st);
 }
 
 int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, fs_match* out,
@@ -521,11 +608,37 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     if (counters) FS_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
     if (a.n_tok == 0 || idx->n_script_tok == 0) return FS_OK;
-    const int32_t m_step = kBlockM - (idx->diag - 1), n_step = kBlockN - (idx->diag - 1);
-    const int32_t tiles_m = static_cast<int32_t>((a.n_tok + m_step - 1) / m_step);
+    const bool mix = idx->diag == kDiagMix;
+    if (mix && !idx->pair) {
+        set_error("the mixed E = 3 / E = 6 schedule needs CTA pairs (FS_OPT_CTA_PAIR = 1)");
+        return FS_E_INVALID;
+    }
+    const int32_t diag_a = mix ? 3 : idx->diag;  // tile geometry of the (first) region
+    const int32_t m_step = kBlockM - (diag_a - 1), n_step = kBlockN - (diag_a - 1);
+    int32_t tiles_m = static_cast<int32_t>((a.n_tok + m_step - 1) / m_step);
     const int32_t tiles_n = static_cast<int32_t>((idx->n_script_tok + n_step - 1) / n_step);
+    int32_t tiles_m6 = 0, tiles_n6 = 0, row0_6 = 0;
+    if (mix) {
+        // fan rows [0, row0_6) are tiled for E = 3 and the rest for E = 6, so that the numbers of
+        // tiles of the two kinds are in the ratio the pattern asks for; row0_6 is a whole number
+        // of E = 3 tile PAIRS (no phantom tile reaches into the other region)
+        const int32_t m6 = kBlockM - 5, n6 = kBlockN - 5;
+        tiles_n6 = static_cast<int32_t>((idx->n_script_tok + n6 - 1) / n6);
+        const double r6 = __builtin_popcount(static_cast<unsigned>(idx->mix_pattern) & 15u) / 4.0;
+        const double w3 = static_cast<double>(tiles_n6) * (1.0 - r6) / m6;
+        const double w6 = static_cast<double>(tiles_n) * r6 / m_step;
+        const double rows3 = (w3 + w6) > 0 ? static_cast<double>(a.n_tok) * w3 / (w3 + w6) : 0.0;
+        int64_t pairs3 = static_cast<int64_t>(rows3 / (2.0 * m_step) + 0.5);
+        const int64_t max_pairs3 = (a.n_tok + 2 * m_step - 1) / (2 * m_step);
+        if (pairs3 > max_pairs3) pairs3 = max_pairs3;
+        tiles_m = static_cast<int32_t>(2 * pairs3);
+        row0_6 = tiles_m * m_step;
+        const int64_t rows6 = a.n_tok > row0_6 ? a.n_tok - row0_6 : 0;
+        tiles_m6 = static_cast<int32_t>((rows6 + m6 - 1) / m6);
+    }
     // (+1 tile: in pair mode an odd tile count is rounded up to a full pair)
-    const int64_t thr_pad = static_cast<int64_t>(tiles_m + 1) * kBlockM;
+    const int64_t thr_pad = mix ? static_cast<int64_t>(row0_6) + static_cast<int64_t>(tiles_m6 + 2) * kBlockM
+                                : static_cast<int64_t>(tiles_m + 1) * kBlockM;
     int64_t want_cand = idx->cand_cap > 0 ? idx->cand_cap : (1 << 20);
     if ((r = fs_index_reserve(idx, a.n_tok, want_cand)) != FS_OK) return r;
     if ((r = embed_batch(idx, st, a, counters, idx->fan_emb, idx->fan_thr, thr_pad)) != FS_OK) return r;
@@ -543,10 +656,16 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.window = idx->window;
     p.diag = idx->diag;
     p.pair = idx->pair;
+    p.f8 = idx->operand_bits == 8;
     p.debug = idx->debug;
     p.ares = idx->ares;
     p.pack = idx->pack;
-    p.shifts_per_stage = idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag;
+    p.shifts_per_stage = mix ? 2 : (idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag);
+    p.tiles_m6 = tiles_m6;
+    p.tiles_n6 = tiles_n6;
+    p.row0_6 = row0_6;
+    idx->last_row0_6 = row0_6;
+    p.mix_pattern = idx->mix_pattern;
     p.base_offset_mode = idx->base_offset_mode;
     p.tiles_m = tiles_m;
     p.tiles_n = tiles_n;

@@ -54,7 +54,9 @@ constexpr int kHaloCols = kBlockN + 8;
 constexpr int kNormTileBytes = kAccumStages * kHaloCols * 4;               // 2112
 // shared-memory budget of distance_kernel<E, ., pair>: the stage ring shrinks by one stage at
 // E = 6, whose epilogue publishes 10 boundary rows per lane quarter instead of <= 4
-__host__ __device__ constexpr int dist_pub_slots(int diag) { return diag > 1 ? 2 * (diag - 1) : 1; }
+constexpr int kDiagMix = 36;  // "diagonal factor" of the schedule that alternates E = 3 and E = 6 tiles
+__host__ __device__ constexpr int diag_max(int diag) { return diag == kDiagMix ? 6 : diag; }
+__host__ __device__ constexpr int dist_pub_slots(int diag) { return diag > 1 ? 2 * (diag_max(diag) - 1) : 1; }
 __host__ __device__ constexpr int dist_pub_bytes(int diag) { return 4 * dist_pub_slots(diag) * kHaloCols * 4; }
 // A-resident mode (CTA pairs, d_pad <= 320): the fan tile (all kAResChunks 64-column chunks,
 // 87 KB) stays in shared memory for the whole sweep over the script tiles; only this CTA's half
@@ -65,7 +67,8 @@ __host__ __device__ constexpr int dist_stage_bytes(bool pair, bool ares) {
     return ares ? kStageABytes : (pair ? 2 * kStageABytes : kStageBytes);
 }
 __host__ __device__ constexpr int dist_stages(int diag, bool pair, bool ares) {
-    return ares ? (diag == 6 ? 5 : 7) : (pair ? (diag == 6 ? 5 : 6) : (diag == 6 ? 3 : 4));
+    return ares ? (diag_max(diag) == 6 ? 5 : 7)
+                : (pair ? (diag_max(diag) == 6 ? 5 : 6) : (diag_max(diag) == 6 ? 3 : 4));
 }
 __host__ __device__ constexpr int dist_smem_bytes(int diag, bool pair, bool ares) {
     return (ares ? kAResBytes : 0) + dist_stages(diag, pair, ares) * dist_stage_bytes(pair, ares) +
@@ -90,10 +93,14 @@ struct DistParams {
     int32_t debug;            // timing experiments only: 1 = skip epilogue math, 2 = skip TMEM loads
     int32_t pack;             // 1: fp16x2-packed epilogue shuffles (E = 3, 6)
     int32_t ares;             // 1: A-resident variant (pair mode, chunks <= kAResChunks)
+    int32_t f8;               // 1: operands are fp8 e4m3 (tcgen05.mma.kind::f8f6f4, K = 32)
     int32_t pair;             // 1: CTA-pair kernel (cta_group::2, M = 2 x 128 fan tiles)
     int32_t shifts_per_stage; // S: MMA shifts served by one smem stage (divides window/E)
     int32_t base_offset_mode; // how shifted descriptors fill base_offset
     int32_t tiles_m, tiles_n;
+    // mixed schedule (diag == kDiagMix): tiles_m/tiles_n describe the E = 3 region [0, row0_6),
+    // tiles_m6/tiles_n6 the E = 6 region [row0_6, M); bit i of mix_pattern = kind of tile i mod 4
+    int32_t tiles_m6, tiles_n6, row0_6, mix_pattern;
     fs_pair* cand;            // candidate output
     int64_t cand_cap;
     unsigned long long* counters;  // [FS_CNT_COUNT]
@@ -146,15 +153,19 @@ struct LshParams {
     int32_t dim, window;
 };
 
+// Operand rows are raw bytes: fp16 (2 B per element) or fp8 e4m3 (1 B per element); the plumbing
+// counts a row in 2-byte units ("dim_pad": fp16 elements, or fp8 elements / 2), so the gather, the
+// tensor maps (plain byte movers) and the 128-byte chunking are the same for both.
+// *_sq: per row (squared norm of the scaled fp32 row, squared norm of its rounding error).
 struct GatherSources {
     const __half* base16;
-    const float* base_sq;
+    const float2* base_sq;
     int64_t n_base;
     const __half* sx16;  // script extras
-    const float* sx_sq;
+    const float2* sx_sq;
     int64_t n_sx;
     const __half* fx16;  // fan extras of this batch
-    const float* fx_sq;
+    const float2* fx_sq;
     int64_t n_fx;
 };
 
@@ -162,13 +173,14 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
                     int grid_limit, cudaStream_t stream);
 int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
-                        __half* dst, float* sq, cudaStream_t stream);
+                        bool f8, __half* dst, float2* sq, cudaStream_t stream);
+int launch_rownorm_max(const float* src, int64_t n_rows, int32_t dim, unsigned int* out, cudaStream_t stream);
 int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t stream);
 int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,
-                  __half* emb, float* tok_sq, int sm_count, cudaStream_t stream);
-int launch_window_norm(const float* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
-                       int32_t window, float coef, float* out, int64_t n_pad,
-                       unsigned long long* window_counter, cudaStream_t stream);
+                  __half* emb, float2* tok_sq, int sm_count, cudaStream_t stream);
+int launch_window_norm(const float2* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
+                       int32_t window, float coef, float kappa, float* out, int64_t n_pad,
+                       unsigned long long* window_counter, unsigned int* rho_out, cudaStream_t stream);
 int launch_sliding_min32(const float* src, float* dst, int64_t n, cudaStream_t stream);
 int launch_rescore(const RescoreParams& p, int sm_count, cudaStream_t stream);
 int launch_lsh(const LshParams& p, int sm_count, cudaStream_t stream);
@@ -348,6 +360,19 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 8-bit operands (e4m3): K = 32 per instruction, same 32 bytes of every operand row as kind::f16
+__device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
         "}\n"
         :
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)

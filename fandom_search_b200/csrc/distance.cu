@@ -144,11 +144,233 @@ __device__ __forceinline__ float diag6_half(const uint32_t (&r)[40], uint32_t (&
     return fmaxf(__low2float(mx), __high2float(mx));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tile schedule of one worker (a CTA, or a CTA pair).  Plain kernels: a contiguous range of
+// linearised (m, n) tiles, n fastest; in pair mode the unit is (pair of consecutive m tiles, n).
+//
+// kDiag == kDiagMix: the fan rows are split in two regions, [0, row0_6) tiled for E = 3 and
+// [row0_6, M) tiled for E = 6, and every worker ALTERNATES between its E = 3 and its E = 6 tiles
+// (p.mix_pattern, 4 tiles per period, bit = 1 -> E = 6).  An E = 3 tile is tensor-bound (two MMA
+// shifts, cheap epilogue), an E = 6 tile is epilogue-bound (one shift, ~1.6x the shuffles): with
+// two TMEM accumulators the MMAs of one kind overlap the epilogue of the other, so both pipes
+// stay busy instead of one waiting for the other.  All three roles walk the same sequence.
+// ---------------------------------------------------------------------------------------------
+struct Tile {
+    int32_t m0, n0;
+    bool e6;         // mix: this tile is of the E = 6 kind
+    bool fan_first;  // first / last script tile of the current fan tile (A-resident mode)
+    bool fan_last;
+};
+
+template <int kDiag, bool kPair>
+struct TileWalk {
+    static constexpr bool kMix = kDiag == kDiagMix;
+    int64_t t3, end3, begin3, t6, end6;
+    int32_t tn3, tn6, row0_6;
+    uint32_t it, pattern, cta_rank;
+
+    __device__ __forceinline__ static void range(int32_t tm, int32_t tn, int64_t worker, int64_t n_workers,
+                                                 int64_t& begin, int64_t& end) {
+        const int64_t units_m = kPair ? (tm + 1) / 2 : tm;
+        const int64_t total = units_m * tn;
+        const int64_t per = (total + n_workers - 1) / n_workers;
+        begin = per * worker;
+        end = min(total, begin + per);
+    }
+    __device__ __forceinline__ TileWalk(const DistParams& p, int64_t worker, int64_t n_workers, uint32_t rank)
+        : t6(0), end6(0), tn3(p.tiles_n), tn6(1), row0_6(0), it(0), pattern(p.mix_pattern), cta_rank(rank) {
+        range(p.tiles_m, p.tiles_n, worker, n_workers, t3, end3);
+        begin3 = t3;
+        if (kMix) {
+            range(p.tiles_m6, p.tiles_n6, worker, n_workers, t6, end6);
+            tn6 = p.tiles_n6;
+            row0_6 = p.row0_6;
+        }
+    }
+    __device__ __forceinline__ bool next(Tile& out) {
+        bool six = false;
+        if (kMix) {
+            const bool has3 = t3 < end3, has6 = t6 < end6;
+            if (!has3 && !has6) return false;
+            six = (pattern >> (it & 3u)) & 1u;
+            ++it;
+            if (six ? !has6 : !has3) six = !six;
+        } else if (t3 >= end3) {
+            return false;
+        }
+        const int64_t u = six ? t6++ : t3++;
+        const int32_t tn = six ? tn6 : tn3;
+        const int64_t um = u / tn;
+        const int32_t un = static_cast<int32_t>(u - um * tn);
+        const int32_t e = kMix ? (six ? 6 : 3) : kDiag;
+        out.m0 = (six ? row0_6 : 0) + static_cast<int32_t>(kPair ? 2 * um + cta_rank : um) * (kBlockM - (e - 1));
+        out.n0 = un * (kBlockN - (e - 1));
+        out.e6 = kMix ? six : kDiag == 6;
+        out.fan_first = u == begin3 || un == 0;
+        out.fan_last = u + 1 == end3 || un + 1 == tn;
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue of one accumulator tile, run by the 16 epilogue warps:
+// warp -> TMEM lane quarter (warp & 3, a hardware restriction) x group of 64 columns.
+//
+// E > 1: out[i][j] = sum_{d<E} acc[i+d][j+d].  The column shift is a register index; the row
+// shift is a warp shuffle for lanes < 32-(E-1).  The last E-1 rows of a quarter need rows of the
+// NEXT quarter (another warp): every warp publishes its first and last E-1 rows to shared memory
+// while it streams its chunks, and after one barrier per tile those few boundary rows (3(E-1) of
+// 128) are summed from shared memory, one column per lane.
+// ---------------------------------------------------------------------------------------------
+template <int kDiag, bool kDump, int kPack>
+__device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t m0, const int32_t n0,
+                                              const int as, const uint32_t tfull_addr, const uint32_t aphase,
+                                              const uint32_t tmem_base, float* halo, float* norm_tile,
+                                              const int warp, const int lane) {
+    constexpr int kMStep = kBlockM - (kDiag - 1);
+    constexpr int kNStep = kBlockN - (kDiag - 1);
+    constexpr int kPubSlots = dist_pub_slots(kDiag);
+    constexpr int kEdge = kDiag - 1;    // boundary rows per side
+    constexpr int kTail0 = 32 - kEdge;  // first lane of the tail rows
+    const int quarter = warp & 3;
+    const int group = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int epi_tid = warp * 32 + lane;  // 0..511
+    // publish slot of this lane: head rows 0..E-2 -> slots 0..E-2, tail rows -> E-1..2E-3
+    const int pub_slot = lane < kEdge ? lane : (lane >= kTail0 ? kEdge + lane - kTail0 : -1);
+    auto pub_at = [&](int q, int slot) -> float* { return halo + (q * kPubSlots + slot) * kHaloCols; };
+
+    const int32_t gi = m0 + row;
+    const bool row_ok = row < kMStep;
+    const float thr = row_ok ? __ldg(p.thr_fan + gi) : INFINITY;  // padded to a tile multiple
+    // rows whose sum needs another warp's rows are finished in the boundary pass
+    const float thr_main = (kDiag > 1 && lane >= kTail0) ? INFINITY : thr;
+    // E > 1: script-window norms of this tile staged once in smem, +inf baked in for the
+    // E-1 columns that belong to the next tile
+    float* ns_tile = norm_tile + as * kHaloCols;
+    if (kDiag > 1 && epi_tid < kHaloCols)
+        ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.norm_script + n0 + epi_tid) : INFINITY;
+    mbar_wait_warp(tfull_addr, aphase, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                           static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
+#pragma unroll 1
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+        const int c0 = group * kEpiCols + ch * 32;  // first column inside the tile
+        uint32_t r[40];
+        __syncwarp();
+        if (p.debug & 2) {
+#pragma unroll
+            for (int x = 0; x < 40; ++x) r[x] = 0u;
+        } else {
+            tmem_ld_32x32(taddr + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            if (kDiag > 1) {
+                if (c0 + 32 < kBlockN) {
+                    tmem_ld_32x8(taddr + ch * 32 + 32, *reinterpret_cast<uint32_t(*)[8]>(&r[32]));
+                } else {
+#pragma unroll
+                    for (int x = 32; x < 40; ++x) r[x] = 0u;
+                }
+            }
+            tmem_ld_wait();
+        }
+        if (p.debug & 1) {
+            if (__uint_as_float(r[0]) == 1.2345e-30f) p.counters[0] = 1;  // keep the loads alive
+            continue;
+        }
+        if (kDiag > 1 && pub_slot >= 0) {
+            uint4* dst = reinterpret_cast<uint4*>(pub_at(quarter, pub_slot) + c0);
+#pragma unroll
+            for (int q = 0; q < 10; ++q)
+                dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        }
+        const int32_t gj0 = n0 + c0;
+        float mx;
+        uint32_t o16[16];
+        if (kDiag == 6 && kPack == 2) {
+            mx = diag6_half(r, o16);  // o16[k] = half2(out[2k], out[2k+1])
+        } else {
+            diag_sum_inplace<kDiag, kPack>(r);  // r[x] <- out[lane][c0 + x]
+            mx = -INFINITY;
+            if (!kDump) {
+#pragma unroll
+                for (int x = 0; x < 32; ++x) mx = fmaxf(mx, __uint_as_float(r[x]));
+            }
+        }
+        auto out_val = [&](int x) {
+            if (kDiag == 6 && kPack == 2) return (x & 1) ? h2_hi(o16[x >> 1]) : h2_lo(o16[x >> 1]);
+            return __uint_as_float(r[x]);
+        };
+        if (kDump) {
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+                if (row_ok && (kDiag == 1 || lane < kTail0) && gi < p.n_fan_tok && c0 + x < kNStep &&
+                    gj0 + x < p.dump_ld)
+                    p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + x] = out_val(x);
+            }
+        } else {
+            // one max over the chunk against thr * (smallest norm of the chunk) rejects
+            // the chunk; the exact per-element test runs only on the rare survivor
+            const float nmin = __ldg(p.norm_min32 + gj0);
+            if (mx > thr_main * nmin) {
+#pragma unroll
+                for (int x = 0; x < 32; ++x) {
+                    const float nsv = (c0 + x < kNStep) ? __ldg(p.norm_script + gj0 + x) : INFINITY;
+                    if (out_val(x) > thr_main * nsv) {
+                        const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
+                        if (slot < static_cast<unsigned long long>(p.cand_cap)) {
+                            p.cand[slot].fan_pos = gi;
+                            p.cand[slot].script_pos = gj0 + x;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (kDiag > 1) {
+        // boundary rows: tail rows of quarters 0..2 (quarter 3's belong to the next tile)
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+#pragma unroll
+        for (int tr = 0; tr < kEdge; ++tr) {
+            const int L = kTail0 + tr;
+            const float thr_l = __shfl_sync(0xffffffffu, thr, L);
+            if (quarter < 3) {
+#pragma unroll
+                for (int it = 0; it < kEpiCols / 32; ++it) {
+                    const int c = group * kEpiCols + it * 32 + lane;
+                    float v = 0.f;
+#pragma unroll
+                    for (int d = 0; d < kDiag; ++d) {
+                        const int lp = L + d;  // row inside this quarter, or lp-32 of the next
+                        const float* src = lp < 32 ? pub_at(quarter, kEdge + lp - kTail0)
+                                                   : pub_at(quarter + 1, lp - 32);
+                        v += src[c + d];
+                    }
+                    const int32_t gr = m0 + quarter * 32 + L;
+                    if (kDump) {
+                        if (gr < p.n_fan_tok && c < kNStep && n0 + c < p.dump_ld)
+                            p.dump[static_cast<int64_t>(gr) * p.dump_ld + n0 + c] = v;
+                    } else if (v > thr_l * ns_tile[c]) {
+                        const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
+                        if (slot < static_cast<unsigned long long>(p.cand_cap)) {
+                            p.cand[slot].fan_pos = gr;
+                            p.cand[slot].script_pos = n0 + c;
+                        }
+                    }
+                }
+            }
+        }
+        // the next tile's chunks overwrite the published rows
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+    }
+}
+
 // kDiag = E: the MMAs accumulate only the shifts {0, E, 2E, ...} (w/E of them) and the epilogue
 // adds E diagonal neighbours, out[i][j] = sum_{d<E} acc[i+d][j+d].  E = 1 is the plain dense
 // contraction.  E > 1 re-uses every partial sum for E windows (w/E times fewer tensor-core
 // flops for bit-for-bit the same set of products, summed in fp32); tiles then overlap by E-1
-// rows/columns (step 128-(E-1) x 256-(E-1)).
+// rows/columns (step 128-(E-1) x 256-(E-1)).  kDiag = kDiagMix alternates E = 3 and E = 6 tiles
+// (TileWalk above).
 //
 // kPair: two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA
 // owns its own 128-window fan tile (and the TMEM accumulator for it) but stages only HALF of
@@ -161,15 +383,21 @@ __device__ __forceinline__ float diag6_half(const uint32_t (&r)[40], uint32_t (&
 // sweeps the script tiles, so only the script half-tile streams (87 instead of 174 KB per
 // tile).  With E >= 3 the L2 -> SM traffic (~6 TB/s chip-wide), not the tensor pipe, is the
 // wall otherwise.
-template <int kDiag, bool kDump, bool kPair, bool kARes, int kPack>
+//
+// kF8: the operand rows hold fp8 e4m3 (128 elements per 128-byte chunk row, K = 32 per MMA) and the
+// MMAs are tcgen05.mma.kind::f8f6f4 -- byte for byte the same tiles, stages and descriptors as
+// fp16; half the operand traffic and half the tensor-pipe work per element of the embedding.
+template <int kDiag, bool kDump, bool kPair, bool kARes, int kPack, bool kF8>
 __global__ void __launch_bounds__(kDistThreads, 1)
 distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 const __grid_constant__ CUtensorMap map_script, const DistParams p) {
     static_assert(!kARes || kPair, "the A-resident variant exists for CTA pairs only");
+    constexpr bool kMix = kDiag == kDiagMix;
+    static_assert(!kMix || (kPair && !kARes), "the mixed schedule exists for plain CTA pairs only");
+    static_assert(!kF8 || (kPair && !kARes), "fp8 operands exist for plain CTA pairs only");
     extern __shared__ uint8_t smem_raw[];
     constexpr int kNumStages = dist_stages(kDiag, kPair, kARes);
     constexpr int kStageSz = dist_stage_bytes(kPair, kARes);
-    constexpr int kPubSlots = dist_pub_slots(kDiag);
     const uint32_t smem_a_res = (smem_u32(smem_raw) + 1023u) & ~1023u;  // resident fan tile (kARes)
     const uint32_t smem_base = smem_a_res + (kARes ? kAResBytes : 0);
     // layout: [resident A] [stages x (A | B)] [barriers] [boundary rows] [norm tile]
@@ -224,25 +452,13 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    // Work units: a contiguous range of linearised (m, n) tiles (n fastest) per CTA; in pair
-    // mode per cluster, the unit being (pair of consecutive m tiles, n).
-    constexpr int kMStep = kBlockM - (kDiag - 1);
-    constexpr int kNStep = kBlockN - (kDiag - 1);
-    const int64_t units_m = kPair ? (p.tiles_m + 1) / 2 : p.tiles_m;
-    const int64_t total_tiles = units_m * p.tiles_n;
     const int64_t n_workers = kPair ? gridDim.x / 2 : gridDim.x;
     const int64_t worker = kPair ? blockIdx.x / 2 : blockIdx.x;
-    const int64_t per_cta = (total_tiles + n_workers - 1) / n_workers;
-    const int64_t tile_begin = per_cta * worker;
-    const int64_t tile_end = min(total_tiles, tile_begin + per_cta);
-    auto tile_m0 = [&](int64_t t) {
-        const int64_t um = t / p.tiles_n;
-        return static_cast<int32_t>((kPair ? 2 * um + cta_rank : um) * kMStep);
-    };
-    auto tile_n0 = [&](int64_t t) { return static_cast<int32_t>(t % p.tiles_n) * kNStep; };
-    const int S = p.shifts_per_stage;                 // MMA shifts served by one smem stage
-    const int shift_groups = (p.window / kDiag) / S;  // stages per 64-column chunk
-    const int stages_per_tile = p.chunks * shift_groups;
+    TileWalk<kDiag, kPair> walk(p, worker, n_workers, cta_rank);
+    Tile tile;
+    constexpr int kShiftRows = kMix ? 3 : kDiag;        // token rows between two MMA shifts
+    const int S = kMix ? 2 : p.shifts_per_stage;       // MMA shifts served by one smem stage
+    const int shift_groups = kMix ? 1 : (p.window / kDiag) / S;  // stages per 64-column chunk
 
     // The two control roles run as WHOLE warps (all lanes converged, one elected lane issues):
     // addresses and descriptors then stay warp-uniform and live in uniform registers.  Run by a
@@ -253,10 +469,10 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         int stage = 0;
         uint32_t phase = 0;
         uint32_t a_phase = 0;
-        for (int64_t t = tile_begin; t < tile_end; ++t) {
-            const int32_t m0 = tile_m0(t);
-            const int32_t n0 = tile_n0(t);
-            if (kARes && (t == tile_begin || t % p.tiles_n == 0)) {
+        while (walk.next(tile)) {
+            const int32_t m0 = tile.m0;
+            const int32_t n0 = tile.n0;
+            if (kARes && tile.fan_first) {
                 // new fan tile: wait until every MMA that read the previous one has retired
                 mbar_wait_warp(aempty_bar, a_phase ^ 1u, 64);
                 if (elect_one()) {
@@ -270,7 +486,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             }
             for (int c = 0; c < p.chunks; ++c) {
                 for (int g = 0; g < shift_groups; ++g) {
-                    const int32_t s0 = g * S * kDiag;  // first token-row shift of this stage
+                    const int32_t s0 = g * S * kShiftRows;  // first token-row shift of this stage
                     mbar_wait_warp(empty_bar(stage), phase ^ 1u, 32);
                     const uint32_t a_dst = smem_base + stage * kStageSz;
                     const uint32_t b_dst = kARes ? a_dst : a_dst + kStageABytes;
@@ -310,14 +526,15 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         int as = 0;
         uint32_t aphase = 0;
         uint32_t a_phase = 0;
-        for (int64_t t = tile_begin; t < tile_end; ++t) {
-            if (kARes && (t == tile_begin || t % p.tiles_n == 0)) {
+        while (walk.next(tile)) {
+            if (kARes && tile.fan_first) {
                 mbar_wait_warp(afull_bar, a_phase, 0);  // the resident fan tile has landed (both CTAs)
                 a_phase ^= 1u;
             }
             mbar_wait_warp(tempty_bar(as), aphase ^ 1u, 0);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
+            const int n_shift = kMix ? (tile.e6 ? 1 : 2) : S;  // an E = 6 tile takes shift 0 only
             uint32_t accumulate = 0;
             for (int c = 0; c < p.chunks; ++c) {
                 // the last chunk may hold fewer than 64 real columns (d_pad is a multiple of
@@ -330,7 +547,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     // resident mode: the fan chunk sits in the resident tile and the stage holds
                     // only script rows; the stage's first shift is then an offset into the tile
                     const uint32_t a_src = kARes ? smem_a_res + c * kStageABytes +
-                                                       static_cast<uint32_t>(g * S * kDiag * 128)
+                                                       static_cast<uint32_t>(g * S * kShiftRows * 128)
                                                  : st_src;
                     const uint32_t b_src = kARes ? st_src : st_src + kStageABytes;
                     // descriptors of (shift 0, k-step 0); every other operand of the stage is
@@ -338,15 +555,17 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     const uint64_t adesc0 = umma_smem_desc(a_src, 0);
                     const uint64_t bdesc0 = umma_smem_desc(b_src, 0);
                     if (elect_one()) {
-                        for (int s = 0; s < S; ++s) {
-                            // row shift inside the stage = s * kDiag rows of 128 B: a plain offset
+                        for (int s = 0; s < n_shift; ++s) {
+                            // row shift inside the stage = s * E rows of 128 B: a plain offset
                             // of the descriptor start address (the 128B swizzle is a function of
                             // the absolute smem address, so base_offset stays 0)
-                            const uint32_t row_off = static_cast<uint32_t>(s * kDiag * 128) >> 4;
+                            const uint32_t row_off = static_cast<uint32_t>(s * kShiftRows * 128) >> 4;
 #pragma unroll 4
                             for (int k = 0; k < ksteps; ++k) {
                                 const uint64_t off = row_off + static_cast<uint32_t>(k * kUmmaK * 2 >> 4);
-                                if (kPair)
+                                if (kF8)
+                                    umma_f8_pair(tmem_d, adesc0 + off, bdesc0 + off, idesc, accumulate);
+                                else if (kPair)
                                     umma_f16_pair(tmem_d, adesc0 + off, bdesc0 + off, idesc, accumulate);
                                 else
                                     umma_f16(tmem_d, adesc0 + off, bdesc0 + off, idesc, accumulate);
@@ -375,7 +594,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     umma_commit(tfull_bar(as));
                 // last script tile of this fan tile: the resident tile may be replaced once
                 // these MMAs have retired
-                if (kARes && (t + 1 == tile_end || (t + 1) % p.tiles_n == 0)) umma_commit_pair(aempty_bar);
+                if (kARes && tile.fan_last) umma_commit_pair(aempty_bar);
             }
             __syncwarp();
             if (++as == kAccumStages) {
@@ -385,153 +604,20 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         }
     } else if (warp < kEpiWarps) {
         // ------------------------------------------------------------ epilogue (16 warps)
-        // warp -> TMEM lane quarter (warp & 3, a hardware restriction) x group of 64 columns.
-        //
-        // E > 1: out[i][j] = sum_{d<E} acc[i+d][j+d].  The column shift is a register index; the
-        // row shift is a warp shuffle for lanes < 32-(E-1).  The last E-1 rows of a quarter need
-        // rows of the NEXT quarter (another warp): every warp publishes its first and last E-1
-        // rows to shared memory while it streams its chunks, and after one barrier per tile those
-        // few boundary rows (3(E-1) of 128) are summed from shared memory, one column per lane.
-        constexpr int kEdge = kDiag - 1;            // boundary rows per side
-        constexpr int kTail0 = 32 - kEdge;          // first lane of the tail rows
-        const int quarter = warp & 3;
-        const int group = warp >> 2;
-        const int row = quarter * 32 + lane;
-        const int epi_tid = warp * 32 + lane;  // 0..511
-        // publish slot of this lane: head rows 0..E-2 -> slots 0..E-2, tail rows -> E-1..2E-3
-        const int pub_slot = lane < kEdge ? lane : (lane >= kTail0 ? kEdge + lane - kTail0 : -1);
-        auto pub_at = [&](int q, int slot) -> float* {
-            return halo + (q * kPubSlots + slot) * kHaloCols;
-        };
         int as = 0;
         uint32_t aphase = 0;
-        for (int64_t t = tile_begin; t < tile_end; ++t) {
-            const int32_t m0 = tile_m0(t);
-            const int32_t n0 = tile_n0(t);
-            const int32_t gi = m0 + row;
-            const bool row_ok = row < kMStep;
-            const float thr = row_ok ? __ldg(p.thr_fan + gi) : INFINITY;  // padded to a tile multiple
-            // rows whose sum needs another warp's rows are finished in the boundary pass
-            const float thr_main = (kDiag > 1 && lane >= kTail0) ? INFINITY : thr;
-            // E > 1: script-window norms of this tile staged once in smem, +inf baked in for the
-            // E-1 columns that belong to the next tile
-            float* ns_tile = norm_tile + as * kHaloCols;
-            if (kDiag > 1 && epi_tid < kHaloCols)
-                ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.norm_script + n0 + epi_tid) : INFINITY;
-            mbar_wait_warp(tfull_bar(as), aphase, 0);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                                   static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
-#pragma unroll 1
-            for (int ch = 0; ch < kEpiCols / 32; ++ch) {
-                const int c0 = group * kEpiCols + ch * 32;  // first column inside the tile
-                uint32_t r[40];
-                __syncwarp();
-                if (p.debug & 2) {
-#pragma unroll
-                    for (int x = 0; x < 40; ++x) r[x] = 0u;
-                } else {
-                    tmem_ld_32x32(taddr + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-                    if (kDiag > 1) {
-                        if (c0 + 32 < kBlockN) {
-                            tmem_ld_32x8(taddr + ch * 32 + 32, *reinterpret_cast<uint32_t(*)[8]>(&r[32]));
-                        } else {
-#pragma unroll
-                            for (int x = 32; x < 40; ++x) r[x] = 0u;
-                        }
-                    }
-                    tmem_ld_wait();
-                }
-                if (p.debug & 1) {
-                    if (__uint_as_float(r[0]) == 1.2345e-30f) p.counters[0] = 1;  // keep the loads alive
-                    continue;
-                }
-                if (kDiag > 1 && pub_slot >= 0) {
-                    uint4* dst = reinterpret_cast<uint4*>(pub_at(quarter, pub_slot) + c0);
-#pragma unroll
-                    for (int q = 0; q < 10; ++q)
-                        dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-                }
-                const int32_t gj0 = n0 + c0;
-                float mx;
-                uint32_t o16[16];
-                if (kDiag == 6 && kPack == 2) {
-                    mx = diag6_half(r, o16);  // o16[k] = half2(out[2k], out[2k+1])
-                } else {
-                    diag_sum_inplace<kDiag, kPack>(r);  // r[x] <- out[lane][c0 + x]
-                    mx = -INFINITY;
-                    if (!kDump) {
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) mx = fmaxf(mx, __uint_as_float(r[x]));
-                    }
-                }
-                auto out_val = [&](int x) {
-                    if (kDiag == 6 && kPack == 2) return (x & 1) ? h2_hi(o16[x >> 1]) : h2_lo(o16[x >> 1]);
-                    return __uint_as_float(r[x]);
-                };
-                if (kDump) {
-#pragma unroll
-                    for (int x = 0; x < 32; ++x) {
-                        if (row_ok && (kDiag == 1 || lane < kTail0) && gi < p.n_fan_tok &&
-                            c0 + x < kNStep && gj0 + x < p.dump_ld)
-                            p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + x] = out_val(x);
-                    }
-                } else {
-                    // one max over the chunk against thr * (smallest norm of the chunk) rejects
-                    // the chunk; the exact per-element test runs only on the rare survivor
-                    const float nmin = __ldg(p.norm_min32 + gj0);
-                    if (mx > thr_main * nmin) {
-#pragma unroll
-                        for (int x = 0; x < 32; ++x) {
-                            const float nsv = (c0 + x < kNStep) ? __ldg(p.norm_script + gj0 + x) : INFINITY;
-                            if (out_val(x) > thr_main * nsv) {
-                                const unsigned long long slot =
-                                    atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
-                                if (slot < static_cast<unsigned long long>(p.cand_cap)) {
-                                    p.cand[slot].fan_pos = gi;
-                                    p.cand[slot].script_pos = gj0 + x;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            if (kDiag > 1) {
-                // boundary rows: tail rows of quarters 0..2 (quarter 3's belong to the next tile)
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-#pragma unroll
-                for (int tr = 0; tr < kEdge; ++tr) {
-                    const int L = kTail0 + tr;
-                    const float thr_l = __shfl_sync(0xffffffffu, thr, L);
-                    if (quarter < 3) {
-#pragma unroll
-                        for (int it = 0; it < kEpiCols / 32; ++it) {
-                            const int c = group * kEpiCols + it * 32 + lane;
-                            float v = 0.f;
-#pragma unroll
-                            for (int d = 0; d < kDiag; ++d) {
-                                const int lp = L + d;  // row inside this quarter, or lp-32 of the next
-                                const float* src = lp < 32 ? pub_at(quarter, kEdge + lp - kTail0)
-                                                           : pub_at(quarter + 1, lp - 32);
-                                v += src[c + d];
-                            }
-                            const int32_t gr = m0 + quarter * 32 + L;
-                            if (kDump) {
-                                if (gr < p.n_fan_tok && c < kNStep && n0 + c < p.dump_ld)
-                                    p.dump[static_cast<int64_t>(gr) * p.dump_ld + n0 + c] = v;
-                            } else if (v > thr_l * ns_tile[c]) {
-                                const unsigned long long slot =
-                                    atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
-                                if (slot < static_cast<unsigned long long>(p.cand_cap)) {
-                                    p.cand[slot].fan_pos = gr;
-                                    p.cand[slot].script_pos = n0 + c;
-                                }
-                            }
-                        }
-                    }
-                }
-                // the next tile's chunks overwrite the published rows
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        while (walk.next(tile)) {
+            if constexpr (kMix) {
+                // kPack: 0 = full-precision shuffles, 1 = packed shuffles, 2 = E = 6 tiles in fp16x2
+                if (tile.e6)
+                    epilogue_tile<6, kDump, kPack>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase, tmem_base,
+                                                   halo, norm_tile, warp, lane);
+                else
+                    epilogue_tile<3, kDump, (kPack ? 1 : 0)>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase,
+                                                             tmem_base, halo, norm_tile, warp, lane);
+            } else {
+                epilogue_tile<kDiag, kDump, kPack>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase, tmem_base,
+                                                   halo, norm_tile, warp, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -604,15 +690,15 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
     return FS_OK;
 }
 
-template <int kDiag, bool kPair, bool kARes, int kPack>
+template <int kDiag, bool kPair, bool kARes, int kPack, bool kF8 = false>
 static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_script,
                              const DistParams& p, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair, kARes, kPack>,
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            dist_smem_bytes(kDiag, kPair, kARes)));
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair, kARes, kPack>,
+        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair, kARes, kPack, kF8>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            dist_smem_bytes(kDiag, kPair, kARes)));
         attr_set = true;
@@ -630,16 +716,20 @@ static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (p.dump)
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair, kARes, kPack>, map_fan, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair, kARes, kPack, kF8>, map_fan, map_script, p));
     else
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair, kARes, kPack>, map_fan, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>, map_fan, map_script, p));
     return FS_OK;
 }
 
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
                     int grid_limit, cudaStream_t stream) {
     const int64_t units_m = p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
-    const int64_t total = units_m * p.tiles_n;
+    int64_t total = units_m * p.tiles_n;
+    if (p.diag == kDiagMix) {
+        const int64_t total6 = static_cast<int64_t>((p.tiles_m6 + 1) / 2) * p.tiles_n6;
+        total = total > total6 ? total : total6;  // per-worker ranges are cut per tile kind
+    }
     if (total <= 0) return FS_OK;
     int grid;
     if (p.pair) {
@@ -649,7 +739,7 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         grid = static_cast<int>(total < grid_limit ? total : grid_limit);
     }
     const bool ares = p.pair && p.ares && p.chunks <= kAResChunks;
-    const int pack = (p.diag == 6) ? p.pack : (p.diag == 3 ? (p.pack ? 1 : 0) : 0);
+    const int pack = (p.diag == 6 || p.diag == kDiagMix) ? p.pack : (p.diag == 3 ? (p.pack ? 1 : 0) : 0);
 #define FS_LAUNCH(E, PAIR, ARES, PACK) \
     return launch_distance_t<E, PAIR, ARES, PACK>(map_fan, map_script, p, grid, stream)
 #define FS_LAUNCH_PACK(E, PAIR, ARES)              \
@@ -664,6 +754,28 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         if (p.pair) FS_LAUNCH_PACK(E, true, false); \
         FS_LAUNCH_PACK(E, false, false);           \
     } while (0)
+    if (p.f8) {
+        // fp8 operands: CTA pairs, streaming fan tile; the epilogue variants that are the defaults
+        if (!p.pair || ares) {
+            set_error("fp8 operands need CTA pairs without the A-resident tile");
+            return FS_E_INVALID;
+        }
+        switch (p.diag) {
+            case 1: return launch_distance_t<1, true, false, 0, true>(map_fan, map_script, p, grid, stream);
+            case 2: return launch_distance_t<2, true, false, 0, true>(map_fan, map_script, p, grid, stream);
+            case 3:
+                if (pack) return launch_distance_t<3, true, false, 1, true>(map_fan, map_script, p, grid, stream);
+                return launch_distance_t<3, true, false, 0, true>(map_fan, map_script, p, grid, stream);
+            case 6:
+                if (pack == 2) return launch_distance_t<6, true, false, 2, true>(map_fan, map_script, p, grid, stream);
+                return launch_distance_t<6, true, false, 1, true>(map_fan, map_script, p, grid, stream);
+            case kDiagMix:
+                return launch_distance_t<kDiagMix, true, false, 2, true>(map_fan, map_script, p, grid, stream);
+            default:
+                set_error("unsupported diagonal factor %d", p.diag);
+                return FS_E_INVALID;
+        }
+    }
     switch (p.diag) {
         case 1:
             if (ares) FS_LAUNCH(1, true, true, 0);
@@ -675,6 +787,14 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
             FS_LAUNCH(2, false, false, 0);
         case 3: FS_LAUNCH_MODE(3);
         case 6: FS_LAUNCH_MODE(6);
+        case kDiagMix:
+            if (!p.pair || ares) {
+                set_error("the mixed E = 3 / E = 6 schedule needs CTA pairs without the A-resident tile");
+                return FS_E_INVALID;
+            }
+            if (pack == 2) FS_LAUNCH(kDiagMix, true, false, 2);
+            if (pack == 1) FS_LAUNCH(kDiagMix, true, false, 1);
+            FS_LAUNCH(kDiagMix, true, false, 0);
         default:
             set_error("unsupported diagonal factor %d", p.diag);
             return FS_E_INVALID;

@@ -7,29 +7,59 @@
 // TMA loads address directly.  HBM-bound: 4 B read + dim_pad*2 B written per token
 // (table rows are L2 hits).
 #include "common.cuh"
+#include <cuda_fp8.h>
 
 namespace fs {
 
-// fp32 rows -> scaled fp16 rows padded to dim_pad, plus the squared norm of the scaled row
+// fp32 rows -> scaled operand rows (fp16, or fp8 e4m3 when kF8) padded to the row length, plus
+// per row the squared norm of the scaled fp32 row and the squared norm of its rounding error
 // (one warp per row).  Used once for the base table and per batch for OOV extras.
+template <bool kF8>
 __global__ void convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int32_t dim,
-                                    int32_t dim_pad, float scale, __half* __restrict__ dst,
-                                    float* __restrict__ sq) {
+                                    int32_t n_elems, float scale, void* __restrict__ dst,
+                                    float2* __restrict__ sq) {
     const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
     const float* s = src + row * dim;
-    __half* d = dst + row * dim_pad;
-    float acc = 0.f;
-    for (int c = lane; c < dim_pad; c += 32) {
-        float v = c < dim ? s[c] * scale : 0.f;
-        const __half h = __float2half_rn(v);
-        d[c] = h;
+    float acc = 0.f, err = 0.f;
+    for (int c = lane; c < n_elems; c += 32) {
+        const float v = c < dim ? s[c] * scale : 0.f;
+        float back;
+        if (kF8) {
+            const __nv_fp8_storage_t q = __nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+            static_cast<uint8_t*>(dst)[row * n_elems + c] = q;
+            back = __half2float(__half(__nv_cvt_fp8_to_halfraw(q, __NV_E4M3)));
+        } else {
+            const __half h = __float2half_rn(v);
+            static_cast<__half*>(dst)[row * n_elems + c] = h;
+            back = __half2float(h);
+        }
         acc = fmaf(v, v, acc);
+        err = fmaf(v - back, v - back, err);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        err += __shfl_xor_sync(0xffffffffu, err, o);
+    }
+    if (lane == 0) sq[row] = make_float2(acc, err);
+}
+
+// max over rows of the squared row norm (global fp8 scale); atomicMax on the bit pattern
+__global__ void rownorm_max_kernel(const float* __restrict__ src, int64_t n_rows, int32_t dim,
+                                   unsigned int* out) {
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    float acc = 0.f;
+    for (int c = lane; c < dim; c += 32) {
+        const float v = src[row * dim + c];
+        if (isfinite(v)) acc = fmaf(v, v, acc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) sq[row] = acc;
+    if (lane == 0) atomicMax(out, __float_as_uint(acc));
 }
 
 // max |x| over a float array (for the global fp16 scale); result via atomicMax on the bit pattern
@@ -52,9 +82,9 @@ constexpr int kGatherUnroll = 4;
 
 __device__ __forceinline__ int4 gather_chunk(const GatherSources& src, const int4* base16,
                                              const int4* sx16, const int4* fx16, int64_t id,
-                                             int32_t chunks16, int32_t c, float* sq) {
+                                             int32_t chunks16, int32_t c, float2* sq) {
     int4 v = make_int4(0, 0, 0, 0);  // unknown ids embed as the zero vector
-    *sq = 0.f;
+    *sq = make_float2(0.f, 0.f);
     if (id >= 0 && id < src.n_base) {
         v = __ldg(base16 + id * chunks16 + c);
         if (c == 0) *sq = __ldg(src.base_sq + id);
@@ -71,7 +101,7 @@ __device__ __forceinline__ int4 gather_chunk(const GatherSources& src, const int
 __global__ void __launch_bounds__(256)
 gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSources src,
               int32_t chunks16 /* dim_pad*2/16 */, int4* __restrict__ emb,
-              float* __restrict__ tok_sq) {
+              float2* __restrict__ tok_sq) {
     const int64_t total = n_tok * chunks16;
     const int4* base16 = reinterpret_cast<const int4*>(src.base16);
     const int4* sx16 = reinterpret_cast<const int4*>(src.sx16);
@@ -86,7 +116,7 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
     int32_t c0 = static_cast<int32_t>(g0 - t0 * chunks16);
     while (g0 < total) {
         int4 v[kGatherUnroll];
-        float sq[kGatherUnroll];
+        float2 sq[kGatherUnroll];
         int64_t t[kGatherUnroll];
         int32_t c[kGatherUnroll];
         int64_t id[kGatherUnroll];
@@ -117,31 +147,45 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
     }
 }
 
-// Per window start t:  norm = sqrt(sum_{k<w} tok_sq[t+k]) when the window lies inside its
-// CSR row, else +inf.  out[t] = coef * norm  (coef = 1-thr-eps on the fan side, 1 on the
-// script side).  out is padded with +inf up to n_pad.
-__global__ void window_norm_kernel(const float* __restrict__ tok_sq, int64_t n_tok,
+// Per window start t, with S = sum_{k<w} tok_sq[t+k].x (squared norm) and R = sum tok_sq[t+k].y
+// (squared rounding error of the operand rows):  out[t] = coef * sqrt(S) - kappa * sqrt(R) when the
+// window lies inside its CSR row, else +inf.  Fan side: coef = 1 - thr - eps (- rho of the script
+// side) and kappa = 1 + rho for fp8 operands, 0 for fp16; script side: coef = 1, kappa = 0 (the
+// true norm).  rho_out (optional) receives max sqrt(R/S), the largest relative rounding error of a
+// window.  out is padded with +inf up to n_pad.
+__global__ void window_norm_kernel(const float2* __restrict__ tok_sq, int64_t n_tok,
                                    const int64_t* __restrict__ off, int32_t n_rows, int32_t window,
-                                   float coef, float* __restrict__ out, int64_t n_pad,
-                                   unsigned long long* window_counter) {
+                                   float coef, float kappa, float* __restrict__ out, int64_t n_pad,
+                                   unsigned long long* window_counter, unsigned int* rho_out) {
     __shared__ int32_t row_hint;
     const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x;
     if (threadIdx.x == 0) row_hint = t0 < n_tok ? csr_row_of(off, n_rows, t0) : 0;
     __syncthreads();
     const int64_t t = t0 + threadIdx.x;
     unsigned int valid = 0;
+    float rho = 0.f;
     if (t < n_pad) {
         float r = INFINITY;
         if (t < n_tok) {
             const int32_t row = csr_row_from_hint(off, n_rows, t, row_hint);
             if (t + window <= __ldg(off + row + 1)) {
-                float s = 0.f;
-                for (int k = 0; k < window; ++k) s += tok_sq[t + k];
-                r = coef * sqrtf(s);
+                float s = 0.f, e = 0.f;
+                for (int k = 0; k < window; ++k) {
+                    const float2 q = tok_sq[t + k];
+                    s += q.x;
+                    e += q.y;
+                }
+                r = coef * sqrtf(s) - kappa * sqrtf(e);
+                if (s > 0.f) rho = sqrtf(e / s);
                 valid = 1;
             }
         }
         out[t] = r;
+    }
+    if (rho_out) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rho = fmaxf(rho, __shfl_xor_sync(0xffffffffu, rho, o));
+        if ((threadIdx.x & 31) == 0 && rho > 0.f) atomicMax(rho_out, __float_as_uint(rho));
     }
     if (window_counter) {
         const unsigned int n = __reduce_add_sync(0xffffffffu, valid);
@@ -167,12 +211,25 @@ int launch_sliding_min32(const float* src, float* dst, int64_t n, cudaStream_t s
 }
 
 int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
-                        __half* dst, float* sq, cudaStream_t stream) {
+                        bool f8, __half* dst, float2* sq, cudaStream_t stream) {
     if (n_rows <= 0) return FS_OK;
     const int threads = 256;
     const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
-    convert_rows_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(src, n_rows, dim,
-                                                                              dim_pad, scale, dst, sq);
+    if (f8)
+        convert_rows_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+            src, n_rows, dim, 2 * dim_pad, scale, dst, sq);
+    else
+        convert_rows_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+            src, n_rows, dim, dim_pad, scale, dst, sq);
+    FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
+int launch_rownorm_max(const float* src, int64_t n_rows, int32_t dim, unsigned int* out, cudaStream_t stream) {
+    if (n_rows <= 0) return FS_OK;
+    const int threads = 256;
+    const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
+    rownorm_max_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(src, n_rows, dim, out);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }
@@ -187,7 +244,7 @@ int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t s
 }
 
 int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,
-                  __half* emb, float* tok_sq, int sm_count, cudaStream_t stream) {
+                  __half* emb, float2* tok_sq, int sm_count, cudaStream_t stream) {
     if (n_tok <= 0) return FS_OK;
     const int32_t chunks16 = dim_pad * 2 / 16;
     const int64_t total = n_tok * chunks16;
@@ -201,14 +258,14 @@ int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, i
     return FS_OK;
 }
 
-int launch_window_norm(const float* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
-                       int32_t window, float coef, float* out, int64_t n_pad,
-                       unsigned long long* window_counter, cudaStream_t stream) {
+int launch_window_norm(const float2* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
+                       int32_t window, float coef, float kappa, float* out, int64_t n_pad,
+                       unsigned long long* window_counter, unsigned int* rho_out, cudaStream_t stream) {
     if (n_pad <= 0) return FS_OK;
     const int threads = 256;
     const int64_t blocks = (n_pad + threads - 1) / threads;
     window_norm_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-        tok_sq, n_tok, off, n_rows, window, coef, out, n_pad, window_counter);
+        tok_sq, n_tok, off, n_rows, window, coef, kappa, out, n_pad, window_counter, rho_out);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }

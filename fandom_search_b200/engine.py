@@ -57,7 +57,9 @@ class DeviceIndex:
         # experiment knobs (the defaults are chosen by the library, see csrc/api.cu)
         for env, opt in (("FANDOM_SEARCH_DIAG", nt.FS_OPT_DIAG), ("FANDOM_SEARCH_CTA_PAIR", nt.FS_OPT_CTA_PAIR),
                          ("FANDOM_SEARCH_A_RESIDENT", nt.FS_OPT_A_RESIDENT),
-                         ("FANDOM_SEARCH_PACKED_SHUFFLE", nt.FS_OPT_PACKED_SHUFFLE)):
+                         ("FANDOM_SEARCH_PACKED_SHUFFLE", nt.FS_OPT_PACKED_SHUFFLE),
+                         ("FANDOM_SEARCH_OPERAND_BITS", nt.FS_OPT_OPERAND_BITS),
+                         ("FANDOM_SEARCH_MIX_PATTERN", nt.FS_OPT_MIX_PATTERN)):
             v = os.environ.get(env)
             if v not in (None, ""):
                 self.set_option(opt, int(v))
@@ -77,6 +79,18 @@ class DeviceIndex:
     # -- knobs ------------------------------------------------------------
     def set_option(self, option, value):
         nt.check(self._lib.fs_index_set_option(self._h, option, value))
+        if option == nt.FS_OPT_OPERAND_BITS:      # the index was re-converted
+            self.dim_pad = int(self._lib.fs_index_get_info(self._h, 1))
+            self.scale = float(self._lib.fs_index_scale(self._h))
+
+    @property
+    def operand_bits(self):
+        """16: fp16 operands, 8: fp8 e4m3 operands of the distance kernel."""
+        return int(self._lib.fs_index_get_info(self._h, 11))
+
+    def info(self, what):
+        """fs_index_get_info(what) (see include/fandom_search.h)."""
+        return int(self._lib.fs_index_get_info(self._h, what))
 
     @property
     def diag(self):
@@ -195,7 +209,10 @@ class DeviceIndex:
     def stage_embed(self, tok_t, off_t, extra_t=None, stream=None):
         torch = _torch()
         n = tok_t.numel()
-        emb = torch.empty((n, self.dim_pad), dtype=torch.float16, device=tok_t.device)
+        if self.operand_bits == 8:      # raw e4m3 bytes (view as torch.float8_e4m3fn)
+            emb = torch.empty((n, self.dim_pad), dtype=torch.uint8, device=tok_t.device)
+        else:
+            emb = torch.empty((n, self.dim_pad), dtype=torch.float16, device=tok_t.device)
         thr = torch.empty((n,), dtype=torch.float32, device=tok_t.device)
         nt.check(self._lib.fs_stage_embed_dev(
             self._h, self._stream(stream), nt.ptr(tok_t), n, nt.ptr(off_t), off_t.numel() - 1,

@@ -208,6 +208,201 @@ def test_half_precision_epilogue_dots():
         idx.close()
 
 
+# ---------------------------------------------------------------------------------------------
+# fp8 e4m3 operands (FS_OPT_OPERAND_BITS = 8): measured rounding error in the pre-filter threshold
+# ---------------------------------------------------------------------------------------------
+def _f8_index(table, script, sx, diag=None, **opts):
+    idx = _device_index(table, script, extra=sx)
+    idx.set_option(nt.FS_OPT_OPERAND_BITS, 8)
+    if diag is not None:
+        idx.set_option(nt.FS_OPT_DIAG, diag)
+    for k, v in opts.items():
+        idx.set_option(k, v)
+    return idx
+
+
+def _e4m3(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.float8_e4m3fn)
+
+
+@pytest.mark.parametrize("diag", [1, 2, 3, 6, 36])
+@pytest.mark.parametrize("seed,dim", [(1, 300), (2, 64), (3, 768), (4, 100), (9, 50)])
+def test_fp8_search_equals_float64_reference(seed, dim, diag):
+    table, sx, fx, script, tok, off = _case(seed, dim=dim)
+    want, wc = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
+    idx = _f8_index(table, script, sx, diag)
+    assert idx.operand_bits == 8 and idx.dim_pad % 32 == 0
+    got, gc = idx.search_host(tok, off, fx)
+    assert _pairs(got) == _pairs(want) and len(got) == len(want) and len(want) > 0
+    wd = {(a, b): d for a, b, d in zip(want['fan_pos'].tolist(), want['script_pos'].tolist(), want['distance'].tolist())}
+    for a, b, d in zip(got['fan_pos'].tolist(), got['script_pos'].tolist(), got['distance'].tolist()):
+        assert abs(d - wd[(a, b)]) <= DIST_TOL
+    assert gc[nt.FS_CNT_WINDOWS] == wc[nt.FS_CNT_WINDOWS]
+    # switching back re-converts the index to fp16
+    idx.set_option(nt.FS_OPT_OPERAND_BITS, 16)
+    got16, _ = idx.search_host(tok, off, fx)
+    assert _pairs(got16) == _pairs(want)
+    idx.close()
+
+
+def test_fp8_gather_is_bit_exact_and_thresholds_hold_the_measured_error():
+    import torch
+    table, sx, fx, script, tok, off = _case(5)
+    idx = _f8_index(table, script, sx)
+    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+    emb, thr = idx.stage_embed(tok_t, off_t, fx_t)
+    torch.cuda.synchronize()
+    allrows = np.concatenate([table, sx, fx], axis=0)
+    scale = np.float32(idx.scale)
+    # scale = 96 / largest row norm of the table and the script extras
+    big = np.sqrt((np.concatenate([table, sx]).astype(np.float64) ** 2).sum(axis=1).max())
+    np.testing.assert_allclose(scale, 96.0 / big, rtol=1e-5)
+    want8 = torch.zeros((len(tok), idx.dim_pad), dtype=torch.uint8)
+    q = _e4m3(allrows[tok] * scale)
+    want8[:, :table.shape[1]] = q.view(torch.uint8)
+    assert torch.equal(emb.cpu(), want8)
+    # thresholds: (1 - thr - eps - rho) |f| - (1 + rho) |f - q(f)| per window, rho from the script side
+    x = allrows.astype(np.float64) * float(scale)
+    back = _e4m3(allrows * scale).float().numpy().astype(np.float64)
+    sq, er = (x ** 2).sum(axis=1), ((x - back) ** 2).sum(axis=1)
+    s_sq = np.array([sq[script[j:j + 6]].sum() for j in range(len(script) - 5)])
+    s_er = np.array([er[script[j:j + 6]].sum() for j in range(len(script) - 5)])
+    rho = np.sqrt(s_er / s_sq).max()
+    assert 0.005 < rho < 0.06
+    thr = thr.cpu().numpy()
+    for a, b in zip(off[:-1], off[1:]):
+        for i in range(int(a), int(b) - 5):
+            f_sq, f_er = sq[tok[i:i + 6]].sum(), er[tok[i:i + 6]].sum()
+            want = (1.0 - 0.1 - 3.0e-3 - rho) * np.sqrt(f_sq) - (1.0 + rho) * np.sqrt(f_er)
+            assert abs(thr[i] - want) <= 2e-5 * np.sqrt(f_sq)
+    idx.close()
+
+
+@pytest.mark.parametrize("diag", [1, 2, 3, 6, 36])
+def test_fp8_dots_match_the_e4m3_contraction(diag):
+    import torch
+    table, sx, fx, script, tok, off = _case(6, plant=False, clustered=False, works=(900, 3, 0, 6, 1400, 700))
+    idx = _f8_index(table, script, sx, diag)
+    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+    dots = idx.stage_dots(tok_t, off_t, fx_t).cpu().numpy()
+    allrows = np.concatenate([table, sx, fx], axis=0)
+    e8 = _e4m3(allrows * np.float32(idx.scale)).float().numpy().astype(np.float64)
+    ef = np.zeros((len(tok) + 6, table.shape[1])); ef[:len(tok)] = e8[tok]
+    es = np.zeros((len(script) + 6, table.shape[1])); es[:len(script)] = e8[script]
+    g = ef @ es.T
+    parts = [g[k:k + len(tok), k:k + len(script)] for k in range(6)]
+    want = sum(parts)
+    # products of e4m3 values are exact; fp32 accumulation + fp16x2 epilogue sums (2^-9 for E = 6)
+    bound = 2.0 ** -9 * sum(np.abs(q) for q in parts) + 1e-4 * np.abs(want).max()
+    assert np.all(np.abs(dots - want) <= bound)
+    idx.close()
+
+
+@pytest.mark.parametrize("diag", [2, 3, 6, 36])
+def test_fp8_candidates_are_a_superset(diag):
+    import torch
+    table, sx, fx, script, tok, off = _case(7, works=(900, 3, 0, 6, 1400, 700))
+    ref = NumpyIndex(table, script, extra=sx)
+    d, fpos = ref.distances(tok, off, fx)
+    idx = _f8_index(table, script, sx, diag)
+    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+    cand, cnt = idx.stage_candidates(tok_t, off_t, fx_t)
+    n = int(cnt.cpu()[nt.FS_CNT_CANDIDATES])
+    cand = cand.cpu().numpy()[:n]
+    got = set(map(tuple, cand.tolist()))
+    assert len(got) == len(cand)
+    ii, jj = np.nonzero(d < 0.1)
+    must = set(zip(fpos[ii].tolist(), ref.spos[jj].tolist()))
+    assert must <= got
+    row_of = {int(p): i for i, p in enumerate(fpos)}
+    col_of = {int(p): j for j, p in enumerate(ref.spos)}
+    worst = max(d[row_of[a], col_of[b]] for a, b in got)
+    assert worst < 0.1 + 0.15            # the fp8 slack is wide but finite
+    assert len(got) <= 4 * len(must) + 64
+    idx.close()
+
+
+def test_fp8_needs_cta_pairs():
+    table, sx, fx, script, tok, off = _case(1, dim=64)
+    idx = _f8_index(table, script, sx)
+    idx.set_option(nt.FS_OPT_CTA_PAIR, 0)
+    with pytest.raises(nt.NativeError):
+        idx.search_host(tok, off, fx)
+    idx.close()
+
+
+@pytest.mark.parametrize("grid", [0, 4])              # 4 CTAs = 2 workers: long tile sequences per worker
+@pytest.mark.parametrize("pack", [0, 1, 2])
+@pytest.mark.parametrize("pattern", [0x5, 0x7, 0x1, 0x0, 0xF, 0x6])
+def test_mixed_schedule_search(pattern, pack, grid):
+    """FS_OPT_DIAG = 36: tiles of the E = 3 and E = 6 kinds alternate over two row regions of the
+    batch; the match set is the float64 reference's whatever the pattern, pack level and grid."""
+    for seed, dim, works in ((1, 300, (200, 3, 0, 6, 397, 150)), (3, 768, (900, 3, 0, 6, 1400, 700)),
+                             (4, 100, (5, 2, 40))):
+        table, sx, fx, script, tok, off = _case(seed, dim=dim, works=works)
+        want, wc = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
+        idx = _device_index(table, script, extra=sx)
+        idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)
+        idx.set_option(nt.FS_OPT_MIX_PATTERN, pattern)
+        idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
+        idx.set_option(nt.FS_OPT_GRID_LIMIT, grid)
+        got, gc = idx.search_host(tok, off, fx)
+        assert _pairs(got) == _pairs(want) and len(got) == len(want)
+        assert gc[nt.FS_CNT_WINDOWS] == wc[nt.FS_CNT_WINDOWS]
+        idx.close()
+
+
+@pytest.mark.parametrize("pattern", [0x5, 0x3])
+def test_mixed_schedule_dots_and_candidates(pattern):
+    import torch
+    table, sx, fx, script, tok, off = _case(6, plant=False, clustered=False, works=(900, 3, 0, 6, 1400, 700))
+    idx = _device_index(table, script, extra=sx)
+    idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)
+    idx.set_option(nt.FS_OPT_MIX_PATTERN, pattern)
+    idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, 1)
+    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+    dots = idx.stage_dots(tok_t, off_t, fx_t).cpu().numpy()
+    allrows = np.concatenate([table, sx, fx], axis=0)
+    e16 = (allrows * np.float32(idx.scale)).astype(np.float16).astype(np.float64)
+    ef = np.zeros((len(tok) + 6, table.shape[1])); ef[:len(tok)] = e16[tok]
+    es = np.zeros((len(script) + 6, table.shape[1])); es[:len(script)] = e16[script]
+    g = ef @ es.T
+    want = sum(g[k:k + len(tok), k:k + len(script)] for k in range(6))
+    assert np.abs(dots - want).max() <= 2e-3 * np.abs(want).max()
+    idx.close()
+    # candidates: every pair once, a superset of the pairs under the threshold
+    table, sx, fx, script, tok, off = _case(7, works=(900, 3, 0, 6, 1400, 700))
+    ref = NumpyIndex(table, script, extra=sx)
+    d, fpos = ref.distances(tok, off, fx)
+    idx = _device_index(table, script, extra=sx)
+    idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)
+    idx.set_option(nt.FS_OPT_MIX_PATTERN, pattern)
+    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+    cand, cnt = idx.stage_candidates(tok_t, off_t, fx_t)
+    n = int(cnt.cpu()[nt.FS_CNT_CANDIDATES])
+    cand = cand.cpu().numpy()[:n]
+    got = set(map(tuple, cand.tolist()))
+    assert len(got) == len(cand)
+    ii, jj = np.nonzero(d < 0.1)
+    assert set(zip(fpos[ii].tolist(), ref.spos[jj].tolist())) <= got
+    idx.close()
+
+
+def test_mixed_schedule_needs_cta_pairs():
+    table, sx, fx, script, tok, off = _case(1, dim=64)
+    idx = _device_index(table, script, extra=sx)
+    idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)
+    idx.set_option(nt.FS_OPT_CTA_PAIR, 0)
+    with pytest.raises(nt.NativeError):
+        idx.search_host(tok, off, fx)
+    idx.close()
+    idx = _device_index(table, script, extra=sx, window=4)
+    with pytest.raises(nt.NativeError):
+        idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)      # window 6 only
+    idx.close()
+
+
 @pytest.mark.parametrize("pack", [1, 2])
 def test_half_precision_epilogue_search(pack):
     for seed, dim in ((1, 300), (2, 64), (4, 100)):

@@ -18,10 +18,12 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, debug=0, pack=None):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, debug=0, pack=None, pattern=None, clocks=False, bits=16):
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
+    if bits != 16:
+        idx.set_option(nt.FS_OPT_OPERAND_BITS, bits)
     idx.set_option(nt.FS_OPT_DIAG, diag)
     idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
     idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
@@ -29,6 +31,8 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
         idx.set_option(99, debug)
     if pack is not None:
         idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
+    if pattern is not None:
+        idx.set_option(nt.FS_OPT_MIX_PATTERN, pattern)
     n_works = max(1, nf // works_len)
     lens = np.full(n_works, (nf + 5 * n_works) // n_works + 1, dtype=np.int64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
@@ -41,18 +45,33 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     idx.search_dev(tok_t, off_t, None, out_t, cnt_t)   # warm-up
     idx.search_dev(tok_t, off_t, None, out_t, cnt_t)
     torch.cuda.synchronize()
+    sampler = None
+    if clocks:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from bench import ClockSampler
+        sampler = ClockSampler(0)
+        sampler.start()
     idx.timing_reset()
     for _ in range(reps):
         idx.search_dev(tok_t, off_t, None, out_t, cnt_t)
     torch.cuda.synchronize()
     ms, n = idx.timing_read()
+    clk = sampler.stop() if sampler else None
     windows = int(cnt_t.cpu()[nt.FS_CNT_WINDOWS])
     per = ms / n * 1e-3
-    res = {"diag": diag, "pair": pair, "debug": debug, "pack": pack, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
-           "kernel_ms": ms / n, "windows_per_s": windows / per,
+    if diag == nt.FS_DIAG_MIX:
+        # executed flops: E = 3 tiles on rows [0, row0_6), E = 6 tiles on the rest
+        f3 = min(1.0, idx.info(10) / max(1, int(off[-1])))
+        exec_factor = f3 * 2 * (128.0 * 256.0) / (126 * 254) + (1 - f3) * (128.0 * 256.0) / (123 * 251)
+    else:
+        exec_factor = (6 // diag) * (128.0 * 256.0) / ((129 - diag) * (257 - diag))
+    if bits == 8:
+        exec_factor *= 1.0   # same element count; idx.dim_pad already counts fp8 elements
+    res = {"bits": bits, "candidates": int(cnt_t.cpu()[nt.FS_CNT_CANDIDATES]), "matches": int(cnt_t.cpu()[nt.FS_CNT_MATCHES]),
+           "diag": diag, "pattern": pattern, "pair": pair, "debug": debug, "pack": pack, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
+           "kernel_ms": ms / n, "windows_per_s": windows / per, "clocks": clk,
            "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
-           "tflops_executed": 2.0 * (6 // diag) * idx.dim_pad * idx.n_script_windows * windows / per / 1e12
-           * (128.0 * 256.0) / ((129 - diag) * (257 - diag))}
+           "tflops_executed": 2.0 * exec_factor * idx.dim_pad * idx.n_script_windows * windows / per / 1e12}
     idx.close()
     del tok_t, out_t
     torch.cuda.empty_cache()
@@ -63,6 +82,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--diag", action="store_true", help="compare the diagonal-sum factors at C2 size")
+    ap.add_argument("--pattern", type=lambda v: int(v, 0), default=None, help="mix pattern (diag 36)")
+    ap.add_argument("--f8", action="store_true", help="fp8 e4m3 operands vs fp16 at C2 size, all diagonal factors")
+    ap.add_argument("--mix", action="store_true", help="compare the mixed E=3/E=6 schedule with E=3 and E=6 at C2 size")
     ap.add_argument("--one", type=int, nargs=4, metavar=("DIAG", "NF", "NS", "D"), help="run a single case")
     ap.add_argument("--pair", type=int, default=0)
     ap.add_argument("--pack", type=int, default=None)
@@ -77,7 +99,22 @@ def main():
         return
     if args.one:
         diag, nf, ns, d = args.one
-        print(json.dumps(run_case(nf, ns, d, 2, rng, diag=diag, pair=args.pair, pack=args.pack)), flush=True)
+        print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag, pair=args.pair, pack=args.pack,
+                                  pattern=args.pattern)), flush=True)
+        return
+    if args.f8:
+        for bits, diag, d, pattern in ((16, 3, 300, None), (8, 3, 300, None), (8, 2, 300, None), (8, 6, 300, None),
+                                       (8, 36, 300, 0x5), (8, 36, 300, 0x1), (8, 1, 300, None), (16, 6, 768, None),
+                                       (8, 6, 768, None), (8, 3, 768, None), (8, 36, 768, 0x5), (8, 3, 300, None)):
+            print(json.dumps(run_case(2_500_000, 25000, d, 20, rng, diag=diag, pair=1, pack=2 if diag in (6, 36) else 1,
+                                      pattern=pattern, clocks=True, bits=bits)), flush=True)
+        return
+    if args.mix:
+        for diag, pair, pack, pattern in ((3, 1, 1, None), (6, 1, 2, None), (6, 2, 2, None), (6, 1, 1, None),
+                                          (36, 1, 2, 0x5), (1, 1, 0, None), (2, 1, 0, None), (3, 0, 1, None),
+                                          (3, 1, 1, None)):
+            print(json.dumps(run_case(2_500_000, 25000, 300, 25, rng, diag=diag, pair=pair, pack=pack,
+                                      pattern=pattern, clocks=True)), flush=True)
         return
     if args.diag:
         for pair in (1, 2):
