@@ -27,7 +27,9 @@ constexpr double kEps = 4.0e-3;
 // fp8 operands: the operand rounding is measured per window; this slack covers what is left (fp32
 // accumulation order in the tensor core, fp16x2-packed epilogue sums <= 2^-9)
 constexpr double kEpsAccum = 3.0e-3;
-constexpr float kF8RowNorm = 96.0f;  // largest scaled row norm of an fp8 table
+// largest scaled row norm of an fp8 table: window token dots, |sum| <= window * norm^2, must still
+// fit the fp16 range of the packed epilogue (norm = 95.7 for 6-gram windows)
+inline float f8_row_norm(int32_t window) { return std::sqrt(55000.0f / static_cast<float>(window)); }
 
 template <typename T>
 static int dev_alloc(T** p, int64_t count) {
@@ -73,7 +75,7 @@ struct fs_index {
     int32_t dim = 0, window = 6;
     int32_t dim_pad = 0;        // operand row length in 2-byte units (fp16 elements, or fp8 elements / 2)
     int32_t dim_pad_elems = 0;  // operand row length in elements
-    int32_t operand_bits = 16;  // 16: fp16 operands, 8: fp8 e4m3 operands
+    int32_t operand_bits = 8;   // 16: fp16 operands, 8: fp8 e4m3 operands (default)
     float rho_script = 0.f;     // fp8: largest relative rounding error of a script window
     int64_t n_extra_rows = 0;
     double threshold = 0.1;
@@ -196,8 +198,8 @@ int fs_index_destroy(fs_index* idx) {
 
 // (Re)builds everything that depends on the operand type: the converted table and script
 // extras, the script token matrix, its window norms and tensor map.  fp16: one global scale
-// 1/max|x|; the fixed slack kEps covers the operand rounding.  fp8 e4m3: scale 96/max|row| (so
-// that six token dots, |sum| <= 6 * 96^2, still fit the fp16 range of the packed epilogue), the
+// 1/max|x|; the fixed slack kEps covers the operand rounding.  fp8 e4m3: scale f8_row_norm/max|row| (so
+// that the window's token dots still fit the fp16 range of the packed epilogue), the
 // rounding error of every row is MEASURED and enters the pre-filter threshold per window
 // (run_pipeline / window_norm_kernel), which keeps the candidate set a guaranteed superset.
 static int prepare_operands(fs_index* idx) {
@@ -233,7 +235,7 @@ static int prepare_operands(fs_index* idx) {
     if (!(h_max > 0.f && std::isfinite(h_max)))
         idx->scale = 1.0f;
     else
-        idx->scale = f8 ? kF8RowNorm / std::sqrt(h_max) : 1.0f / h_max;
+        idx->scale = f8 ? f8_row_norm(idx->window) / std::sqrt(h_max) : 1.0f / h_max;
     if ((r = launch_convert_rows(idx->table32, idx->n_base, idx->dim, idx->dim_pad, idx->scale, f8,
                                  idx->table16, idx->table_sq, st)) != FS_OK)
         return r;

@@ -144,6 +144,30 @@ __device__ __forceinline__ float diag6_half(const uint32_t (&r)[40], uint32_t (&
     return fmaxf(__low2float(mx), __high2float(mx));
 }
 
+// E = 3 in fp16x2 arithmetic (kPack == 2): out pair k = (a[2k], a[2k+1]) + (a[2k+1], a[2k+2])@(lane+1)
+// + (a[2k+2], a[2k+3])@(lane+2).  Three roundings per output (one per packed term, two HADD2 less
+// the exact first): |error| <= 3 * 2^-11 * sum_d |a_d| <= 1.5e-3 |f||s|, inside the pre-filter slack.
+__device__ __forceinline__ float diag3_half(const uint32_t (&r)[40], uint32_t (&o)[16]) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    auto f = [&](int x) { return __uint_as_float(r[x]); };
+    auto add2 = [](uint32_t a, uint32_t b) {
+        const __half2 s = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+        return *reinterpret_cast<const uint32_t*>(&s);
+    };
+    uint32_t pk[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) pk[k] = pack_h2(f(2 * k), f(2 * k + 1));
+    __half2 mx = __float2half2_rn(-60000.f);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t q1 = __shfl_down_sync(kFull, pack_h2(f(2 * k + 1), f(2 * k + 2)), 1);
+        const uint32_t q2 = __shfl_down_sync(kFull, pk[k + 1], 2);
+        o[k] = add2(add2(pk[k], q1), q2);
+        mx = __hmax2(mx, *reinterpret_cast<const __half2*>(&o[k]));
+    }
+    return fmaxf(__low2float(mx), __high2float(mx));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Tile schedule of one worker (a CTA, or a CTA pair).  Plain kernels: a contiguous range of
 // linearised (m, n) tiles, n fastest; in pair mode the unit is (pair of consecutive m tiles, n).
@@ -287,8 +311,9 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
         const int32_t gj0 = n0 + c0;
         float mx;
         uint32_t o16[16];
-        if (kDiag == 6 && kPack == 2) {
-            mx = diag6_half(r, o16);  // o16[k] = half2(out[2k], out[2k+1])
+        constexpr bool kHalf = kPack == 2 && (kDiag == 6 || kDiag == 3);
+        if (kHalf) {
+            mx = kDiag == 6 ? diag6_half(r, o16) : diag3_half(r, o16);  // o16[k] = half2(out[2k], out[2k+1])
         } else {
             diag_sum_inplace<kDiag, kPack>(r);  // r[x] <- out[lane][c0 + x]
             mx = -INFINITY;
@@ -298,7 +323,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
             }
         }
         auto out_val = [&](int x) {
-            if (kDiag == 6 && kPack == 2) return (x & 1) ? h2_hi(o16[x >> 1]) : h2_lo(o16[x >> 1]);
+            if (kHalf) return (x & 1) ? h2_hi(o16[x >> 1]) : h2_lo(o16[x >> 1]);
             return __uint_as_float(r[x]);
         };
         if (kDump) {
@@ -613,8 +638,8 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                     epilogue_tile<6, kDump, kPack>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase, tmem_base,
                                                    halo, norm_tile, warp, lane);
                 else
-                    epilogue_tile<3, kDump, (kPack ? 1 : 0)>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase,
-                                                             tmem_base, halo, norm_tile, warp, lane);
+                    epilogue_tile<3, kDump, kPack>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase, tmem_base,
+                                                   halo, norm_tile, warp, lane);
             } else {
                 epilogue_tile<kDiag, kDump, kPack>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase, tmem_base,
                                                    halo, norm_tile, warp, lane);
@@ -739,12 +764,12 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         grid = static_cast<int>(total < grid_limit ? total : grid_limit);
     }
     const bool ares = p.pair && p.ares && p.chunks <= kAResChunks;
-    const int pack = (p.diag == 6 || p.diag == kDiagMix) ? p.pack : (p.diag == 3 ? (p.pack ? 1 : 0) : 0);
+    const int pack = (p.diag == 6 || p.diag == 3 || p.diag == kDiagMix) ? p.pack : 0;
 #define FS_LAUNCH(E, PAIR, ARES, PACK) \
     return launch_distance_t<E, PAIR, ARES, PACK>(map_fan, map_script, p, grid, stream)
 #define FS_LAUNCH_PACK(E, PAIR, ARES)              \
     do {                                           \
-        if (pack == 2 && E == 6) FS_LAUNCH(E, PAIR, ARES, (E == 6 ? 2 : 1)); \
+        if (pack == 2) FS_LAUNCH(E, PAIR, ARES, 2); \
         if (pack >= 1) FS_LAUNCH(E, PAIR, ARES, 1); \
         FS_LAUNCH(E, PAIR, ARES, 0);               \
     } while (0)
@@ -764,8 +789,8 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
             case 1: return launch_distance_t<1, true, false, 0, true>(map_fan, map_script, p, grid, stream);
             case 2: return launch_distance_t<2, true, false, 0, true>(map_fan, map_script, p, grid, stream);
             case 3:
-                if (pack) return launch_distance_t<3, true, false, 1, true>(map_fan, map_script, p, grid, stream);
-                return launch_distance_t<3, true, false, 0, true>(map_fan, map_script, p, grid, stream);
+                if (pack == 2) return launch_distance_t<3, true, false, 2, true>(map_fan, map_script, p, grid, stream);
+                return launch_distance_t<3, true, false, 1, true>(map_fan, map_script, p, grid, stream);
             case 6:
                 if (pack == 2) return launch_distance_t<6, true, false, 2, true>(map_fan, map_script, p, grid, stream);
                 return launch_distance_t<6, true, false, 1, true>(map_fan, map_script, p, grid, stream);

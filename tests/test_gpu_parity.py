@@ -22,9 +22,14 @@ pytestmark = pytest.mark.gpu
 DIST_TOL = 1e-12
 
 
-def _device_index(*a, **kw):
+def _device_index(*a, bits=16, **kw):
+    """fp16 operands unless asked otherwise (the library default is fp8, see _f8_index and
+    test_library_defaults): the stage-level expectations below are written for fp16."""
     from fandom_search_b200.engine import DeviceIndex
-    return DeviceIndex(*a, **kw)
+    idx = DeviceIndex(*a, **kw)
+    if bits is not None and idx.operand_bits != bits:
+        idx.set_option(nt.FS_OPT_OPERAND_BITS, bits)
+    return idx
 
 
 def _case(seed, vocab=800, dim=300, n_script=700, works=(200, 3, 0, 6, 397, 150), n_extra_s=3,
@@ -93,13 +98,14 @@ def test_search_equals_float64_reference(seed, dim, diag, pair):
     idx.close()
 
 
+@pytest.mark.parametrize("bits", [16, 8])
 @pytest.mark.parametrize("window", [3, 4, 5, 7, 8])
-def test_other_window_sizes(window):
+def test_other_window_sizes(window, bits):
     """window_size is a keyword of analyze (search.py:337); the kernel picks E = 3, 2 or 1."""
     table, sx, fx, script, tok, off = _case(20 + window, dim=100)
     ref = NumpyIndex(table, script, extra=sx, window=window)
     want, wc = ref.search_host(tok, off, fx)
-    idx = _device_index(table, script, extra=sx, window=window)
+    idx = _device_index(table, script, extra=sx, window=window, bits=bits)
     assert idx.diag == (3 if window % 3 == 0 else 2 if window % 2 == 0 else 1)   # dim 100 < 416
     got, gc = idx.search_host(tok, off, fx)
     assert _pairs(got) == _pairs(want) and len(want) > 0
@@ -151,7 +157,21 @@ def test_gather_is_bit_exact_and_norms_match():
     assert np.all(np.isinf(thr[~valid])) and np.all(np.isfinite(thr[valid]))
     coef = 1.0 - 0.1 - 4.0e-3
     np.testing.assert_allclose(thr[valid], coef * wantn[valid], rtol=2e-6)
-    assert idx.diag == 3 and idx.cta_pair == 1      # defaults for 6-gram windows
+    idx.close()
+
+
+def test_library_defaults():
+    """6-gram windows, d = 300: fp8 operands, E = 3, CTA pairs; wide embeddings take E = 6."""
+    table, sx, fx, script, tok, off = _case(5)
+    idx = _device_index(table, script, extra=sx, bits=None)
+    assert idx.operand_bits == 8 and idx.diag == 3 and idx.cta_pair == 1
+    want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
+    got, _ = idx.search_host(tok, off, fx)
+    assert _pairs(got) == _pairs(want)
+    idx.close()
+    table, sx, fx, script, tok, off = _case(3, dim=768)
+    idx = _device_index(table, script, extra=sx, bits=None)
+    assert idx.operand_bits == 8 and idx.diag == 6
     idx.close()
 
 
@@ -181,14 +201,15 @@ def test_tensor_core_dots_match_fp16_contraction(diag, shifts, pair):
     idx.close()
 
 
-def test_half_precision_epilogue_dots():
-    """E = 6 with the diagonal summed in fp16x2 arithmetic (pack level 2): looser tolerance,
+@pytest.mark.parametrize("diag", [3, 6])
+def test_half_precision_epilogue_dots(diag):
+    """E = 3, 6 with the diagonal summed in fp16x2 arithmetic (pack level 2): looser tolerance,
     bounded by 2^-9 * sum of the six partial-dot magnitudes."""
     import torch
     table, sx, fx, script, tok, off = _case(6, plant=False, clustered=False)
     for pair in (0, 1, 2):
         idx = _device_index(table, script, extra=sx)
-        idx.set_option(nt.FS_OPT_DIAG, 6)
+        idx.set_option(nt.FS_OPT_DIAG, diag)
         idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, 2)
         idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
         idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
@@ -212,8 +233,7 @@ def test_half_precision_epilogue_dots():
 # fp8 e4m3 operands (FS_OPT_OPERAND_BITS = 8): measured rounding error in the pre-filter threshold
 # ---------------------------------------------------------------------------------------------
 def _f8_index(table, script, sx, diag=None, **opts):
-    idx = _device_index(table, script, extra=sx)
-    idx.set_option(nt.FS_OPT_OPERAND_BITS, 8)
+    idx = _device_index(table, script, extra=sx, bits=8)
     if diag is not None:
         idx.set_option(nt.FS_OPT_DIAG, diag)
     for k, v in opts.items():
@@ -226,12 +246,14 @@ def _e4m3(x):
     return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.float8_e4m3fn)
 
 
+@pytest.mark.parametrize("pack", [1, 2])
 @pytest.mark.parametrize("diag", [1, 2, 3, 6, 36])
 @pytest.mark.parametrize("seed,dim", [(1, 300), (2, 64), (3, 768), (4, 100), (9, 50)])
-def test_fp8_search_equals_float64_reference(seed, dim, diag):
+def test_fp8_search_equals_float64_reference(seed, dim, diag, pack):
     table, sx, fx, script, tok, off = _case(seed, dim=dim)
     want, wc = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
     idx = _f8_index(table, script, sx, diag)
+    idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
     assert idx.operand_bits == 8 and idx.dim_pad % 32 == 0
     got, gc = idx.search_host(tok, off, fx)
     assert _pairs(got) == _pairs(want) and len(got) == len(want) and len(want) > 0
@@ -255,9 +277,9 @@ def test_fp8_gather_is_bit_exact_and_thresholds_hold_the_measured_error():
     torch.cuda.synchronize()
     allrows = np.concatenate([table, sx, fx], axis=0)
     scale = np.float32(idx.scale)
-    # scale = 96 / largest row norm of the table and the script extras
+    # scale = sqrt(55000 / window) / largest row norm of the table and the script extras
     big = np.sqrt((np.concatenate([table, sx]).astype(np.float64) ** 2).sum(axis=1).max())
-    np.testing.assert_allclose(scale, 96.0 / big, rtol=1e-5)
+    np.testing.assert_allclose(scale, np.sqrt(55000.0 / 6) / big, rtol=1e-5)
     want8 = torch.zeros((len(tok), idx.dim_pad), dtype=torch.uint8)
     q = _e4m3(allrows[tok] * scale)
     want8[:, :table.shape[1]] = q.view(torch.uint8)
@@ -403,14 +425,15 @@ def test_mixed_schedule_needs_cta_pairs():
     idx.close()
 
 
+@pytest.mark.parametrize("diag", [3, 6])
 @pytest.mark.parametrize("pack", [1, 2])
-def test_half_precision_epilogue_search(pack):
+def test_half_precision_epilogue_search(pack, diag):
     for seed, dim in ((1, 300), (2, 64), (4, 100)):
         table, sx, fx, script, tok, off = _case(seed, dim=dim)
         want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
         for pair in (0, 1, 2):
             idx = _device_index(table, script, extra=sx)
-            idx.set_option(nt.FS_OPT_DIAG, 6)
+            idx.set_option(nt.FS_OPT_DIAG, diag)
             idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
             idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
             idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)

@@ -103,11 +103,10 @@ def main():
                                   pattern=args.pattern)), flush=True)
         return
     if args.f8:
-        for bits, diag, d, pattern in ((16, 3, 300, None), (8, 3, 300, None), (8, 2, 300, None), (8, 6, 300, None),
-                                       (8, 36, 300, 0x5), (8, 36, 300, 0x1), (8, 1, 300, None), (16, 6, 768, None),
-                                       (8, 6, 768, None), (8, 3, 768, None), (8, 36, 768, 0x5), (8, 3, 300, None)):
-            print(json.dumps(run_case(2_500_000, 25000, d, 20, rng, diag=diag, pair=1, pack=2 if diag in (6, 36) else 1,
-                                      pattern=pattern, clocks=True, bits=bits)), flush=True)
+        for bits, diag, d, pack in ((16, 3, 300, 1), (16, 3, 300, 2), (8, 3, 300, 1), (8, 3, 300, 2), (8, 2, 300, 0),
+                                    (8, 6, 300, 2), (8, 6, 768, 2), (8, 3, 768, 2), (8, 3, 300, 2)):
+            print(json.dumps(run_case(2_500_000, 25000, d, 20, rng, diag=diag, pair=1, pack=pack,
+                                      clocks=True, bits=bits)), flush=True)
         return
     if args.mix:
         for diag, pair, pack, pattern in ((3, 1, 1, None), (6, 1, 2, None), (6, 2, 2, None), (6, 1, 1, None),
