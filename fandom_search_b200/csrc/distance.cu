@@ -120,19 +120,18 @@ __device__ __forceinline__ void diag_sum_inplace(uint32_t (&r)[40]) {
 // and every HADD2 result is rounded to fp16: |error| <= 4 * 2^-11 * sum_k |G_k| <= 2^-9 |f||s|
 // (G_k = the six partial dots of the window, sum |G_k| <= |f||s|), covered by the pre-filter
 // slack; the decision is re-made in float64.  On return o[k] = half2(out[2k], out[2k+1]).
-__device__ __forceinline__ float diag6_half(const uint32_t (&r)[40], uint32_t (&o)[16]) {
+__device__ __forceinline__ float diag6_half(const uint32_t (&r)[40], const uint32_t (&pk)[20], uint32_t (&o)[16]) {
     constexpr uint32_t kFull = 0xffffffffu;
     auto f = [&](int x) { return __uint_as_float(r[x]); };
     auto add2 = [](uint32_t a, uint32_t b) {
         const __half2 s = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
         return *reinterpret_cast<const uint32_t*>(&s);
     };
-    // D2 pair k = (a[2k], a[2k+1]) + (a[2k+1], a[2k+2])@(lane+1),  k = 0..17
+    // D2 pair k = (a[2k], a[2k+1]) + (a[2k+1], a[2k+2])@(lane+1),  k = 0..17   (pk[k] = (a[2k], a[2k+1]))
     uint32_t d2[18];
 #pragma unroll
     for (int k = 0; k < 18; ++k)
-        d2[k] = add2(pack_h2(f(2 * k), f(2 * k + 1)),
-                     __shfl_down_sync(kFull, pack_h2(f(2 * k + 1), f(2 * k + 2)), 1));
+        d2[k] = add2(pk[k], __shfl_down_sync(kFull, pack_h2(f(2 * k + 1), f(2 * k + 2)), 1));
     // out pair k = D2[k] + D2[k+1]@(lane+2) + D2[k+2]@(lane+4),  k = 0..15
     __half2 mx = __float2half2_rn(-60000.f);
 #pragma unroll
@@ -145,18 +144,15 @@ __device__ __forceinline__ float diag6_half(const uint32_t (&r)[40], uint32_t (&
 }
 
 // E = 3 in fp16x2 arithmetic (kPack == 2): out pair k = (a[2k], a[2k+1]) + (a[2k+1], a[2k+2])@(lane+1)
-// + (a[2k+2], a[2k+3])@(lane+2).  Three roundings per output (one per packed term, two HADD2 less
-// the exact first): |error| <= 3 * 2^-11 * sum_d |a_d| <= 1.5e-3 |f||s|, inside the pre-filter slack.
-__device__ __forceinline__ float diag3_half(const uint32_t (&r)[40], uint32_t (&o)[16]) {
+// + (a[2k+2], a[2k+3])@(lane+2).  Three roundings per output: |error| <= 3 * 2^-11 * sum_d |a_d|
+// <= 1.5e-3 |f||s|, inside the pre-filter slack.
+__device__ __forceinline__ float diag3_half(const uint32_t (&r)[40], const uint32_t (&pk)[20], uint32_t (&o)[16]) {
     constexpr uint32_t kFull = 0xffffffffu;
     auto f = [&](int x) { return __uint_as_float(r[x]); };
     auto add2 = [](uint32_t a, uint32_t b) {
         const __half2 s = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
         return *reinterpret_cast<const uint32_t*>(&s);
     };
-    uint32_t pk[17];
-#pragma unroll
-    for (int k = 0; k < 17; ++k) pk[k] = pack_h2(f(2 * k), f(2 * k + 1));
     __half2 mx = __float2half2_rn(-60000.f);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -164,6 +160,22 @@ __device__ __forceinline__ float diag3_half(const uint32_t (&r)[40], uint32_t (&
         const uint32_t q2 = __shfl_down_sync(kFull, pk[k + 1], 2);
         o[k] = add2(add2(pk[k], q1), q2);
         mx = __hmax2(mx, *reinterpret_cast<const __half2*>(&o[k]));
+    }
+    return fmaxf(__low2float(mx), __high2float(mx));
+}
+
+// E = 2 in fp16x2 arithmetic: out pair k = (a[2k], a[2k+1]) + (a[2k+1], a[2k+2])@(lane+1): one shuffle
+// per two outputs, two roundings per output.
+__device__ __forceinline__ float diag2_half(const uint32_t (&r)[40], const uint32_t (&pk)[20], uint32_t (&o)[16]) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    auto f = [&](int x) { return __uint_as_float(r[x]); };
+    __half2 mx = __float2half2_rn(-60000.f);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t q1 = __shfl_down_sync(kFull, pack_h2(f(2 * k + 1), f(2 * k + 2)), 1);
+        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&pk[k]), *reinterpret_cast<const __half2*>(&q1));
+        o[k] = *reinterpret_cast<const uint32_t*>(&sum);
+        mx = __hmax2(mx, sum);
     }
     return fmaxf(__low2float(mx), __high2float(mx));
 }
@@ -263,6 +275,10 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     // publish slot of this lane: head rows 0..E-2 -> slots 0..E-2, tail rows -> E-1..2E-3
     const int pub_slot = lane < kEdge ? lane : (lane >= kTail0 ? kEdge + lane - kTail0 : -1);
     auto pub_at = [&](int q, int slot) -> float* { return halo + (q * kPubSlots + slot) * kHaloCols; };
+    // kPack == 2: the whole diagonal sum runs on fp16x2 pairs, and the boundary rows are published as halves
+    constexpr bool kHalf = kPack == 2 && (kDiag == 6 || kDiag == 3 || kDiag == 2);
+    __half* halo_h = reinterpret_cast<__half*>(halo);
+    auto pub_half_at = [&](int q, int slot) -> __half* { return halo_h + (q * kPubSlots + slot) * kHaloCols; };
 
     const int32_t gi = m0 + row;
     const bool row_ok = row < kMStep;
@@ -302,18 +318,29 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
             if (__uint_as_float(r[0]) == 1.2345e-30f) p.counters[0] = 1;  // keep the loads alive
             continue;
         }
-        if (kDiag > 1 && pub_slot >= 0) {
-            uint4* dst = reinterpret_cast<uint4*>(pub_at(quarter, pub_slot) + c0);
+        uint32_t pk[20];
+        if (kHalf) {
 #pragma unroll
-            for (int q = 0; q < 10; ++q)
-                dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            for (int k = 0; k < 20; ++k) pk[k] = pack_h2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+        }
+        if (kDiag > 1 && pub_slot >= 0) {
+            if (kHalf) {
+                uint4* dst = reinterpret_cast<uint4*>(pub_half_at(quarter, pub_slot) + c0);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            } else {
+                uint4* dst = reinterpret_cast<uint4*>(pub_at(quarter, pub_slot) + c0);
+#pragma unroll
+                for (int q = 0; q < 10; ++q)
+                    dst[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            }
         }
         const int32_t gj0 = n0 + c0;
         float mx;
         uint32_t o16[16];
-        constexpr bool kHalf = kPack == 2 && (kDiag == 6 || kDiag == 3);
         if (kHalf) {
-            mx = kDiag == 6 ? diag6_half(r, o16) : diag3_half(r, o16);  // o16[k] = half2(out[2k], out[2k+1])
+            // o16[k] = half2(out[2k], out[2k+1])
+            mx = kDiag == 6 ? diag6_half(r, pk, o16) : (kDiag == 3 ? diag3_half(r, pk, o16) : diag2_half(r, pk, o16));
         } else {
             diag_sum_inplace<kDiag, kPack>(r);  // r[x] <- out[lane][c0 + x]
             mx = -INFINITY;
@@ -367,9 +394,15 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
 #pragma unroll
                     for (int d = 0; d < kDiag; ++d) {
                         const int lp = L + d;  // row inside this quarter, or lp-32 of the next
-                        const float* src = lp < 32 ? pub_at(quarter, kEdge + lp - kTail0)
-                                                   : pub_at(quarter + 1, lp - 32);
-                        v += src[c + d];
+                        if (kHalf) {
+                            const __half* src = lp < 32 ? pub_half_at(quarter, kEdge + lp - kTail0)
+                                                        : pub_half_at(quarter + 1, lp - 32);
+                            v += __half2float(src[c + d]);
+                        } else {
+                            const float* src = lp < 32 ? pub_at(quarter, kEdge + lp - kTail0)
+                                                       : pub_at(quarter + 1, lp - 32);
+                            v += src[c + d];
+                        }
                     }
                     const int32_t gr = m0 + quarter * 32 + L;
                     if (kDump) {
@@ -764,7 +797,7 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         grid = static_cast<int>(total < grid_limit ? total : grid_limit);
     }
     const bool ares = p.pair && p.ares && p.chunks <= kAResChunks;
-    const int pack = (p.diag == 6 || p.diag == 3 || p.diag == kDiagMix) ? p.pack : 0;
+    const int pack = (p.diag == 6 || p.diag == 3 || p.diag == kDiagMix) ? p.pack : (p.diag == 2 && p.pack == 2 ? 2 : 0);
 #define FS_LAUNCH(E, PAIR, ARES, PACK) \
     return launch_distance_t<E, PAIR, ARES, PACK>(map_fan, map_script, p, grid, stream)
 #define FS_LAUNCH_PACK(E, PAIR, ARES)              \
@@ -787,7 +820,9 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         }
         switch (p.diag) {
             case 1: return launch_distance_t<1, true, false, 0, true>(map_fan, map_script, p, grid, stream);
-            case 2: return launch_distance_t<2, true, false, 0, true>(map_fan, map_script, p, grid, stream);
+            case 2:
+                if (pack == 2) return launch_distance_t<2, true, false, 2, true>(map_fan, map_script, p, grid, stream);
+                return launch_distance_t<2, true, false, 0, true>(map_fan, map_script, p, grid, stream);
             case 3:
                 if (pack == 2) return launch_distance_t<3, true, false, 2, true>(map_fan, map_script, p, grid, stream);
                 return launch_distance_t<3, true, false, 1, true>(map_fan, map_script, p, grid, stream);
@@ -807,6 +842,11 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
             if (p.pair) FS_LAUNCH(1, true, false, 0);
             FS_LAUNCH(1, false, false, 0);
         case 2:
+            if (pack == 2) {
+                if (ares) FS_LAUNCH(2, true, true, 2);
+                if (p.pair) FS_LAUNCH(2, true, false, 2);
+                FS_LAUNCH(2, false, false, 2);
+            }
             if (ares) FS_LAUNCH(2, true, true, 0);
             if (p.pair) FS_LAUNCH(2, true, false, 0);
             FS_LAUNCH(2, false, false, 0);

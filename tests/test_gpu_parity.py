@@ -201,7 +201,7 @@ def test_tensor_core_dots_match_fp16_contraction(diag, shifts, pair):
     idx.close()
 
 
-@pytest.mark.parametrize("diag", [3, 6])
+@pytest.mark.parametrize("diag", [2, 3, 6])
 def test_half_precision_epilogue_dots(diag):
     """E = 3, 6 with the diagonal summed in fp16x2 arithmetic (pack level 2): looser tolerance,
     bounded by 2^-9 * sum of the six partial-dot magnitudes."""
@@ -425,7 +425,7 @@ def test_mixed_schedule_needs_cta_pairs():
     idx.close()
 
 
-@pytest.mark.parametrize("diag", [3, 6])
+@pytest.mark.parametrize("diag", [2, 3, 6])
 @pytest.mark.parametrize("pack", [1, 2])
 def test_half_precision_epilogue_search(pack, diag):
     for seed, dim in ((1, 300), (2, 64), (4, 100)):

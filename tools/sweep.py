@@ -18,12 +18,13 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, debug=0, pack=None, pattern=None, clocks=False, bits=16):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, debug=0, pack=None, pattern=None, clocks=False, bits=8):
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
-    if bits != 16:
-        idx.set_option(nt.FS_OPT_OPERAND_BITS, bits)
+    if pair != 1:
+        bits = 16      # fp8 operands exist for plain CTA pairs only
+    idx.set_option(nt.FS_OPT_OPERAND_BITS, bits)
     idx.set_option(nt.FS_OPT_DIAG, diag)
     idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
     idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
@@ -82,6 +83,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--diag", action="store_true", help="compare the diagonal-sum factors at C2 size")
+    ap.add_argument("--bits", type=int, default=8, help="operand bits for --one (8 = fp8 e4m3, 16 = fp16)")
     ap.add_argument("--pattern", type=lambda v: int(v, 0), default=None, help="mix pattern (diag 36)")
     ap.add_argument("--f8", action="store_true", help="fp8 e4m3 operands vs fp16 at C2 size, all diagonal factors")
     ap.add_argument("--mix", action="store_true", help="compare the mixed E=3/E=6 schedule with E=3 and E=6 at C2 size")
@@ -100,11 +102,11 @@ def main():
     if args.one:
         diag, nf, ns, d = args.one
         print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag, pair=args.pair, pack=args.pack,
-                                  pattern=args.pattern)), flush=True)
+                                  pattern=args.pattern, bits=args.bits)), flush=True)
         return
     if args.f8:
-        for bits, diag, d, pack in ((16, 3, 300, 1), (16, 3, 300, 2), (8, 3, 300, 1), (8, 3, 300, 2), (8, 2, 300, 0),
-                                    (8, 6, 300, 2), (8, 6, 768, 2), (8, 3, 768, 2), (8, 3, 300, 2)):
+        for bits, diag, d, pack in ((16, 3, 300, 2), (8, 3, 300, 2), (8, 2, 300, 2), (8, 2, 300, 0), (8, 6, 300, 2),
+                                    (8, 6, 768, 2), (8, 3, 768, 2), (8, 2, 768, 2), (16, 6, 768, 2), (8, 3, 300, 2)):
             print(json.dumps(run_case(2_500_000, 25000, d, 20, rng, diag=diag, pair=1, pack=pack,
                                       clocks=True, bits=bits)), flush=True)
         return
