@@ -140,7 +140,6 @@ struct fs_index {
     // options
     int32_t diag = 1;              // diagonal-sum factor E of the distance kernel
     int32_t pair = 0;              // CTA-pair (cta_group::2) kernel
-    int32_t debug = 0;
     int32_t ares = 0;              // A-resident variant of the pair kernel
     int32_t pack = 2;              // epilogue diagonal sums: 0 fp32 shuffles, 1 fp16x2 shuffles, 2 fp16x2 arithmetic
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
@@ -425,9 +424,6 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             }
             idx->shifts_per_stage = static_cast<int32_t>(value);
             return FS_OK;
-        case 99:  // timing experiments (results invalid)
-            idx->debug = static_cast<int32_t>(value);
-            return FS_OK;
         case FS_OPT_PACKED_SHUFFLE:
             idx->pack = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int32_t>(value));
             return FS_OK;
@@ -659,7 +655,6 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.diag = idx->diag;
     p.pair = idx->pair;
     p.f8 = idx->operand_bits == 8;
-    p.debug = idx->debug;
     p.ares = idx->ares;
     p.pack = idx->pack;
     p.shifts_per_stage = mix ? 2 : (idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag);

@@ -90,7 +90,6 @@ struct DistParams {
     int32_t last_chunk_ksteps;// UMMA K-steps (16 columns) in the last chunk: 1..4
     int32_t window;           // 6
     int32_t diag;             // E: epilogue adds E diagonal neighbours, MMAs do window/E shifts
-    int32_t debug;            // timing experiments only: 1 = skip epilogue math, 2 = skip TMEM loads
     int32_t pack;             // 1: fp16x2-packed epilogue shuffles (E = 3, 6)
     int32_t ares;             // 1: A-resident variant (pair mode, chunks <= kAResChunks)
     int32_t f8;               // 1: operands are fp8 e4m3 (tcgen05.mma.kind::f8f6f4, K = 32)
@@ -409,6 +408,25 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
           "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
+        : "memory");
+}
+
+// 32 columns at taddr plus the 8 halo columns at taddr8, in ONE asm statement: with two statements
+// ptxas re-uses the first registers for the second load and copies all 32 results away first
+__device__ __forceinline__ void tmem_ld_32x40(uint32_t taddr, uint32_t taddr8, uint32_t (&r)[40]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%40];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%32, %33, %34, %35, %36, %37, %38, %39}, [%41];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]),
+          "=r"(r[38]), "=r"(r[39])
+        : "r"(taddr), "r"(taddr8)
         : "memory");
 }
 

@@ -18,7 +18,7 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, debug=0, pack=None, pattern=None, clocks=False, bits=8):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, pack=None, pattern=None, clocks=False, bits=8):
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
@@ -28,8 +28,6 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     idx.set_option(nt.FS_OPT_DIAG, diag)
     idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
     idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
-    if debug:
-        idx.set_option(99, debug)
     if pack is not None:
         idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
     if pattern is not None:
@@ -69,7 +67,7 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     if bits == 8:
         exec_factor *= 1.0   # same element count; idx.dim_pad already counts fp8 elements
     res = {"bits": bits, "candidates": int(cnt_t.cpu()[nt.FS_CNT_CANDIDATES]), "matches": int(cnt_t.cpu()[nt.FS_CNT_MATCHES]),
-           "diag": diag, "pattern": pattern, "pair": pair, "debug": debug, "pack": pack, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
+           "diag": diag, "pattern": pattern, "pair": pair, "pack": pack, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
            "kernel_ms": ms / n, "windows_per_s": windows / per, "clocks": clk,
            "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
            "tflops_executed": 2.0 * exec_factor * idx.dim_pad * idx.n_script_windows * windows / per / 1e12}
@@ -90,15 +88,8 @@ def main():
     ap.add_argument("--one", type=int, nargs=4, metavar=("DIAG", "NF", "NS", "D"), help="run a single case")
     ap.add_argument("--pair", type=int, default=0)
     ap.add_argument("--pack", type=int, default=None)
-    ap.add_argument("--debug-exp", action="store_true", help="epilogue timing experiments (invalid results)")
     args = ap.parse_args()
     rng = np.random.default_rng(0)
-    if args.debug_exp:
-        for diag, pair, pack in ((6, 2, 2), (6, 1, 2), (3, 2, 1)):
-            for debug in (0, 1, 2, 3):
-                print(json.dumps(run_case(2_500_000, 25000, 300, 3, rng, diag=diag, pair=pair, debug=debug,
-                                          pack=pack)), flush=True)
-        return
     if args.one:
         diag, nf, ns, d = args.one
         print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag, pair=args.pair, pack=args.pack,
