@@ -120,24 +120,28 @@ __device__ __forceinline__ void diag_sum_inplace(uint32_t (&r)[40]) {
 // and every HADD2 result is rounded to fp16: |error| <= 4 * 2^-11 * sum_k |G_k| <= 2^-9 |f||s|
 // (G_k = the six partial dots of the window, sum |G_k| <= |f||s|), covered by the pre-filter
 // slack; the decision is re-made in float64.  On return o[k] = half2(out[2k], out[2k+1]).
-__device__ __forceinline__ float diag6_half(const uint32_t (&r)[40], const uint32_t (&pk)[20], uint32_t (&o)[16]) {
+// pk[k] = half2(a[2k], a[2k+1]) for the 40 loaded columns; odd(k) = half2(a[2k+1], a[2k+2]) is a byte
+// permute of two neighbours, so the fp32 accumulators are dead once pk is built (the next chunk's
+// TMEM load is issued into the same registers while this chunk is summed).
+__device__ __forceinline__ uint32_t h2_odd(const uint32_t (&pk)[20], int k) {
+    return __byte_perm(pk[k], pk[k + 1], 0x5432);
+}
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) {
+    const __half2 s = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&s);
+}
+
+__device__ __forceinline__ float diag6_half(const uint32_t (&pk)[20], uint32_t (&o)[16]) {
     constexpr uint32_t kFull = 0xffffffffu;
-    auto f = [&](int x) { return __uint_as_float(r[x]); };
-    auto add2 = [](uint32_t a, uint32_t b) {
-        const __half2 s = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
-        return *reinterpret_cast<const uint32_t*>(&s);
-    };
-    // D2 pair k = (a[2k], a[2k+1]) + (a[2k+1], a[2k+2])@(lane+1),  k = 0..17   (pk[k] = (a[2k], a[2k+1]))
+    // D2 pair k = (a[2k], a[2k+1]) + (a[2k+1], a[2k+2])@(lane+1),  k = 0..17
     uint32_t d2[18];
 #pragma unroll
-    for (int k = 0; k < 18; ++k)
-        d2[k] = add2(pk[k], __shfl_down_sync(kFull, pack_h2(f(2 * k + 1), f(2 * k + 2)), 1));
+    for (int k = 0; k < 18; ++k) d2[k] = h2_add(pk[k], __shfl_down_sync(kFull, h2_odd(pk, k), 1));
     // out pair k = D2[k] + D2[k+1]@(lane+2) + D2[k+2]@(lane+4),  k = 0..15
     __half2 mx = __float2half2_rn(-60000.f);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        o[k] = add2(add2(d2[k], __shfl_down_sync(kFull, d2[k + 1], 2)),
-                    __shfl_down_sync(kFull, d2[k + 2], 4));
+        o[k] = h2_add(h2_add(d2[k], __shfl_down_sync(kFull, d2[k + 1], 2)), __shfl_down_sync(kFull, d2[k + 2], 4));
         mx = __hmax2(mx, *reinterpret_cast<const __half2*>(&o[k]));
     }
     return fmaxf(__low2float(mx), __high2float(mx));
@@ -146,19 +150,14 @@ __device__ __forceinline__ float diag6_half(const uint32_t (&r)[40], const uint3
 // E = 3 in fp16x2 arithmetic (kPack == 2): out pair k = (a[2k], a[2k+1]) + (a[2k+1], a[2k+2])@(lane+1)
 // + (a[2k+2], a[2k+3])@(lane+2).  Three roundings per output: |error| <= 3 * 2^-11 * sum_d |a_d|
 // <= 1.5e-3 |f||s|, inside the pre-filter slack.
-__device__ __forceinline__ float diag3_half(const uint32_t (&r)[40], const uint32_t (&pk)[20], uint32_t (&o)[16]) {
+__device__ __forceinline__ float diag3_half(const uint32_t (&pk)[20], uint32_t (&o)[16]) {
     constexpr uint32_t kFull = 0xffffffffu;
-    auto f = [&](int x) { return __uint_as_float(r[x]); };
-    auto add2 = [](uint32_t a, uint32_t b) {
-        const __half2 s = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
-        return *reinterpret_cast<const uint32_t*>(&s);
-    };
     __half2 mx = __float2half2_rn(-60000.f);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const uint32_t q1 = __shfl_down_sync(kFull, pack_h2(f(2 * k + 1), f(2 * k + 2)), 1);
+        const uint32_t q1 = __shfl_down_sync(kFull, h2_odd(pk, k), 1);
         const uint32_t q2 = __shfl_down_sync(kFull, pk[k + 1], 2);
-        o[k] = add2(add2(pk[k], q1), q2);
+        o[k] = h2_add(h2_add(pk[k], q1), q2);
         mx = __hmax2(mx, *reinterpret_cast<const __half2*>(&o[k]));
     }
     return fmaxf(__low2float(mx), __high2float(mx));
@@ -166,16 +165,13 @@ __device__ __forceinline__ float diag3_half(const uint32_t (&r)[40], const uint3
 
 // E = 2 in fp16x2 arithmetic: out pair k = (a[2k], a[2k+1]) + (a[2k+1], a[2k+2])@(lane+1): one shuffle
 // per two outputs, two roundings per output.
-__device__ __forceinline__ float diag2_half(const uint32_t (&r)[40], const uint32_t (&pk)[20], uint32_t (&o)[16]) {
+__device__ __forceinline__ float diag2_half(const uint32_t (&pk)[20], uint32_t (&o)[16]) {
     constexpr uint32_t kFull = 0xffffffffu;
-    auto f = [&](int x) { return __uint_as_float(r[x]); };
     __half2 mx = __float2half2_rn(-60000.f);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const uint32_t q1 = __shfl_down_sync(kFull, pack_h2(f(2 * k + 1), f(2 * k + 2)), 1);
-        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&pk[k]), *reinterpret_cast<const __half2*>(&q1));
-        o[k] = *reinterpret_cast<const uint32_t*>(&sum);
-        mx = __hmax2(mx, sum);
+        o[k] = h2_add(pk[k], __shfl_down_sync(kFull, h2_odd(pk, k), 1));
+        mx = __hmax2(mx, *reinterpret_cast<const __half2*>(&o[k]));
     }
     return fmaxf(__low2float(mx), __high2float(mx));
 }
@@ -258,11 +254,17 @@ struct TileWalk {
 // while it streams its chunks, and after one barrier per tile those few boundary rows (3(E-1) of
 // 128) are summed from shared memory, one column per lane.
 // ---------------------------------------------------------------------------------------------
-template <int kDiag, bool kDump, int kPack>
+//
+// The accumulator is handed back to the MMA issuer (tempty) as soon as its last column has been read
+// into registers, BEFORE the boundary pass.  kPack == 2 publishes the boundary rows as halves into
+// one of two buffers (`halo` is already the buffer of this accumulator stage), so a single barrier
+// per tile is enough: the buffer is next written two tiles later, after every warp has passed the
+// following tile's barrier.
+template <int kDiag, bool kDump, int kPack, bool kPair>
 __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t m0, const int32_t n0,
-                                              const int as, const uint32_t tfull_addr, const uint32_t aphase,
-                                              const uint32_t tmem_base, float* halo, float* norm_tile,
-                                              const int warp, const int lane) {
+                                              const int as, const uint32_t tfull_addr, const uint32_t tempty_addr,
+                                              const uint32_t aphase, const uint32_t tmem_base, float* halo,
+                                              float* norm_tile, const int warp, const int lane) {
     constexpr int kMStep = kBlockM - (kDiag - 1);
     constexpr int kNStep = kBlockN - (kDiag - 1);
     constexpr int kPubSlots = dist_pub_slots(kDiag);
@@ -294,26 +296,33 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                            static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
-#pragma unroll 1
-    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
-        const int c0 = group * kEpiCols + ch * 32;  // first column inside the tile
-        uint32_t r[40];
-        __syncwarp();
-        // prefetch the chunk's smallest script norm: its latency hides behind the TMEM load
-        const float nmin = kDump ? 0.f : __ldg(p.norm_min32 + n0 + c0);
+    uint32_t r[40];
+    auto load_chunk = [&](int ch) {
         if (kDiag > 1) {
             // the 8 halo columns of the LAST chunk lie outside the tile: any readable columns do
             // (they only enter outputs >= kNStep, which carry +inf norms)
-            const int halo_off = (c0 + 32 < kBlockN) ? 32 : 24;
+            const int halo_off = (group * kEpiCols + ch * 32 + 32 < kBlockN) ? 32 : 24;
             tmem_ld_32x40(taddr + ch * 32, taddr + ch * 32 + halo_off, r);
         } else {
             tmem_ld_32x32(taddr + ch * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         }
+    };
+    // kHalf: the accumulators are dead once packed, so the load of chunk ch+1 is issued before chunk
+    // ch is summed and its latency hides behind the shuffles
+    if (kHalf) load_chunk(0);
+#pragma unroll 1
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+        const int c0 = group * kEpiCols + ch * 32;  // first column inside the tile
+        __syncwarp();
+        // prefetch the chunk's smallest script norm: its latency hides behind the TMEM load
+        const float nmin = kDump ? 0.f : __ldg(p.norm_min32 + n0 + c0);
+        if (!kHalf) load_chunk(ch);
         tmem_ld_wait();
         uint32_t pk[20];
         if (kHalf) {
 #pragma unroll
             for (int k = 0; k < 20; ++k) pk[k] = pack_h2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+            if (ch + 1 < kEpiCols / 32) load_chunk(ch + 1);
         }
         if (kDiag > 1 && pub_slot >= 0) {
             if (kHalf) {
@@ -332,7 +341,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
         uint32_t o16[16];
         if (kHalf) {
             // o16[k] = half2(out[2k], out[2k+1])
-            mx = kDiag == 6 ? diag6_half(r, pk, o16) : (kDiag == 3 ? diag3_half(r, pk, o16) : diag2_half(r, pk, o16));
+            mx = kDiag == 6 ? diag6_half(pk, o16) : (kDiag == 3 ? diag3_half(pk, o16) : diag2_half(pk, o16));
         } else {
             diag_sum_inplace<kDiag, kPack>(r);  // r[x] <- out[lane][c0 + x]
             mx = -INFINITY;
@@ -369,6 +378,15 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                 }
             }
         }
+    }
+    // every accumulator column of this warp is in registers: release the TMEM stage
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (kPair)
+            mbar_arrive_leader(tempty_addr);  // the leader's MMA waits for both CTAs
+        else
+            mbar_arrive(tempty_addr);
     }
     if (kDiag > 1) {
         // boundary rows: tail rows of quarters 0..2 (quarter 3's belong to the next tile)
@@ -409,8 +427,8 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                 }
             }
         }
-        // the next tile's chunks overwrite the published rows
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        // single-buffered rows (fp32 layout): the next tile's chunks overwrite them
+        if (!kHalf) asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
     }
 }
 
@@ -443,7 +461,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     static_assert(!kARes || kPair, "the A-resident variant exists for CTA pairs only");
     constexpr bool kMix = kDiag == kDiagMix;
     static_assert(!kMix || (kPair && !kARes), "the mixed schedule exists for plain CTA pairs only");
-    static_assert(!kF8 || (kPair && !kARes), "fp8 operands exist for plain CTA pairs only");
+    static_assert(!kF8 || kPair, "fp8 operands exist for CTA pairs only");
     extern __shared__ uint8_t smem_raw[];
     constexpr int kNumStages = dist_stages(kDiag, kPair, kARes);
     constexpr int kStageSz = dist_stage_bytes(kPair, kARes);
@@ -655,26 +673,21 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         // ------------------------------------------------------------ epilogue (16 warps)
         int as = 0;
         uint32_t aphase = 0;
+        // kPack == 2: two half-precision boundary-row buffers, one per accumulator stage
+        constexpr bool kHalfRows = kPack == 2 && (diag_max(kDiag) == 6 || kDiag == 3 || kDiag == 2);
         while (walk.next(tile)) {
+            float* halo_t = halo + (kHalfRows ? as * (dist_pub_bytes(kDiag) / 8) : 0);
             if constexpr (kMix) {
-                // kPack: 0 = full-precision shuffles, 1 = packed shuffles, 2 = E = 6 tiles in fp16x2
+                // kPack: 0 = full-precision shuffles, 1 = packed shuffles, 2 = fp16x2 arithmetic
                 if (tile.e6)
-                    epilogue_tile<6, kDump, kPack>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase, tmem_base,
-                                                   halo, norm_tile, warp, lane);
+                    epilogue_tile<6, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
+                                                          aphase, tmem_base, halo_t, norm_tile, warp, lane);
                 else
-                    epilogue_tile<3, kDump, kPack>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase, tmem_base,
-                                                   halo, norm_tile, warp, lane);
+                    epilogue_tile<3, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
+                                                          aphase, tmem_base, halo_t, norm_tile, warp, lane);
             } else {
-                epilogue_tile<kDiag, kDump, kPack>(p, tile.m0, tile.n0, as, tfull_bar(as), aphase, tmem_base,
-                                                   halo, norm_tile, warp, lane);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (kPair)
-                    mbar_arrive_leader(tempty_bar(as));  // the leader's MMA waits for both CTAs
-                else
-                    mbar_arrive(tempty_bar(as));
+                epilogue_tile<kDiag, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
+                                                          aphase, tmem_base, halo_t, norm_tile, warp, lane);
             }
             if (++as == kAccumStages) {
                 as = 0;
@@ -804,9 +817,16 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         FS_LAUNCH_PACK(E, false, false);           \
     } while (0)
     if (p.f8) {
-        // fp8 operands: CTA pairs, streaming fan tile; the epilogue variants that are the defaults
-        if (!p.pair || ares) {
-            set_error("fp8 operands need CTA pairs without the A-resident tile");
+        // fp8 operands: CTA pairs; the epilogue variants that are the defaults
+        if (!p.pair) {
+            set_error("fp8 operands need CTA pairs");
+            return FS_E_INVALID;
+        }
+        if (ares) {
+            // resident fan tile: the two diagonal factors that are defaults, fp16x2 epilogue
+            if (p.diag == 3) return launch_distance_t<3, true, true, 2, true>(map_fan, map_script, p, grid, stream);
+            if (p.diag == 6) return launch_distance_t<6, true, true, 2, true>(map_fan, map_script, p, grid, stream);
+            set_error("fp8 operands with the A-resident tile exist for diagonal factors 3 and 6");
             return FS_E_INVALID;
         }
         switch (p.diag) {

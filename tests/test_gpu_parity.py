@@ -345,6 +345,20 @@ def test_fp8_candidates_are_a_superset(diag):
     idx.close()
 
 
+@pytest.mark.parametrize("diag", [3, 6])
+def test_fp8_resident_fan_tile(diag):
+    for seed, dim, works in ((1, 300, (200, 3, 0, 6, 397, 150)), (4, 100, (900, 3, 0, 6, 1400, 700))):
+        table, sx, fx, script, tok, off = _case(seed, dim=dim, works=works)
+        want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
+        for grid in (0, 4):
+            idx = _f8_index(table, script, sx, diag)
+            idx.set_option(nt.FS_OPT_A_RESIDENT, 1)
+            idx.set_option(nt.FS_OPT_GRID_LIMIT, grid)
+            got, _ = idx.search_host(tok, off, fx)
+            assert _pairs(got) == _pairs(want) and len(got) == len(want)
+            idx.close()
+
+
 def test_fp8_needs_cta_pairs():
     table, sx, fx, script, tok, off = _case(1, dim=64)
     idx = _f8_index(table, script, sx)

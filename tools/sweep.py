@@ -22,8 +22,8 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
-    if pair != 1:
-        bits = 16      # fp8 operands exist for plain CTA pairs only
+    if pair == 0:
+        bits = 16      # fp8 operands exist for CTA pairs only
     idx.set_option(nt.FS_OPT_OPERAND_BITS, bits)
     idx.set_option(nt.FS_OPT_DIAG, diag)
     idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
@@ -96,9 +96,10 @@ def main():
                                   pattern=args.pattern, bits=args.bits)), flush=True)
         return
     if args.f8:
-        for bits, diag, d, pack in ((16, 3, 300, 2), (8, 3, 300, 2), (8, 2, 300, 2), (8, 2, 300, 0), (8, 6, 300, 2),
-                                    (8, 6, 768, 2), (8, 3, 768, 2), (8, 2, 768, 2), (16, 6, 768, 2), (8, 3, 300, 2)):
-            print(json.dumps(run_case(2_500_000, 25000, d, 20, rng, diag=diag, pair=1, pack=pack,
+        for bits, diag, d, pack, pair in ((16, 3, 300, 2, 1), (8, 3, 300, 2, 1), (8, 3, 300, 2, 2), (8, 6, 300, 2, 1),
+                                          (8, 6, 300, 2, 2), (8, 2, 300, 2, 1), (8, 6, 768, 2, 1), (8, 3, 768, 2, 1),
+                                          (16, 6, 768, 2, 1), (8, 3, 300, 2, 2)):
+            print(json.dumps(run_case(2_500_000, 25000, d, 20, rng, diag=diag, pair=pair, pack=pack,
                                       clocks=True, bits=bits)), flush=True)
         return
     if args.mix:
