@@ -53,18 +53,19 @@ def main():
     off[-1] = args.tokens
     tok_t, off_t, _ = idx.to_device(tok, off)
     idx.reserve(args.tokens, 1 << 20)
-    res = {"tokens": args.tokens, "dim": args.dim, "dim_pad": idx.dim_pad, "hbm_peak_gbs": peaks["hbm_gbs"]}
+    res = {"tokens": args.tokens, "dim": args.dim, "dim_pad": idx.dim_pad, "operand_bits": idx.operand_bits,
+           "hbm_peak_gbs": peaks["hbm_gbs"]}
 
     ms = timeit(lambda: idx.stage_embed(tok_t, off_t))
-    bytes_embed = args.tokens * (4 + idx.dim_pad * 2 + 4 + 4 + 24 + 4)   # + tok_sq write, 6-tap read (L2), thr write
-    bytes_alg = args.tokens * (4 + idx.dim_pad * 2)
+    row_bytes = idx.dim_pad * idx.operand_bits // 8        # fp8: 1 B per element, fp16: 2
+    bytes_alg = args.tokens * (4 + row_bytes)
     res["embed"] = {"ms": ms, "algorithmic_gbs": bytes_alg / ms / 1e6, "frac_of_hbm_peak": bytes_alg / ms / 1e6 / peaks["hbm_gbs"],
                     "tokens_per_s": args.tokens / ms * 1e3, "note": "gather + window norms + torch.empty of outputs"}
 
     # write-only reference: how fast can this GPU stream zeros into a buffer of the same size?
-    buf = torch.empty(args.tokens * idx.dim_pad, dtype=torch.float16, device="cuda")
+    buf = torch.empty(args.tokens * row_bytes, dtype=torch.uint8, device="cuda")
     ms = timeit(lambda: buf.zero_())
-    res["memset_same_bytes"] = {"ms": ms, "gbs": buf.numel() * 2 / ms / 1e6}
+    res["memset_same_bytes"] = {"ms": ms, "gbs": buf.numel() / ms / 1e6}
     del buf
     out_t = torch.empty((1 << 22, 2), dtype=torch.int32, device="cuda")
     cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
