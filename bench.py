@@ -467,7 +467,8 @@ def run_native_arm(args):
             "config": {"workload": WORKLOAD, "script_windows": n_script_windows,
                        "windows_per_step_per_gpu": step_windows // max(args.steps, 1),
                        "parallelism": "work-sharded x%d, script index replicated" % world,
-                       "l2": "inputs larger than L2 (1.6 GB fp16 token matrix per step)",
+                       "l2": "inputs larger than L2 (%.1f GB %s token matrix per step)"
+                             % ((0.8, "fp8") if bits == 8 else (1.6, "fp16")),
                        "precision": ("fp8 e4m3 tcgen05 pre-filter (fp32 accumulate; every window's measured rounding "
                                      "error is in its threshold: guaranteed superset) + float64 rescoring"
                                      if bits == 8 else
