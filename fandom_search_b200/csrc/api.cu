@@ -23,9 +23,9 @@ constexpr int kTimingRing = 256;
 // epilogue of E = 6 (pack level 2) <= 2^-9 |f||s| (distance.cu); fp32 accumulation and fp32
 // norms add ~1e-5.  Every pair with float64 cos > 1-thr passes
 // cos_approx > 1-thr-kEps.
-constexpr double kEps = 4.0e-3;
-// fp8 operands: the operand rounding is measured per window; this slack covers what is left (fp32
-// accumulation order in the tensor core, fp16x2-packed epilogue sums <= 2^-9)
+// The operand rounding (fp8 or fp16) is measured per window and enters the pre-filter bound; this
+// slack covers what is left: fp32 accumulation order in the tensor core and the fp16x2 epilogue
+// sums (<= 2^-9 |f||s|).
 constexpr double kEpsAccum = 3.0e-3;
 // largest scaled row norm of an fp8 table: window token dots, |sum| <= window * norm^2, must still
 // fit the fp16 range of the packed epilogue (norm = 95.7 for 6-gram windows)
@@ -76,7 +76,6 @@ struct fs_index {
     int32_t dim_pad = 0;        // operand row length in 2-byte units (fp16 elements, or fp8 elements / 2)
     int32_t dim_pad_elems = 0;  // operand row length in elements
     int32_t operand_bits = 8;   // 16: fp16 operands, 8: fp8 e4m3 operands (default)
-    float rho_script = 0.f;     // fp8: largest relative rounding error of a script window
     int64_t n_extra_rows = 0;
     double threshold = 0.1;
     float scale = 1.f;
@@ -96,8 +95,8 @@ struct fs_index {
     int64_t n_script_windows = 0;
     __half* script_emb = nullptr;
     float2* script_tok_sq = nullptr;
-    float* script_norm = nullptr;
-    float* script_norm_min = nullptr;
+    float2* script_norm = nullptr;      // (B_j, D_j) per script window start
+    float2* script_norm_min = nullptr;  // (min B, max D) over 32 columns
     int32_t tiles_n = 0;
     CUtensorMap map_script;
 
@@ -111,7 +110,7 @@ struct fs_index {
     int64_t sq_cap = 0;
     float2* fan_tok_sq = nullptr;
     int64_t thr_cap = 0;
-    float* fan_thr = nullptr;
+    float2* fan_thr = nullptr;  // (A_i, C_i) per fan window start
     int64_t cand_cap = 0;
     fs_pair* cand = nullptr;
     int64_t fx_cap = 0;  // fan extra rows
@@ -197,10 +196,10 @@ int fs_index_destroy(fs_index* idx) {
 
 // (Re)builds everything that depends on the operand type: the converted table and script
 // extras, the script token matrix, its window norms and tensor map.  fp16: one global scale
-// 1/max|x|; the fixed slack kEps covers the operand rounding.  fp8 e4m3: scale f8_row_norm/max|row| (so
-// that the window's token dots still fit the fp16 range of the packed epilogue), the
-// rounding error of every row is MEASURED and enters the pre-filter threshold per window
-// (run_pipeline / window_norm_kernel), which keeps the candidate set a guaranteed superset.
+// 1/max|x|.  fp8 e4m3: scale f8_row_norm/max|row| (so that the window's token dots still fit the
+// fp16 range of the packed epilogue).  In both cases the rounding error of every row is MEASURED
+// (including underflow of rows that are tiny next to the largest) and enters the pre-filter bound
+// per window (window_norm_kernel), which keeps the candidate set a guaranteed superset.
 static int prepare_operands(fs_index* idx) {
     cudaStream_t st = idx->stream;
     const bool f8 = idx->operand_bits == 8;
@@ -250,12 +249,12 @@ static int prepare_operands(fs_index* idx) {
     FS_CUDA_CHECK(cudaMemsetAsync(idx->script_tok_sq + idx->n_script_tok, 0, sizeof(float2) * 8, st));
     unsigned long long* d_cnt = idx->h_counters;
     FS_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
-    unsigned int* d_rho = reinterpret_cast<unsigned int*>(d_cnt);  // slot 0 (candidates) is unused here
+    const float coef = static_cast<float>(1.0 - idx->threshold - kEpsAccum);
     if ((r = launch_window_norm(idx->script_tok_sq, idx->n_script_tok, idx->script_off, idx->n_scripts,
-                                idx->window, 1.0f, 0.0f, idx->script_norm, n_pad, d_cnt + FS_CNT_WINDOWS,
-                                d_rho, st)) != FS_OK)
+                                idx->window, coef, true, idx->script_norm, n_pad, d_cnt + FS_CNT_WINDOWS,
+                                st)) != FS_OK)
         return r;
-    if ((r = launch_sliding_min32(idx->script_norm, idx->script_norm_min, n_pad, st)) != FS_OK) return r;
+    if ((r = launch_sliding_minmax32(idx->script_norm, idx->script_norm_min, n_pad, st)) != FS_OK) return r;
     unsigned long long h_cnt[FS_CNT_COUNT];
     FS_CUDA_CHECK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     if (idx->n_script_tok > 0)
@@ -263,8 +262,6 @@ static int prepare_operands(fs_index* idx) {
             return r;
     FS_CUDA_CHECK(cudaStreamSynchronize(st));
     idx->n_script_windows = static_cast<int64_t>(h_cnt[FS_CNT_WINDOWS]);
-    const unsigned int rho_bits = static_cast<unsigned int>(h_cnt[0] & 0xffffffffull);
-    memcpy(&idx->rho_script, &rho_bits, sizeof(float));
     return FS_OK;
 }
 
@@ -570,7 +567,7 @@ int check_batch(const fs_index* idx, const BatchArgs& a, const char* who) {
 
 // gather + window thresholds of one batch into the index workspace
 int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned long long* counters,
-                __half* emb_out, float* thr_out, int64_t thr_pad) {
+                __half* emb_out, float2* thr_out, int64_t thr_pad) {
     int r;
     if (a.n_extra > 0) {
         if ((r = dev_grow(&idx->fx16, &idx->fx_cap, a.n_extra * idx->dim_pad)) != FS_OK) return r;
@@ -586,17 +583,10 @@ int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned lon
         return r;
     // zero the halo so the window sums never read stale squares
     FS_CUDA_CHECK(cudaMemsetAsync(idx->fan_tok_sq + a.n_tok, 0, sizeof(float2) * 8, st));
-    // fp16: fixed slack.  fp8: with qf, qs the rounded windows, errF = |f - qf|, errS = |s - qs| <=
-    // rho |s| and |qs| <= (1 + rho) |s| (rho = rho_script):
-    //   qf.qs >= f.s - errF |qs| - |f| errS,
-    // so every pair with f.s > (1 - thr) |f||s| has  qf.qs > [(1 - thr - rho) |f| - (1 + rho) errF] |s|.
-    const bool f8 = idx->operand_bits == 8;
-    const float coef = static_cast<float>(f8 ? 1.0 - idx->threshold - kEpsAccum - idx->rho_script
-                                             : 1.0 - idx->threshold - kEps);
-    const float kappa = f8 ? 1.0f + idx->rho_script : 0.0f;
+    // fan side of the pre-filter bound: (|f|, |f - qf|) per window (window_norm_kernel)
     return launch_window_norm(idx->fan_tok_sq, a.n_tok, a.off, static_cast<int32_t>(a.n_works),
-                              idx->window, coef, kappa, thr_out, thr_pad,
-                              counters ? counters + FS_CNT_WINDOWS : nullptr, nullptr, st);
+                              idx->window, 0.0f, false, thr_out, thr_pad,
+                              counters ? counters + FS_CNT_WINDOWS : nullptr, st);
 }
 
 int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, fs_match* out,
@@ -644,9 +634,9 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     CUtensorMap map_fan;
     if ((r = make_token_map(&map_fan, idx->fan_emb, a.n_tok, idx->dim_pad)) != FS_OK) return r;
     DistParams p{};
-    p.thr_fan = idx->fan_thr;
-    p.norm_script = idx->script_norm;
-    p.norm_min32 = idx->script_norm_min;
+    p.fan_ac = idx->fan_thr;
+    p.script_bd = idx->script_norm;
+    p.script_mm32 = idx->script_norm_min;
     p.n_fan_tok = a.n_tok;
     p.n_script_tok = idx->n_script_tok;
     p.chunks = (idx->dim_pad + kChunkK - 1) / kChunkK;
@@ -872,7 +862,7 @@ int fs_stage_embed_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t 
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     if ((r = fs_index_reserve(idx, n_tok, idx->cand_cap > 0 ? idx->cand_cap : 1024)) != FS_OK) return r;
     return embed_batch(idx, static_cast<cudaStream_t>(stream), a, nullptr,
-                       static_cast<__half*>(emb_out), thr_out, n_tok);
+                       static_cast<__half*>(emb_out), reinterpret_cast<float2*>(thr_out), n_tok);
 }
 
 int fs_stage_dots_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n_tok,

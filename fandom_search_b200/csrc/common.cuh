@@ -51,7 +51,7 @@ constexpr int kProducerWarp = kEpiWarps;               // single-thread roles ge
 constexpr int kMmaWarp = kEpiWarps + 1;                // warp ids (scheduler priority)
 constexpr int kDistThreads = 32 * (kEpiWarps + 2);     // 576
 constexpr int kHaloCols = kBlockN + 8;
-constexpr int kNormTileBytes = kAccumStages * kHaloCols * 4;               // 2112
+constexpr int kNormTileBytes = kAccumStages * kHaloCols * 8;               // 4224: (B, D) per column
 // shared-memory budget of distance_kernel<E, ., pair>: the stage ring shrinks by one stage at
 // E = 6, whose epilogue publishes 10 boundary rows per lane quarter instead of <= 4
 constexpr int kDiagMix = 36;  // "diagonal factor" of the schedule that alternates E = 3 and E = 6 tiles
@@ -81,9 +81,10 @@ static_assert(dist_smem_bytes(1, false, false) <= 232448 && dist_smem_bytes(3, t
               "distance kernel exceeds the 227 KB shared memory limit");
 
 struct DistParams {
-    const float* thr_fan;     // [Mpad]  (1 - thr - eps) * |fan window|, +inf when invalid
-    const float* norm_script; // [Npad]  |script window|, +inf when invalid
-    const float* norm_min32;  // [Npad]  min(norm_script[j .. j+31])
+    // pre-filter: keep (i, j) iff acc_ij > A_i * B_j - C_i * D_j  (window_norm_kernel, embed.cu)
+    const float2* fan_ac;       // [Mpad]  (A_i, C_i) = (|fan window|, |its rounding error|), NaN when invalid
+    const float2* script_bd;    // [Npad]  (B_j, D_j) = ((1-thr-eps)|s| - err, |s| + err), NaN when invalid
+    const float2* script_mm32;  // [Npad]  (min B, max D) over columns j .. j+31
     int64_t n_fan_tok;        // rows of the fan token matrix (M)
     int64_t n_script_tok;     // rows of the script token matrix (N)
     int32_t chunks;           // ceil(dim_pad / 64) 64-column chunks
@@ -178,9 +179,9 @@ int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t s
 int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,
                   __half* emb, float2* tok_sq, int sm_count, cudaStream_t stream);
 int launch_window_norm(const float2* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
-                       int32_t window, float coef, float kappa, float* out, int64_t n_pad,
-                       unsigned long long* window_counter, unsigned int* rho_out, cudaStream_t stream);
-int launch_sliding_min32(const float* src, float* dst, int64_t n, cudaStream_t stream);
+                       int32_t window, float coef, bool script_side, float2* out, int64_t n_pad,
+                       unsigned long long* window_counter, cudaStream_t stream);
+int launch_sliding_minmax32(const float2* src, float2* dst, int64_t n, cudaStream_t stream);
 int launch_rescore(const RescoreParams& p, int sm_count, cudaStream_t stream);
 int launch_lsh(const LshParams& p, int sm_count, cudaStream_t stream);
 int launch_hash_build(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,

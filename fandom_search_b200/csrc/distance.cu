@@ -20,10 +20,11 @@
 //   warp 16 lane 0 : TMA producer       (cp.async.bulk.tensor, mbarrier stage ring)
 //   warp 17 lane 0 : tcgen05.mma issuer (128x256x16, fp32 accumulators in TMEM, 2 buffers)
 //
-// Epilogue.  acc[i][j] > thr_fan[i] * norm_script[j]  <=>  cos > 1 - thr - eps, with
-// thr_fan = (1-thr-eps)*|fanwin_i| (+inf for windows that straddle a work boundary) and
-// norm_script = |scriptwin_j| (+inf for invalid).  Survivors are appended to a global
-// candidate list through an atomic cursor; they are re-scored in float64 afterwards.
+// Epilogue.  A pair survives iff  acc[i][j] > A_i * B_j - C_i * D_j  with (A, C) = (|fanwin_i|, norm of
+// its operand rounding error) and (B, D) = ((1-thr-eps)|scriptwin_j| - error, |scriptwin_j| + error),
+// NaN for windows that straddle a work/script boundary (window_norm_kernel, embed.cu): a guaranteed
+// superset of {cos > 1 - thr}.  Survivors are appended to a global candidate list through an atomic
+// cursor; they are re-scored in float64 afterwards.
 #include "common.cuh"
 
 namespace fs {
@@ -197,24 +198,30 @@ struct Tile {
 template <int kDiag, bool kPair>
 struct TileWalk {
     static constexpr bool kMix = kDiag == kDiagMix;
-    int64_t t3, end3, begin3, t6, end6;
-    int32_t tn3, tn6, row0_6;
+    // remaining tiles and (m unit, n tile) of the next one, per tile kind; the pair is advanced
+    // incrementally (one 64-bit division per kind in the constructor, none per tile)
+    int64_t left3, left6;
+    int32_t um3, un3, tn3, um6, un6, tn6, row0_6;
     uint32_t it, pattern, cta_rank;
+    bool first;
 
     __device__ __forceinline__ static void range(int32_t tm, int32_t tn, int64_t worker, int64_t n_workers,
-                                                 int64_t& begin, int64_t& end) {
+                                                 int64_t& left, int32_t& um, int32_t& un) {
         const int64_t units_m = kPair ? (tm + 1) / 2 : tm;
         const int64_t total = units_m * tn;
         const int64_t per = (total + n_workers - 1) / n_workers;
-        begin = per * worker;
-        end = min(total, begin + per);
+        const int64_t begin = per * worker;
+        const int64_t end = min(total, begin + per);
+        left = end > begin ? end - begin : 0;
+        um = tn > 0 ? static_cast<int32_t>(begin / tn) : 0;
+        un = tn > 0 ? static_cast<int32_t>(begin - static_cast<int64_t>(um) * tn) : 0;
     }
     __device__ __forceinline__ TileWalk(const DistParams& p, int64_t worker, int64_t n_workers, uint32_t rank)
-        : t6(0), end6(0), tn3(p.tiles_n), tn6(1), row0_6(0), it(0), pattern(p.mix_pattern), cta_rank(rank) {
-        range(p.tiles_m, p.tiles_n, worker, n_workers, t3, end3);
-        begin3 = t3;
+        : left6(0), um6(0), un6(0), tn3(p.tiles_n), tn6(1), row0_6(0), it(0), pattern(p.mix_pattern),
+          cta_rank(rank), first(true) {
+        range(p.tiles_m, p.tiles_n, worker, n_workers, left3, um3, un3);
         if (kMix) {
-            range(p.tiles_m6, p.tiles_n6, worker, n_workers, t6, end6);
+            range(p.tiles_m6, p.tiles_n6, worker, n_workers, left6, um6, un6);
             tn6 = p.tiles_n6;
             row0_6 = p.row0_6;
         }
@@ -222,24 +229,39 @@ struct TileWalk {
     __device__ __forceinline__ bool next(Tile& out) {
         bool six = false;
         if (kMix) {
-            const bool has3 = t3 < end3, has6 = t6 < end6;
+            const bool has3 = left3 > 0, has6 = left6 > 0;
             if (!has3 && !has6) return false;
             six = (pattern >> (it & 3u)) & 1u;
             ++it;
             if (six ? !has6 : !has3) six = !six;
-        } else if (t3 >= end3) {
+        } else if (left3 <= 0) {
             return false;
         }
-        const int64_t u = six ? t6++ : t3++;
+        const int32_t um = six ? um6 : um3;
+        const int32_t un = six ? un6 : un3;
         const int32_t tn = six ? tn6 : tn3;
-        const int64_t um = u / tn;
-        const int32_t un = static_cast<int32_t>(u - um * tn);
         const int32_t e = kMix ? (six ? 6 : 3) : kDiag;
         out.m0 = (six ? row0_6 : 0) + static_cast<int32_t>(kPair ? 2 * um + cta_rank : um) * (kBlockM - (e - 1));
         out.n0 = un * (kBlockN - (e - 1));
         out.e6 = kMix ? six : kDiag == 6;
-        out.fan_first = u == begin3 || un == 0;
-        out.fan_last = u + 1 == end3 || un + 1 == tn;
+        // advance this kind
+        int32_t un_next = un + 1, um_next = um;
+        if (un_next == tn) {
+            un_next = 0;
+            ++um_next;
+        }
+        if (six) {
+            un6 = un_next;
+            um6 = um_next;
+            --left6;
+        } else {
+            un3 = un_next;
+            um3 = um_next;
+            --left3;
+        }
+        out.fan_first = first || un == 0;
+        out.fan_last = (six ? left6 : left3) == 0 || un + 1 == tn;
+        first = false;
         return true;
     }
 };
@@ -264,7 +286,7 @@ template <int kDiag, bool kDump, int kPack, bool kPair>
 __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t m0, const int32_t n0,
                                               const int as, const uint32_t tfull_addr, const uint32_t tempty_addr,
                                               const uint32_t aphase, const uint32_t tmem_base, float* halo,
-                                              float* norm_tile, const int warp, const int lane) {
+                                              float2* norm_tile, const int warp, const int lane) {
     constexpr int kMStep = kBlockM - (kDiag - 1);
     constexpr int kNStep = kBlockN - (kDiag - 1);
     constexpr int kPubSlots = dist_pub_slots(kDiag);
@@ -284,15 +306,17 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
 
     const int32_t gi = m0 + row;
     const bool row_ok = row < kMStep;
-    const float thr = row_ok ? __ldg(p.thr_fan + gi) : INFINITY;  // padded to a tile multiple
+    const float kNaN = __int_as_float(0x7fc00000);
+    // (A_i, C_i) of this lane's fan window (padded to a tile multiple); NaN = never a candidate
+    const float2 ac = row_ok ? __ldg(p.fan_ac + gi) : make_float2(kNaN, kNaN);
     // rows whose sum needs another warp's rows are finished in the boundary pass
-    const float thr_main = (kDiag > 1 && lane >= kTail0) ? INFINITY : thr;
-    // E > 1: script-window norms of this tile staged once in smem, +inf baked in for the
-    // E-1 columns that belong to the next tile
-    float* ns_tile = norm_tile + as * kHaloCols;
+    const float a_main = (kDiag > 1 && lane >= kTail0) ? kNaN : ac.x;
+    // E > 1: (B_j, D_j) of this tile staged once in smem, NaN baked in for the E-1 columns that
+    // belong to the next tile
+    float2* ns_tile = norm_tile + as * kHaloCols;
     if (kDiag > 1 && epi_tid < kHaloCols)
-        ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.norm_script + n0 + epi_tid) : INFINITY;
-    mbar_wait_warp(tfull_addr, aphase, 0);
+        ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.script_bd + n0 + epi_tid) : make_float2(kNaN, kNaN);
+    mbar_wait_warp(tfull_addr, aphase, 32);  // early warps back off: their polling competes for issue slots with the late ones
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                            static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
@@ -314,8 +338,8 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     for (int ch = 0; ch < kEpiCols / 32; ++ch) {
         const int c0 = group * kEpiCols + ch * 32;  // first column inside the tile
         __syncwarp();
-        // prefetch the chunk's smallest script norm: its latency hides behind the TMEM load
-        const float nmin = kDump ? 0.f : __ldg(p.norm_min32 + n0 + c0);
+        // prefetch the chunk's (min B, max D): the latency hides behind the TMEM load
+        const float2 mm = kDump ? make_float2(0.f, 0.f) : __ldg(p.script_mm32 + n0 + c0);
         if (!kHalf) load_chunk(ch);
         tmem_ld_wait();
         uint32_t pk[20];
@@ -362,13 +386,13 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                     p.dump[static_cast<int64_t>(gi) * p.dump_ld + gj0 + x] = out_val(x);
             }
         } else {
-            // one max over the chunk against thr * (smallest norm of the chunk) rejects
-            // the chunk; the exact per-element test runs only on the rare survivor
-            if (mx > thr_main * nmin) {
+            // one max over the chunk against the smallest bound of the chunk rejects the chunk;
+            // the exact per-element test runs only on the rare survivor
+            if (mx > fmaf(-ac.y, mm.y, a_main * mm.x)) {
 #pragma unroll
                 for (int x = 0; x < 32; ++x) {
-                    const float nsv = (c0 + x < kNStep) ? __ldg(p.norm_script + gj0 + x) : INFINITY;
-                    if (out_val(x) > thr_main * nsv) {
+                    const float2 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float2(kNaN, kNaN);
+                    if (out_val(x) > fmaf(-ac.y, bd.y, a_main * bd.x)) {
                         const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                         if (slot < static_cast<unsigned long long>(p.cand_cap)) {
                             p.cand[slot].fan_pos = gi;
@@ -394,7 +418,8 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
 #pragma unroll
         for (int tr = 0; tr < kEdge; ++tr) {
             const int L = kTail0 + tr;
-            const float thr_l = __shfl_sync(0xffffffffu, thr, L);
+            const float a_l = __shfl_sync(0xffffffffu, ac.x, L);
+            const float c_l = __shfl_sync(0xffffffffu, ac.y, L);
             if (quarter < 3) {
 #pragma unroll
                 for (int it = 0; it < kEpiCols / 32; ++it) {
@@ -417,7 +442,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                     if (kDump) {
                         if (gr < p.n_fan_tok && c < kNStep && n0 + c < p.dump_ld)
                             p.dump[static_cast<int64_t>(gr) * p.dump_ld + n0 + c] = v;
-                    } else if (v > thr_l * ns_tile[c]) {
+                    } else if (v > fmaf(-c_l, ns_tile[c].y, a_l * ns_tile[c].x)) {
                         const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                         if (slot < static_cast<unsigned long long>(p.cand_cap)) {
                             p.cand[slot].fan_pos = gr;
@@ -479,7 +504,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
-    float* norm_tile = halo + dist_pub_bytes(kDiag) / 4;
+    float2* norm_tile = reinterpret_cast<float2*>(halo + dist_pub_bytes(kDiag) / 4);
 
     // Warp roles.  The warp scheduler prefers the HIGHEST warp id among eligible warps, so the
     // two single-thread roles that everything else waits for get the two highest ids: with

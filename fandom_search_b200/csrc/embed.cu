@@ -147,25 +147,30 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
     }
 }
 
-// Per window start t, with S = sum_{k<w} tok_sq[t+k].x (squared norm) and R = sum tok_sq[t+k].y
-// (squared rounding error of the operand rows):  out[t] = coef * sqrt(S) - kappa * sqrt(R) when the
-// window lies inside its CSR row, else +inf.  Fan side: coef = 1 - thr - eps (- rho of the script
-// side) and kappa = 1 + rho for fp8 operands, 0 for fp16; script side: coef = 1, kappa = 0 (the
-// true norm).  rho_out (optional) receives max sqrt(R/S), the largest relative rounding error of a
-// window.  out is padded with +inf up to n_pad.
+// Per window start t, with n = sqrt(sum_{k<w} tok_sq[t+k].x) (norm of the scaled fp32 window) and
+// e = sqrt(sum tok_sq[t+k].y) (norm of the rounding error of its operand rows):
+//   fan side    out[t] = (n, e)                    = (A_i, C_i)
+//   script side out[t] = (coef * n - e, n + e)     = (B_j, D_j),  coef = 1 - thr - eps
+// when the window lies inside its CSR row, else (NaN, NaN) -- every comparison with NaN is false,
+// whatever the sign of the other factor.  The distance epilogue keeps a pair iff
+//   acc_ij > A_i * B_j - C_i * D_j.
+// With qf, qs the rounded windows:  qf.qs >= f.s - |f - qf| |qs| - |f| |s - qs|  and  |qs| <= n_s + e_s,
+// so every pair with f.s > (1 - thr) |f||s| passes: each window carries its own measured slack and a
+// badly represented window (rows that underflow the operand format) only widens its own row/column.
+// out is padded with (NaN, NaN) up to n_pad.
 __global__ void window_norm_kernel(const float2* __restrict__ tok_sq, int64_t n_tok,
                                    const int64_t* __restrict__ off, int32_t n_rows, int32_t window,
-                                   float coef, float kappa, float* __restrict__ out, int64_t n_pad,
-                                   unsigned long long* window_counter, unsigned int* rho_out) {
+                                   float coef, int script_side, float2* __restrict__ out, int64_t n_pad,
+                                   unsigned long long* window_counter) {
     __shared__ int32_t row_hint;
     const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x;
     if (threadIdx.x == 0) row_hint = t0 < n_tok ? csr_row_of(off, n_rows, t0) : 0;
     __syncthreads();
     const int64_t t = t0 + threadIdx.x;
     unsigned int valid = 0;
-    float rho = 0.f;
     if (t < n_pad) {
-        float r = INFINITY;
+        const float nan = __int_as_float(0x7fc00000);
+        float2 r = make_float2(nan, nan);
         if (t < n_tok) {
             const int32_t row = csr_row_from_hint(off, n_rows, t, row_hint);
             if (t + window <= __ldg(off + row + 1)) {
@@ -175,17 +180,12 @@ __global__ void window_norm_kernel(const float2* __restrict__ tok_sq, int64_t n_
                     s += q.x;
                     e += q.y;
                 }
-                r = coef * sqrtf(s) - kappa * sqrtf(e);
-                if (s > 0.f) rho = sqrtf(e / s);
+                const float n = sqrtf(s), en = sqrtf(e);
+                r = script_side ? make_float2(coef * n - en, n + en) : make_float2(n, en);
                 valid = 1;
             }
         }
         out[t] = r;
-    }
-    if (rho_out) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rho = fmaxf(rho, __shfl_xor_sync(0xffffffffu, rho, o));
-        if ((threadIdx.x & 31) == 0 && rho > 0.f) atomicMax(rho_out, __float_as_uint(rho));
     }
     if (window_counter) {
         const unsigned int n = __reduce_add_sync(0xffffffffu, valid);
@@ -193,19 +193,24 @@ __global__ void window_norm_kernel(const float2* __restrict__ tok_sq, int64_t n_
     }
 }
 
-// dst[j] = min(src[j .. j+31]) (clamped at n): lets the distance epilogue reject a whole
-// 32-column chunk with one compare of its largest accumulator
-__global__ void sliding_min32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+// dst[j] = (min B[j .. j+31], max D[j .. j+31]) over the valid (non-NaN) entries, clamped at n: lets
+// the distance epilogue reject a whole 32-column chunk with one compare of its largest accumulator
+// (A * minB - C * maxD <= A * B_j - C * D_j for A, C, D >= 0).  No valid entry: (+inf, 0).
+__global__ void sliding_minmax32_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int64_t n) {
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    float m = INFINITY;
-    for (int k = 0; k < 32 && j + k < n; ++k) m = fminf(m, src[j + k]);
-    dst[j] = m;
+    float mn = INFINITY, mx = 0.f;
+    for (int k = 0; k < 32 && j + k < n; ++k) {
+        const float2 v = src[j + k];
+        mn = fminf(mn, v.x);  // fminf / fmaxf return the non-NaN operand
+        mx = fmaxf(mx, v.y);
+    }
+    dst[j] = make_float2(mn, mx);
 }
 
-int launch_sliding_min32(const float* src, float* dst, int64_t n, cudaStream_t stream) {
+int launch_sliding_minmax32(const float2* src, float2* dst, int64_t n, cudaStream_t stream) {
     if (n <= 0) return FS_OK;
-    sliding_min32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+    sliding_minmax32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }
@@ -259,13 +264,13 @@ int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, i
 }
 
 int launch_window_norm(const float2* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
-                       int32_t window, float coef, float kappa, float* out, int64_t n_pad,
-                       unsigned long long* window_counter, unsigned int* rho_out, cudaStream_t stream) {
+                       int32_t window, float coef, bool script_side, float2* out, int64_t n_pad,
+                       unsigned long long* window_counter, cudaStream_t stream) {
     if (n_pad <= 0) return FS_OK;
     const int threads = 256;
     const int64_t blocks = (n_pad + threads - 1) / threads;
     window_norm_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-        tok_sq, n_tok, off, n_rows, window, coef, kappa, out, n_pad, window_counter, rho_out);
+        tok_sq, n_tok, off, n_rows, window, coef, script_side ? 1 : 0, out, n_pad, window_counter);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }

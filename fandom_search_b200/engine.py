@@ -213,7 +213,7 @@ class DeviceIndex:
             emb = torch.empty((n, self.dim_pad), dtype=torch.uint8, device=tok_t.device)
         else:
             emb = torch.empty((n, self.dim_pad), dtype=torch.float16, device=tok_t.device)
-        thr = torch.empty((n,), dtype=torch.float32, device=tok_t.device)
+        thr = torch.empty((n, 2), dtype=torch.float32, device=tok_t.device)   # (|window|, |rounding error|)
         nt.check(self._lib.fs_stage_embed_dev(
             self._h, self._stream(stream), nt.ptr(tok_t), n, nt.ptr(off_t), off_t.numel() - 1,
             nt.ptr(extra_t), 0 if extra_t is None else extra_t.shape[0], nt.ptr(emb), nt.ptr(thr)))

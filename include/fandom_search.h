@@ -187,7 +187,9 @@ int fs_exact_join_host(fs_index* idx,
  * Stage-level entry points used by the parity tests and by bench.py to time
  * one kernel at a time.  All pointers are DEVICE pointers.
  */
-/* token gather + window norms: emb_out [n_tok, dim_pad] fp16, thr_out [n_tok] float */
+/* token gather + window norms: emb_out [n_tok, dim_pad] operand rows (e4m3 bytes, or fp16);
+ * thr_out [n_tok][2] float = per window start (norm of the scaled window, norm of the rounding
+ * error of its operand rows), NaN where the window leaves its work */
 int fs_stage_embed_dev(fs_index* idx, void* stream,
                        const int32_t* tok, int64_t n_tok,
                        const int64_t* off, int64_t n_works,
