@@ -75,6 +75,7 @@ struct fs_index {
     int32_t dim = 0, window = 6;
     int32_t dim_pad = 0;        // operand row length in 2-byte units (fp16 elements, or fp8 elements / 2)
     int32_t dim_pad_elems = 0;  // operand row length in elements
+    float row_limit_sq = 0.f;   // squared norm of the longest scaled row of the index
     int32_t operand_bits = 8;   // 16: fp16 operands, 8: fp8 e4m3 operands (default)
     int64_t n_extra_rows = 0;
     double threshold = 0.1;
@@ -218,27 +219,33 @@ static int prepare_operands(fs_index* idx) {
     if ((r = dev_alloc(&idx->script_emb, idx->n_script_tok * idx->dim_pad)) != FS_OK) return r;
     unsigned int* d_max = reinterpret_cast<unsigned int*>(idx->h_counters);
     FS_CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
-    if (f8) {
-        if ((r = launch_rownorm_max(idx->table32, idx->n_base, idx->dim, d_max, st)) != FS_OK) return r;
-        if ((r = launch_rownorm_max(idx->sx32, idx->n_sx, idx->dim, d_max, st)) != FS_OK) return r;
-    } else {
-        if ((r = launch_absmax(idx->table32, idx->n_base * idx->dim, d_max, st)) != FS_OK) return r;
-        if ((r = launch_absmax(idx->sx32, idx->n_sx * idx->dim, d_max, st)) != FS_OK) return r;
+    // slot 0: largest squared row norm; slot 1: largest |element| (fp16 scale)
+    if ((r = launch_rownorm_max(idx->table32, idx->n_base, idx->dim, d_max, st)) != FS_OK) return r;
+    if ((r = launch_rownorm_max(idx->sx32, idx->n_sx, idx->dim, d_max, st)) != FS_OK) return r;
+    if (!f8) {
+        if ((r = launch_absmax(idx->table32, idx->n_base * idx->dim, d_max + 1, st)) != FS_OK) return r;
+        if ((r = launch_absmax(idx->sx32, idx->n_sx * idx->dim, d_max + 1, st)) != FS_OK) return r;
     }
-    unsigned int h_max_bits = 0;
-    FS_CUDA_CHECK(cudaMemcpyAsync(&h_max_bits, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    unsigned int h_max_bits[2] = {0, 0};
+    FS_CUDA_CHECK(cudaMemcpyAsync(h_max_bits, d_max, sizeof(h_max_bits), cudaMemcpyDeviceToHost, st));
     FS_CUDA_CHECK(cudaStreamSynchronize(st));
-    float h_max;
-    memcpy(&h_max, &h_max_bits, sizeof(float));
-    if (!(h_max > 0.f && std::isfinite(h_max)))
-        idx->scale = 1.0f;
-    else
-        idx->scale = f8 ? f8_row_norm(idx->window) / std::sqrt(h_max) : 1.0f / h_max;
-    if ((r = launch_convert_rows(idx->table32, idx->n_base, idx->dim, idx->dim_pad, idx->scale, f8,
+    float h_norm_sq, h_abs;
+    memcpy(&h_norm_sq, &h_max_bits[0], sizeof(float));
+    memcpy(&h_abs, &h_max_bits[1], sizeof(float));
+    idx->scale = 1.0f;
+    if (f8 && h_norm_sq > 0.f && std::isfinite(h_norm_sq))
+        idx->scale = f8_row_norm(idx->window) / std::sqrt(h_norm_sq);
+    else if (!f8 && h_abs > 0.f && std::isfinite(h_abs))
+        idx->scale = 1.0f / h_abs;
+    // no per-batch row may be longer than the longest row of the index (see convert_rows_kernel)
+    idx->row_limit_sq = (h_norm_sq > 0.f && std::isfinite(h_norm_sq))
+                            ? h_norm_sq * idx->scale * idx->scale * 1.0001f
+                            : 0.f;
+    if ((r = launch_convert_rows(idx->table32, idx->n_base, idx->dim, idx->dim_pad, idx->scale, f8, 0.f,
                                  idx->table16, idx->table_sq, st)) != FS_OK)
         return r;
-    if ((r = launch_convert_rows(idx->sx32, idx->n_sx, idx->dim, idx->dim_pad, idx->scale, f8, idx->sx16,
-                                 idx->sx_sq, st)) != FS_OK)
+    if ((r = launch_convert_rows(idx->sx32, idx->n_sx, idx->dim, idx->dim_pad, idx->scale, f8, 0.f,
+                                 idx->sx16, idx->sx_sq, st)) != FS_OK)
         return r;
     const int64_t n_pad = static_cast<int64_t>(idx->tiles_n) * kBlockN;
     GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16, idx->sx_sq,
@@ -573,7 +580,8 @@ int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned lon
         if ((r = dev_grow(&idx->fx16, &idx->fx_cap, a.n_extra * idx->dim_pad)) != FS_OK) return r;
         if ((r = dev_grow(&idx->fx_sq, &idx->fxsq_cap, a.n_extra)) != FS_OK) return r;
         if ((r = launch_convert_rows(a.extra, a.n_extra, idx->dim, idx->dim_pad, idx->scale,
-                                     idx->operand_bits == 8, idx->fx16, idx->fx_sq, st)) != FS_OK)
+                                     idx->operand_bits == 8, idx->row_limit_sq, idx->fx16, idx->fx_sq,
+                                     st)) != FS_OK)
             return r;
     }
     GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16,  idx->sx_sq,

@@ -173,7 +173,7 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
                     int grid_limit, cudaStream_t stream);
 int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
-                        bool f8, __half* dst, float2* sq, cudaStream_t stream);
+                        bool f8, float limit_sq, __half* dst, float2* sq, cudaStream_t stream);
 int launch_rownorm_max(const float* src, int64_t n_rows, int32_t dim, unsigned int* out, cudaStream_t stream);
 int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t stream);
 int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,

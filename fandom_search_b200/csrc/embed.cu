@@ -16,34 +16,43 @@ namespace fs {
 // (one warp per row).  Used once for the base table and per batch for OOV extras.
 template <bool kF8>
 __global__ void convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int32_t dim,
-                                    int32_t n_elems, float scale, void* __restrict__ dst,
+                                    int32_t n_elems, float scale, float limit_sq, void* __restrict__ dst,
                                     float2* __restrict__ sq) {
     const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
     const float* s = src + row * dim;
-    float acc = 0.f, err = 0.f;
+    float acc = 0.f;
+    for (int c = lane; c < dim; c += 32) {
+        const float v = s[c] * scale;
+        acc = fmaf(v, v, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    // A per-batch row longer than the longest row of the index would overflow the fp16 range of
+    // the epilogue sums: its operand is shrunk to the limit and its error set to +inf, which turns
+    // every window it belongs to into an unconditional candidate (decided by the float64 rescoring
+    // from the untouched fp32 row).
+    const bool clamp = limit_sq > 0.f && acc > limit_sq;
+    const float shrink = clamp ? sqrtf(limit_sq / acc) : 1.f;
+    float err = 0.f;
     for (int c = lane; c < n_elems; c += 32) {
         const float v = c < dim ? s[c] * scale : 0.f;
         float back;
         if (kF8) {
-            const __nv_fp8_storage_t q = __nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+            const __nv_fp8_storage_t q = __nv_cvt_float_to_fp8(v * shrink, __NV_SATFINITE, __NV_E4M3);
             static_cast<uint8_t*>(dst)[row * n_elems + c] = q;
             back = __half2float(__half(__nv_cvt_fp8_to_halfraw(q, __NV_E4M3)));
         } else {
-            const __half h = __float2half_rn(v);
+            const __half h = __float2half_rn(v * shrink);
             static_cast<__half*>(dst)[row * n_elems + c] = h;
             back = __half2float(h);
         }
-        acc = fmaf(v, v, acc);
         err = fmaf(v - back, v - back, err);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        err += __shfl_xor_sync(0xffffffffu, err, o);
-    }
-    if (lane == 0) sq[row] = make_float2(acc, err);
+    for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+    if (lane == 0) sq[row] = make_float2(acc, clamp ? INFINITY : err);
 }
 
 // max over rows of the squared row norm (global fp8 scale); atomicMax on the bit pattern
@@ -216,16 +225,16 @@ int launch_sliding_minmax32(const float2* src, float2* dst, int64_t n, cudaStrea
 }
 
 int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
-                        bool f8, __half* dst, float2* sq, cudaStream_t stream) {
+                        bool f8, float limit_sq, __half* dst, float2* sq, cudaStream_t stream) {
     if (n_rows <= 0) return FS_OK;
     const int threads = 256;
     const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
     if (f8)
         convert_rows_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-            src, n_rows, dim, 2 * dim_pad, scale, dst, sq);
+            src, n_rows, dim, 2 * dim_pad, scale, limit_sq, dst, sq);
     else
         convert_rows_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-            src, n_rows, dim, dim_pad, scale, dst, sq);
+            src, n_rows, dim, dim_pad, scale, limit_sq, dst, sq);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }

@@ -743,11 +743,19 @@ def test_heterogeneous_row_norms(bits):
     tok[50:62] = big
     tok[70:76] = [5, 6, 5, 6, 5, 6]
     tok[80:86] = 6                      # an all-zero window
+    # a per-batch (fan-side) row 1000 x longer than any row of the index, parallel to a table row that
+    # stands alone in a script window: cosine 1, far outside the operand range chosen for the index
+    fx = fx.copy()
+    fx[0] = 1000.0 * table[big]
+    id_fx0 = table.shape[0] + sx.shape[0]
+    script[300:306] = [6, 6, big, 6, 6, 6]
+    tok[90:96] = [6, 6, id_fx0, 6, 6, 6]
     ref = NumpyIndex(table, script, extra=sx)
     want, _ = ref.search_host(tok, off, fx)
     idx = _device_index(table, script, extra=sx, bits=bits)
     got, _ = idx.search_host(tok, off, fx)
     assert _pairs(got) == _pairs(want) and len(want) > 20
+    assert (90, 300) in _pairs(want)
     for diag, pack in ((6, 2), (2, 2), (3, 1), (1, 0)):
         idx.set_option(nt.FS_OPT_DIAG, diag)
         idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
