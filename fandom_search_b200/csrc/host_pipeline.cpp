@@ -334,22 +334,61 @@ int64_t fs_records_best(const fs_match* matches, const int32_t* tie, int64_t n, 
         if (tx != ty) return tx < ty;
         return x.script_pos < y.script_pos;
     });
+    // A fan word at global position `pos` receives records from the windows starting at
+    // pos-w+1 .. pos, which arrive here in ascending order: a ring of 8 >= w open positions is
+    // enough, and every position below the current window start is final and can be emitted --
+    // no hash map, no final sort (rows come out ordered by position = by (work, word)).
     struct Best {
+        int64_t pos;
         double combined;
         double distance;
         int32_t window_ix, match_ix, lev;
-        bool set;
     };
-    std::vector<int64_t> keys;  // global fan token position of each winner
-    std::unordered_map<int64_t, Best> best;
-    best.reserve(static_cast<size_t>(n) * 2 + 16);
+    constexpr int kRing = 8;
+    if (window > kRing) {
+        fs::set_error("fs_records_best: window > 8");
+        return INT64_MIN;
+    }
+    Best ring[kRing];
+    for (auto& e : ring) e.pos = -1;
+    int64_t rows = 0, w = 0;
+    auto emit = [&](const Best& bb) {
+        if (rows < cap_out) {
+            while (w + 1 < n_works && tok_off[w + 1] <= bb.pos) ++w;
+            out_work[rows] = static_cast<int32_t>(w);
+            out_word[rows] = static_cast<int32_t>(bb.pos - tok_off[w]);
+            out_window_ix[rows] = bb.window_ix;
+            out_match_ix[rows] = bb.match_ix;
+            out_distance[rows] = bb.distance;
+            out_lev[rows] = bb.lev;
+        }
+        ++rows;
+    };
+    auto flush_below = [&](int64_t limit) {  // emit open positions < limit in ascending order
+        int64_t lo = INT64_MAX;
+        for (const auto& e : ring)
+            if (e.pos >= 0 && e.pos < lo) lo = e.pos;
+        if (lo == INT64_MAX) return;
+        if (limit - lo > kRing) limit = lo + kRing;  // open positions span less than the ring
+        for (int64_t pos = lo; pos < limit; ++pos) {
+            Best& e = ring[pos % kRing];
+            if (e.pos == pos) {
+                emit(e);
+                e.pos = -1;
+            }
+        }
+    };
     std::string fan_ctx, match_str;
-    int64_t run_start = 0;
+    int64_t run_start = 0, cur_p = -1;
     for (int64_t r = 0; r < n; ++r) {
         const fs_match& m = matches[order[r]];
         if (r > 0 && matches[order[r - 1]].fan_pos != m.fan_pos) run_start = r;
         if (r - run_start >= topk) continue;  // NearestFilter(10)
         if (m.script_pos < 0 || m.script_pos + window > n_script_words) continue;
+        if (m.fan_pos != cur_p) {  // positions before this window start are final
+            flush_below(m.fan_pos);
+            cur_p = m.fan_pos;
+        }
         // str(list of Token) vs str(Span): "[a, b, c]" vs "a b c"  (search.py:123,189)
         fan_ctx.assign("[");
         match_str.clear();
@@ -369,30 +408,16 @@ int64_t fs_records_best(const fs_match* matches, const int32_t* tie, int64_t n, 
         const double combined = m.distance * lev;
         for (int k = 0; k < window; ++k) {
             const int64_t pos = static_cast<int64_t>(m.fan_pos) + k;
-            auto it = best.find(pos);
-            if (it == best.end()) {
-                best.emplace(pos, Best{combined, m.distance, k, m.script_pos, lev, true});
-                keys.push_back(pos);
-            } else if (combined < it->second.combined) {  // first minimal record wins ties
-                it->second = Best{combined, m.distance, k, m.script_pos, lev, true};
+            Best& e = ring[pos % kRing];
+            if (e.pos != pos) {
+                e = Best{pos, combined, m.distance, k, m.script_pos, lev};
+            } else if (combined < e.combined) {  // first minimal record wins ties
+                e = Best{pos, combined, m.distance, k, m.script_pos, lev};
             }
         }
     }
-    const int64_t rows = static_cast<int64_t>(keys.size());
+    flush_below(INT64_MAX);
     if (rows > cap_out) return -rows;
-    std::sort(keys.begin(), keys.end());
-    int64_t w = 0;
-    for (int64_t i = 0; i < rows; ++i) {
-        const int64_t pos = keys[i];
-        while (w + 1 < n_works && tok_off[w + 1] <= pos) ++w;
-        const Best& bb = best[pos];
-        out_work[i] = static_cast<int32_t>(w);
-        out_word[i] = static_cast<int32_t>(pos - tok_off[w]);
-        out_window_ix[i] = bb.window_ix;
-        out_match_ix[i] = bb.match_ix;
-        out_distance[i] = bb.distance;
-        out_lev[i] = bb.lev;
-    }
     return rows;
 }
 

@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <utility>
 #include <vector>
 
 #include "../../include/fandom_search.h"
@@ -50,7 +51,11 @@ void decode_utf8(const char* s, int64_t n, std::vector<uint32_t>& out) {
 extern "C" {
 
 // Unit-cost Levenshtein distance over code points (replaces Levenshtein.distance,
-// /root/reference search.py:14,190).  Two-row dynamic programme.
+// /root/reference search.py:14,190).  The shorter string is the pattern: up to 64 code points it
+// runs as Myers' bit-vector algorithm in Hyyro's formulation for the global distance (one 64-bit
+// word carries a whole column of the dynamic programme: ~12 word operations per code point of the
+// longer string instead of one cell update per pair of code points); longer patterns fall back to
+// the two-row dynamic programme.  Both give the same integer.
 int32_t fs_levenshtein_utf8(const char* a, int64_t a_len, const char* b, int64_t b_len) {
     if (a_len < 0 || b_len < 0 || (a_len > 0 && !a) || (b_len > 0 && !b)) return -1;
     thread_local std::vector<uint32_t> ua, ub;
@@ -61,6 +66,65 @@ int32_t fs_levenshtein_utf8(const char* a, int64_t a_len, const char* b, int64_t
     const std::vector<uint32_t>& y = ua.size() >= ub.size() ? ub : ua;  // shorter
     const size_t n = y.size();
     if (n == 0) return static_cast<int32_t>(x.size());
+    if (n <= 64) {
+        // match masks of the pattern: a direct table for ASCII, a short list for everything else
+        thread_local uint64_t ascii_eq[128];
+        thread_local std::vector<std::pair<uint32_t, uint64_t>> other_eq;
+        other_eq.clear();
+        for (size_t j = 0; j < n; ++j)
+            if (y[j] < 128) ascii_eq[y[j]] = 0;
+        for (size_t j = 0; j < n; ++j) {
+            const uint64_t bit = 1ull << j;
+            if (y[j] < 128) {
+                ascii_eq[y[j]] |= bit;
+            } else {
+                bool found = false;
+                for (auto& e : other_eq)
+                    if (e.first == y[j]) {
+                        e.second |= bit;
+                        found = true;
+                        break;
+                    }
+                if (!found) other_eq.emplace_back(y[j], bit);
+            }
+        }
+        // characters of the text that do not occur in the pattern must read an all-zero mask:
+        // the ASCII table is only valid for the pattern's own characters, so test membership
+        thread_local uint8_t ascii_in[128];
+        for (size_t j = 0; j < n; ++j)
+            if (y[j] < 128) ascii_in[y[j]] = 1;
+        const uint64_t top = 1ull << (n - 1);
+        uint64_t pv = n == 64 ? ~0ull : ((1ull << n) - 1), mv = 0;
+        int32_t score = static_cast<int32_t>(n);
+        for (size_t i = 0; i < x.size(); ++i) {
+            const uint32_t c = x[i];
+            uint64_t eq = 0;
+            if (c < 128) {
+                if (ascii_in[c]) eq = ascii_eq[c];
+            } else {
+                for (const auto& e : other_eq)
+                    if (e.first == c) {
+                        eq = e.second;
+                        break;
+                    }
+            }
+            const uint64_t xv = eq | mv;
+            const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
+            uint64_t ph = mv | ~(xh | pv);
+            uint64_t mh = pv & xh;
+            if (ph & top)
+                ++score;
+            else if (mh & top)
+                --score;
+            ph = (ph << 1) | 1ull;
+            mh <<= 1;
+            pv = mh | ~(xv | ph);
+            mv = ph & xv;
+        }
+        for (size_t j = 0; j < n; ++j)
+            if (y[j] < 128) ascii_in[y[j]] = 0;
+        return score;
+    }
     row.resize(n + 1);
     for (size_t j = 0; j <= n; ++j) row[j] = static_cast<int32_t>(j);
     for (size_t i = 1; i <= x.size(); ++i) {

@@ -222,3 +222,76 @@ def test_native_float_repr_matches_python():
         n = lib.fs_format_py_float(x, buf, 64)
         assert buf.value.decode() == repr(x), (repr(x), buf.value)
         assert n == len(repr(x))
+
+
+def test_levenshtein_bit_vector_and_fallback_match_the_oracle():
+    """fs_levenshtein_utf8 (Myers/Hyyro bit-vector up to 64 code points, two-row DP beyond) against
+    the oracle's plain DP on 30 k random pairs: ASCII, accents, CJK, astral plane, lengths 0-90."""
+    import random
+    from fandom_search_b200 import text as T
+    from oracle import reference_search as ora
+    random.seed(3)
+    alph = "ab cdé日本,[]😀xyz"
+    bad=0
+    for it in range(30000):
+        la=random.randint(0,90); lb=random.randint(0,90)
+        if it%3==0: la=min(la,20); lb=min(lb,20)
+        a=''.join(random.choice(alph) for _ in range(la))
+        if random.random()<0.5:
+            # b = mutated a
+            b=list(a)
+            for _ in range(random.randint(0,6)):
+                r=random.random()
+                if r<0.33 and b: b.pop(random.randrange(len(b)))
+                elif r<0.66: b.insert(random.randint(0,len(b)), random.choice(alph))
+                elif b: b[random.randrange(len(b))]=random.choice(alph)
+            b=''.join(b)
+        else:
+            b=''.join(random.choice(alph) for _ in range(lb))
+        x=T.levenshtein(a,b); y=ora.levenshtein(a,b)
+        if x!=y:
+            bad+=1
+    assert bad == 0
+
+def test_records_best_against_python_restatement():
+    """fs_records_best (sorted single pass with a ring of open positions) == search.py:182-226 restated
+    in plain Python: top-10 per window, Levenshtein, six records per pair, first minimal record wins."""
+    import numpy as np
+    from fandom_search_b200 import text as T, _native as nt
+    from oracle import reference_search as ora
+    rng = np.random.default_rng(5)
+    vocab=["w%03d"%i for i in range(300)]+["é%d"%i for i in range(20)]
+    for trial in range(40):
+        nw=int(rng.integers(1,6))
+        works=[[vocab[i] for i in rng.integers(0,len(vocab),int(rng.integers(6,60)))] for _ in range(nw)]
+        batch=T.Batch.from_token_lists(works)
+        script=[vocab[i] for i in rng.integers(0,len(vocab),80)]
+        enc=[w.encode() for w in script]; soff=np.zeros(len(enc)+1,np.int64); np.cumsum([len(e) for e in enc],out=soff[1:]); blob=b''.join(enc)
+        tokoff=np.asarray(batch.tok_off)
+        n=int(rng.integers(0,120))
+        m=np.zeros(n,dtype=nt.MATCH_DTYPE)
+        recs=[]
+        for i in range(n):
+            w=int(rng.integers(0,nw)); L=len(works[w])
+            fp=int(rng.integers(0,L-5)); sp=int(rng.integers(0,75))
+            m[i]=(tokoff[w]+fp, sp, float(rng.choice([0.0,0.01,0.05,0.05,0.09])), w, 0)
+        # unique (fan_pos, script_pos)
+        _,ui=np.unique(np.stack([m['fan_pos'],m['script_pos']],1),axis=0,return_index=True); m=m[np.sort(ui)]
+        best=T.records_best(m,None,6,10,batch,blob,soff)
+        # python restatement
+        byw={}
+        for r in m: byw.setdefault(int(r['fan_pos']),[]).append(r)
+        want={}
+        for fp in sorted(byw):
+            cands=sorted(byw[fp], key=lambda r:(r['distance'], r['script_pos']))[:10]
+            w=int(cands[0]['work']); loc=fp-int(tokoff[w])
+            for r in cands:
+                sp=int(r['script_pos'])
+                ctx="["+", ".join(works[w][loc:loc+6])+"]"; ms=" ".join(script[sp:sp+6])
+                lev=ora.levenshtein(ms,ctx); comb=float(r['distance'])*lev
+                for k in range(6):
+                    key=(w,loc+k)
+                    if key not in want or comb<want[key][0]: want[key]=(comb,float(r['distance']),k,sp,lev)
+        got={(int(a),int(b)):(float(d)*int(l),float(d),int(k),int(mi),int(l)) for a,b,k,mi,d,l in zip(best['work'],best['word'],best['window_ix'],best['match_ix'],best['distance'],best['lev'])}
+        assert list(got)==sorted(got), "order"
+        assert got==want, (trial, len(got), len(want))
