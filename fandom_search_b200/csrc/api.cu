@@ -75,6 +75,7 @@ struct fs_index {
     int32_t dim = 0, window = 6;
     int32_t dim_pad = 0;        // operand row length in 2-byte units (fp16 elements, or fp8 elements / 2)
     int32_t dim_pad_elems = 0;  // operand row length in elements
+    bool ready = false;         // operand tables built (false after a failed re-conversion)
     float row_limit_sq = 0.f;   // squared norm of the longest scaled row of the index
     int32_t operand_bits = 8;   // 16: fp16 operands, 8: fp8 e4m3 operands (default)
     int64_t n_extra_rows = 0;
@@ -204,6 +205,7 @@ int fs_index_destroy(fs_index* idx) {
 static int prepare_operands(fs_index* idx) {
     cudaStream_t st = idx->stream;
     const bool f8 = idx->operand_bits == 8;
+    idx->ready = false;
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     FS_CUDA_CHECK(cudaDeviceSynchronize());
     idx->dim_pad_elems = static_cast<int32_t>(round_up(idx->dim, f8 ? 2 * kUmmaK : kUmmaK));  // K of one tcgen05.mma
@@ -269,6 +271,7 @@ static int prepare_operands(fs_index* idx) {
             return r;
     FS_CUDA_CHECK(cudaStreamSynchronize(st));
     idx->n_script_windows = static_cast<int64_t>(h_cnt[FS_CNT_WINDOWS]);
+    idx->ready = true;
     return FS_OK;
 }
 
@@ -560,6 +563,10 @@ struct BatchArgs {
 };
 
 int check_batch(const fs_index* idx, const BatchArgs& a, const char* who) {
+    if (idx && !idx->ready) {
+        set_error("%s: the index is unusable (a re-conversion of its operands failed)", who);
+        return FS_E_INVALID;
+    }
     if (!idx || a.n_tok < 0 || a.n_works < 0 || (a.n_tok > 0 && !a.tok) || !a.off || a.n_extra < 0 ||
         (a.n_extra > 0 && !a.extra)) {
         set_error("%s: invalid argument", who);
