@@ -141,7 +141,7 @@ struct fs_index {
     // options
     int32_t diag = 1;              // diagonal-sum factor E of the distance kernel
     int32_t pair = 0;              // CTA-pair (cta_group::2) kernel
-    int32_t ares = 0;              // A-resident variant of the pair kernel
+    int32_t ares = 1;              // A-resident variant of the pair kernel (used when the row fits: <= 640 B)
     int32_t pack = 2;              // epilogue diagonal sums: 0 fp32 shuffles, 1 fp16x2 shuffles, 2 fp16x2 arithmetic
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
     int64_t last_row0_6 = 0;

@@ -245,6 +245,12 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, ui
     }
 }
 
+// every lane polls: for waits that almost always succeed at once (the MMA issuer's)
+__device__ __forceinline__ void mbar_wait_all(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
 // one elected lane of a converged warp (the same lane every time: lowest active)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -377,6 +383,34 @@ __device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t adesc, ui
         :
         : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// One tcgen05.mma from the two 32-bit halves of its shared-memory descriptors: `hi` (stride, version,
+// swizzle mode) is the same constant for every operand, `lo` = start address >> 4 | LBO << 16, so an
+// operand at a byte offset inside the stage is lo + (offset >> 4) -- one 32-bit add with an immediate
+// when the offset is a compile-time constant (the 14-bit address field cannot carry: a stage lies
+// inside one CTA's 228 KB of shared memory).
+template <bool kPair, bool kF8>
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+    if (kPair && kF8) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %4, p;\n\t}\n"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+    } else if (kPair) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 // arrive on the mbarrier at this offset in BOTH CTAs once the leader's MMAs retired
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {

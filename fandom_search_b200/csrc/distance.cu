@@ -27,6 +27,8 @@
 // cursor; they are re-scored in float64 afterwards.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace fs {
 
 // ---------------------------------------------------------------------------------------------
@@ -623,17 +625,38 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 mbar_wait_warp(afull_bar, a_phase, 0);  // the resident fan tile has landed (both CTAs)
                 a_phase ^= 1u;
             }
-            mbar_wait_warp(tempty_bar(as), aphase ^ 1u, 0);
+            mbar_wait_all(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
             const int n_shift = kMix ? (tile.e6 ? 1 : 2) : S;  // an E = 6 tile takes shift 0 only
             uint32_t accumulate = 0;
+            // This warp is the only issuer of the CTA pair and runs one dependent instruction stream:
+            // every instruction it spends per MMA is time the tensor pipe waits (ncu: the warp was
+            // busy 100 % of the kernel at ~29 instructions per MMA, the tensor pipe 67 % active).
+            // Descriptors are therefore {lo + constant, hi}: a full 128-byte chunk of S shifts is
+            // issued as S x 4 MMAs whose operand offsets are immediates.
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            auto desc_lo = [](uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); };
+            auto issue_full_chunk = [&](auto shifts, uint32_t a_lo, uint32_t b_lo) {
+                constexpr int kS = decltype(shifts)::value;
+#pragma unroll
+                for (int s = 0; s < kS; ++s) {
+#pragma unroll
+                    for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+                        // row shift s * E rows of 128 B, K-step k * 32 B (the 128B swizzle is a
+                        // function of the absolute smem address, so base_offset stays 0)
+                        const uint32_t off = static_cast<uint32_t>((s * kShiftRows * 128 + k * kUmmaK * 2) >> 4);
+                        umma_lohi<kPair, kF8>(tmem_d, a_lo + off, b_lo + off, kDescHi, idesc, accumulate);
+                        accumulate = 1;
+                    }
+                }
+            };
             for (int c = 0; c < p.chunks; ++c) {
                 // the last chunk may hold fewer than 64 real columns (d_pad is a multiple of
                 // 16, not 64): its trailing K-steps are all-zero TMA fill and are skipped
                 const int ksteps = (c == p.chunks - 1) ? p.last_chunk_ksteps : kChunkK / kUmmaK;
                 for (int g = 0; g < shift_groups; ++g) {
-                    mbar_wait_warp(full_bar(stage), phase, 0);
+                    mbar_wait_all(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t st_src = smem_base + stage * kStageSz;
                     // resident mode: the fan chunk sits in the resident tile and the stage holds
@@ -642,26 +665,22 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                                                        static_cast<uint32_t>(g * S * kShiftRows * 128)
                                                  : st_src;
                     const uint32_t b_src = kARes ? st_src : st_src + kStageABytes;
-                    // descriptors of (shift 0, k-step 0); every other operand of the stage is
-                    // this plus a byte offset >> 4 in the 14-bit start-address field
-                    const uint64_t adesc0 = umma_smem_desc(a_src, 0);
-                    const uint64_t bdesc0 = umma_smem_desc(b_src, 0);
+                    const uint32_t a_lo = desc_lo(a_src), b_lo = desc_lo(b_src);
                     if (elect_one()) {
-                        for (int s = 0; s < n_shift; ++s) {
-                            // row shift inside the stage = s * E rows of 128 B: a plain offset
-                            // of the descriptor start address (the 128B swizzle is a function of
-                            // the absolute smem address, so base_offset stays 0)
-                            const uint32_t row_off = static_cast<uint32_t>(s * kShiftRows * 128) >> 4;
-#pragma unroll 4
-                            for (int k = 0; k < ksteps; ++k) {
-                                const uint64_t off = row_off + static_cast<uint32_t>(k * kUmmaK * 2 >> 4);
-                                if (kF8)
-                                    umma_f8_pair(tmem_d, adesc0 + off, bdesc0 + off, idesc, accumulate);
-                                else if (kPair)
-                                    umma_f16_pair(tmem_d, adesc0 + off, bdesc0 + off, idesc, accumulate);
-                                else
-                                    umma_f16(tmem_d, adesc0 + off, bdesc0 + off, idesc, accumulate);
-                                accumulate = 1;
+                        if (ksteps == kChunkK / kUmmaK && n_shift == 1) {
+                            issue_full_chunk(std::integral_constant<int, 1>{}, a_lo, b_lo);
+                        } else if (ksteps == kChunkK / kUmmaK && n_shift == 2) {
+                            issue_full_chunk(std::integral_constant<int, 2>{}, a_lo, b_lo);
+                        } else if (ksteps == kChunkK / kUmmaK && n_shift == 3) {
+                            issue_full_chunk(std::integral_constant<int, 3>{}, a_lo, b_lo);
+                        } else {
+                            for (int s = 0; s < n_shift; ++s) {
+                                for (int k = 0; k < ksteps; ++k) {
+                                    const uint32_t off =
+                                        static_cast<uint32_t>((s * kShiftRows * 128 + k * kUmmaK * 2) >> 4);
+                                    umma_lohi<kPair, kF8>(tmem_d, a_lo + off, b_lo + off, kDescHi, idesc, accumulate);
+                                    accumulate = 1;
+                                }
                             }
                         }
                         // frees the smem stage (in both CTAs) when these MMAs retire
@@ -847,12 +866,11 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
             set_error("fp8 operands need CTA pairs");
             return FS_E_INVALID;
         }
-        if (ares) {
-            // resident fan tile: the two diagonal factors that are defaults, fp16x2 epilogue
+        if (ares && pack == 2 && (p.diag == 3 || p.diag == 6)) {
+            // resident fan tile: built for the two default diagonal factors with the fp16x2 epilogue;
+            // every other combination streams the fan tile
             if (p.diag == 3) return launch_distance_t<3, true, true, 2, true>(map_fan, map_script, p, grid, stream);
-            if (p.diag == 6) return launch_distance_t<6, true, true, 2, true>(map_fan, map_script, p, grid, stream);
-            set_error("fp8 operands with the A-resident tile exist for diagonal factors 3 and 6");
-            return FS_E_INVALID;
+            return launch_distance_t<6, true, true, 2, true>(map_fan, map_script, p, grid, stream);
         }
         switch (p.diag) {
             case 1: return launch_distance_t<1, true, false, 0, true>(map_fan, map_script, p, grid, stream);
@@ -889,8 +907,8 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         case 3: FS_LAUNCH_MODE(3);
         case 6: FS_LAUNCH_MODE(6);
         case kDiagMix:
-            if (!p.pair || ares) {
-                set_error("the mixed E = 3 / E = 6 schedule needs CTA pairs without the A-resident tile");
+            if (!p.pair) {
+                set_error("the mixed E = 3 / E = 6 schedule needs CTA pairs");
                 return FS_E_INVALID;
             }
             if (pack == 2) FS_LAUNCH(kDiagMix, true, false, 2);

@@ -96,9 +96,9 @@ def main():
                                   pattern=args.pattern, bits=args.bits)), flush=True)
         return
     if args.f8:
-        for bits, diag, d, pack, pair in ((16, 3, 300, 2, 1), (8, 3, 300, 2, 1), (8, 3, 300, 2, 2), (8, 6, 300, 2, 1),
-                                          (8, 6, 300, 2, 2), (8, 2, 300, 2, 1), (8, 6, 768, 2, 1), (8, 3, 768, 2, 1),
-                                          (16, 6, 768, 2, 1), (8, 3, 300, 2, 2)):
+        for bits, diag, d, pack, pair in ((16, 3, 300, 2, 1), (16, 3, 300, 2, 2), (8, 3, 300, 2, 1), (8, 3, 300, 2, 2),
+                                          (8, 6, 300, 2, 1), (8, 6, 300, 2, 2), (8, 2, 300, 2, 1), (8, 6, 768, 2, 1),
+                                          (8, 3, 768, 2, 1), (16, 6, 768, 2, 1), (8, 3, 300, 2, 2)):
             print(json.dumps(run_case(2_500_000, 25000, d, 20, rng, diag=diag, pair=pair, pack=pack,
                                       clocks=True, bits=bits)), flush=True)
         return
