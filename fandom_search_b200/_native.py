@@ -25,7 +25,6 @@ FS_CNT_WINDOWS = 3
 FS_CNT_COUNT = 4
 
 FS_OPT_SHIFTS_PER_STAGE = 1
-FS_OPT_BASE_OFFSET_MODE = 2
 FS_OPT_GRID_LIMIT = 3
 FS_OPT_DIAG = 4
 FS_OPT_CTA_PAIR = 5

@@ -146,7 +146,6 @@ struct fs_index {
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
     int64_t last_row0_6 = 0;
     int32_t mix_pattern = 0x5;     // diag == kDiagMix: bit i = kind of tile i mod 4 (1 -> E = 6)
-    int32_t base_offset_mode = 0;
     int32_t grid_limit = 0;
 
     // timing ring
@@ -469,9 +468,6 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             }
             idx->mix_pattern = static_cast<int32_t>(value);
             return FS_OK;
-        case FS_OPT_BASE_OFFSET_MODE:
-            idx->base_offset_mode = value ? 1 : 0;
-            return FS_OK;
         case FS_OPT_GRID_LIMIT:
             idx->grid_limit = static_cast<int32_t>(value < 0 ? 0 : value);
             return FS_OK;
@@ -668,7 +664,6 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.row0_6 = row0_6;
     idx->last_row0_6 = row0_6;
     p.mix_pattern = idx->mix_pattern;
-    p.base_offset_mode = idx->base_offset_mode;
     p.tiles_m = tiles_m;
     p.tiles_n = tiles_n;
     p.cand = (mode == Mode::kCandidates) ? cand_out : idx->cand;

@@ -96,7 +96,6 @@ struct DistParams {
     int32_t f8;               // 1: operands are fp8 e4m3 (tcgen05.mma.kind::f8f6f4, K = 32)
     int32_t pair;             // 1: CTA-pair kernel (cta_group::2, M = 2 x 128 fan tiles)
     int32_t shifts_per_stage; // S: MMA shifts served by one smem stage (divides window/E)
-    int32_t base_offset_mode; // how shifted descriptors fill base_offset
     int32_t tiles_m, tiles_n;
     // mixed schedule (diag == kDiagMix): tiles_m/tiles_n describe the E = 3 region [0, row0_6),
     // tiles_m6/tiles_n6 the E = 6 region [row0_6, M); bit i of mix_pattern = kind of tile i mod 4

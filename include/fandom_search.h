@@ -89,7 +89,6 @@ enum {
 /* Options for fs_index_set_option. */
 enum {
     FS_OPT_SHIFTS_PER_STAGE = 1, /* MMA token-row shifts served by one smem stage (0 = all) */
-    FS_OPT_BASE_OFFSET_MODE = 2, /* 0/1: UMMA descriptor base_offset handling for shifted rows */
     FS_OPT_GRID_LIMIT = 3,       /* max CTAs of the persistent distance kernel (0 = #SMs)  */
     FS_OPT_CTA_PAIR = 5,         /* 1: two CTAs of a cluster share one tcgen05.mma.cta_group::2
                                     (M = 2 x 128 fan windows, each CTA stages half the script tile) */

@@ -2,7 +2,10 @@
 
 Run on a B200:  python tools/probe_gemm.py
 Compares fs_stage_dots_dev (tcgen05 path, dense dump) against a numpy contraction of the
-same fp16-rounded operands for every (shifts_per_stage, base_offset_mode) variant.
+same fp16-rounded operands for every shifts_per_stage variant of the dense (E = 1) fp16 kernel.
+(The first run of this probe, profiles/r01_probe_gemm_variants.log, also tried filling the
+descriptor's base_offset field for shifted rows: only base_offset = 0 reproduces the contraction,
+the 128B swizzle being a function of the absolute shared-memory address; that knob is gone.)
 """
 import sys
 import time
@@ -37,16 +40,16 @@ def main():
     tok_f = rng.integers(0, V, 600).astype(np.int32)
     off = np.array([0, 200, 203, 600], np.int64)
     idx = DeviceIndex(table, tok_s, window=w, threshold=0.1)
+    for opt, val in ((nt.FS_OPT_OPERAND_BITS, 16), (nt.FS_OPT_DIAG, 1), (nt.FS_OPT_CTA_PAIR, 0),
+                     (nt.FS_OPT_A_RESIDENT, 0)):
+        idx.set_option(opt, val)
     print("scale", idx.scale, "dim_pad", idx.dim_pad, "sms", idx.sm_count, flush=True)
     ref = ref_dots(table, idx.scale, tok_f, tok_s, w)
     tok_t, off_t, _ = idx.to_device(tok_f, off)
     results = {}
     for S in (1, 2, 3, 6):
-        for bo in (0, 1):
-            if S == 1 and bo == 1:
-                continue
+        for bo in (0,):
             idx.set_option(nt.FS_OPT_SHIFTS_PER_STAGE, S)
-            idx.set_option(nt.FS_OPT_BASE_OFFSET_MODE, bo)
             dots = idx.stage_dots(tok_t, off_t)
             torch.cuda.synchronize()
             got = dots.cpu().numpy()
@@ -60,7 +63,6 @@ def main():
         return 1
     S, bo = max(good)
     idx.set_option(nt.FS_OPT_SHIFTS_PER_STAGE, S)
-    idx.set_option(nt.FS_OPT_BASE_OFFSET_MODE, bo)
 
     # full search vs float64 brute force on planted data
     tok_f2 = tok_f.copy()
@@ -100,9 +102,11 @@ def main():
     off2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     tok_f3 = rng.integers(0, V2, int(off2[-1])).astype(np.int32)
     idx2 = DeviceIndex(table2, tok_s2, window=w, threshold=0.1)
+    for opt, val in ((nt.FS_OPT_OPERAND_BITS, 16), (nt.FS_OPT_DIAG, 1), (nt.FS_OPT_CTA_PAIR, 0),
+                     (nt.FS_OPT_A_RESIDENT, 0)):
+        idx2.set_option(opt, val)
     for (S, bo) in good:
         idx2.set_option(nt.FS_OPT_SHIFTS_PER_STAGE, S)
-        idx2.set_option(nt.FS_OPT_BASE_OFFSET_MODE, bo)
         tok_t, off_t, _ = idx2.to_device(tok_f3, off2)
         out_t = torch.empty(24 << 20, dtype=torch.uint8, device="cuda")
         cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
