@@ -2,9 +2,10 @@
 
 The path shards by cluster of fanworks: cluster i is searched entirely by rank
 i % WORLD_SIZE against a replicated script index (the reference's own unit of parallelism is
-the file, search.py:382-385).  There is NO collective on the data path; the only exchange is
-returning each cluster's (small) record list to rank 0 for the aggregate CSV
-(search.py:388-399), done with gather_object over the default process group.
+the file, search.py:382-385).  There is NO collective on the data path: every rank writes the
+batch CSVs of its clusters, and after one barrier rank 0 assembles the aggregate CSV
+(search.py:388-399) from those files.  (analyze_scripts, the multi-script pass, still returns its
+record lists to rank 0 with gather_object.)
 """
 import os
 
@@ -27,6 +28,18 @@ def init_process_group():
         else:
             dist.init_process_group('gloo', rank=rank, world_size=world)
     return rank, world
+
+
+def barrier():
+    """All ranks wait for each other (host-side control only; nothing on the data path)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = init_process_group()
+    if world > 1:
+        if torch.cuda.is_available():
+            dist.barrier(device_ids=[torch.cuda.current_device()])
+        else:
+            dist.barrier()
 
 
 def cluster_owner(cluster_index, world):

@@ -593,35 +593,35 @@ def analyze(args,
     # ctypes releases the GIL inside the native calls, so plain threads are enough.
     from concurrent.futures import ThreadPoolExecutor
     mine = [(i, c) for i, c in enumerate(fan_clusters, start=start) if i % world == rank]
-    my_records = {}
 
     def finish(i, prep, found):
-        # rows are formatted ONCE: the batch file and the aggregate share the same text
-        text = ann_index.records_text_prepared(prep, *found)
-        _write_text(text, batch_filename.format(i))
-        return i, text
+        # rows are formatted ONCE, natively; the aggregate is assembled from the batch files
+        _write_text(ann_index.records_text_prepared(prep, *found), batch_filename.format(i))
+        return i
 
+    import collections
     with ThreadPoolExecutor(max_workers=1) as prep_pool, ThreadPoolExecutor(max_workers=1) as post_pool:
         pending = prep_pool.submit(ann_index.prepare, mine[0][1]) if mine else None
-        finishing = []
+        in_flight = collections.deque()      # at most two clusters' buffers are alive at a time
         for k, (i, fan_cluster) in enumerate(mine):
             print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
             prep = pending.result()
             pending = prep_pool.submit(ann_index.prepare, mine[k + 1][1]) if k + 1 < len(mine) else None
             found = ann_index.search_prepared(prep)
-            finishing.append(post_pool.submit(finish, i, prep, found))
-        for fut in finishing:
-            i, text = fut.result()
-            my_records[i] = text
+            in_flight.append(post_pool.submit(finish, i, prep, found))
+            del prep, found
+            while len(in_flight) > 2:
+                in_flight.popleft().result()
+        while in_flight:
+            in_flight.popleft().result()
 
     if world > 1:
-        from .parallel import gather_cluster_records
-        my_records = gather_cluster_records(my_records, rank, world)
+        # every rank has written its own batch files (same directory, one node): rank 0 only has
+        # to wait for them -- no record ever crosses ranks
+        from .parallel import barrier
+        barrier()
         if rank != 0:
             return
-    # header row (search.py:367) + the rows of every cluster in cluster order (search.py:388)
-    aggregate = format_records([new_record_structure['fields']]).encode('utf-8') + b''.join(
-        my_records[i] for i in sorted(my_records))
 
     i = 0
     today_str = '-{:%Y%m%d}.csv'.format(datetime.date.today())
@@ -630,4 +630,11 @@ def analyze(args,
         i += 1
         today_str = '-{:%Y%m%d}-{}.csv'.format(datetime.date.today(), i)
         name_check = filename_base.format(today_str)
-    _write_text(aggregate, name_check)
+    # header row (search.py:367) + the rows of every cluster in cluster order (search.py:388),
+    # streamed from the batch files: memory stays flat however large the corpus is
+    import shutil
+    with open(name_check, 'wb') as out:
+        out.write(format_records([new_record_structure['fields']]).encode('utf-8'))
+        for ci in range(start, start + len(fan_clusters)):
+            with open(batch_filename.format(ci), 'rb') as part:
+                shutil.copyfileobj(part, out, 1 << 22)
