@@ -75,6 +75,7 @@ struct fs_index {
     int32_t dim = 0, window = 6;
     int32_t dim_pad = 0;        // operand row length in 2-byte units (fp16 elements, or fp8 elements / 2)
     int32_t dim_pad_elems = 0;  // operand row length in elements
+    bool diag_user = false;     // FS_OPT_DIAG was set by the caller (else chosen per operand type)
     bool ready = false;         // operand tables built (false after a failed re-conversion)
     float row_limit_sq = 0.f;   // squared norm of the longest scaled row of the index
     int32_t operand_bits = 8;   // 16: fp16 operands, 8: fp8 e4m3 operands (default)
@@ -209,6 +210,18 @@ static int prepare_operands(fs_index* idx) {
     FS_CUDA_CHECK(cudaDeviceSynchronize());
     idx->dim_pad_elems = static_cast<int32_t>(round_up(idx->dim, f8 ? 2 * kUmmaK : kUmmaK));  // K of one tcgen05.mma
     idx->dim_pad = f8 ? idx->dim_pad_elems / 2 : idx->dim_pad_elems;
+    if (!idx->diag_user) {
+        // Default diagonal factor (all variants are parity-tested and selectable): E = 3 runs two MMA
+        // shifts per K-step and a cheap epilogue, E = 6 one shift and an epilogue with 1.6x the
+        // shuffles; E = 6 pays once the embedding is wide.  Measured crossover at C2 size:
+        // 512 elements for fp8 operands (56.9 vs 56.1 M windows/s; 53.1 vs 45.2 at 640), 416 for fp16.
+        const int32_t wide = f8 ? 512 : 416;
+        if (idx->window % 6 == 0 && idx->dim_pad_elems >= wide)
+            idx->diag = 6;
+        else
+            idx->diag = idx->window % 3 == 0 ? 3 : (idx->window % 2 == 0 ? 2 : 1);
+        idx->shifts_per_stage = 0;
+    }
     void* stale[] = {idx->table16, idx->sx16, idx->script_emb, idx->fan_emb, idx->fx16};
     for (void* q : stale)
         if (q) cudaFree(q);
@@ -320,15 +333,6 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     idx->n_sx = n_extra;
     idx->n_script_tok = n_script_tok;
     idx->n_scripts = static_cast<int32_t>(n_scripts);
-    // Defaults of the distance kernel (all variants are parity-tested and selectable):
-    // CTA pairs, and the diagonal factor that balances the tensor pipe against the warp-shuffle
-    // pipe (measured ~0.5 warp-shuffles/clk/SM): E = 3 costs 2 shuffles per accumulator element
-    // against 2*ksteps MMAs per tile, E = 6 costs 3.1 against ksteps -- E = 6 only pays once the
-    // embedding is wide (d_pad >= 416: 26 M vs 18 M windows/s at d = 768).
-    if (window % 6 == 0 && idx->dim_pad >= 416)
-        idx->diag = 6;
-    else
-        idx->diag = window % 3 == 0 ? 3 : (window % 2 == 0 ? 2 : 1);
     idx->pair = 1;
 
 #define FS_TRY(expr)                    \
@@ -442,6 +446,7 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
         case FS_OPT_DIAG:
             if (value == kDiagMix && idx->window == 6) {
                 idx->diag = kDiagMix;  // alternate E = 3 and E = 6 tiles
+                idx->diag_user = true;
                 idx->shifts_per_stage = 0;
                 return FS_OK;
             }
@@ -450,6 +455,7 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
                 return FS_E_INVALID;
             }
             idx->diag = static_cast<int32_t>(value);
+            idx->diag_user = true;
             idx->shifts_per_stage = 0;
             return FS_OK;
         case FS_OPT_OPERAND_BITS: {
