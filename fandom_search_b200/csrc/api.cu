@@ -211,11 +211,13 @@ static int prepare_operands(fs_index* idx) {
     idx->dim_pad_elems = static_cast<int32_t>(round_up(idx->dim, f8 ? 2 * kUmmaK : kUmmaK));  // K of one tcgen05.mma
     idx->dim_pad = f8 ? idx->dim_pad_elems / 2 : idx->dim_pad_elems;
     if (!idx->diag_user) {
-        // Default diagonal factor (all variants are parity-tested and selectable): E = 3 runs two MMA
-        // shifts per K-step and a cheap epilogue, E = 6 one shift and an epilogue with 1.6x the
-        // shuffles; E = 6 pays once the embedding is wide.  Measured crossover at C2 size:
-        // 512 elements for fp8 operands (56.9 vs 56.1 M windows/s; 53.1 vs 45.2 at 640), 416 for fp16.
-        const int32_t wide = f8 ? 512 : 416;
+        // Default diagonal factor (all variants are parity-tested and selectable).  E = 6 runs one MMA
+        // shift per K-step (a sixth of the dense tensor work) and leaves the rest to the epilogue; since
+        // the epilogue rejects almost every chunk from its row maxima before summing a diagonal, that
+        // is the faster split for fp8 operands at every width (C2 workload, M windows/s, E=6 vs E=3:
+        // 86.5 vs 82.2 at d=300, 72.7 vs 55.4 at d=512, 56.4 vs 35.9 at d=768).  fp16 operands keep
+        // E = 3 below 416 elements (their MMAs cost twice as much; measured before the rejection).
+        const int32_t wide = f8 ? 0 : 416;
         if (idx->window % 6 == 0 && idx->dim_pad_elems >= wide)
             idx->diag = 6;
         else

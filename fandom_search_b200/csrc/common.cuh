@@ -70,9 +70,13 @@ __host__ __device__ constexpr int dist_stages(int diag, bool pair, bool ares) {
     return ares ? (diag_max(diag) == 6 ? 5 : 7)
                 : (pair ? (diag_max(diag) == 6 ? 5 : 6) : (diag_max(diag) == 6 ? 3 : 4));
 }
+// per published boundary row and 32-column chunk, the maximum of the row over the chunk's 40 loaded
+// columns (one half; 8 chunks per tile, two buffers): lets the boundary pass reject a chunk at once
+__host__ __device__ constexpr int dist_rowmax_bytes(int diag) { return 2 * 4 * dist_pub_slots(diag) * 8 * 2; }
 __host__ __device__ constexpr int dist_smem_bytes(int diag, bool pair, bool ares) {
     return (ares ? kAResBytes : 0) + dist_stages(diag, pair, ares) * dist_stage_bytes(pair, ares) +
-           1024 /*align slack*/ + 256 /*barriers*/ + dist_pub_bytes(diag) + kNormTileBytes;
+           1024 /*align slack*/ + 256 /*barriers*/ + dist_pub_bytes(diag) + kNormTileBytes +
+           dist_rowmax_bytes(diag);
 }
 static_assert(dist_smem_bytes(1, false, false) <= 232448 && dist_smem_bytes(3, true, false) <= 232448 &&
                   dist_smem_bytes(6, true, false) <= 232448 && dist_smem_bytes(6, false, false) <= 232448 &&

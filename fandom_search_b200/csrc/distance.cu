@@ -288,7 +288,7 @@ template <int kDiag, bool kDump, int kPack, bool kPair>
 __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t m0, const int32_t n0,
                                               const int as, const uint32_t tfull_addr, const uint32_t tempty_addr,
                                               const uint32_t aphase, const uint32_t tmem_base, float* halo,
-                                              float2* norm_tile, const int warp, const int lane) {
+                                              float2* norm_tile, __half* rowmax, const int warp, const int lane) {
     constexpr int kMStep = kBlockM - (kDiag - 1);
     constexpr int kNStep = kBlockN - (kDiag - 1);
     constexpr int kPubSlots = dist_pub_slots(kDiag);
@@ -381,6 +381,10 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
 #pragma unroll
             for (int k = 1; k < 20; ++k) m = hmax(m, pk[k]);
             m = hmax(m, __byte_perm(m, m, 0x1032));  // both halves = the row maximum
+            // boundary rows also publish it: the boundary pass rejects its chunks the same way
+            if (kDiag > 1 && pub_slot >= 0)
+                reinterpret_cast<uint16_t*>(rowmax)[(quarter * kPubSlots + pub_slot) * 8 + (c0 >> 5)] =
+                    static_cast<uint16_t>(m & 0xffffu);
             uint32_t bsum;
             if (kDiag == 6) {
                 const uint32_t b01 = h2_add(m, __shfl_down_sync(0xffffffffu, m, 1));
@@ -446,15 +450,40 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     if (kDiag > 1) {
         // boundary rows: tail rows of quarters 0..2 (quarter 3's belong to the next tile)
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        float a_l[kEdge > 0 ? kEdge : 1], c_l[kEdge > 0 ? kEdge : 1];  // (kDiag == 1 never gets here)
 #pragma unroll
         for (int tr = 0; tr < kEdge; ++tr) {
-            const int L = kTail0 + tr;
-            const float a_l = __shfl_sync(0xffffffffu, ac.x, L);
-            const float c_l = __shfl_sync(0xffffffffu, ac.y, L);
-            if (quarter < 3) {
+            a_l[tr] = __shfl_sync(0xffffffffu, ac.x, kTail0 + tr);
+            c_l[tr] = __shfl_sync(0xffffffffu, ac.y, kTail0 + tr);
+        }
+        if (quarter < 3) {
 #pragma unroll
-                for (int it = 0; it < kEpiCols / 32; ++it) {
-                    const int c = group * kEpiCols + it * 32 + lane;
+            for (int it = 0; it < kEpiCols / 32; ++it) {
+                const int cc = group * (kEpiCols / 32) + it;  // 32-column chunk of the tile
+                const int c = cc * 32 + lane;
+                // kHalf: upper bound of each boundary row's sums over this chunk from the published
+                // row maxima (summed in the order of `v` below: fp32 addition is monotone), against
+                // the chunk's smallest pre-filter bound -- the same rejection as in the main pass
+                float rmx[2 * (kEdge > 0 ? kEdge : 1)];  // row maxima: tail rows of this quarter, head rows of the next
+                float2 mm = make_float2(0.f, 0.f);
+                if (kHalf && !kDump) {
+#pragma unroll
+                    for (int s2 = 0; s2 < kEdge; ++s2) {
+                        rmx[s2] = __half2float(rowmax[(quarter * kPubSlots + kEdge + s2) * 8 + cc]);
+                        rmx[kEdge + s2] = __half2float(rowmax[((quarter + 1) * kPubSlots + s2) * 8 + cc]);
+                    }
+                    mm = __ldg(p.script_mm32 + n0 + cc * 32);
+                }
+#pragma unroll
+                for (int tr = 0; tr < kEdge; ++tr) {
+                    const int L = kTail0 + tr;
+                    if (kHalf && !kDump) {
+                        // rows L .. L+E-1 = entries tr .. tr+E-1 of rmx, summed in the order of `v`
+                        float bsum = 0.f;
+#pragma unroll
+                        for (int d = 0; d < kDiag; ++d) bsum += rmx[tr + d];
+                        if (!(bsum > fmaf(-c_l[tr], mm.y, a_l[tr] * mm.x))) continue;
+                    }
                     float v = 0.f;
 #pragma unroll
                     for (int d = 0; d < kDiag; ++d) {
@@ -473,7 +502,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                     if (kDump) {
                         if (gr < p.n_fan_tok && c < kNStep && n0 + c < p.dump_ld)
                             p.dump[static_cast<int64_t>(gr) * p.dump_ld + n0 + c] = v;
-                    } else if (v > fmaf(-c_l, ns_tile[c].y, a_l * ns_tile[c].x)) {
+                    } else if (v > fmaf(-c_l[tr], ns_tile[c].y, a_l[tr] * ns_tile[c].x)) {
                         const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                         if (slot < static_cast<unsigned long long>(p.cand_cap)) {
                             p.cand[slot].fan_pos = gr;
@@ -536,6 +565,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
     float2* norm_tile = reinterpret_cast<float2*>(halo + dist_pub_bytes(kDiag) / 4);
+    __half* rowmax_base = reinterpret_cast<__half*>(norm_tile + kAccumStages * kHaloCols);
 
     // Warp roles.  The warp scheduler prefers the HIGHEST warp id among eligible warps, so the
     // two single-thread roles that everything else waits for get the two highest ids: with
@@ -750,17 +780,18 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         constexpr bool kHalfRows = kPack == 2 && (diag_max(kDiag) == 6 || kDiag == 3 || kDiag == 2);
         while (walk.next(tile)) {
             float* halo_t = halo + (kHalfRows ? as * (dist_pub_bytes(kDiag) / 8) : 0);
+            __half* rowmax_t = rowmax_base + as * (dist_rowmax_bytes(kDiag) / 4);
             if constexpr (kMix) {
                 // kPack: 0 = full-precision shuffles, 1 = packed shuffles, 2 = fp16x2 arithmetic
                 if (tile.e6)
                     epilogue_tile<6, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
-                                                          aphase, tmem_base, halo_t, norm_tile, warp, lane);
+                                                          aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane);
                 else
                     epilogue_tile<3, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
-                                                          aphase, tmem_base, halo_t, norm_tile, warp, lane);
+                                                          aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane);
             } else {
                 epilogue_tile<kDiag, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
-                                                          aphase, tmem_base, halo_t, norm_tile, warp, lane);
+                                                          aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane);
             }
             if (++as == kAccumStages) {
                 as = 0;

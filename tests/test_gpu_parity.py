@@ -168,11 +168,10 @@ def test_gather_is_bit_exact_and_norms_match():
 
 
 def test_library_defaults():
-    """6-gram windows, d = 300: fp8 operands, E = 3, CTA pairs, resident fan tile, fp16x2 epilogue;
-    wide embeddings take E = 6."""
+    """6-gram windows: fp8 operands, E = 6, CTA pairs, resident fan tile, fp16x2 epilogue."""
     table, sx, fx, script, tok, off = _case(5)
     idx = _device_index(table, script, extra=sx, bits=None)
-    assert idx.operand_bits == 8 and idx.diag == 3 and idx.cta_pair == 1 and idx.info(7) == 1 and idx.info(8) == 2
+    assert idx.operand_bits == 8 and idx.diag == 6 and idx.cta_pair == 1 and idx.info(7) == 1 and idx.info(8) == 2
     want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
     got, _ = idx.search_host(tok, off, fx)
     assert _pairs(got) == _pairs(want)
