@@ -30,9 +30,7 @@ FS_OPT_DIAG = 4
 FS_OPT_CTA_PAIR = 5
 FS_OPT_A_RESIDENT = 6
 FS_OPT_PACKED_SHUFFLE = 7
-FS_OPT_MIX_PATTERN = 8
 FS_OPT_OPERAND_BITS = 9
-FS_DIAG_MIX = 36
 
 FS_MATCH_EXACT = 1
 FS_MATCH_LSH_SHIFT = 8

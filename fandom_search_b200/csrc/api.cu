@@ -145,8 +145,6 @@ struct fs_index {
     int32_t ares = 1;              // A-resident variant of the pair kernel (used when the row fits: <= 640 B)
     int32_t pack = 2;              // epilogue diagonal sums: 0 fp32 shuffles, 1 fp16x2 shuffles, 2 fp16x2 arithmetic
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
-    int64_t last_row0_6 = 0;
-    int32_t mix_pattern = 0x5;     // diag == kDiagMix: bit i = kind of tile i mod 4 (1 -> E = 6)
     int32_t grid_limit = 0;
 
     // timing ring
@@ -426,10 +424,6 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
     if (!idx) return FS_E_INVALID;
     switch (option) {
         case FS_OPT_SHIFTS_PER_STAGE:
-            if (idx->diag == kDiagMix) {
-                set_error("the mixed schedule fixes the shifts per stage");
-                return FS_E_INVALID;
-            }
             if (value < 0 || value > 8 || (value > 0 && (idx->window / idx->diag) % value != 0)) {
                 set_error("shifts per stage must divide window/diag and be <= 8 (0 = all)");
                 return FS_E_INVALID;
@@ -446,14 +440,8 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             idx->pair = value ? 1 : 0;
             return FS_OK;
         case FS_OPT_DIAG:
-            if (value == kDiagMix && idx->window == 6) {
-                idx->diag = kDiagMix;  // alternate E = 3 and E = 6 tiles
-                idx->diag_user = true;
-                idx->shifts_per_stage = 0;
-                return FS_OK;
-            }
             if (!(value == 1 || value == 2 || value == 3 || value == 6) || idx->window % value != 0) {
-                set_error("diagonal factor must be 1, 2, 3 or 6 and divide the window (36 = mixed 3/6, window 6)");
+                set_error("diagonal factor must be 1, 2, 3 or 6 and divide the window");
                 return FS_E_INVALID;
             }
             idx->diag = static_cast<int32_t>(value);
@@ -469,13 +457,6 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             idx->operand_bits = static_cast<int32_t>(value);
             return prepare_operands(idx);
         }
-        case FS_OPT_MIX_PATTERN:
-            if (value < 0 || value > 15) {
-                set_error("mix pattern is a 4-bit mask (bit i: tile i mod 4 is of the E = 6 kind)");
-                return FS_E_INVALID;
-            }
-            idx->mix_pattern = static_cast<int32_t>(value);
-            return FS_OK;
         case FS_OPT_GRID_LIMIT:
             idx->grid_limit = static_cast<int32_t>(value < 0 ? 0 : value);
             return FS_OK;
@@ -517,9 +498,7 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
         case 6: return idx->pair;
         case 7: return idx->ares;
         case 8: return idx->pack;
-        case 9: return idx->mix_pattern;
         case 11: return idx->operand_bits;
-        case 10: return idx->last_row0_6;  // mixed schedule: first fan row of the E = 6 region (last launch)
         default: return -1;
     }
 }
@@ -615,37 +594,11 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     if (counters) FS_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
     if (a.n_tok == 0 || idx->n_script_tok == 0) return FS_OK;
-    const bool mix = idx->diag == kDiagMix;
-    if (mix && !idx->pair) {
-        set_error("the mixed E = 3 / E = 6 schedule needs CTA pairs (FS_OPT_CTA_PAIR = 1)");
-        return FS_E_INVALID;
-    }
-    const int32_t diag_a = mix ? 3 : idx->diag;  // tile geometry of the (first) region
-    const int32_t m_step = kBlockM - (diag_a - 1), n_step = kBlockN - (diag_a - 1);
-    int32_t tiles_m = static_cast<int32_t>((a.n_tok + m_step - 1) / m_step);
+    const int32_t m_step = dist_m_step(idx->diag), n_step = kBlockN - (idx->diag - 1);
+    const int32_t tiles_m = static_cast<int32_t>((a.n_tok + m_step - 1) / m_step);
     const int32_t tiles_n = static_cast<int32_t>((idx->n_script_tok + n_step - 1) / n_step);
-    int32_t tiles_m6 = 0, tiles_n6 = 0, row0_6 = 0;
-    if (mix) {
-        // fan rows [0, row0_6) are tiled for E = 3 and the rest for E = 6, so that the numbers of
-        // tiles of the two kinds are in the ratio the pattern asks for; row0_6 is a whole number
-        // of E = 3 tile PAIRS (no phantom tile reaches into the other region)
-        const int32_t m6 = kBlockM - 5, n6 = kBlockN - 5;
-        tiles_n6 = static_cast<int32_t>((idx->n_script_tok + n6 - 1) / n6);
-        const double r6 = __builtin_popcount(static_cast<unsigned>(idx->mix_pattern) & 15u) / 4.0;
-        const double w3 = static_cast<double>(tiles_n6) * (1.0 - r6) / m6;
-        const double w6 = static_cast<double>(tiles_n) * r6 / m_step;
-        const double rows3 = (w3 + w6) > 0 ? static_cast<double>(a.n_tok) * w3 / (w3 + w6) : 0.0;
-        int64_t pairs3 = static_cast<int64_t>(rows3 / (2.0 * m_step) + 0.5);
-        const int64_t max_pairs3 = (a.n_tok + 2 * m_step - 1) / (2 * m_step);
-        if (pairs3 > max_pairs3) pairs3 = max_pairs3;
-        tiles_m = static_cast<int32_t>(2 * pairs3);
-        row0_6 = tiles_m * m_step;
-        const int64_t rows6 = a.n_tok > row0_6 ? a.n_tok - row0_6 : 0;
-        tiles_m6 = static_cast<int32_t>((rows6 + m6 - 1) / m6);
-    }
     // (+1 tile: in pair mode an odd tile count is rounded up to a full pair)
-    const int64_t thr_pad = mix ? static_cast<int64_t>(row0_6) + static_cast<int64_t>(tiles_m6 + 2) * kBlockM
-                                : static_cast<int64_t>(tiles_m + 1) * kBlockM;
+    const int64_t thr_pad = static_cast<int64_t>(tiles_m + 1) * kBlockM;
     int64_t want_cand = idx->cand_cap > 0 ? idx->cand_cap : (1 << 20);
     if ((r = fs_index_reserve(idx, a.n_tok, want_cand)) != FS_OK) return r;
     if ((r = embed_batch(idx, st, a, counters, idx->fan_emb, idx->fan_thr, thr_pad)) != FS_OK) return r;
@@ -666,12 +619,7 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.f8 = idx->operand_bits == 8;
     p.ares = idx->ares;
     p.pack = idx->pack;
-    p.shifts_per_stage = mix ? 2 : (idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag);
-    p.tiles_m6 = tiles_m6;
-    p.tiles_n6 = tiles_n6;
-    p.row0_6 = row0_6;
-    idx->last_row0_6 = row0_6;
-    p.mix_pattern = idx->mix_pattern;
+    p.shifts_per_stage = idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag;
     p.tiles_m = tiles_m;
     p.tiles_n = tiles_n;
     p.cand = (mode == Mode::kCandidates) ? cand_out : idx->cand;

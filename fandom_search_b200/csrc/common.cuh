@@ -54,9 +54,9 @@ constexpr int kHaloCols = kBlockN + 8;
 constexpr int kNormTileBytes = kAccumStages * kHaloCols * 8;               // 4224: (B, D) per column
 // shared-memory budget of distance_kernel<E, ., pair>: the stage ring shrinks by one stage at
 // E = 6, whose epilogue publishes 10 boundary rows per lane quarter instead of <= 4
-constexpr int kDiagMix = 36;  // "diagonal factor" of the schedule that alternates E = 3 and E = 6 tiles
-__host__ __device__ constexpr int diag_max(int diag) { return diag == kDiagMix ? 6 : diag; }
-__host__ __device__ constexpr int dist_pub_slots(int diag) { return diag > 1 ? 2 * (diag_max(diag) - 1) : 1; }
+// fan windows produced per 128-row tile (tiles overlap by E-1 rows)
+__host__ __device__ constexpr int dist_m_step(int diag) { return kBlockM - (diag - 1); }
+__host__ __device__ constexpr int dist_pub_slots(int diag) { return diag > 1 ? 2 * (diag - 1) : 1; }
 __host__ __device__ constexpr int dist_pub_bytes(int diag) { return 4 * dist_pub_slots(diag) * kHaloCols * 4; }
 // A-resident mode (CTA pairs, d_pad <= 320): the fan tile (all kAResChunks 64-column chunks,
 // 87 KB) stays in shared memory for the whole sweep over the script tiles; only this CTA's half
@@ -67,8 +67,7 @@ __host__ __device__ constexpr int dist_stage_bytes(bool pair, bool ares) {
     return ares ? kStageABytes : (pair ? 2 * kStageABytes : kStageBytes);
 }
 __host__ __device__ constexpr int dist_stages(int diag, bool pair, bool ares) {
-    return ares ? (diag_max(diag) == 6 ? 5 : 7)
-                : (pair ? (diag_max(diag) == 6 ? 5 : 6) : (diag_max(diag) == 6 ? 3 : 4));
+    return ares ? (diag == 6 ? 5 : 7) : (pair ? (diag == 6 ? 5 : 6) : (diag == 6 ? 3 : 4));
 }
 // per published boundary row and 32-column chunk, the maximum of the row over the chunk's 40 loaded
 // columns (one half; 8 chunks per tile, two buffers): lets the boundary pass reject a chunk at once
@@ -101,9 +100,6 @@ struct DistParams {
     int32_t pair;             // 1: CTA-pair kernel (cta_group::2, M = 2 x 128 fan tiles)
     int32_t shifts_per_stage; // S: MMA shifts served by one smem stage (divides window/E)
     int32_t tiles_m, tiles_n;
-    // mixed schedule (diag == kDiagMix): tiles_m/tiles_n describe the E = 3 region [0, row0_6),
-    // tiles_m6/tiles_n6 the E = 6 region [row0_6, M); bit i of mix_pattern = kind of tile i mod 4
-    int32_t tiles_m6, tiles_n6, row0_6, mix_pattern;
     fs_pair* cand;            // candidate output
     int64_t cand_cap;
     unsigned long long* counters;  // [FS_CNT_COUNT]

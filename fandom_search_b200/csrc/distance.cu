@@ -180,36 +180,27 @@ __device__ __forceinline__ float diag2_half(const uint32_t (&pk)[20], uint32_t (
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile schedule of one worker (a CTA, or a CTA pair).  Plain kernels: a contiguous range of
-// linearised (m, n) tiles, n fastest; in pair mode the unit is (pair of consecutive m tiles, n).
-//
-// kDiag == kDiagMix: the fan rows are split in two regions, [0, row0_6) tiled for E = 3 and
-// [row0_6, M) tiled for E = 6, and every worker ALTERNATES between its E = 3 and its E = 6 tiles
-// (p.mix_pattern, 4 tiles per period, bit = 1 -> E = 6).  An E = 3 tile is tensor-bound (two MMA
-// shifts, cheap epilogue), an E = 6 tile is epilogue-bound (one shift, ~1.6x the shuffles): with
-// two TMEM accumulators the MMAs of one kind overlap the epilogue of the other, so both pipes
-// stay busy instead of one waiting for the other.  All three roles walk the same sequence.
+// Tile schedule of one worker (a CTA, or a CTA pair): a contiguous range of linearised (m, n)
+// tiles, n fastest; in pair mode the unit is (pair of consecutive m tiles, n).  All three roles
+// walk the same sequence; (m unit, n tile) is advanced incrementally (one 64-bit division in the
+// constructor, none per tile).
 // ---------------------------------------------------------------------------------------------
 struct Tile {
     int32_t m0, n0;
-    bool e6;         // mix: this tile is of the E = 6 kind
     bool fan_first;  // first / last script tile of the current fan tile (A-resident mode)
     bool fan_last;
 };
 
 template <int kDiag, bool kPair>
 struct TileWalk {
-    static constexpr bool kMix = kDiag == kDiagMix;
-    // remaining tiles and (m unit, n tile) of the next one, per tile kind; the pair is advanced
-    // incrementally (one 64-bit division per kind in the constructor, none per tile)
-    int64_t left3, left6;
-    int32_t um3, un3, tn3, um6, un6, tn6, row0_6;
-    uint32_t it, pattern, cta_rank;
+    int64_t left;
+    int32_t um, un, tn;
+    uint32_t cta_rank;
     bool first;
 
-    __device__ __forceinline__ static void range(int32_t tm, int32_t tn, int64_t worker, int64_t n_workers,
-                                                 int64_t& left, int32_t& um, int32_t& un) {
-        const int64_t units_m = kPair ? (tm + 1) / 2 : tm;
+    __device__ __forceinline__ TileWalk(const DistParams& p, int64_t worker, int64_t n_workers, uint32_t rank)
+        : tn(p.tiles_n), cta_rank(rank), first(true) {
+        const int64_t units_m = kPair ? (p.tiles_m + 1) / 2 : p.tiles_m;
         const int64_t total = units_m * tn;
         const int64_t per = (total + n_workers - 1) / n_workers;
         const int64_t begin = per * worker;
@@ -218,51 +209,17 @@ struct TileWalk {
         um = tn > 0 ? static_cast<int32_t>(begin / tn) : 0;
         un = tn > 0 ? static_cast<int32_t>(begin - static_cast<int64_t>(um) * tn) : 0;
     }
-    __device__ __forceinline__ TileWalk(const DistParams& p, int64_t worker, int64_t n_workers, uint32_t rank)
-        : left6(0), um6(0), un6(0), tn3(p.tiles_n), tn6(1), row0_6(0), it(0), pattern(p.mix_pattern),
-          cta_rank(rank), first(true) {
-        range(p.tiles_m, p.tiles_n, worker, n_workers, left3, um3, un3);
-        if (kMix) {
-            range(p.tiles_m6, p.tiles_n6, worker, n_workers, left6, um6, un6);
-            tn6 = p.tiles_n6;
-            row0_6 = p.row0_6;
-        }
-    }
     __device__ __forceinline__ bool next(Tile& out) {
-        bool six = false;
-        if (kMix) {
-            const bool has3 = left3 > 0, has6 = left6 > 0;
-            if (!has3 && !has6) return false;
-            six = (pattern >> (it & 3u)) & 1u;
-            ++it;
-            if (six ? !has6 : !has3) six = !six;
-        } else if (left3 <= 0) {
-            return false;
-        }
-        const int32_t um = six ? um6 : um3;
-        const int32_t un = six ? un6 : un3;
-        const int32_t tn = six ? tn6 : tn3;
-        const int32_t e = kMix ? (six ? 6 : 3) : kDiag;
-        out.m0 = (six ? row0_6 : 0) + static_cast<int32_t>(kPair ? 2 * um + cta_rank : um) * (kBlockM - (e - 1));
-        out.n0 = un * (kBlockN - (e - 1));
-        out.e6 = kMix ? six : kDiag == 6;
-        // advance this kind
-        int32_t un_next = un + 1, um_next = um;
-        if (un_next == tn) {
-            un_next = 0;
-            ++um_next;
-        }
-        if (six) {
-            un6 = un_next;
-            um6 = um_next;
-            --left6;
-        } else {
-            un3 = un_next;
-            um3 = um_next;
-            --left3;
-        }
+        if (left <= 0) return false;
+        out.m0 = static_cast<int32_t>(kPair ? 2 * um + cta_rank : um) * dist_m_step(kDiag);
+        out.n0 = un * (kBlockN - (kDiag - 1));
         out.fan_first = first || un == 0;
-        out.fan_last = (six ? left6 : left3) == 0 || un + 1 == tn;
+        --left;
+        out.fan_last = left == 0 || un + 1 == tn;
+        if (++un == tn) {
+            un = 0;
+            ++um;
+        }
         first = false;
         return true;
     }
@@ -521,8 +478,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
 // adds E diagonal neighbours, out[i][j] = sum_{d<E} acc[i+d][j+d].  E = 1 is the plain dense
 // contraction.  E > 1 re-uses every partial sum for E windows (w/E times fewer tensor-core
 // flops for bit-for-bit the same set of products, summed in fp32); tiles then overlap by E-1
-// rows/columns (step 128-(E-1) x 256-(E-1)).  kDiag = kDiagMix alternates E = 3 and E = 6 tiles
-// (TileWalk above).
+// rows/columns (step 128-(E-1) x 256-(E-1)).
 //
 // kPair: two CTAs of a cluster (one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA
 // owns its own 128-window fan tile (and the TMEM accumulator for it) but stages only HALF of
@@ -544,8 +500,6 @@ __global__ void __launch_bounds__(kDistThreads, 1)
 distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 const __grid_constant__ CUtensorMap map_script, const DistParams p) {
     static_assert(!kARes || kPair, "the A-resident variant exists for CTA pairs only");
-    constexpr bool kMix = kDiag == kDiagMix;
-    static_assert(!kMix || (kPair && !kARes), "the mixed schedule exists for plain CTA pairs only");
     static_assert(!kF8 || kPair, "fp8 operands exist for CTA pairs only");
     extern __shared__ uint8_t smem_raw[];
     constexpr int kNumStages = dist_stages(kDiag, kPair, kARes);
@@ -609,9 +563,9 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     const int64_t worker = kPair ? blockIdx.x / 2 : blockIdx.x;
     TileWalk<kDiag, kPair> walk(p, worker, n_workers, cta_rank);
     Tile tile;
-    constexpr int kShiftRows = kMix ? 3 : kDiag;        // token rows between two MMA shifts
-    const int S = kMix ? 2 : p.shifts_per_stage;       // MMA shifts served by one smem stage
-    const int shift_groups = kMix ? 1 : (p.window / kDiag) / S;  // stages per 64-column chunk
+    constexpr int kShiftRows = kDiag;                   // token rows between two MMA shifts
+    const int S = p.shifts_per_stage;                   // MMA shifts served by one smem stage
+    const int shift_groups = (p.window / kDiag) / S;    // stages per 64-column chunk
 
     // The two control roles run as WHOLE warps (all lanes converged, one elected lane issues):
     // addresses and descriptors then stay warp-uniform and live in uniform registers.  Run by a
@@ -687,7 +641,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
             mbar_wait_all(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
-            const int n_shift = kMix ? (tile.e6 ? 1 : 2) : S;  // an E = 6 tile takes shift 0 only
+            const int n_shift = S;
             uint32_t accumulate = 0;
             // This warp is the only issuer of the CTA pair and runs one dependent instruction stream:
             // every instruction it spends per MMA is time the tensor pipe waits (ncu: the warp was
@@ -777,22 +731,12 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
         int as = 0;
         uint32_t aphase = 0;
         // kPack == 2: two half-precision boundary-row buffers, one per accumulator stage
-        constexpr bool kHalfRows = kPack == 2 && (diag_max(kDiag) == 6 || kDiag == 3 || kDiag == 2);
+        constexpr bool kHalfRows = kPack == 2 && (kDiag == 6 || kDiag == 3 || kDiag == 2);
         while (walk.next(tile)) {
             float* halo_t = halo + (kHalfRows ? as * (dist_pub_bytes(kDiag) / 8) : 0);
             __half* rowmax_t = rowmax_base + as * (dist_rowmax_bytes(kDiag) / 4);
-            if constexpr (kMix) {
-                // kPack: 0 = full-precision shuffles, 1 = packed shuffles, 2 = fp16x2 arithmetic
-                if (tile.e6)
-                    epilogue_tile<6, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
-                                                          aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane);
-                else
-                    epilogue_tile<3, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
-                                                          aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane);
-            } else {
-                epilogue_tile<kDiag, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
-                                                          aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane);
-            }
+            epilogue_tile<kDiag, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
+                                                      aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane);
             if (++as == kAccumStages) {
                 as = 0;
                 aphase ^= 1u;
@@ -891,11 +835,7 @@ static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
                     int grid_limit, cudaStream_t stream) {
     const int64_t units_m = p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
-    int64_t total = units_m * p.tiles_n;
-    if (p.diag == kDiagMix) {
-        const int64_t total6 = static_cast<int64_t>((p.tiles_m6 + 1) / 2) * p.tiles_n6;
-        total = total > total6 ? total : total6;  // per-worker ranges are cut per tile kind
-    }
+    const int64_t total = units_m * p.tiles_n;
     if (total <= 0) return FS_OK;
     int grid;
     if (p.pair) {
@@ -905,7 +845,7 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         grid = static_cast<int>(total < grid_limit ? total : grid_limit);
     }
     const bool ares = p.pair && p.ares && p.chunks <= kAResChunks;
-    const int pack = (p.diag == 6 || p.diag == 3 || p.diag == kDiagMix) ? p.pack : (p.diag == 2 && p.pack == 2 ? 2 : 0);
+    const int pack = (p.diag == 6 || p.diag == 3) ? p.pack : (p.diag == 2 && p.pack == 2 ? 2 : 0);
 #define FS_LAUNCH(E, PAIR, ARES, PACK) \
     return launch_distance_t<E, PAIR, ARES, PACK>(map_fan, map_script, p, grid, stream)
 #define FS_LAUNCH_PACK(E, PAIR, ARES)              \
@@ -943,8 +883,6 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
             case 6:
                 if (pack == 2) return launch_distance_t<6, true, false, 2, true>(map_fan, map_script, p, grid, stream);
                 return launch_distance_t<6, true, false, 1, true>(map_fan, map_script, p, grid, stream);
-            case kDiagMix:
-                return launch_distance_t<kDiagMix, true, false, 2, true>(map_fan, map_script, p, grid, stream);
             default:
                 set_error("unsupported diagonal factor %d", p.diag);
                 return FS_E_INVALID;
@@ -966,14 +904,6 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
             FS_LAUNCH(2, false, false, 0);
         case 3: FS_LAUNCH_MODE(3);
         case 6: FS_LAUNCH_MODE(6);
-        case kDiagMix:
-            if (!p.pair) {
-                set_error("the mixed E = 3 / E = 6 schedule needs CTA pairs");
-                return FS_E_INVALID;
-            }
-            if (pack == 2) FS_LAUNCH(kDiagMix, true, false, 2);
-            if (pack == 1) FS_LAUNCH(kDiagMix, true, false, 1);
-            FS_LAUNCH(kDiagMix, true, false, 0);
         default:
             set_error("unsupported diagonal factor %d", p.diag);
             return FS_E_INVALID;

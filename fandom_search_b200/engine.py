@@ -58,8 +58,7 @@ class DeviceIndex:
         for env, opt in (("FANDOM_SEARCH_DIAG", nt.FS_OPT_DIAG), ("FANDOM_SEARCH_CTA_PAIR", nt.FS_OPT_CTA_PAIR),
                          ("FANDOM_SEARCH_A_RESIDENT", nt.FS_OPT_A_RESIDENT),
                          ("FANDOM_SEARCH_PACKED_SHUFFLE", nt.FS_OPT_PACKED_SHUFFLE),
-                         ("FANDOM_SEARCH_OPERAND_BITS", nt.FS_OPT_OPERAND_BITS),
-                         ("FANDOM_SEARCH_MIX_PATTERN", nt.FS_OPT_MIX_PATTERN)):
+                         ("FANDOM_SEARCH_OPERAND_BITS", nt.FS_OPT_OPERAND_BITS)):
             v = os.environ.get(env)
             if v not in (None, ""):
                 self.set_option(opt, int(v))

@@ -100,13 +100,9 @@ enum {
                                     (tcgen05.mma.kind::f8f6f4; the rounding error of every window is
                                     measured and enters its pre-filter threshold, so the candidates stay
                                     a guaranteed superset; CTA pairs only).  Re-converts the index.   */
-    FS_OPT_MIX_PATTERN = 8,      /* FS_OPT_DIAG = 36 only: 4-bit mask, bit i = 1 -> tile i mod 4 of every
-                                    worker is of the E = 6 kind (default 0x5: strict alternation)   */
     FS_OPT_DIAG = 4              /* 1 (dense), 2, 3 or 6: the tensor cores accumulate window/E shifts
                                     and the epilogue adds E diagonal neighbours (same products,
-                                    E-fold fewer tensor-core flops); 36 (window 6, CTA pairs): tiles
-                                    of the E = 3 and E = 6 kinds alternate, so the tensor-bound MMAs of
-                                    one overlap the shuffle-bound epilogue of the other           */
+                                    E-fold fewer tensor-core flops)                            */
 };
 
 int fs_abi_version(void);
@@ -144,8 +140,7 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value);
  * FS_MATCH_LSH_SHIFT.  n_tables = 0 switches the mode off. */
 int fs_index_set_lsh(fs_index* idx, const double* normals, int32_t n_tables, int32_t n_bits);
 /* what = 0: script windows, 1: dim_pad, 2: SM count, 3: candidate capacity, 4: shifts per stage,
- * 5: diagonal factor, 6: CTA pair, 7: A-resident, 8: pack level, 9: mix pattern,
- * 10: first fan row of the E = 6 region in the last mixed-schedule launch, 11: operand bits */
+ * 5: diagonal factor, 6: CTA pair, 7: A-resident, 8: pack level, 11: operand bits */
 int64_t fs_index_get_info(const fs_index* idx, int32_t what);
 
 /*

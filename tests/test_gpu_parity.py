@@ -254,7 +254,7 @@ def _e4m3(x):
 
 
 @pytest.mark.parametrize("pack", [1, 2])
-@pytest.mark.parametrize("diag", [1, 2, 3, 6, 36])
+@pytest.mark.parametrize("diag", [1, 2, 3, 6])
 @pytest.mark.parametrize("seed,dim", [(1, 300), (2, 64), (3, 768), (4, 100), (9, 50)])
 def test_fp8_search_equals_float64_reference(seed, dim, diag, pack):
     table, sx, fx, script, tok, off = _case(seed, dim=dim)
@@ -307,7 +307,7 @@ def test_fp8_gather_is_bit_exact_and_thresholds_hold_the_measured_error():
     idx.close()
 
 
-@pytest.mark.parametrize("diag", [1, 2, 3, 6, 36])
+@pytest.mark.parametrize("diag", [1, 2, 3, 6])
 def test_fp8_dots_match_the_e4m3_contraction(diag):
     import torch
     table, sx, fx, script, tok, off = _case(6, plant=False, clustered=False, works=(900, 3, 0, 6, 1400, 700))
@@ -327,7 +327,7 @@ def test_fp8_dots_match_the_e4m3_contraction(diag):
     idx.close()
 
 
-@pytest.mark.parametrize("diag", [2, 3, 6, 36])
+@pytest.mark.parametrize("diag", [2, 3, 6])
 def test_fp8_candidates_are_a_superset(diag):
     import torch
     table, sx, fx, script, tok, off = _case(7, works=(900, 3, 0, 6, 1400, 700))
@@ -371,77 +371,6 @@ def test_fp8_needs_cta_pairs():
     idx.set_option(nt.FS_OPT_CTA_PAIR, 0)
     with pytest.raises(nt.NativeError):
         idx.search_host(tok, off, fx)
-    idx.close()
-
-
-@pytest.mark.parametrize("grid", [0, 4])              # 4 CTAs = 2 workers: long tile sequences per worker
-@pytest.mark.parametrize("pack", [0, 1, 2])
-@pytest.mark.parametrize("pattern", [0x5, 0x7, 0x1, 0x0, 0xF, 0x6])
-def test_mixed_schedule_search(pattern, pack, grid):
-    """FS_OPT_DIAG = 36: tiles of the E = 3 and E = 6 kinds alternate over two row regions of the
-    batch; the match set is the float64 reference's whatever the pattern, pack level and grid."""
-    for seed, dim, works in ((1, 300, (200, 3, 0, 6, 397, 150)), (3, 768, (900, 3, 0, 6, 1400, 700)),
-                             (4, 100, (5, 2, 40))):
-        table, sx, fx, script, tok, off = _case(seed, dim=dim, works=works)
-        want, wc = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
-        idx = _device_index(table, script, extra=sx)
-        idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)
-        idx.set_option(nt.FS_OPT_MIX_PATTERN, pattern)
-        idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
-        idx.set_option(nt.FS_OPT_GRID_LIMIT, grid)
-        got, gc = idx.search_host(tok, off, fx)
-        assert _pairs(got) == _pairs(want) and len(got) == len(want)
-        assert gc[nt.FS_CNT_WINDOWS] == wc[nt.FS_CNT_WINDOWS]
-        idx.close()
-
-
-@pytest.mark.parametrize("pattern", [0x5, 0x3])
-def test_mixed_schedule_dots_and_candidates(pattern):
-    import torch
-    table, sx, fx, script, tok, off = _case(6, plant=False, clustered=False, works=(900, 3, 0, 6, 1400, 700))
-    idx = _device_index(table, script, extra=sx)
-    idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)
-    idx.set_option(nt.FS_OPT_MIX_PATTERN, pattern)
-    idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, 1)
-    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
-    dots = idx.stage_dots(tok_t, off_t, fx_t).cpu().numpy()
-    allrows = np.concatenate([table, sx, fx], axis=0)
-    e16 = (allrows * np.float32(idx.scale)).astype(np.float16).astype(np.float64)
-    ef = np.zeros((len(tok) + 6, table.shape[1])); ef[:len(tok)] = e16[tok]
-    es = np.zeros((len(script) + 6, table.shape[1])); es[:len(script)] = e16[script]
-    g = ef @ es.T
-    want = sum(g[k:k + len(tok), k:k + len(script)] for k in range(6))
-    assert np.abs(dots - want).max() <= 2e-3 * np.abs(want).max()
-    idx.close()
-    # candidates: every pair once, a superset of the pairs under the threshold
-    table, sx, fx, script, tok, off = _case(7, works=(900, 3, 0, 6, 1400, 700))
-    ref = NumpyIndex(table, script, extra=sx)
-    d, fpos = ref.distances(tok, off, fx)
-    idx = _device_index(table, script, extra=sx)
-    idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)
-    idx.set_option(nt.FS_OPT_MIX_PATTERN, pattern)
-    tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
-    cand, cnt = idx.stage_candidates(tok_t, off_t, fx_t)
-    n = int(cnt.cpu()[nt.FS_CNT_CANDIDATES])
-    cand = cand.cpu().numpy()[:n]
-    got = set(map(tuple, cand.tolist()))
-    assert len(got) == len(cand)
-    ii, jj = np.nonzero(d < 0.1)
-    assert set(zip(fpos[ii].tolist(), ref.spos[jj].tolist())) <= got
-    idx.close()
-
-
-def test_mixed_schedule_needs_cta_pairs():
-    table, sx, fx, script, tok, off = _case(1, dim=64)
-    idx = _device_index(table, script, extra=sx)
-    idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)
-    idx.set_option(nt.FS_OPT_CTA_PAIR, 0)
-    with pytest.raises(nt.NativeError):
-        idx.search_host(tok, off, fx)
-    idx.close()
-    idx = _device_index(table, script, extra=sx, window=4)
-    with pytest.raises(nt.NativeError):
-        idx.set_option(nt.FS_OPT_DIAG, nt.FS_DIAG_MIX)      # window 6 only
     idx.close()
 
 

@@ -18,7 +18,7 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, pack=None, pattern=None, clocks=False, bits=8):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, pack=None, clocks=False, bits=8):
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
@@ -30,8 +30,6 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
     if pack is not None:
         idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
-    if pattern is not None:
-        idx.set_option(nt.FS_OPT_MIX_PATTERN, pattern)
     n_works = max(1, nf // works_len)
     lens = np.full(n_works, (nf + 5 * n_works) // n_works + 1, dtype=np.int64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
@@ -58,16 +56,9 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     clk = sampler.stop() if sampler else None
     windows = int(cnt_t.cpu()[nt.FS_CNT_WINDOWS])
     per = ms / n * 1e-3
-    if diag == nt.FS_DIAG_MIX:
-        # executed flops: E = 3 tiles on rows [0, row0_6), E = 6 tiles on the rest
-        f3 = min(1.0, idx.info(10) / max(1, int(off[-1])))
-        exec_factor = f3 * 2 * (128.0 * 256.0) / (126 * 254) + (1 - f3) * (128.0 * 256.0) / (123 * 251)
-    else:
-        exec_factor = (6 // diag) * (128.0 * 256.0) / ((129 - diag) * (257 - diag))
-    if bits == 8:
-        exec_factor *= 1.0   # same element count; idx.dim_pad already counts fp8 elements
+    exec_factor = (6 // diag) * (128.0 * 256.0) / ((129 - diag) * (257 - diag))
     res = {"bits": bits, "candidates": int(cnt_t.cpu()[nt.FS_CNT_CANDIDATES]), "matches": int(cnt_t.cpu()[nt.FS_CNT_MATCHES]),
-           "diag": diag, "pattern": pattern, "pair": pair, "pack": pack, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
+           "diag": diag, "pair": pair, "pack": pack, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
            "kernel_ms": ms / n, "windows_per_s": windows / per, "clocks": clk,
            "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
            "tflops_executed": 2.0 * exec_factor * idx.dim_pad * idx.n_script_windows * windows / per / 1e12}
@@ -82,9 +73,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--diag", action="store_true", help="compare the diagonal-sum factors at C2 size")
     ap.add_argument("--bits", type=int, default=8, help="operand bits for --one (8 = fp8 e4m3, 16 = fp16)")
-    ap.add_argument("--pattern", type=lambda v: int(v, 0), default=None, help="mix pattern (diag 36)")
     ap.add_argument("--f8", action="store_true", help="fp8 e4m3 operands vs fp16 at C2 size, all diagonal factors")
-    ap.add_argument("--mix", action="store_true", help="compare the mixed E=3/E=6 schedule with E=3 and E=6 at C2 size")
     ap.add_argument("--one", type=int, nargs=4, metavar=("DIAG", "NF", "NS", "D"), help="run a single case")
     ap.add_argument("--pair", type=int, default=0)
     ap.add_argument("--pack", type=int, default=None)
@@ -93,7 +82,7 @@ def main():
     if args.one:
         diag, nf, ns, d = args.one
         print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag, pair=args.pair, pack=args.pack,
-                                  pattern=args.pattern, bits=args.bits)), flush=True)
+                                  bits=args.bits)), flush=True)
         return
     if args.f8:
         for bits, diag, d, pack, pair in ((16, 3, 300, 2, 1), (16, 3, 300, 2, 2), (8, 3, 300, 2, 1), (8, 3, 300, 2, 2),
@@ -101,13 +90,6 @@ def main():
                                           (8, 3, 768, 2, 1), (16, 6, 768, 2, 1), (8, 3, 300, 2, 2)):
             print(json.dumps(run_case(2_500_000, 25000, d, 20, rng, diag=diag, pair=pair, pack=pack,
                                       clocks=True, bits=bits)), flush=True)
-        return
-    if args.mix:
-        for diag, pair, pack, pattern in ((3, 1, 1, None), (6, 1, 2, None), (6, 2, 2, None), (6, 1, 1, None),
-                                          (36, 1, 2, 0x5), (1, 1, 0, None), (2, 1, 0, None), (3, 0, 1, None),
-                                          (3, 1, 1, None)):
-            print(json.dumps(run_case(2_500_000, 25000, 300, 25, rng, diag=diag, pair=pair, pack=pack,
-                                      pattern=pattern, clocks=True)), flush=True)
         return
     if args.diag:
         for pair in (1, 2):
