@@ -279,7 +279,7 @@ static int prepare_operands(fs_index* idx) {
     unsigned long long h_cnt[FS_CNT_COUNT];
     FS_CUDA_CHECK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     if (idx->n_script_tok > 0)
-        if ((r = make_token_map(&idx->map_script, idx->script_emb, idx->n_script_tok, idx->dim_pad)) != FS_OK)
+        if ((r = make_token_map(&idx->map_script, idx->script_emb, idx->n_script_tok, idx->dim_pad, kBoxRows)) != FS_OK)
             return r;
     FS_CUDA_CHECK(cudaStreamSynchronize(st));
     idx->n_script_windows = static_cast<int64_t>(h_cnt[FS_CNT_WINDOWS]);
@@ -413,8 +413,8 @@ int fs_index_reserve(fs_index* idx, int64_t max_tokens, int64_t max_candidates) 
     if ((r = dev_grow(&idx->fan_emb, &idx->emb_cap, max_tokens * idx->dim_pad)) != FS_OK) return r;
     idx->tok_cap = idx->emb_cap / idx->dim_pad;
     if ((r = dev_grow(&idx->fan_tok_sq, &idx->sq_cap, max_tokens + 8)) != FS_OK) return r;
-    // tiles step by 128 - (E-1) rows but always read 128 thresholds
-    if ((r = dev_grow(&idx->fan_thr, &idx->thr_cap, (max_tokens / (kBlockM - 8) + 3) * kBlockM)) != FS_OK)
+    // per-window bounds, padded to whole tiles of the SMALLEST row step any variant uses (E = 6: 108)
+    if ((r = dev_grow(&idx->fan_thr, &idx->thr_cap, (max_tokens / dist_m_step(6) + 3) * kBlockM)) != FS_OK)
         return r;
     if ((r = dev_grow(&idx->cand, &idx->cand_cap, max_candidates)) != FS_OK) return r;
     return FS_OK;
@@ -601,10 +601,19 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     const int64_t thr_pad = static_cast<int64_t>(tiles_m + 1) * kBlockM;
     int64_t want_cand = idx->cand_cap > 0 ? idx->cand_cap : (1 << 20);
     if ((r = fs_index_reserve(idx, a.n_tok, want_cand)) != FS_OK) return r;
+    if (thr_pad > idx->thr_cap || a.n_tok > idx->tok_cap) {  // the workspace must hold whole tiles
+        set_error("internal: workspace too small (%lld > %lld bounds, %lld > %lld tokens)",
+                  static_cast<long long>(thr_pad), static_cast<long long>(idx->thr_cap),
+                  static_cast<long long>(a.n_tok), static_cast<long long>(idx->tok_cap));
+        return FS_E_INVALID;
+    }
     if ((r = embed_batch(idx, st, a, counters, idx->fan_emb, idx->fan_thr, thr_pad)) != FS_OK) return r;
 
     CUtensorMap map_fan;
-    if ((r = make_token_map(&map_fan, idx->fan_emb, a.n_tok, idx->dim_pad)) != FS_OK) return r;
+    if ((r = make_token_map(&map_fan, idx->fan_emb, a.n_tok, idx->dim_pad, kBoxRows)) != FS_OK) return r;
+    // E = 6 loads the fan tile as four overlapping boxes of 32 rows (common.cuh)
+    CUtensorMap map_fan32;
+    if ((r = make_token_map(&map_fan32, idx->fan_emb, a.n_tok, idx->dim_pad, kOverlapBoxRows)) != FS_OK) return r;
     DistParams p{};
     p.fan_ac = idx->fan_thr;
     p.script_bd = idx->script_norm;
@@ -630,7 +639,7 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     const int grid_limit = idx->grid_limit > 0 ? idx->grid_limit : idx->sm_count;
     const int slot = static_cast<int>(idx->ev_count % kTimingRing);
     FS_CUDA_CHECK(cudaEventRecord(idx->ev_start[slot], st));
-    if ((r = launch_distance(map_fan, idx->map_script, p, grid_limit, st)) != FS_OK) return r;
+    if ((r = launch_distance(map_fan, map_fan32, idx->map_script, p, grid_limit, st)) != FS_OK) return r;
     FS_CUDA_CHECK(cudaEventRecord(idx->ev_stop[slot], st));
     idx->ev_count++;
     if (mode != Mode::kSearch) return FS_OK;

@@ -52,12 +52,19 @@ constexpr int kMmaWarp = kEpiWarps + 1;                // warp ids (scheduler pr
 constexpr int kDistThreads = 32 * (kEpiWarps + 2);     // 576
 constexpr int kHaloCols = kBlockN + 8;
 constexpr int kNormTileBytes = kAccumStages * kHaloCols * 8;               // 4224: (B, D) per column
-// shared-memory budget of distance_kernel<E, ., pair>: the stage ring shrinks by one stage at
-// E = 6, whose epilogue publishes 10 boundary rows per lane quarter instead of <= 4
-// fan windows produced per 128-row tile (tiles overlap by E-1 rows)
-__host__ __device__ constexpr int dist_m_step(int diag) { return kBlockM - (diag - 1); }
-__host__ __device__ constexpr int dist_pub_slots(int diag) { return diag > 1 ? 2 * (diag - 1) : 1; }
-__host__ __device__ constexpr int dist_pub_bytes(int diag) { return 4 * dist_pub_slots(diag) * kHaloCols * 4; }
+// E = 6 (one MMA shift, no row offsets inside a stage): the four 32-lane TMEM quarters of a tile
+// hold OVERLAPPING fan rows, quarter q = rows [27 q, 27 q + 32) of the tile (four TMA boxes of 32
+// rows), so every quarter sums its own diagonals -- no boundary rows to publish, no boundary
+// pass, no barrier among the epilogue warps -- at the price of 108 instead of 123 windows per tile.
+constexpr int kQuarterRows6 = 32 - 5;
+constexpr int kOverlapBoxRows = 32;
+constexpr int kOverlapABytes = 4 * kOverlapBoxRows * 128;  // 16384: fan bytes of one stage at E = 6
+// fan windows produced per 128-row tile (tiles overlap by E-1 rows; E = 6: per quarter)
+__host__ __device__ constexpr int dist_m_step(int diag) { return diag == 6 ? 4 * kQuarterRows6 : kBlockM - (diag - 1); }
+__host__ __device__ constexpr int dist_pub_slots(int diag) { return (diag > 1 && diag != 6) ? 2 * (diag - 1) : 1; }
+__host__ __device__ constexpr int dist_pub_bytes(int diag) {
+    return diag == 6 ? 0 : 4 * dist_pub_slots(diag) * kHaloCols * 4;
+}
 // A-resident mode (CTA pairs, d_pad <= 320): the fan tile (all kAResChunks 64-column chunks,
 // 87 KB) stays in shared memory for the whole sweep over the script tiles; only this CTA's half
 // of the script tile streams through the stage ring (17 KB per stage).
@@ -67,11 +74,14 @@ __host__ __device__ constexpr int dist_stage_bytes(bool pair, bool ares) {
     return ares ? kStageABytes : (pair ? 2 * kStageABytes : kStageBytes);
 }
 __host__ __device__ constexpr int dist_stages(int diag, bool pair, bool ares) {
-    return ares ? (diag == 6 ? 5 : 7) : (pair ? (diag == 6 ? 5 : 6) : (diag == 6 ? 3 : 4));
+    (void)diag;
+    return ares ? 7 : (pair ? 6 : 4);
 }
 // per published boundary row and 32-column chunk, the maximum of the row over the chunk's 40 loaded
 // columns (one half; 8 chunks per tile, two buffers): lets the boundary pass reject a chunk at once
-__host__ __device__ constexpr int dist_rowmax_bytes(int diag) { return 2 * 4 * dist_pub_slots(diag) * 8 * 2; }
+__host__ __device__ constexpr int dist_rowmax_bytes(int diag) {
+    return diag == 6 ? 0 : 2 * 4 * dist_pub_slots(diag) * 8 * 2;
+}
 __host__ __device__ constexpr int dist_smem_bytes(int diag, bool pair, bool ares) {
     return (ares ? kAResBytes : 0) + dist_stages(diag, pair, ares) * dist_stage_bytes(pair, ares) +
            1024 /*align slack*/ + 256 /*barriers*/ + dist_pub_bytes(diag) + kNormTileBytes +
@@ -168,9 +178,9 @@ struct GatherSources {
     int64_t n_fx;
 };
 
-int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad);
-int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
-                    int grid_limit, cudaStream_t stream);
+int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad, int32_t box_rows);
+int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, const CUtensorMap& map_script,
+                    const DistParams& p, int grid_limit, cudaStream_t stream);
 int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
                         bool f8, float limit_sq, __half* dst, float2* sq, cudaStream_t stream);
 int launch_rownorm_max(const float* src, int64_t n_rows, int32_t dim, unsigned int* out, cudaStream_t stream);

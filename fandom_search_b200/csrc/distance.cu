@@ -246,17 +246,18 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                                               const int as, const uint32_t tfull_addr, const uint32_t tempty_addr,
                                               const uint32_t aphase, const uint32_t tmem_base, float* halo,
                                               float2* norm_tile, __half* rowmax, const int warp, const int lane) {
-    constexpr int kMStep = kBlockM - (kDiag - 1);
+    constexpr bool kOverlap = kDiag == 6;  // lane quarters hold overlapping fan rows: nothing crosses quarters
+    constexpr int kMStep = dist_m_step(kDiag);
     constexpr int kNStep = kBlockN - (kDiag - 1);
     constexpr int kPubSlots = dist_pub_slots(kDiag);
     constexpr int kEdge = kDiag - 1;    // boundary rows per side
     constexpr int kTail0 = 32 - kEdge;  // first lane of the tail rows
     const int quarter = warp & 3;
     const int group = warp >> 2;
-    const int row = quarter * 32 + lane;
+    const int row = quarter * (kOverlap ? kQuarterRows6 : 32) + lane;  // fan row inside the tile
     const int epi_tid = warp * 32 + lane;  // 0..511
     // publish slot of this lane: head rows 0..E-2 -> slots 0..E-2, tail rows -> E-1..2E-3
-    const int pub_slot = lane < kEdge ? lane : (lane >= kTail0 ? kEdge + lane - kTail0 : -1);
+    const int pub_slot = kOverlap ? -1 : (lane < kEdge ? lane : (lane >= kTail0 ? kEdge + lane - kTail0 : -1));
     auto pub_at = [&](int q, int slot) -> float* { return halo + (q * kPubSlots + slot) * kHaloCols; };
     // kPack == 2: the whole diagonal sum runs on fp16x2 pairs, and the boundary rows are published as halves
     constexpr bool kHalf = kPack == 2 && (kDiag == 6 || kDiag == 3 || kDiag == 2);
@@ -264,7 +265,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     auto pub_half_at = [&](int q, int slot) -> __half* { return halo_h + (q * kPubSlots + slot) * kHaloCols; };
 
     const int32_t gi = m0 + row;
-    const bool row_ok = row < kMStep;
+    const bool row_ok = kOverlap ? lane < kQuarterRows6 : row < kMStep;
     const float kNaN = __int_as_float(0x7fc00000);
     // (A_i, C_i) of this lane's fan window (padded to a tile multiple); NaN = never a candidate
     const float2 ac = row_ok ? __ldg(p.fan_ac + gi) : make_float2(kNaN, kNaN);
@@ -273,7 +274,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     // E > 1: (B_j, D_j) of this tile staged once in smem, NaN baked in for the E-1 columns that
     // belong to the next tile
     float2* ns_tile = norm_tile + as * kHaloCols;
-    if (kDiag > 1 && epi_tid < kHaloCols)
+    if (kDiag > 1 && !kOverlap && epi_tid < kHaloCols)
         ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.script_bd + n0 + epi_tid) : make_float2(kNaN, kNaN);
     mbar_wait_warp(tfull_addr, aphase, 32);  // early warps back off: their polling competes for issue slots with the late ones
     tc_fence_after();
@@ -339,7 +340,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
             for (int k = 1; k < 20; ++k) m = hmax(m, pk[k]);
             m = hmax(m, __byte_perm(m, m, 0x1032));  // both halves = the row maximum
             // boundary rows also publish it: the boundary pass rejects its chunks the same way
-            if (kDiag > 1 && pub_slot >= 0)
+            if (kDiag > 1 && !kOverlap && pub_slot >= 0)
                 reinterpret_cast<uint16_t*>(rowmax)[(quarter * kPubSlots + pub_slot) * 8 + (c0 >> 5)] =
                     static_cast<uint16_t>(m & 0xffffu);
             uint32_t bsum;
@@ -404,7 +405,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
         else
             mbar_arrive(tempty_addr);
     }
-    if (kDiag > 1) {
+    if (kDiag > 1 && !kOverlap) {
         // boundary rows: tail rows of quarters 0..2 (quarter 3's belong to the next tile)
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         float a_l[kEdge > 0 ? kEdge : 1], c_l[kEdge > 0 ? kEdge : 1];  // (kDiag == 1 never gets here)
@@ -497,10 +498,11 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
 // fp16; half the operand traffic and half the tensor-pipe work per element of the embedding.
 template <int kDiag, bool kDump, bool kPair, bool kARes, int kPack, bool kF8>
 __global__ void __launch_bounds__(kDistThreads, 1)
-distance_kernel(const __grid_constant__ CUtensorMap map_fan,
+distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_constant__ CUtensorMap map_fan32,
                 const __grid_constant__ CUtensorMap map_script, const DistParams p) {
     static_assert(!kARes || kPair, "the A-resident variant exists for CTA pairs only");
     static_assert(!kF8 || kPair, "fp8 operands exist for CTA pairs only");
+    constexpr bool kOverlap = kDiag == 6;  // overlapping lane quarters (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     constexpr int kNumStages = dist_stages(kDiag, kPair, kARes);
     constexpr int kStageSz = dist_stage_bytes(kPair, kARes);
@@ -531,7 +533,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
     const bool leader = cta_rank == 0;
 
     if (warp == kProducerWarp && lane == 0) {
-        tma_prefetch_desc(&map_fan);
+        tma_prefetch_desc(kOverlap ? &map_fan32 : &map_fan);
         tma_prefetch_desc(&map_script);
         for (int s = 0; s < kNumStages; ++s) {
             mbar_init(full_bar(s), 1);
@@ -583,10 +585,16 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                 // new fan tile: wait until every MMA that read the previous one has retired
                 mbar_wait_warp(aempty_bar, a_phase ^ 1u, 64);
                 if (elect_one()) {
-                    if (leader) mbar_expect_tx(afull_bar, 2 * p.chunks * kStageABytes);
-                    for (int c = 0; c < p.chunks; ++c)
-                        tma_load_2d_pair(smem_a_res + c * kStageABytes, &map_fan, afull_bar,
-                                         c * kChunkK, m0);
+                    if (leader) mbar_expect_tx(afull_bar, 2 * p.chunks * (kOverlap ? kOverlapABytes : kStageABytes));
+                    for (int c = 0; c < p.chunks; ++c) {
+                        if (kOverlap) {
+                            for (int q = 0; q < 4; ++q)
+                                tma_load_2d_pair(smem_a_res + c * kStageABytes + q * (kOverlapBoxRows * 128),
+                                                 &map_fan32, afull_bar, c * kChunkK, m0 + q * kQuarterRows6);
+                        } else {
+                            tma_load_2d_pair(smem_a_res + c * kStageABytes, &map_fan, afull_bar, c * kChunkK, m0);
+                        }
+                    }
                 }
                 __syncwarp();
                 a_phase ^= 1u;
@@ -605,13 +613,27 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan,
                                              n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
                         } else if (kPair) {
                             // this CTA stages its own fan rows and script rows [128 r, 128 r + 136)
-                            if (leader) mbar_expect_tx(full_bar(stage), 2 * kPairStageBytes);
-                            tma_load_2d_pair(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
+                            if (leader)
+                                mbar_expect_tx(full_bar(stage),
+                                               2 * (kOverlap ? kOverlapABytes + kStageABytes : kPairStageBytes));
+                            if (kOverlap) {
+                                for (int q = 0; q < 4; ++q)
+                                    tma_load_2d_pair(a_dst + q * (kOverlapBoxRows * 128), &map_fan32, full_bar(stage),
+                                                     c * kChunkK, m0 + q * kQuarterRows6);
+                            } else {
+                                tma_load_2d_pair(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
+                            }
                             tma_load_2d_pair(b_dst, &map_script, full_bar(stage), c * kChunkK,
                                              n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
                         } else {
-                            mbar_expect_tx(full_bar(stage), kStageBytes);
-                            tma_load_2d(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
+                            mbar_expect_tx(full_bar(stage), kOverlap ? kOverlapABytes + 2 * kStageABytes : kStageBytes);
+                            if (kOverlap) {
+                                for (int q = 0; q < 4; ++q)
+                                    tma_load_2d(a_dst + q * (kOverlapBoxRows * 128), &map_fan32, full_bar(stage),
+                                                c * kChunkK, m0 + q * kQuarterRows6);
+                            } else {
+                                tma_load_2d(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
+                            }
                             tma_load_2d(b_dst, &map_script, full_bar(stage), c * kChunkK, n0 + s0);
                             tma_load_2d(b_dst + kStageABytes, &map_script, full_bar(stage),
                                         c * kChunkK, n0 + s0 + kBoxRows);
@@ -777,8 +799,8 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-// tensor map over a row-major fp16 matrix [rows, dim_pad]; box = 64 columns x 136 rows, SW128
-int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad) {
+// tensor map over a row-major matrix [rows, dim_pad] of 2-byte units; box = 64 columns (128 B) x box_rows, SW128
+int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad, int32_t box_rows) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -787,7 +809,7 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
     if (rows < 1) rows = 1;
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim_pad), static_cast<cuuint64_t>(rows)};
     cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim_pad) * sizeof(__half)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(kBoxRows)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -801,8 +823,8 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
 }
 
 template <int kDiag, bool kPair, bool kARes, int kPack, bool kF8 = false>
-static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_script,
-                             const DistParams& p, int grid, cudaStream_t stream) {
+static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_fan32,
+                             const CUtensorMap& map_script, const DistParams& p, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>,
@@ -826,14 +848,14 @@ static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (p.dump)
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair, kARes, kPack, kF8>, map_fan, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair, kARes, kPack, kF8>, map_fan, map_fan32, map_script, p));
     else
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>, map_fan, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>, map_fan, map_fan32, map_script, p));
     return FS_OK;
 }
 
-int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, const DistParams& p,
-                    int grid_limit, cudaStream_t stream) {
+int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, const CUtensorMap& map_script,
+                    const DistParams& p, int grid_limit, cudaStream_t stream) {
     const int64_t units_m = p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
     const int64_t total = units_m * p.tiles_n;
     if (total <= 0) return FS_OK;
@@ -847,7 +869,7 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
     const bool ares = p.pair && p.ares && p.chunks <= kAResChunks;
     const int pack = (p.diag == 6 || p.diag == 3) ? p.pack : (p.diag == 2 && p.pack == 2 ? 2 : 0);
 #define FS_LAUNCH(E, PAIR, ARES, PACK) \
-    return launch_distance_t<E, PAIR, ARES, PACK>(map_fan, map_script, p, grid, stream)
+    return launch_distance_t<E, PAIR, ARES, PACK>(map_fan, map_fan32, map_script, p, grid, stream)
 #define FS_LAUNCH_PACK(E, PAIR, ARES)              \
     do {                                           \
         if (pack == 2) FS_LAUNCH(E, PAIR, ARES, 2); \
@@ -869,20 +891,20 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_script, c
         if (ares && pack == 2 && (p.diag == 3 || p.diag == 6)) {
             // resident fan tile: built for the two default diagonal factors with the fp16x2 epilogue;
             // every other combination streams the fan tile
-            if (p.diag == 3) return launch_distance_t<3, true, true, 2, true>(map_fan, map_script, p, grid, stream);
-            return launch_distance_t<6, true, true, 2, true>(map_fan, map_script, p, grid, stream);
+            if (p.diag == 3) return launch_distance_t<3, true, true, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
+            return launch_distance_t<6, true, true, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
         }
         switch (p.diag) {
-            case 1: return launch_distance_t<1, true, false, 0, true>(map_fan, map_script, p, grid, stream);
+            case 1: return launch_distance_t<1, true, false, 0, true>(map_fan, map_fan32, map_script, p, grid, stream);
             case 2:
-                if (pack == 2) return launch_distance_t<2, true, false, 2, true>(map_fan, map_script, p, grid, stream);
-                return launch_distance_t<2, true, false, 0, true>(map_fan, map_script, p, grid, stream);
+                if (pack == 2) return launch_distance_t<2, true, false, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
+                return launch_distance_t<2, true, false, 0, true>(map_fan, map_fan32, map_script, p, grid, stream);
             case 3:
-                if (pack == 2) return launch_distance_t<3, true, false, 2, true>(map_fan, map_script, p, grid, stream);
-                return launch_distance_t<3, true, false, 1, true>(map_fan, map_script, p, grid, stream);
+                if (pack == 2) return launch_distance_t<3, true, false, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
+                return launch_distance_t<3, true, false, 1, true>(map_fan, map_fan32, map_script, p, grid, stream);
             case 6:
-                if (pack == 2) return launch_distance_t<6, true, false, 2, true>(map_fan, map_script, p, grid, stream);
-                return launch_distance_t<6, true, false, 1, true>(map_fan, map_script, p, grid, stream);
+                if (pack == 2) return launch_distance_t<6, true, false, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
+                return launch_distance_t<6, true, false, 1, true>(map_fan, map_fan32, map_script, p, grid, stream);
             default:
                 set_error("unsupported diagonal factor %d", p.diag);
                 return FS_E_INVALID;
