@@ -655,6 +655,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
         int as = 0;
         uint32_t aphase = 0;
         uint32_t a_phase = 0;
+        uint32_t st_src = smem_base;  // shared-memory address of the current stage
         while (walk.next(tile)) {
             if (kARes && tile.fan_first) {
                 mbar_wait_warp(afull_bar, a_phase, 0);  // the resident fan tile has landed (both CTAs)
@@ -663,7 +664,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
             mbar_wait_all(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
-            const int n_shift = S;
+            const int n_shift = kDiag == 6 ? 1 : S;  // E = 6: the window is one shift
             uint32_t accumulate = 0;
             // This warp is the only issuer of the CTA pair and runs one dependent instruction stream:
             // every instruction it spends per MMA is time the tensor pipe waits (ncu: the warp was
@@ -672,12 +673,13 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
             // issued as S x 4 MMAs whose operand offsets are immediates.
             constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
             auto desc_lo = [](uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); };
-            auto issue_full_chunk = [&](auto shifts, uint32_t a_lo, uint32_t b_lo) {
+            auto issue_chunk = [&](auto shifts, auto ksteps_c, uint32_t a_lo, uint32_t b_lo) {
                 constexpr int kS = decltype(shifts)::value;
+                constexpr int kK = decltype(ksteps_c)::value;
 #pragma unroll
                 for (int s = 0; s < kS; ++s) {
 #pragma unroll
-                    for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+                    for (int k = 0; k < kK; ++k) {
                         // row shift s * E rows of 128 B, K-step k * 32 B (the 128B swizzle is a
                         // function of the absolute smem address, so base_offset stays 0)
                         const uint32_t off = static_cast<uint32_t>((s * kShiftRows * 128 + k * kUmmaK * 2) >> 4);
@@ -686,14 +688,22 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                     }
                 }
             };
+            auto issue_shifts = [&](auto shifts, int ksteps, uint32_t a_lo, uint32_t b_lo) {
+                switch (ksteps) {  // the last chunk of a row may hold 1..3 K-steps only
+                    case 4: issue_chunk(shifts, std::integral_constant<int, 4>{}, a_lo, b_lo); break;
+                    case 3: issue_chunk(shifts, std::integral_constant<int, 3>{}, a_lo, b_lo); break;
+                    case 2: issue_chunk(shifts, std::integral_constant<int, 2>{}, a_lo, b_lo); break;
+                    default: issue_chunk(shifts, std::integral_constant<int, 1>{}, a_lo, b_lo); break;
+                }
+            };
             for (int c = 0; c < p.chunks; ++c) {
                 // the last chunk may hold fewer than 64 real columns (d_pad is a multiple of
                 // 16, not 64): its trailing K-steps are all-zero TMA fill and are skipped
-                const int ksteps = (c == p.chunks - 1) ? p.last_chunk_ksteps : kChunkK / kUmmaK;
+                const bool last_chunk = c == p.chunks - 1;
+                const int ksteps = last_chunk ? p.last_chunk_ksteps : kChunkK / kUmmaK;
                 for (int g = 0; g < shift_groups; ++g) {
                     mbar_wait_all(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t st_src = smem_base + stage * kStageSz;
                     // resident mode: the fan chunk sits in the resident tile and the stage holds
                     // only script rows; the stage's first shift is then an offset into the tile
                     const uint32_t a_src = kARes ? smem_a_res + c * kStageABytes +
@@ -702,12 +712,12 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                     const uint32_t b_src = kARes ? st_src : st_src + kStageABytes;
                     const uint32_t a_lo = desc_lo(a_src), b_lo = desc_lo(b_src);
                     if (elect_one()) {
-                        if (ksteps == kChunkK / kUmmaK && n_shift == 1) {
-                            issue_full_chunk(std::integral_constant<int, 1>{}, a_lo, b_lo);
-                        } else if (ksteps == kChunkK / kUmmaK && n_shift == 2) {
-                            issue_full_chunk(std::integral_constant<int, 2>{}, a_lo, b_lo);
-                        } else if (ksteps == kChunkK / kUmmaK && n_shift == 3) {
-                            issue_full_chunk(std::integral_constant<int, 3>{}, a_lo, b_lo);
+                        if (n_shift == 1) {
+                            issue_shifts(std::integral_constant<int, 1>{}, ksteps, a_lo, b_lo);
+                        } else if (n_shift == 2) {
+                            issue_shifts(std::integral_constant<int, 2>{}, ksteps, a_lo, b_lo);
+                        } else if (n_shift == 3) {
+                            issue_shifts(std::integral_constant<int, 3>{}, ksteps, a_lo, b_lo);
                         } else {
                             for (int s = 0; s < n_shift; ++s) {
                                 for (int k = 0; k < ksteps; ++k) {
@@ -723,26 +733,27 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                             umma_commit_pair(empty_bar(stage));
                         else
                             umma_commit(empty_bar(stage));
+                        if (last_chunk && g + 1 == shift_groups) {
+                            // accumulator tile complete (in both CTAs)
+                            if (kPair)
+                                umma_commit_pair(tfull_bar(as));
+                            else
+                                umma_commit(tfull_bar(as));
+                            // last script tile of this fan tile: the resident tile may be replaced
+                            // once these MMAs have retired
+                            if (kARes && tile.fan_last) umma_commit_pair(aempty_bar);
+                        }
                     }
                     __syncwarp();
                     accumulate = 1;
+                    st_src += kStageSz;
                     if (++stage == kNumStages) {
                         stage = 0;
+                        st_src = smem_base;
                         phase ^= 1u;
                     }
                 }
             }
-            // accumulator tile complete (in both CTAs)
-            if (elect_one()) {
-                if (kPair)
-                    umma_commit_pair(tfull_bar(as));
-                else
-                    umma_commit(tfull_bar(as));
-                // last script tile of this fan tile: the resident tile may be replaced once
-                // these MMAs have retired
-                if (kARes && tile.fan_last) umma_commit_pair(aempty_bar);
-            }
-            __syncwarp();
             if (++as == kAccumStages) {
                 as = 0;
                 aphase ^= 1u;
