@@ -276,7 +276,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     float2* ns_tile = norm_tile + as * kHaloCols;
     if (kDiag > 1 && !kOverlap && epi_tid < kHaloCols)
         ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.script_bd + n0 + epi_tid) : make_float2(kNaN, kNaN);
-    mbar_wait_warp(tfull_addr, aphase, 32);  // early warps back off: their polling competes for issue slots with the late ones
+    mbar_wait_warp(tfull_addr, aphase, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                            static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
