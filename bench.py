@@ -141,6 +141,7 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.lines = []
+        self.first = 0      # index of the first sample taken inside the timed regions
 
     def start(self):
         try:
@@ -157,6 +158,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def count(self):
+        return len(self.lines)
+
+    def mark(self):
+        """The timed regions start now: earlier samples (warm-up) are not reported."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -167,7 +175,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in self.lines[self.first:]:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -324,10 +332,19 @@ def run_native_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL_DEBUG=VERSION makes NCCL print a banner on STDOUT, next to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints a version banner on STDOUT when its communicator is created; stdout carries
+        # the one JSON line, so it is pointed at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if world > 1:
@@ -367,11 +384,21 @@ def run_native_arm(args):
         return len(m), counters
 
     # ---- value: inputs resident in HBM ------------------------------------------------------
-    for s in range(args.warmup):
-        step_resident(s)
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    for s in range(args.warmup):
+        step_resident(s)
+    # nvidia-smi can take a second to deliver its first sample (longer on an 8-GPU box): keep the
+    # GPU under the same load, untimed, until the sampler is live, so that the short timed regions
+    # below are covered
+    t_wait = time.perf_counter()
+    extra = 0
+    while sampler.proc is not None and sampler.count() == 0 and time.perf_counter() - t_wait < 4.0:
+        step_resident(args.warmup + extra)
+        extra += 1
+        torch.cuda.synchronize()
+    barrier()
+    sampler.mark()
     index.timing_reset()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -381,7 +408,6 @@ def run_native_arm(args):
     ev1.record()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
     kernel_ms, launches = index.timing_read()
     step_windows = sum(windows_of[(args.warmup + s) % n_distinct] for s in range(args.steps))
     counters = cnt_t.cpu().numpy()
@@ -401,6 +427,7 @@ def run_native_arm(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop()     # samples of both timed regions (resident and end-to-end)
     h2d = sum(clusters[(args.warmup + s) % n_distinct][0].nbytes + clusters[(args.warmup + s) % n_distinct][1].nbytes
               for s in range(args.steps))
 
