@@ -559,7 +559,8 @@ def test_full_size_cluster_properties():
     script = synth.make_script_tokens(lex, 25000).astype(np.int32)
     words, off = synth.synth_csr_batch(lex, script, range(500))
     tok = words.astype(np.int32)
-    idx = _device_index(lex.table_all, script)
+    idx = _device_index(lex.table_all, script, bits=None)       # the library defaults: fp8, E = 6, ...
+    assert idx.operand_bits == 8 and idx.diag == 6
     m, cnt = idx.search_host(tok, off, cap=1 << 20)
     assert cnt[nt.FS_CNT_WINDOWS] == int(np.maximum(np.diff(off) - 5, 0).sum())
     # (1) every hash-join pair is found by the distance path, flagged exact, |distance| ~ 0
@@ -586,6 +587,14 @@ def test_full_size_cluster_properties():
     a = np.sort(m, order=['fan_pos', 'script_pos'])
     b = np.sort(m2, order=['fan_pos', 'script_pos'])
     assert a.tobytes() == b.tobytes() and np.array_equal(cnt, cnt2)
+    # (5) every other kernel family ends in the same float64-decided match set: fp8 E = 3 (boundary
+    # pass), fp16 E = 3, fp16 dense -- only the candidate counts differ
+    key = np.sort(m['fan_pos'].astype(np.int64) * 100000 + m['script_pos'])
+    for opts in ((nt.FS_OPT_DIAG, 3), (nt.FS_OPT_OPERAND_BITS, 16), (nt.FS_OPT_DIAG, 1)):
+        idx.set_option(*opts)
+        mo, co = idx.search_host(tok, off, cap=1 << 20)
+        assert np.array_equal(key, np.sort(mo['fan_pos'].astype(np.int64) * 100000 + mo['script_pos'])), opts
+        assert co[nt.FS_CNT_CANDIDATES] >= co[nt.FS_CNT_MATCHES] == len(m)
     idx.close()
 
 
