@@ -102,6 +102,7 @@ struct fs_index {
     float2* script_norm_min = nullptr;  // (min B, max D) over 32 columns
     int32_t tiles_n = 0;
     CUtensorMap map_script;
+    CUtensorMap map_script128;  // boxes of 128 rows (E = 6: no halo rows)
 
     unsigned long long* hash_table = nullptr;
     uint32_t hash_slots = 0;
@@ -279,8 +280,12 @@ static int prepare_operands(fs_index* idx) {
     unsigned long long h_cnt[FS_CNT_COUNT];
     FS_CUDA_CHECK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     if (idx->n_script_tok > 0)
+    {
         if ((r = make_token_map(&idx->map_script, idx->script_emb, idx->n_script_tok, idx->dim_pad, kBoxRows)) != FS_OK)
             return r;
+        if ((r = make_token_map(&idx->map_script128, idx->script_emb, idx->n_script_tok, idx->dim_pad, 128)) != FS_OK)
+            return r;
+    }
     FS_CUDA_CHECK(cudaStreamSynchronize(st));
     idx->n_script_windows = static_cast<int64_t>(h_cnt[FS_CNT_WINDOWS]);
     idx->ready = true;
@@ -639,7 +644,8 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     const int grid_limit = idx->grid_limit > 0 ? idx->grid_limit : idx->sm_count;
     const int slot = static_cast<int>(idx->ev_count % kTimingRing);
     FS_CUDA_CHECK(cudaEventRecord(idx->ev_start[slot], st));
-    if ((r = launch_distance(map_fan, map_fan32, idx->map_script, p, grid_limit, st)) != FS_OK) return r;
+    if ((r = launch_distance(map_fan, map_fan32, idx->map_script, idx->map_script128, p, grid_limit, st)) != FS_OK)
+        return r;
     FS_CUDA_CHECK(cudaEventRecord(idx->ev_stop[slot], st));
     idx->ev_count++;
     if (mode != Mode::kSearch) return FS_OK;

@@ -59,6 +59,7 @@ constexpr int kNormTileBytes = kAccumStages * kHaloCols * 8;               // 42
 constexpr int kQuarterRows6 = 32 - 5;
 constexpr int kOverlapBoxRows = 32;
 constexpr int kOverlapABytes = 4 * kOverlapBoxRows * 128;  // 16384: fan bytes of one stage at E = 6
+constexpr int kOverlapBBytes = 128 * 128;                  // 16384: script bytes of one box at E = 6 (no halo rows)
 // fan windows produced per 128-row tile (tiles overlap by E-1 rows; E = 6: per quarter)
 __host__ __device__ constexpr int dist_m_step(int diag) { return diag == 6 ? 4 * kQuarterRows6 : kBlockM - (diag - 1); }
 __host__ __device__ constexpr int dist_pub_slots(int diag) { return (diag > 1 && diag != 6) ? 2 * (diag - 1) : 1; }
@@ -180,7 +181,7 @@ struct GatherSources {
 
 int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad, int32_t box_rows);
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, const CUtensorMap& map_script,
-                    const DistParams& p, int grid_limit, cudaStream_t stream);
+                    const CUtensorMap& map_script128, const DistParams& p, int grid_limit, cudaStream_t stream);
 int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
                         bool f8, float limit_sq, __half* dst, float2* sq, cudaStream_t stream);
 int launch_rownorm_max(const float* src, int64_t n_rows, int32_t dim, unsigned int* out, cudaStream_t stream);

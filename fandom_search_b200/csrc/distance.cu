@@ -499,7 +499,8 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
 template <int kDiag, bool kDump, bool kPair, bool kARes, int kPack, bool kF8>
 __global__ void __launch_bounds__(kDistThreads, 1)
 distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_constant__ CUtensorMap map_fan32,
-                const __grid_constant__ CUtensorMap map_script, const DistParams p) {
+                const __grid_constant__ CUtensorMap map_script, const __grid_constant__ CUtensorMap map_script128,
+                const DistParams p) {
     static_assert(!kARes || kPair, "the A-resident variant exists for CTA pairs only");
     static_assert(!kF8 || kPair, "fp8 operands exist for CTA pairs only");
     constexpr bool kOverlap = kDiag == 6;  // overlapping lane quarters (common.cuh)
@@ -534,7 +535,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
 
     if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(kOverlap ? &map_fan32 : &map_fan);
-        tma_prefetch_desc(&map_script);
+        tma_prefetch_desc(kOverlap ? &map_script128 : &map_script);
         for (int s = 0; s < kNumStages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -608,14 +609,15 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                     if (elect_one()) {
                         if (kARes) {
                             // only this CTA's half of the script tile streams
-                            if (leader) mbar_expect_tx(full_bar(stage), 2 * kStageABytes);
-                            tma_load_2d_pair(b_dst, &map_script, full_bar(stage), c * kChunkK,
-                                             n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
+                            // (E = 6 reads no row beyond its 128: boxes without the 8 halo rows)
+                            if (leader) mbar_expect_tx(full_bar(stage), 2 * (kOverlap ? kOverlapBBytes : kStageABytes));
+                            tma_load_2d_pair(b_dst, kOverlap ? &map_script128 : &map_script, full_bar(stage),
+                                             c * kChunkK, n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
                         } else if (kPair) {
                             // this CTA stages its own fan rows and script rows [128 r, 128 r + 136)
                             if (leader)
                                 mbar_expect_tx(full_bar(stage),
-                                               2 * (kOverlap ? kOverlapABytes + kStageABytes : kPairStageBytes));
+                                               2 * (kOverlap ? kOverlapABytes + kOverlapBBytes : kPairStageBytes));
                             if (kOverlap) {
                                 for (int q = 0; q < 4; ++q)
                                     tma_load_2d_pair(a_dst + q * (kOverlapBoxRows * 128), &map_fan32, full_bar(stage),
@@ -623,10 +625,10 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                             } else {
                                 tma_load_2d_pair(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
                             }
-                            tma_load_2d_pair(b_dst, &map_script, full_bar(stage), c * kChunkK,
-                                             n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
+                            tma_load_2d_pair(b_dst, kOverlap ? &map_script128 : &map_script, full_bar(stage),
+                                             c * kChunkK, n0 + s0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
                         } else {
-                            mbar_expect_tx(full_bar(stage), kOverlap ? kOverlapABytes + 2 * kStageABytes : kStageBytes);
+                            mbar_expect_tx(full_bar(stage), kOverlap ? kOverlapABytes + 2 * kOverlapBBytes : kStageBytes);
                             if (kOverlap) {
                                 for (int q = 0; q < 4; ++q)
                                     tma_load_2d(a_dst + q * (kOverlapBoxRows * 128), &map_fan32, full_bar(stage),
@@ -634,9 +636,11 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                             } else {
                                 tma_load_2d(a_dst, &map_fan, full_bar(stage), c * kChunkK, m0 + s0);
                             }
-                            tma_load_2d(b_dst, &map_script, full_bar(stage), c * kChunkK, n0 + s0);
-                            tma_load_2d(b_dst + kStageABytes, &map_script, full_bar(stage),
-                                        c * kChunkK, n0 + s0 + kBoxRows);
+                            tma_load_2d(b_dst, kOverlap ? &map_script128 : &map_script, full_bar(stage), c * kChunkK,
+                                        n0 + s0);
+                            tma_load_2d(b_dst + (kOverlap ? kOverlapBBytes : kStageABytes),
+                                        kOverlap ? &map_script128 : &map_script, full_bar(stage), c * kChunkK,
+                                        n0 + s0 + (kOverlap ? 128 : kBoxRows));
                         }
                     }
                     __syncwarp();
@@ -835,7 +839,8 @@ int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim
 
 template <int kDiag, bool kPair, bool kARes, int kPack, bool kF8 = false>
 static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_fan32,
-                             const CUtensorMap& map_script, const DistParams& p, int grid, cudaStream_t stream) {
+                             const CUtensorMap& map_script, const CUtensorMap& map_script128, const DistParams& p,
+                             int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>,
@@ -859,14 +864,14 @@ static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (p.dump)
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair, kARes, kPack, kF8>, map_fan, map_fan32, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, true, kPair, kARes, kPack, kF8>, map_fan, map_fan32, map_script, map_script128, p));
     else
-        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>, map_fan, map_fan32, map_script, p));
+        FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>, map_fan, map_fan32, map_script, map_script128, p));
     return FS_OK;
 }
 
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, const CUtensorMap& map_script,
-                    const DistParams& p, int grid_limit, cudaStream_t stream) {
+                    const CUtensorMap& map_script128, const DistParams& p, int grid_limit, cudaStream_t stream) {
     const int64_t units_m = p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
     const int64_t total = units_m * p.tiles_n;
     if (total <= 0) return FS_OK;
@@ -880,7 +885,7 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, co
     const bool ares = p.pair && p.ares && p.chunks <= kAResChunks;
     const int pack = (p.diag == 6 || p.diag == 3) ? p.pack : (p.diag == 2 && p.pack == 2 ? 2 : 0);
 #define FS_LAUNCH(E, PAIR, ARES, PACK) \
-    return launch_distance_t<E, PAIR, ARES, PACK>(map_fan, map_fan32, map_script, p, grid, stream)
+    return launch_distance_t<E, PAIR, ARES, PACK>(map_fan, map_fan32, map_script, map_script128, p, grid, stream)
 #define FS_LAUNCH_PACK(E, PAIR, ARES)              \
     do {                                           \
         if (pack == 2) FS_LAUNCH(E, PAIR, ARES, 2); \
@@ -902,20 +907,20 @@ int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, co
         if (ares && pack == 2 && (p.diag == 3 || p.diag == 6)) {
             // resident fan tile: built for the two default diagonal factors with the fp16x2 epilogue;
             // every other combination streams the fan tile
-            if (p.diag == 3) return launch_distance_t<3, true, true, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
-            return launch_distance_t<6, true, true, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
+            if (p.diag == 3) return launch_distance_t<3, true, true, 2, true>(map_fan, map_fan32, map_script, map_script128, p, grid, stream);
+            return launch_distance_t<6, true, true, 2, true>(map_fan, map_fan32, map_script, map_script128, p, grid, stream);
         }
         switch (p.diag) {
-            case 1: return launch_distance_t<1, true, false, 0, true>(map_fan, map_fan32, map_script, p, grid, stream);
+            case 1: return launch_distance_t<1, true, false, 0, true>(map_fan, map_fan32, map_script, map_script128, p, grid, stream);
             case 2:
-                if (pack == 2) return launch_distance_t<2, true, false, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
-                return launch_distance_t<2, true, false, 0, true>(map_fan, map_fan32, map_script, p, grid, stream);
+                if (pack == 2) return launch_distance_t<2, true, false, 2, true>(map_fan, map_fan32, map_script, map_script128, p, grid, stream);
+                return launch_distance_t<2, true, false, 0, true>(map_fan, map_fan32, map_script, map_script128, p, grid, stream);
             case 3:
-                if (pack == 2) return launch_distance_t<3, true, false, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
-                return launch_distance_t<3, true, false, 1, true>(map_fan, map_fan32, map_script, p, grid, stream);
+                if (pack == 2) return launch_distance_t<3, true, false, 2, true>(map_fan, map_fan32, map_script, map_script128, p, grid, stream);
+                return launch_distance_t<3, true, false, 1, true>(map_fan, map_fan32, map_script, map_script128, p, grid, stream);
             case 6:
-                if (pack == 2) return launch_distance_t<6, true, false, 2, true>(map_fan, map_fan32, map_script, p, grid, stream);
-                return launch_distance_t<6, true, false, 1, true>(map_fan, map_fan32, map_script, p, grid, stream);
+                if (pack == 2) return launch_distance_t<6, true, false, 2, true>(map_fan, map_fan32, map_script, map_script128, p, grid, stream);
+                return launch_distance_t<6, true, false, 1, true>(map_fan, map_fan32, map_script, map_script128, p, grid, stream);
             default:
                 set_error("unsupported diagonal factor %d", p.diag);
                 return FS_E_INVALID;
