@@ -87,7 +87,10 @@ class Vocab:
 
     def encode_files(self, paths, threads=None):
         if threads is None:
-            threads = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)
+            # leave two cores to the thread that drives the GPU and to the post-processing thread:
+            # with every core tokenising, the kernel launches of the search call queue up behind them
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4
+            threads = max(1, min(16, cores) - 2)
         arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
         h = self._lib.fs_batch_encode_files(self._h, arr, len(paths), threads)
         if not h:
