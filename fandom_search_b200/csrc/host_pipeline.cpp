@@ -44,22 +44,89 @@ inline uint64_t hash_bytes(const char* p, int64_t n) { return fs_murmurhash64a(p
 // ---------------------------------------------------------------------------------------
 // vocabulary
 // ---------------------------------------------------------------------------------------
+// Open-addressing table whose 16-byte slots hold short keys INLINE: a word of up to 8 bytes (most
+// of any vocabulary) is matched with one 64-bit compare against the slot itself -- one cache line
+// per probe instead of slot -> key offsets -> key bytes -> row id.  Longer keys keep the 64-bit hash
+// in the slot and are verified against the key blob.
 struct fs_vocab {
+    struct Slot {
+        uint64_t key8;  // short key: its bytes, zero padded; long key: its 64-bit hash
+        int32_t row;    // short key: embedding row id; long key: key index
+        int32_t len;    // 0 = empty; 1..8 = short key length; -1 = long key
+    };
     std::string blob;                 // concatenated keys
     std::vector<int64_t> key_off;     // [n+1]
     std::vector<int32_t> key_row;     // [n]
-    std::vector<int32_t> slots;       // open addressing: key index or -1
+    std::vector<Slot> slots;
     uint64_t mask = 0;
 
-    int32_t find(const char* p, int64_t n) const {
-        uint64_t s = hash_bytes(p, n) & mask;
+    static uint64_t mix(uint64_t x) {  // splitmix64 finaliser
+        x ^= x >> 30;
+        x *= 0xbf58476d1ce4e5b9ULL;
+        x ^= x >> 27;
+        x *= 0x94d049bb133111ebULL;
+        x ^= x >> 31;
+        return x;
+    }
+    static uint64_t load8(const char* p, int64_t n) {  // n <= 8 bytes, zero padded
+        uint64_t v = 0;
+        memcpy(&v, p, static_cast<size_t>(n));
+        return v;
+    }
+    // `padded`: at least 8 bytes are readable at p (the batch text buffer has that slack)
+    int32_t find(const char* p, int64_t n, bool padded = false) const {
+        if (n <= 0) return -1;
+        if (n <= 8) {
+            uint64_t k8;
+            if (padded) {
+                memcpy(&k8, p, 8);
+                if (n < 8) k8 &= (1ULL << (8 * n)) - 1;
+            } else {
+                k8 = load8(p, n);
+            }
+            uint64_t s = mix(k8 + static_cast<uint64_t>(n)) & mask;
+            while (true) {
+                const Slot& e = slots[s];
+                if (e.len == 0) return -1;
+                if (e.len == n && e.key8 == k8) return e.row;
+                s = (s + 1) & mask;
+            }
+        }
+        const uint64_t h = hash_bytes(p, n);
+        uint64_t s = h & mask;
         while (true) {
-            const int32_t k = slots[s];
-            if (k < 0) return -1;
-            const int64_t a = key_off[k], len = key_off[k + 1] - a;
-            if (len == n && memcmp(blob.data() + a, p, static_cast<size_t>(n)) == 0) return key_row[k];
+            const Slot& e = slots[s];
+            if (e.len == 0) return -1;
+            if (e.len == -1 && e.key8 == h) {
+                const int64_t a = key_off[e.row], len = key_off[e.row + 1] - a;
+                if (len == n && memcmp(blob.data() + a, p, static_cast<size_t>(n)) == 0) return key_row[e.row];
+            }
             s = (s + 1) & mask;
         }
+    }
+    // insert or overwrite (duplicate key: the LAST entry wins, like building a Python dict)
+    void insert(int64_t k) {
+        const int64_t a = key_off[k], n = key_off[k + 1] - a;
+        const char* p = blob.data() + a;
+        if (n <= 0) return;
+        if (n <= 8) {
+            const uint64_t k8 = load8(p, n);
+            uint64_t s = mix(k8 + static_cast<uint64_t>(n)) & mask;
+            while (slots[s].len != 0 && !(slots[s].len == n && slots[s].key8 == k8)) s = (s + 1) & mask;
+            slots[s] = Slot{k8, key_row[k], static_cast<int32_t>(n)};
+            return;
+        }
+        const uint64_t h = hash_bytes(p, n);
+        uint64_t s = h & mask;
+        while (slots[s].len != 0) {
+            const Slot& e = slots[s];
+            if (e.len == -1 && e.key8 == h) {
+                const int64_t oa = key_off[e.row], olen = key_off[e.row + 1] - oa;
+                if (olen == n && memcmp(blob.data() + oa, p, static_cast<size_t>(n)) == 0) break;
+            }
+            s = (s + 1) & mask;
+        }
+        slots[s] = Slot{h, static_cast<int32_t>(k), -1};
     }
 };
 
@@ -135,23 +202,8 @@ fs_vocab* fs_vocab_create(const char* keys_blob, const int64_t* key_offsets, con
     uint64_t cap = 16;
     while (cap < static_cast<uint64_t>(n_keys) * 2 + 2) cap <<= 1;
     v->mask = cap - 1;
-    v->slots.assign(cap, -1);
-    for (int64_t k = 0; k < n_keys; ++k) {
-        const int64_t a = v->key_off[k], len = v->key_off[k + 1] - a;
-        uint64_t s = hash_bytes(v->blob.data() + a, len) & v->mask;
-        bool dup = false;
-        while (v->slots[s] >= 0) {
-            const int32_t o = v->slots[s];
-            const int64_t oa = v->key_off[o], olen = v->key_off[o + 1] - oa;
-            if (olen == len && memcmp(v->blob.data() + oa, v->blob.data() + a, static_cast<size_t>(len)) == 0) {
-                dup = true;  // duplicate key: the LAST entry wins, like building a Python dict
-                v->slots[s] = static_cast<int32_t>(k);
-                break;
-            }
-            s = (s + 1) & v->mask;
-        }
-        if (!dup) v->slots[s] = static_cast<int32_t>(k);
-    }
+    v->slots.assign(cap, fs_vocab::Slot{0, 0, 0});
+    for (int64_t k = 0; k < n_keys; ++k) v->insert(k);
     return v;
 }
 
@@ -196,7 +248,8 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
         sizes[k] = static_cast<int64_t>(st.st_size);
     });
     for (int64_t k = 0; k < n_files; ++k) b->file_off[k + 1] = b->file_off[k] + sizes[k];
-    b->text.alloc(static_cast<size_t>(b->file_off[n_files]));
+    b->text.alloc(static_cast<size_t>(b->file_off[n_files]) + 8);  // + slack for 8-byte key loads
+    memset(b->text.data() + b->file_off[n_files], 0, 8);
     std::vector<int64_t> counts(n_files, 0);
     parallel_for(n_files, n_threads, [&](int64_t k) {
         if (b->file_status[k] || sizes[k] == 0) return;
@@ -236,7 +289,7 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
             if (i >= len) break;
             const int64_t s = i;
             while (i < len && !is_ws(static_cast<unsigned char>(text[i]))) ++i;
-            tok[o] = v->find(text + s, i - s);  // -1 = OOV for now
+            tok[o] = v->find(text + s, i - s, true);  // -1 = OOV for now
             st[o] = base + s;
             en[o] = base + i;
             ++o;
@@ -275,7 +328,7 @@ int64_t fs_batch_info(const fs_batch* b, int32_t what) {
         case 0: return static_cast<int64_t>(b->file_status.size());
         case 1: return static_cast<int64_t>(b->tok.size());
         case 2: return static_cast<int64_t>(b->oov_start.size());
-        case 3: return static_cast<int64_t>(b->text.size());
+        case 3: return b->file_off.empty() ? 0 : b->file_off.back();  // (the buffer has 8 bytes of slack behind)
         default: return -1;
     }
 }

@@ -140,6 +140,37 @@ def test_native_vocab_and_batch(golden_dir, tmp_path):
         vocab.encode_files([str(tmp_path / "missing.txt")])
 
 
+def test_native_vocab_short_and_long_keys(tmp_path):
+    """The vocabulary table keeps keys of <= 8 bytes inline and longer ones by hash: every length,
+    keys that are prefixes of each other, and near-misses must resolve like a Python dict."""
+    import types
+    import numpy as np
+    from fandom_search_b200 import text
+    rng = np.random.default_rng(77)
+    alphabet = "abcdé日x"
+    keys = {}
+    for n in range(1, 21):
+        for _ in range(60):
+            w = "".join(alphabet[i] for i in rng.integers(0, len(alphabet), n))
+            keys.setdefault(w, len(keys) * 3 + 1)
+    for w in ("a", "aa", "aaaaaaaa", "aaaaaaaaa", "aaaaaaa", "aaaaaaab"):
+        keys.setdefault(w, len(keys) * 3 + 1)
+    vocab = text.Vocab(types.SimpleNamespace(key_to_row=keys))
+    for w, r in keys.items():
+        assert vocab.lookup(w) == r, w
+    misses = [w + "a" for w in keys if w + "a" not in keys] + [w[:-1] for w in keys if w[:-1] not in keys]
+    for w in misses:
+        assert vocab.lookup(w) == -1, w
+    # through the file tokeniser (8-byte loads at the very end of the text buffer included)
+    words = list(keys)[::7] + misses[::11]
+    words = [w for w in words if w]
+    (tmp_path / "t.txt").write_text(" ".join(words), encoding="utf-8")
+    b = vocab.encode_files([str(tmp_path / "t.txt")], threads=2)
+    oov = b.oov_strings()
+    for w, t in zip(words, b.tok.tolist()):
+        assert t == (keys[w] if w in keys else -(1 + oov.index(w))), w
+
+
 def test_multi_script_pass_equals_separate_runs(cpu_device, golden_dir, tmp_path, monkeypatch):
     """N4: indexing two scripts side by side and searching once == two single-script runs."""
     lines = open(os.path.join(golden_dir, "script.txt"), encoding="utf-8").read().splitlines()
