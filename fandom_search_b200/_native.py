@@ -31,6 +31,7 @@ FS_OPT_CTA_PAIR = 5
 FS_OPT_A_RESIDENT = 6
 FS_OPT_PACKED_SHUFFLE = 7
 FS_OPT_OPERAND_BITS = 9
+FS_OPT_TILE_GROUP = 10
 
 FS_MATCH_EXACT = 1
 FS_MATCH_LSH_SHIFT = 8

@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("FS_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE,
                                             stderr=subprocess.STDOUT, text=True)))

@@ -146,6 +146,7 @@ struct fs_index {
     int32_t ares = 1;              // A-resident variant of the pair kernel (used when the row fits: <= 640 B)
     int32_t pack = 2;              // epilogue diagonal sums: 0 fp32 shuffles, 1 fp16x2 shuffles, 2 fp16x2 arithmetic
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
+    int32_t tile_group = 1;        // grouped stages where the kernel has them (FS_OPT_TILE_GROUP)
     int32_t grid_limit = 0;
 
     // timing ring
@@ -465,6 +466,9 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
         case FS_OPT_GRID_LIMIT:
             idx->grid_limit = static_cast<int32_t>(value < 0 ? 0 : value);
             return FS_OK;
+        case FS_OPT_TILE_GROUP:
+            idx->tile_group = value ? 1 : 0;
+            return FS_OK;
         default:
             set_error("unknown option %d", option);
             return FS_E_INVALID;
@@ -504,6 +508,7 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
         case 7: return idx->ares;
         case 8: return idx->pack;
         case 11: return idx->operand_bits;
+        case 12: return idx->tile_group;
         default: return -1;
     }
 }
@@ -634,6 +639,7 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.ares = idx->ares;
     p.pack = idx->pack;
     p.shifts_per_stage = idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag;
+    p.group = idx->tile_group;
     p.tiles_m = tiles_m;
     p.tiles_n = tiles_n;
     p.cand = (mode == Mode::kCandidates) ? cand_out : idx->cand;

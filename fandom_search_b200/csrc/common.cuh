@@ -71,6 +71,9 @@ __host__ __device__ constexpr int dist_pub_bytes(int diag) {
 // of the script tile streams through the stage ring (17 KB per stage).
 constexpr int kAResChunks = 5;
 constexpr int kAResBytes = kAResChunks * kStageABytes;  // 87040
+// Grouped stages (A-resident, E = 6): a script tile's chunks share one full/empty barrier pair, and the
+// ring also takes the part of the resident area that a narrow embedding leaves unused.
+constexpr int kGroupMaxChunks = 3;
 __host__ __device__ constexpr int dist_stage_bytes(bool pair, bool ares) {
     return ares ? kStageABytes : (pair ? 2 * kStageABytes : kStageBytes);
 }
@@ -110,6 +113,8 @@ struct DistParams {
     int32_t f8;               // 1: operands are fp8 e4m3 (tcgen05.mma.kind::f8f6f4, K = 32)
     int32_t pair;             // 1: CTA-pair kernel (cta_group::2, M = 2 x 128 fan tiles)
     int32_t shifts_per_stage; // S: MMA shifts served by one smem stage (divides window/E)
+    int32_t group;            // 1: (A-resident, E = 6, chunks <= kGroupMaxChunks) all chunks of a script tile
+                              //    land on ONE barrier and are issued as one block of MMAs
     int32_t tiles_m, tiles_n;
     fs_pair* cand;            // candidate output
     int64_t cand_cap;
@@ -420,6 +425,25 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
             "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n"
             ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+// the same MMA under a guard predicate (`enable` is warp-uniform): K-steps that a short last chunk
+// does not have are skipped without a branch in the issuing warp's instruction stream
+template <bool kF8>
+__device__ __forceinline__ void umma_lohi_pair_if(uint32_t enable, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                  uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    if (kF8) {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], da, db, %4, p;\n\t}\n"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate), "r"(enable) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+            "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}\n"
+            ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate), "r"(enable) : "memory");
     }
 }
 // arrive on the mbarrier at this offset in BOTH CTAs once the leader's MMAs retired

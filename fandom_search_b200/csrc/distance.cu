@@ -29,6 +29,23 @@
 
 #include <type_traits>
 
+#ifdef FS_TIMELINE
+// Debug build only (FS_NVCC_EXTRA=-DFS_TIMELINE): clock64 stamps of CTA 0, read back with
+// fs_debug_timeline; [role][tile][slot], roles 0 producer, 1 MMA issuer, 2 + w epilogue warp w.
+constexpr int kTlRoles = 2 + 16, kTlTiles = 64, kTlSlots = 12;
+__device__ long long g_timeline[kTlRoles][kTlTiles][kTlSlots];
+#define FS_TL(role, tile, slot)                                                                   \
+    do {                                                                                          \
+        if (blockIdx.x == 0 && (tile) < kTlTiles && (threadIdx.x & 31) == 0)                      \
+            g_timeline[role][tile][slot] = clock64();                                             \
+    } while (0)
+extern "C" int fs_debug_timeline(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define FS_TL(role, tile, slot) do { } while (0)
+#endif
+
 namespace fs {
 
 // ---------------------------------------------------------------------------------------------
@@ -245,7 +262,9 @@ template <int kDiag, bool kDump, int kPack, bool kPair>
 __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t m0, const int32_t n0,
                                               const int as, const uint32_t tfull_addr, const uint32_t tempty_addr,
                                               const uint32_t aphase, const uint32_t tmem_base, float* halo,
-                                              float2* norm_tile, __half* rowmax, const int warp, const int lane) {
+                                              float2* norm_tile, __half* rowmax, const int warp, const int lane,
+                                              const int tl_tile = 0) {
+    (void)tl_tile;
     constexpr bool kOverlap = kDiag == 6;  // lane quarters hold overlapping fan rows: nothing crosses quarters
     constexpr int kMStep = dist_m_step(kDiag);
     constexpr int kNStep = kBlockN - (kDiag - 1);
@@ -278,6 +297,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
         ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.script_bd + n0 + epi_tid) : make_float2(kNaN, kNaN);
     mbar_wait_warp(tfull_addr, aphase, 0);
     tc_fence_after();
+    FS_TL(2 + warp, tl_tile, 1);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                            static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
     uint32_t r[40];
@@ -397,6 +417,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
         }
     }
     // every accumulator column of this warp is in registers: release the TMEM stage
+    FS_TL(2 + warp, tl_tile, 2);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
@@ -569,6 +590,17 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
     constexpr int kShiftRows = kDiag;                   // token rows between two MMA shifts
     const int S = p.shifts_per_stage;                   // MMA shifts served by one smem stage
     const int shift_groups = (p.window / kDiag) / S;    // stages per 64-column chunk
+    // Grouped stages (A-resident, E = 6, narrow embeddings): the chunks of a script tile are one unit of
+    // the ring -- one full/empty barrier pair per TILE, so the MMA issuer makes one wait and one elected
+    // block of MMAs per tile instead of one per chunk (its instruction stream, ~85 instructions per
+    // chunk, was what paced the kernel: profiles/r01_timeline_s2.txt).  The ring starts right behind the
+    // resident chunks actually used and holds n_groups tiles.
+    const bool grouped = kARes && kOverlap && p.group != 0 && p.chunks <= kGroupMaxChunks;
+    const uint32_t group_ring = smem_a_res + static_cast<uint32_t>(p.chunks) * kStageABytes;
+    const int n_groups_fit = (kAResBytes - p.chunks * kStageABytes + kNumStages * kStageSz) / (p.chunks * kStageSz);
+    const int n_groups = n_groups_fit < kNumStages ? n_groups_fit : kNumStages;
+    int grp = 0;
+    uint32_t gphase = 0;
 
     // The two control roles run as WHOLE warps (all lanes converged, one elected lane issues):
     // addresses and descriptors then stay warp-uniform and live in uniform registers.  Run by a
@@ -579,7 +611,10 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         uint32_t a_phase = 0;
+        int tl_tile = -1;
         while (walk.next(tile)) {
+            ++tl_tile;
+            FS_TL(0, tl_tile, 0);
             const int32_t m0 = tile.m0;
             const int32_t n0 = tile.n0;
             if (kARes && tile.fan_first) {
@@ -600,10 +635,30 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                 __syncwarp();
                 a_phase ^= 1u;
             }
+            if (grouped) {
+                // one barrier pair per script tile: all its chunks land on full_bar(grp)
+                mbar_wait_warp(empty_bar(grp), gphase ^ 1u, 32);
+                FS_TL(0, tl_tile, 1);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(full_bar(grp), 2 * p.chunks * kOverlapBBytes);
+                    const uint32_t dst = group_ring + static_cast<uint32_t>(grp * p.chunks) * kStageSz;
+                    for (int c = 0; c < p.chunks; ++c)
+                        tma_load_2d_pair(dst + c * kStageSz, &map_script128, full_bar(grp), c * kChunkK,
+                                         n0 + static_cast<int32_t>(cta_rank) * (kBlockN / 2));
+                }
+                __syncwarp();
+                FS_TL(0, tl_tile, 2);
+                if (++grp == n_groups) {
+                    grp = 0;
+                    gphase ^= 1u;
+                }
+                continue;
+            }
             for (int c = 0; c < p.chunks; ++c) {
                 for (int g = 0; g < shift_groups; ++g) {
                     const int32_t s0 = g * S * kShiftRows;  // first token-row shift of this stage
                     mbar_wait_warp(empty_bar(stage), phase ^ 1u, 32);
+                    FS_TL(0, tl_tile, 1 + 2 * (c < 5 ? c : 4));
                     const uint32_t a_dst = smem_base + stage * kStageSz;
                     const uint32_t b_dst = kARes ? a_dst : a_dst + kStageABytes;
                     if (elect_one()) {
@@ -644,6 +699,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                         }
                     }
                     __syncwarp();
+                    FS_TL(0, tl_tile, 2 + 2 * (c < 5 ? c : 4));
                     if (++stage == kNumStages) {
                         stage = 0;
                         phase ^= 1u;
@@ -660,14 +716,62 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
         uint32_t aphase = 0;
         uint32_t a_phase = 0;
         uint32_t st_src = smem_base;  // shared-memory address of the current stage
+        // grouped stages: bit 4c+k set = K-step k of chunk c exists
+        uint32_t group_en = 0;
+        for (int c = 0; c < p.chunks && c < kGroupMaxChunks; ++c)
+            group_en |= ((1u << (c == p.chunks - 1 ? p.last_chunk_ksteps : kChunkK / kUmmaK)) - 1u) << (4 * c);
+        int tl_tile = -1;
         while (walk.next(tile)) {
+            ++tl_tile;
+            FS_TL(1, tl_tile, 0);
             if (kARes && tile.fan_first) {
                 mbar_wait_warp(afull_bar, a_phase, 0);  // the resident fan tile has landed (both CTAs)
                 a_phase ^= 1u;
             }
             mbar_wait_all(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
+            FS_TL(1, tl_tile, 1);
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
+            if (kARes && kOverlap && grouped) {
+                // whole tile: one wait, one elected block; every operand offset is an immediate
+                // relative to the resident tile (A) and to the group's first stage (B)
+                constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+                mbar_wait_all(full_bar(grp), gphase);
+                tc_fence_after();
+                FS_TL(1, tl_tile, 2);
+                const uint32_t a_lo = ((smem_a_res & 0x3FFFFu) >> 4) | (1u << 16);
+                const uint32_t b_src = group_ring + static_cast<uint32_t>(grp * p.chunks) * kStageSz;
+                const uint32_t b_lo = ((b_src & 0x3FFFFu) >> 4) | (1u << 16);
+                if (elect_one()) {
+#pragma unroll
+                    for (int c = 0; c < kGroupMaxChunks; ++c) {
+#pragma unroll
+                        for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+                            const uint32_t a_off = static_cast<uint32_t>((c * kStageABytes + k * kUmmaK * 2) >> 4);
+                            const uint32_t b_off = static_cast<uint32_t>((c * kStageSz + k * kUmmaK * 2) >> 4);
+                            if (c == 0 && k == 0)
+                                umma_lohi<kPair, kF8>(tmem_d, a_lo, b_lo, kHi, idesc, 0u);
+                            else
+                                umma_lohi_pair_if<kF8>((group_en >> (4 * c + k)) & 1u, tmem_d, a_lo + a_off,
+                                                       b_lo + b_off, kHi, idesc, 1u);
+                        }
+                    }
+                    umma_commit_pair(empty_bar(grp));   // the group's stages are free (both CTAs) ...
+                    umma_commit_pair(tfull_bar(as));    // ... and the accumulator tile is complete
+                    if (tile.fan_last) umma_commit_pair(aempty_bar);
+                }
+                __syncwarp();
+                FS_TL(1, tl_tile, 3);
+                if (++grp == n_groups) {
+                    grp = 0;
+                    gphase ^= 1u;
+                }
+                if (++as == kAccumStages) {
+                    as = 0;
+                    aphase ^= 1u;
+                }
+                continue;
+            }
             const int n_shift = kDiag == 6 ? 1 : S;  // E = 6: the window is one shift
             uint32_t accumulate = 0;
             // This warp is the only issuer of the CTA pair and runs one dependent instruction stream:
@@ -708,6 +812,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                 for (int g = 0; g < shift_groups; ++g) {
                     mbar_wait_all(full_bar(stage), phase);
                     tc_fence_after();
+                    FS_TL(1, tl_tile, 2 + 2 * (c < 4 ? c : 4));
                     // resident mode: the fan chunk sits in the resident tile and the stage holds
                     // only script rows; the stage's first shift is then an offset into the tile
                     const uint32_t a_src = kARes ? smem_a_res + c * kStageABytes +
@@ -749,6 +854,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                         }
                     }
                     __syncwarp();
+                    FS_TL(1, tl_tile, 3 + 2 * (c < 4 ? c : 4));
                     accumulate = 1;
                     st_src += kStageSz;
                     if (++stage == kNumStages) {
@@ -769,11 +875,15 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
         uint32_t aphase = 0;
         // kPack == 2: two half-precision boundary-row buffers, one per accumulator stage
         constexpr bool kHalfRows = kPack == 2 && (kDiag == 6 || kDiag == 3 || kDiag == 2);
+        int tl_tile = -1;
         while (walk.next(tile)) {
+            ++tl_tile;
+            FS_TL(2 + warp, tl_tile, 0);
             float* halo_t = halo + (kHalfRows ? as * (dist_pub_bytes(kDiag) / 8) : 0);
             __half* rowmax_t = rowmax_base + as * (dist_rowmax_bytes(kDiag) / 4);
             epilogue_tile<kDiag, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
-                                                      aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane);
+                                                      aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane, tl_tile);
+            FS_TL(2 + warp, tl_tile, 3);
             if (++as == kAccumStages) {
                 as = 0;
                 aphase ^= 1u;

@@ -100,6 +100,10 @@ enum {
                                     (tcgen05.mma.kind::f8f6f4; the rounding error of every window is
                                     measured and enters its pre-filter threshold, so the candidates stay
                                     a guaranteed superset; CTA pairs only).  Re-converts the index.   */
+    FS_OPT_TILE_GROUP = 10,      /* 1 (default): with the resident fan tile, E = 6 and an embedding of at
+                                    most three 128-byte chunks per row, all chunks of a script tile land
+                                    on one barrier and are issued as one block of MMAs; 0: one stage,
+                                    one barrier and one issue block per chunk                        */
     FS_OPT_DIAG = 4              /* 1 (dense), 2, 3 or 6: the tensor cores accumulate window/E shifts
                                     and the epilogue adds E diagonal neighbours (same products,
                                     E-fold fewer tensor-core flops)                            */

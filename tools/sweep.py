@@ -18,7 +18,7 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, pack=None, clocks=False, bits=8):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, pack=None, clocks=False, bits=8, group=None):
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
@@ -30,6 +30,8 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
     if pack is not None:
         idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
+    if group is not None:
+        idx.set_option(nt.FS_OPT_TILE_GROUP, group)
     n_works = max(1, nf // works_len)
     lens = np.full(n_works, (nf + 5 * n_works) // n_works + 1, dtype=np.int64)
     off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
@@ -58,7 +60,7 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     per = ms / n * 1e-3
     exec_factor = (6 // diag) * (128.0 * 256.0) / ((129 - diag) * (257 - diag))
     res = {"bits": bits, "candidates": int(cnt_t.cpu()[nt.FS_CNT_CANDIDATES]), "matches": int(cnt_t.cpu()[nt.FS_CNT_MATCHES]),
-           "diag": diag, "pair": pair, "pack": pack, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
+           "diag": diag, "pair": pair, "pack": pack, "group": group, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
            "kernel_ms": ms / n, "windows_per_s": windows / per, "clocks": clk,
            "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
            "tflops_executed": 2.0 * exec_factor * idx.dim_pad * idx.n_script_windows * windows / per / 1e12}
@@ -77,12 +79,14 @@ def main():
     ap.add_argument("--one", type=int, nargs=4, metavar=("DIAG", "NF", "NS", "D"), help="run a single case")
     ap.add_argument("--pair", type=int, default=0)
     ap.add_argument("--pack", type=int, default=None)
+    ap.add_argument("--group", type=int, default=None, help="FS_OPT_TILE_GROUP for --one (default: library default)")
+    ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     rng = np.random.default_rng(0)
     if args.one:
         diag, nf, ns, d = args.one
-        print(json.dumps(run_case(nf, ns, d, 3, rng, diag=diag, pair=args.pair, pack=args.pack,
-                                  bits=args.bits)), flush=True)
+        print(json.dumps(run_case(nf, ns, d, args.reps, rng, diag=diag, pair=args.pair, pack=args.pack,
+                                  bits=args.bits, group=args.group, clocks=True)), flush=True)
         return
     if args.f8:
         for bits, diag, d, pack, pair in ((16, 3, 300, 2, 1), (16, 3, 300, 2, 2), (8, 3, 300, 2, 1), (8, 3, 300, 2, 2),
