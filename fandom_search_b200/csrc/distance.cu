@@ -263,7 +263,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                                               const int as, const uint32_t tfull_addr, const uint32_t tempty_addr,
                                               const uint32_t aphase, const uint32_t tmem_base, float* halo,
                                               float2* norm_tile, __half* rowmax, const int warp, const int lane,
-                                              const int tl_tile = 0) {
+                                              const float2 (&mm_pre)[kEpiCols / 32], const int tl_tile = 0) {
     (void)tl_tile;
     constexpr bool kOverlap = kDiag == 6;  // lane quarters hold overlapping fan rows: nothing crosses quarters
     constexpr int kMStep = dist_m_step(kDiag);
@@ -280,6 +280,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     auto pub_at = [&](int q, int slot) -> float* { return halo + (q * kPubSlots + slot) * kHaloCols; };
     // kPack == 2: the whole diagonal sum runs on fp16x2 pairs, and the boundary rows are published as halves
     constexpr bool kHalf = kPack == 2 && (kDiag == 6 || kDiag == 3 || kDiag == 2);
+    const bool early_release = kHalf && (p.group & 2) != 0;
     __half* halo_h = reinterpret_cast<__half*>(halo);
     auto pub_half_at = [&](int q, int slot) -> __half* { return halo_h + (q * kPubSlots + slot) * kHaloCols; };
 
@@ -318,15 +319,29 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     for (int ch = 0; ch < kEpiCols / 32; ++ch) {
         const int c0 = group * kEpiCols + ch * 32;  // first column inside the tile
         __syncwarp();
-        // prefetch the chunk's (min B, max D): the latency hides behind the TMEM load
-        const float2 mm = kDump ? make_float2(0.f, 0.f) : __ldg(p.script_mm32 + n0 + c0);
+        // the chunk's (min B, max D), loaded by the caller one tile ahead (an L2 round trip per chunk
+        // sat on this warp's critical path when it was loaded here)
+        const float2 mm = kDump ? make_float2(0.f, 0.f) : mm_pre[ch];
         if (!kHalf) load_chunk(ch);
         tmem_ld_wait();
         uint32_t pk[20];
         if (kHalf) {
 #pragma unroll
             for (int k = 0; k < 20; ++k) pk[k] = pack_h2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
-            if (ch + 1 < kEpiCols / 32) load_chunk(ch + 1);
+            if (ch + 1 < kEpiCols / 32) {
+                load_chunk(ch + 1);
+            } else if (early_release) {
+                // the last accumulator column of this warp is packed: hand the TMEM stage back NOW, so
+                // that the next MMAs into it are issued under the sums and tests of this chunk
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (kPair)
+                        mbar_arrive_leader(tempty_addr);
+                    else
+                        mbar_arrive(tempty_addr);
+                }
+            }
         }
         if (kDiag > 1 && pub_slot >= 0) {
             if (kHalf) {
@@ -355,14 +370,27 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                 const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
                 return *reinterpret_cast<const uint32_t*>(&m);
             };
-            uint32_t m = pk[0];
+            // Two maxima per row: outputs x < 16 only read columns [0, 21) and outputs x >= 16 only
+            // columns [16, 37), so m = half2(max of columns 0..23, max of columns 16..39) bounds the two
+            // halves of the chunk separately, in the SAME three shuffles -- on text that shares its
+            // frequent words with the script (large single dots scattered over the chunk) far fewer
+            // chunks reach the full diagonal sum.
+            uint32_t ma = pk[0], mb = pk[8], mc = pk[12];
 #pragma unroll
-            for (int k = 1; k < 20; ++k) m = hmax(m, pk[k]);
-            m = hmax(m, __byte_perm(m, m, 0x1032));  // both halves = the row maximum
-            // boundary rows also publish it: the boundary pass rejects its chunks the same way
-            if (kDiag > 1 && !kOverlap && pub_slot >= 0)
+            for (int k = 1; k < 8; ++k) ma = hmax(ma, pk[k]);        // columns 0..15
+#pragma unroll
+            for (int k = 9; k < 12; ++k) mb = hmax(mb, pk[k]);       // columns 16..23
+#pragma unroll
+            for (int k = 13; k < 20; ++k) mc = hmax(mc, pk[k]);      // columns 24..39
+            const uint32_t m_lo = hmax(ma, mb), m_hi = hmax(mb, mc);
+            const uint32_t m = hmax(__byte_perm(m_lo, m_hi, 0x5410), __byte_perm(m_lo, m_hi, 0x7632));
+            // boundary rows publish the maximum of the whole row: the boundary pass rejects its chunks
+            // the same way
+            if (kDiag > 1 && !kOverlap && pub_slot >= 0) {
+                const uint32_t m_all = hmax(m, __byte_perm(m, m, 0x1032));
                 reinterpret_cast<uint16_t*>(rowmax)[(quarter * kPubSlots + pub_slot) * 8 + (c0 >> 5)] =
-                    static_cast<uint16_t>(m & 0xffffu);
+                    static_cast<uint16_t>(m_all & 0xffffu);
+            }
             uint32_t bsum;
             if (kDiag == 6) {
                 const uint32_t b01 = h2_add(m, __shfl_down_sync(0xffffffffu, m, 1));
@@ -372,7 +400,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
             } else {
                 bsum = h2_add(m, __shfl_down_sync(0xffffffffu, m, 1));
             }
-            if (!__any_sync(0xffffffffu, h2_lo(bsum) > thr_chunk)) continue;
+            if (!__any_sync(0xffffffffu, h2_lo(bsum) > thr_chunk || h2_hi(bsum) > thr_chunk)) continue;
         }
         float mx;
         uint32_t o16[16];
@@ -418,13 +446,15 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     }
     // every accumulator column of this warp is in registers: release the TMEM stage
     FS_TL(2 + warp, tl_tile, 2);
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-        if (kPair)
-            mbar_arrive_leader(tempty_addr);  // the leader's MMA waits for both CTAs
-        else
-            mbar_arrive(tempty_addr);
+    if (!early_release) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            if (kPair)
+                mbar_arrive_leader(tempty_addr);  // the leader's MMA waits for both CTAs
+            else
+                mbar_arrive(tempty_addr);
+        }
     }
     if (kDiag > 1 && !kOverlap) {
         // boundary rows: tail rows of quarters 0..2 (quarter 3's belong to the next tile)
@@ -595,7 +625,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
     // block of MMAs per tile instead of one per chunk (its instruction stream, ~85 instructions per
     // chunk, was what paced the kernel: profiles/r01_timeline_s2.txt).  The ring starts right behind the
     // resident chunks actually used and holds n_groups tiles.
-    const bool grouped = kARes && kOverlap && p.group != 0 && p.chunks <= kGroupMaxChunks;
+    const bool grouped = kARes && kOverlap && (p.group & 1) != 0 && p.chunks <= kGroupMaxChunks;
     const uint32_t group_ring = smem_a_res + static_cast<uint32_t>(p.chunks) * kStageABytes;
     const int n_groups_fit = (kAResBytes - p.chunks * kStageABytes + kNumStages * kStageSz) / (p.chunks * kStageSz);
     const int n_groups = n_groups_fit < kNumStages ? n_groups_fit : kNumStages;
@@ -728,6 +758,8 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
                 mbar_wait_warp(afull_bar, a_phase, 0);  // the resident fan tile has landed (both CTAs)
                 a_phase ^= 1u;
             }
+            // (every lane polls, no naps: this wait is on the accumulator round trip -- one polling
+            // lane napping 20 ns cost 10 %, profiles/r01_sweep_early.jsonl)
             mbar_wait_all(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
             FS_TL(1, tl_tile, 1);
@@ -876,18 +908,35 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
         // kPack == 2: two half-precision boundary-row buffers, one per accumulator stage
         constexpr bool kHalfRows = kPack == 2 && (kDiag == 6 || kDiag == 3 || kDiag == 2);
         int tl_tile = -1;
-        while (walk.next(tile)) {
+        // (min B, max D) of this warp's 32-column chunks, fetched one tile ahead of its use
+        auto load_mm = [&](const Tile& t, float2 (&mm)[kEpiCols / 32]) {
+#pragma unroll
+            for (int ch = 0; ch < kEpiCols / 32; ++ch)
+                mm[ch] = kDump ? make_float2(0.f, 0.f)
+                               : __ldg(p.script_mm32 + t.n0 + (warp >> 2) * kEpiCols + ch * 32);
+        };
+        Tile next_tile;
+        float2 mm_cur[kEpiCols / 32], mm_next[kEpiCols / 32];
+        bool have = walk.next(tile);
+        if (have) load_mm(tile, mm_cur);
+        while (have) {
+            const bool have_next = walk.next(next_tile);
+            if (have_next) load_mm(next_tile, mm_next);
             ++tl_tile;
             FS_TL(2 + warp, tl_tile, 0);
             float* halo_t = halo + (kHalfRows ? as * (dist_pub_bytes(kDiag) / 8) : 0);
             __half* rowmax_t = rowmax_base + as * (dist_rowmax_bytes(kDiag) / 4);
             epilogue_tile<kDiag, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
-                                                      aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane, tl_tile);
+                                                      aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane, mm_cur, tl_tile);
             FS_TL(2 + warp, tl_tile, 3);
             if (++as == kAccumStages) {
                 as = 0;
                 aphase ^= 1u;
             }
+            have = have_next;
+            tile = next_tile;
+#pragma unroll
+            for (int ch = 0; ch < kEpiCols / 32; ++ch) mm_cur[ch] = mm_next[ch];
         }
     }
 

@@ -100,10 +100,12 @@ enum {
                                     (tcgen05.mma.kind::f8f6f4; the rounding error of every window is
                                     measured and enters its pre-filter threshold, so the candidates stay
                                     a guaranteed superset; CTA pairs only).  Re-converts the index.   */
-    FS_OPT_TILE_GROUP = 10,      /* 1 (default): with the resident fan tile, E = 6 and an embedding of at
-                                    most three 128-byte chunks per row, all chunks of a script tile land
-                                    on one barrier and are issued as one block of MMAs; 0: one stage,
-                                    one barrier and one issue block per chunk                        */
+    FS_OPT_TILE_GROUP = 10,      /* bit 0 (default on): with the resident fan tile, E = 6 and an embedding
+                                    of at most three 128-byte chunks per row, all chunks of a script tile
+                                    land on one barrier and are issued as one block of MMAs (off: one
+                                    stage, one barrier and one issue block per chunk); bit 1 (default
+                                    on): the fp16x2 epilogue hands the accumulator back as soon as its
+                                    last column is packed, before the sums                          */
     FS_OPT_DIAG = 4              /* 1 (dense), 2, 3 or 6: the tensor cores accumulate window/E shifts
                                     and the epilogue adds E diagonal neighbours (same products,
                                     E-fold fewer tensor-core flops)                            */
@@ -144,7 +146,7 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value);
  * FS_MATCH_LSH_SHIFT.  n_tables = 0 switches the mode off. */
 int fs_index_set_lsh(fs_index* idx, const double* normals, int32_t n_tables, int32_t n_bits);
 /* what = 0: script windows, 1: dim_pad, 2: SM count, 3: candidate capacity, 4: shifts per stage,
- * 5: diagonal factor, 6: CTA pair, 7: A-resident, 8: pack level, 11: operand bits */
+ * 5: diagonal factor, 6: CTA pair, 7: A-resident, 8: pack level, 11: operand bits, 12: tile-group bits */
 int64_t fs_index_get_info(const fs_index* idx, int32_t what);
 
 /*
