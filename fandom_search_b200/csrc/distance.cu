@@ -263,7 +263,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                                               const int as, const uint32_t tfull_addr, const uint32_t tempty_addr,
                                               const uint32_t aphase, const uint32_t tmem_base, float* halo,
                                               float2* norm_tile, __half* rowmax, const int warp, const int lane,
-                                              const float2 (&mm_pre)[kEpiCols / 32], const int tl_tile = 0) {
+                                              const int tl_tile = 0) {
     (void)tl_tile;
     constexpr bool kOverlap = kDiag == 6;  // lane quarters hold overlapping fan rows: nothing crosses quarters
     constexpr int kMStep = dist_m_step(kDiag);
@@ -319,9 +319,9 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     for (int ch = 0; ch < kEpiCols / 32; ++ch) {
         const int c0 = group * kEpiCols + ch * 32;  // first column inside the tile
         __syncwarp();
-        // the chunk's (min B, max D), loaded by the caller one tile ahead (an L2 round trip per chunk
-        // sat on this warp's critical path when it was loaded here)
-        const float2 mm = kDump ? make_float2(0.f, 0.f) : mm_pre[ch];
+        // prefetch the chunk's (min B, max D): the latency hides behind the TMEM load.  (Fetching it
+        // one tile ahead in the caller changed nothing and cost 8 live registers -> spills.)
+        const float2 mm = kDump ? make_float2(0.f, 0.f) : __ldg(p.script_mm32 + n0 + c0);
         if (!kHalf) load_chunk(ch);
         tmem_ld_wait();
         uint32_t pk[20];
@@ -908,35 +908,18 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
         // kPack == 2: two half-precision boundary-row buffers, one per accumulator stage
         constexpr bool kHalfRows = kPack == 2 && (kDiag == 6 || kDiag == 3 || kDiag == 2);
         int tl_tile = -1;
-        // (min B, max D) of this warp's 32-column chunks, fetched one tile ahead of its use
-        auto load_mm = [&](const Tile& t, float2 (&mm)[kEpiCols / 32]) {
-#pragma unroll
-            for (int ch = 0; ch < kEpiCols / 32; ++ch)
-                mm[ch] = kDump ? make_float2(0.f, 0.f)
-                               : __ldg(p.script_mm32 + t.n0 + (warp >> 2) * kEpiCols + ch * 32);
-        };
-        Tile next_tile;
-        float2 mm_cur[kEpiCols / 32], mm_next[kEpiCols / 32];
-        bool have = walk.next(tile);
-        if (have) load_mm(tile, mm_cur);
-        while (have) {
-            const bool have_next = walk.next(next_tile);
-            if (have_next) load_mm(next_tile, mm_next);
+        while (walk.next(tile)) {
             ++tl_tile;
             FS_TL(2 + warp, tl_tile, 0);
             float* halo_t = halo + (kHalfRows ? as * (dist_pub_bytes(kDiag) / 8) : 0);
             __half* rowmax_t = rowmax_base + as * (dist_rowmax_bytes(kDiag) / 4);
             epilogue_tile<kDiag, kDump, kPack, kPair>(p, tile.m0, tile.n0, as, tfull_bar(as), tempty_bar(as),
-                                                      aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane, mm_cur, tl_tile);
+                                                      aphase, tmem_base, halo_t, norm_tile, rowmax_t, warp, lane, tl_tile);
             FS_TL(2 + warp, tl_tile, 3);
             if (++as == kAccumStages) {
                 as = 0;
                 aphase ^= 1u;
             }
-            have = have_next;
-            tile = next_tile;
-#pragma unroll
-            for (int ch = 0; ch < kEpiCols / 32; ++ch) mm_cur[ch] = mm_next[ch];
         }
     }
 
