@@ -276,6 +276,15 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
     b->tok.alloc(static_cast<size_t>(T));
     b->tok_start.alloc(static_cast<size_t>(T));
     b->tok_end.alloc(static_cast<size_t>(T));
+    // Out-of-vocabulary tokens are collected per file while the text is hot in the tokenising thread's
+    // cache: (token index, length, key) with key = the bytes themselves for words of <= 8 bytes, else
+    // their 64-bit hash.  The serial pass below then only walks these compact lists.
+    struct OovTok {
+        int64_t t;
+        uint64_t key;
+        int32_t len;
+    };
+    std::vector<std::vector<OovTok>> oov_of_file(static_cast<size_t>(n_files));
     parallel_for(n_files, n_threads, [&](int64_t k) {
         const char* text = b->text.data() + b->file_off[k];
         const int64_t len = sizes[k], base = b->file_off[k];
@@ -283,37 +292,77 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
         int32_t* tok = b->tok.data();
         int64_t* st = b->tok_start.data();
         int64_t* en = b->tok_end.data();
+        std::vector<OovTok>& oov = oov_of_file[static_cast<size_t>(k)];
         int64_t i = 0;
         while (i < len) {
             while (i < len && is_ws(static_cast<unsigned char>(text[i]))) ++i;
             if (i >= len) break;
             const int64_t s = i;
             while (i < len && !is_ws(static_cast<unsigned char>(text[i]))) ++i;
-            tok[o] = v->find(text + s, i - s, true);  // -1 = OOV for now
+            const int64_t n = i - s;
+            const int32_t row = v->find(text + s, n, true);  // -1 = OOV for now
+            tok[o] = row;
             st[o] = base + s;
             en[o] = base + i;
+            if (row < 0) {
+                uint64_t key;
+                if (n <= 8) {
+                    memcpy(&key, text + s, 8);  // (the text buffer has 8 bytes of slack)
+                    if (n < 8) key &= (1ULL << (8 * n)) - 1;
+                } else {
+                    key = hash_bytes(text + s, n);
+                }
+                oov.push_back(OovTok{o, key, static_cast<int32_t>(n > INT32_MAX ? INT32_MAX : n)});
+            }
             ++o;
         }
     });
     lap("tokenise+lookup");
-    // serial pass over the OOV tokens only: number the unique strings in order of appearance
-    std::unordered_map<std::string, int32_t> uniq;
+    // Serial pass over the OOV tokens only: number the unique strings in order of appearance (files in
+    // order, tokens in order).  Open addressing on (length, key); long words are verified against the
+    // bytes of their first occurrence.
+    struct OovSlot {
+        uint64_t key;
+        int64_t first_start;
+        int32_t len;  // 0 = empty
+        int32_t id;
+    };
+    std::vector<OovSlot> table(4096, OovSlot{0, 0, 0, 0});
+    uint64_t tmask = table.size() - 1;
     const char* text = b->text.data();
-    for (int64_t t = 0; t < T; ++t) {
-        if (b->tok.data()[t] >= 0) continue;
-        const int64_t s = b->tok_start.data()[t], e = b->tok_end.data()[t];
-        std::string key(text + s, static_cast<size_t>(e - s));
-        auto it = uniq.find(key);
-        int32_t u;
-        if (it == uniq.end()) {
-            u = static_cast<int32_t>(uniq.size());
-            uniq.emplace(std::move(key), u);
-            b->oov_start.push_back(s);
-            b->oov_end.push_back(e);
-        } else {
-            u = it->second;
+    auto slot_of = [&](const std::vector<OovSlot>& tab, uint64_t mask, uint64_t key, int32_t len, int64_t start) {
+        uint64_t sl = fs_vocab::mix(key + static_cast<uint64_t>(len)) & mask;
+        while (true) {
+            const OovSlot& e = tab[sl];
+            if (e.len == 0) return sl;
+            if (e.len == len && e.key == key &&
+                (len <= 8 || memcmp(text + e.first_start, text + start, static_cast<size_t>(len)) == 0))
+                return sl;
+            sl = (sl + 1) & mask;
         }
-        b->tok.data()[t] = -(1 + u);
+    };
+    for (int64_t k = 0; k < n_files; ++k) {
+        for (const OovTok& w : oov_of_file[static_cast<size_t>(k)]) {
+            const int64_t s = b->tok_start.data()[w.t];
+            const int64_t wlen = b->tok_end.data()[w.t] - s;
+            const int32_t len = static_cast<int32_t>(wlen > INT32_MAX ? INT32_MAX : wlen);
+            uint64_t sl = slot_of(table, tmask, w.key, len, s);
+            if (table[sl].len == 0) {
+                table[sl] = OovSlot{w.key, s, len, static_cast<int32_t>(b->oov_start.size())};
+                b->oov_start.push_back(s);
+                b->oov_end.push_back(s + wlen);
+                if (b->oov_start.size() * 2 > table.size()) {  // grow and re-insert
+                    std::vector<OovSlot> bigger(table.size() * 4, OovSlot{0, 0, 0, 0});
+                    const uint64_t bmask = bigger.size() - 1;
+                    for (const OovSlot& e : table)
+                        if (e.len != 0) bigger[slot_of(bigger, bmask, e.key, e.len, e.first_start)] = e;
+                    table.swap(bigger);
+                    tmask = bmask;
+                    sl = slot_of(table, tmask, w.key, len, s);
+                }
+            }
+            b->tok.data()[w.t] = -(1 + table[sl].id);
+        }
     }
     lap("oov");
     return b;

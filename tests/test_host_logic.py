@@ -171,6 +171,38 @@ def test_native_vocab_short_and_long_keys(tmp_path):
         assert t == (keys[w] if w in keys else -(1 + oov.index(w))), w
 
 
+def test_native_oov_numbering_many_and_long_words(tmp_path):
+    """Unique out-of-vocabulary strings are numbered in order of first appearance over the batch
+    (files in order): several thousand of them (the table grows), lengths 1..30, words that share
+    their first 8 bytes, across three files tokenised by different threads."""
+    import types
+    import numpy as np
+    from fandom_search_b200 import text
+    rng = np.random.default_rng(5)
+    known = {"k%d" % i: i for i in range(50)}
+    pool = []
+    for i in range(6000):
+        n = int(rng.integers(1, 31))
+        pool.append(("q%dé" % i + "abcdefgh" * 4)[:n] if i % 3 else "samehead" + str(i))
+    pool = [w for w in dict.fromkeys(pool) if w not in known]
+    files = []
+    all_words = []
+    for f in range(3):
+        words = [pool[int(j)] if rng.random() < 0.7 else "k%d" % int(rng.integers(0, 50))
+                 for j in rng.integers(0, len(pool), 9000)]
+        (tmp_path / ("f%d.txt" % f)).write_text(" ".join(words), encoding="utf-8")
+        files.append(str(tmp_path / ("f%d.txt" % f)))
+        all_words += words
+    vocab = text.Vocab(types.SimpleNamespace(key_to_row=known))
+    b = vocab.encode_files(files, threads=3)
+    want_oov = list(dict.fromkeys(w for w in all_words if w not in known))
+    assert len(want_oov) > 2048
+    assert b.oov_strings() == want_oov
+    index = {w: i for i, w in enumerate(want_oov)}
+    want_tok = [known[w] if w in known else -(1 + index[w]) for w in all_words]
+    assert b.tok.tolist() == want_tok
+
+
 def test_multi_script_pass_equals_separate_runs(cpu_device, golden_dir, tmp_path, monkeypatch):
     """N4: indexing two scripts side by side and searching once == two single-script runs."""
     lines = open(os.path.join(golden_dir, "script.txt"), encoding="utf-8").read().splitlines()
