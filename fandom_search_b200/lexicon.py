@@ -159,6 +159,18 @@ class Lexicon:
             m[i, list(idx)] = 1.0
         return m
 
+    def oov_rows_at(self, ids):
+        """float32 [len(ids), d] 3-hot rows of the OOV registry entries `ids` (registry indices,
+        i.e. row id - n_rows), built with three vectorised scatters."""
+        ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+        m = np.zeros((len(ids), self.dim), dtype=np.float32)
+        if len(ids):
+            hot = np.array([self._oov_hot[int(i)] for i in ids], dtype=np.int64).reshape(len(ids), 3)
+            rows = np.arange(len(ids))
+            for k in range(3):
+                m[rows, hot[:, k]] = 1.0
+        return m
+
     def vector(self, text):
         """float32 row exactly as mk_vectors would fill it (search.py:73-83)."""
         r = self.row_id(text)

@@ -271,15 +271,25 @@ class AnnIndexSearch(object):
                 self.spacy_model._vocab = _text.Vocab(lex)
             batch = self.spacy_model._vocab.encode_files(filenames)
             tok = numpy.array(batch.tok, dtype=numpy.int32)        # private copy
+            offs = numpy.array(batch.tok_off, dtype=numpy.int64)
+            extra = None
             if len(batch.oov_start):
+                # only the OOV positions are touched (a few % of the tokens): registry ids of the
+                # batch's unique OOV strings, then batch-local numbering of the fan-side OOV rows
                 oov_ids = numpy.array([lex.row_id(w) for w in batch.oov_strings()], dtype=numpy.int32)
-                neg = tok < 0
-                tok[neg] = oov_ids[-tok[neg] - 1]
-        else:
-            fans = [self._tokenize_file(fn) for fn in filenames]
-            batch = _text.Batch.from_token_lists(fans)
-            tok = numpy.concatenate([lex.row_ids(f) for f in fans] +
-                                    [numpy.zeros(0, numpy.int32)]).astype(numpy.int32)
+                pos = numpy.flatnonzero(tok < 0)
+                ids = oov_ids[-tok[pos] - 1]
+                is_new = ids >= n_fixed
+                if is_new.any():
+                    uniq, inv = numpy.unique(ids[is_new], return_inverse=True)
+                    ids[is_new] = (n_fixed + inv).astype(numpy.int32)
+                    extra = lex.oov_rows_at(uniq.astype(numpy.int64) - lex.n_rows)
+                tok[pos] = ids
+            return {'filenames': list(filenames), 'batch': batch, 'tok': tok, 'offs': offs, 'extra': extra}
+        fans = [self._tokenize_file(fn) for fn in filenames]
+        batch = _text.Batch.from_token_lists(fans)
+        tok = numpy.concatenate([lex.row_ids(f) for f in fans] +
+                                [numpy.zeros(0, numpy.int32)]).astype(numpy.int32)
         offs = numpy.array(batch.tok_off, dtype=numpy.int64)
         # batch-local numbering of the fan-side OOV rows
         extra = None
@@ -287,8 +297,7 @@ class AnnIndexSearch(object):
         if is_new.any():
             uniq, inv = numpy.unique(tok[is_new], return_inverse=True)
             tok[is_new] = (n_fixed + inv).astype(numpy.int32)
-            extra = numpy.concatenate(
-                [lex.oov_rows(int(u) - lex.n_rows, int(u) - lex.n_rows + 1) for u in uniq], axis=0)
+            extra = lex.oov_rows_at(uniq.astype(numpy.int64) - lex.n_rows)
         return {'filenames': list(filenames), 'batch': batch, 'tok': tok, 'offs': offs, 'extra': extra}
 
     def run_prepared(self, prep):
