@@ -609,20 +609,27 @@ def analyze(args,
         return i
 
     import collections
-    with ThreadPoolExecutor(max_workers=1) as prep_pool, ThreadPoolExecutor(max_workers=1) as post_pool:
-        pending = prep_pool.submit(ann_index.prepare, mine[0][1]) if mine else None
-        in_flight = collections.deque()      # at most two clusters' buffers are alive at a time
-        for k, (i, fan_cluster) in enumerate(mine):
-            print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
-            prep = pending.result()
-            pending = prep_pool.submit(ann_index.prepare, mine[k + 1][1]) if k + 1 < len(mine) else None
-            found = ann_index.search_prepared(prep)
-            in_flight.append(post_pool.submit(finish, i, prep, found))
-            del prep, found
-            while len(in_flight) > 2:
+    # The GPU-driving thread re-takes the GIL after every native call; with the default 5 ms switch
+    # interval it would wait that long behind the Python parts of the two helper threads.
+    switch_interval = sys.getswitchinterval()
+    sys.setswitchinterval(2e-4)
+    try:
+        with ThreadPoolExecutor(max_workers=1) as prep_pool, ThreadPoolExecutor(max_workers=1) as post_pool:
+            pending = prep_pool.submit(ann_index.prepare, mine[0][1]) if mine else None
+            in_flight = collections.deque()      # at most two clusters' buffers are alive at a time
+            for k, (i, fan_cluster) in enumerate(mine):
+                print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
+                prep = pending.result()
+                pending = prep_pool.submit(ann_index.prepare, mine[k + 1][1]) if k + 1 < len(mine) else None
+                found = ann_index.search_prepared(prep)
+                in_flight.append(post_pool.submit(finish, i, prep, found))
+                del prep, found
+                while len(in_flight) > 2:
+                    in_flight.popleft().result()
+            while in_flight:
                 in_flight.popleft().result()
-        while in_flight:
-            in_flight.popleft().result()
+    finally:
+        sys.setswitchinterval(switch_interval)
 
     if world > 1:
         # every rank has written its own batch files (same directory, one node): rank 0 only has
