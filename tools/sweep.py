@@ -22,12 +22,16 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
-    if pair == 0:
-        bits = 16      # fp8 operands exist for CTA pairs only
-    idx.set_option(nt.FS_OPT_OPERAND_BITS, bits)
-    idx.set_option(nt.FS_OPT_DIAG, diag)
-    idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
-    idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
+    if diag is None:
+        # library defaults (what search.py runs): fp8, E = 6, CTA pairs, resident fan tile where it fits
+        diag, pair, bits = idx.diag, 2 if idx.info(7) else idx.cta_pair, idx.operand_bits
+    else:
+        if pair == 0:
+            bits = 16      # fp8 operands exist for CTA pairs only
+        idx.set_option(nt.FS_OPT_OPERAND_BITS, bits)
+        idx.set_option(nt.FS_OPT_DIAG, diag)
+        idx.set_option(nt.FS_OPT_CTA_PAIR, 1 if pair else 0)
+        idx.set_option(nt.FS_OPT_A_RESIDENT, 1 if pair == 2 else 0)
     if pack is not None:
         idx.set_option(nt.FS_OPT_PACKED_SHUFFLE, pack)
     if group is not None:
@@ -58,7 +62,8 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     clk = sampler.stop() if sampler else None
     windows = int(cnt_t.cpu()[nt.FS_CNT_WINDOWS])
     per = ms / n * 1e-3
-    exec_factor = (6 // diag) * (128.0 * 256.0) / ((129 - diag) * (257 - diag))
+    m_step = 108 if diag == 6 else 129 - diag      # E = 6: overlapping lane quarters
+    exec_factor = (6 // diag) * (128.0 * 256.0) / (m_step * (257 - diag))
     res = {"bits": bits, "candidates": int(cnt_t.cpu()[nt.FS_CNT_CANDIDATES]), "matches": int(cnt_t.cpu()[nt.FS_CNT_MATCHES]),
            "diag": diag, "pair": pair, "pack": pack, "group": group, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
            "kernel_ms": ms / n, "windows_per_s": windows / per, "clocks": clk,
@@ -73,6 +78,7 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--defaults", action="store_true", help="the C5 grid with the library's default kernel")
     ap.add_argument("--diag", action="store_true", help="compare the diagonal-sum factors at C2 size")
     ap.add_argument("--bits", type=int, default=8, help="operand bits for --one (8 = fp8 e4m3, 16 = fp16)")
     ap.add_argument("--f8", action="store_true", help="fp8 e4m3 operands vs fp16 at C2 size, all diagonal factors")
@@ -87,6 +93,14 @@ def main():
         diag, nf, ns, d = args.one
         print(json.dumps(run_case(nf, ns, d, args.reps, rng, diag=diag, pair=args.pair, pack=args.pack,
                                   bits=args.bits, group=args.group, clocks=True)), flush=True)
+        return
+    if args.defaults:
+        for d in (300, 768):
+            for ns in (1000, 10000, 100000):
+                for nf in (100_000, 1_000_000, 10_000_000):
+                    if nf * ns * d > 3.1e15:
+                        continue
+                    print(json.dumps(run_case(nf, ns, d, 3, rng, diag=None)), flush=True)
         return
     if args.f8:
         for bits, diag, d, pack, pair in ((16, 3, 300, 2, 1), (16, 3, 300, 2, 2), (8, 3, 300, 2, 1), (8, 3, 300, 2, 2),
