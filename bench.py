@@ -22,7 +22,8 @@ Numbers on the JSON line
             window (nominal d): with the diagonal factor E = 3 the tensor cores accumulate 2 of
             the 6 window shifts and the epilogue adds 3 diagonal neighbours, so the same
             products cost E times fewer tensor flops.  Per SURVEY 8d the two numbers are kept
-            apart: `frac` is a tensor-pipe roofline fraction; `algorithmic_advantage` =
+            apart: `frac` is a tensor-pipe roofline fraction (useful flops only; `issued_tflops`
+            adds the flops spent on tile overlap and row padding); `algorithmic_advantage` =
             windows/s / (peak / F_dense), F_dense = 2*(6*300)*24995, is NOT a roofline fraction
   cpu_baseline  the oracle's port of the reference algorithm (per-window LSH loop over the nearpy
             stand-in) on a bounded sample of the same workload, on this box's host cores
@@ -464,6 +465,12 @@ def run_native_arm(args):
     launch_s = kernel_ms / max(launches, 1) * 1e-3
     achieved_tflops = f_exec * win_per_launch / launch_s / 1e12 if launches else 0.0
     dense_equiv_tflops = f_dense * win_per_launch / launch_s / 1e12 if launches else 0.0
+    # tensor-core flops the kernel ISSUES per useful (executed) flop: tiles overlap by E-1 rows and
+    # columns (E = 6: 108 of 128 rows, overlapping TMEM lane quarters), rows are padded to the K-step
+    m_eff = (108.0 if diag == 6 else 129.0 - diag) / 128.0
+    n_eff = (257.0 - diag) / 256.0
+    k_eff = float(DIM) / float(index.info(1))
+    issue_factor = 1.0 / (m_eff * n_eff * k_eff)
     traffic = None
     prof = os.path.join(ROOT, "profiles", "distance_kernel_ncu_summary.json")
     if os.path.exists(prof):
@@ -521,7 +528,10 @@ def run_native_arm(args):
                          "flop_per_window_executed": f_exec, "flop_per_window_dense": f_dense,
                          "diagonal_factor": diag, "cta_pair": index.cta_pair,
                          "dense_equivalent_tflops": dense_equiv_tflops,
-                         "algorithmic_advantage": dense_equiv_tflops / roof["sustained"]},
+                         "algorithmic_advantage": dense_equiv_tflops / roof["sustained"],
+                         "issued_tflops": achieved_tflops * issue_factor,
+                         "issued_frac": achieved_tflops * issue_factor / roof["sustained"],
+                         "useful_share_of_issued": 1.0 / issue_factor},
             "cpu_baseline": cpu_baseline,
             "cpu_exhaustive_gemm": cpu_exhaustive,
         }
