@@ -301,6 +301,70 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     FS_TL(2 + warp, tl_tile, 1);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                            static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
+    if (kHalf && kDiag == 6 && !kDump && (p.group & 4) != 0) {
+        // Both 32-column chunks of this warp in one pass.  All 72 columns are loaded at once and the
+        // accumulator stage is handed back immediately; the row maxima are taken on the fp32 values
+        // (FMNMX3) and only the two maxima are rounded -- rounding is monotone, so
+        // half(max(a)) == max(half(a)) and the bound is bit for bit the one of the per-chunk pass --
+        // and the 20 fp32 -> fp16x2 packs of a chunk are spent only on a chunk that survives.
+        uint32_t q[72];
+        {
+            const int halo_off = (group * kEpiCols + 64 < kBlockN) ? 64 : 56;  // (see load_chunk below)
+            tmem_ld_32x72(taddr, taddr + halo_off, q);
+        }
+        float2 mm2[2];
+        mm2[0] = __ldg(p.script_mm32 + n0 + group * kEpiCols);
+        mm2[1] = __ldg(p.script_mm32 + n0 + group * kEpiCols + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            if (kPair)
+                mbar_arrive_leader(tempty_addr);
+            else
+                mbar_arrive(tempty_addr);
+        }
+        auto f = [&](int i) { return __uint_as_float(q[i]); };
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int b = 32 * ch;
+            float ma = f(b), mb = f(b + 16), mc = f(b + 24);
+#pragma unroll
+            for (int k = 1; k < 16; ++k) ma = fmaxf(ma, f(b + k));        // columns 0..15
+#pragma unroll
+            for (int k = 17; k < 24; ++k) mb = fmaxf(mb, f(b + k));       // columns 16..23
+#pragma unroll
+            for (int k = 25; k < 40; ++k) mc = fmaxf(mc, f(b + k));       // columns 24..39
+            const uint32_t m = pack_h2(fmaxf(ma, mb), fmaxf(mb, mc));
+            const uint32_t b01 = h2_add(m, __shfl_down_sync(0xffffffffu, m, 1));
+            const uint32_t bsum =
+                h2_add(h2_add(b01, __shfl_down_sync(0xffffffffu, b01, 2)), __shfl_down_sync(0xffffffffu, b01, 4));
+            const float thr_chunk = fmaf(-ac.y, mm2[ch].y, a_main * mm2[ch].x);
+            if (!__any_sync(0xffffffffu, h2_lo(bsum) > thr_chunk || h2_hi(bsum) > thr_chunk)) continue;
+            uint32_t pk[20], o16[16];
+#pragma unroll
+            for (int k = 0; k < 20; ++k) pk[k] = pack_h2(f(b + 2 * k), f(b + 2 * k + 1));
+            const float mx = diag6_half(pk, o16);
+            if (mx > thr_chunk) {
+                const int c0 = group * kEpiCols + b;
+                const int32_t gj0 = n0 + c0;
+#pragma unroll
+                for (int x = 0; x < 32; ++x) {
+                    const float2 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float2(kNaN, kNaN);
+                    const float v = (x & 1) ? h2_hi(o16[x >> 1]) : h2_lo(o16[x >> 1]);
+                    if (v > fmaf(-ac.y, bd.y, a_main * bd.x)) {
+                        const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
+                        if (slot < static_cast<unsigned long long>(p.cand_cap)) {
+                            p.cand[slot].fan_pos = gi;
+                            p.cand[slot].script_pos = gj0 + x;
+                        }
+                    }
+                }
+            }
+        }
+        FS_TL(2 + warp, tl_tile, 2);
+        return;
+    }
     uint32_t r[40];
     auto load_chunk = [&](int ch) {
         if (kDiag > 1) {

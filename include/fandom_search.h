@@ -105,7 +105,10 @@ enum {
                                     land on one barrier and are issued as one block of MMAs (off: one
                                     stage, one barrier and one issue block per chunk); bit 1 (default
                                     on): the fp16x2 epilogue hands the accumulator back as soon as its
-                                    last column is packed, before the sums                          */
+                                    last column is packed, before the sums; bit 2 (default on, E = 6):
+                                    an epilogue warp loads both of its 32-column chunks at once, hands
+                                    the accumulator back, takes the row maxima on the fp32 values and
+                                    packs to fp16x2 only the chunks that survive the bound          */
     FS_OPT_DIAG = 4              /* 1 (dense), 2, 3 or 6: the tensor cores accumulate window/E shifts
                                     and the epilogue adds E diagonal neighbours (same products,
                                     E-fold fewer tensor-core flops)                            */

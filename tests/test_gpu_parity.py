@@ -172,7 +172,7 @@ def test_library_defaults():
     table, sx, fx, script, tok, off = _case(5)
     idx = _device_index(table, script, extra=sx, bits=None)
     assert idx.operand_bits == 8 and idx.diag == 6 and idx.cta_pair == 1 and idx.info(7) == 1 and idx.info(8) == 2
-    assert idx.info(12) == 3          # grouped stages + early accumulator release
+    assert idx.info(12) == 7          # grouped stages + early accumulator release + one-pass epilogue
     want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
     got, _ = idx.search_host(tok, off, fx)
     assert _pairs(got) == _pairs(want)
@@ -369,12 +369,13 @@ def test_fp8_resident_fan_tile(diag):
 @pytest.mark.parametrize("dim", [300, 200, 100])
 def test_grouped_stages_and_early_release(dim):
     """FS_OPT_TILE_GROUP: one barrier pair and one block of MMAs per script tile (bit 0), accumulator
-    handed back before the sums (bit 1).  dim 300/200/100 = 3/2/1 chunks per row with 2/3/4 K-steps
+    handed back before the sums (bit 1), both chunks of a warp in one pass with fp32 row maxima
+    (bit 2).  dim 300/200/100 = 3/2/1 chunks per row with 2/3/4 K-steps
     in the last one; a 4-CTA grid makes every CTA wrap its ring of tile groups many times."""
     table, sx, fx, script, tok, off = _case(11, dim=dim, works=(900, 3, 0, 6, 1400, 700))
     want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
     dots = {}
-    for group in (0, 1, 2, 3):
+    for group in (0, 1, 2, 3, 4, 7):
         for grid in (0, 4):
             idx = _f8_index(table, script, sx, 6)
             idx.set_option(nt.FS_OPT_A_RESIDENT, 1)
