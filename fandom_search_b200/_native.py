@@ -22,7 +22,10 @@ FS_CNT_CANDIDATES = 0
 FS_CNT_MATCHES = 1
 FS_CNT_EXACT = 2
 FS_CNT_WINDOWS = 3
-FS_CNT_COUNT = 4
+FS_CNT_OVERFLOW = 4
+FS_CNT_COUNT = 5
+FS_OVERFLOW_CANDIDATES = 1
+FS_OVERFLOW_MATCHES = 2
 
 FS_OPT_SHIFTS_PER_STAGE = 1
 FS_OPT_GRID_LIMIT = 3
@@ -32,6 +35,7 @@ FS_OPT_A_RESIDENT = 6
 FS_OPT_PACKED_SHUFFLE = 7
 FS_OPT_OPERAND_BITS = 9
 FS_OPT_TILE_GROUP = 10
+FS_OPT_PREFILTER_DIMS = 11
 
 FS_MATCH_EXACT = 1
 FS_MATCH_LSH_SHIFT = 8
@@ -59,6 +63,8 @@ SIGNATURES = {
     "fs_index_get_info": (_i64, [_vp, _i32]),
     "fs_search_csr_dev": (ctypes.c_int, [_vp, _vp] + _BATCHX + [_vp, _i64, _vp]),
     "fs_search_csr_host": (ctypes.c_int, [_vp] + _BATCHX + [_vp, _i64, _vp]),
+    "fs_search_submit": (ctypes.c_int, [_vp] + _BATCHX + [_i64, ctypes.POINTER(_i32)]),
+    "fs_search_collect": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp]),
     "fs_exact_join_dev": (ctypes.c_int, [_vp, _vp] + _BATCH + [_vp, _i64, _vp]),
     "fs_exact_join_host": (ctypes.c_int, [_vp] + _BATCH + [_vp, _i64, _vp]),
     "fs_stage_embed_dev": (ctypes.c_int, [_vp, _vp] + _BATCHX + [_vp, _vp]),
@@ -85,6 +91,8 @@ SIGNATURES = {
     "fs_format_py_float": (_i64, [_f64, ctypes.c_char_p, _i64]),
     "fs_records_best": (_i64, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64,
                                _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "fs_records_best_mt": (_i64, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32]),
 }
 
 _lib = None
@@ -110,7 +118,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.fs_abi_version() != 1:
+    if lib.fs_abi_version() != 2:
         raise RuntimeError("libfandom_search.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1,4 +1,5 @@
 // C ABI of the reuse-search hot path (see include/fandom_search.h).
+#include <algorithm>
 #include <cstdarg>
 #include <new>
 #include <vector>
@@ -27,6 +28,8 @@ constexpr int kTimingRing = 256;
 // slack covers what is left: fp32 accumulation order in the tensor core and the fp16x2 epilogue
 // sums (<= 2^-9 |f||s|).
 constexpr double kEpsAccum = 3.0e-3;
+// automatic choice of the pre-filter columns: keep this share of the table's energy (choose_kept_columns)
+constexpr double kAutoKeepEnergy = 0.83;
 // largest scaled row norm of an fp8 table: window token dots, |sum| <= window * norm^2, must still
 // fit the fp16 range of the packed epilogue (norm = 95.7 for 6-gram windows)
 inline float f8_row_norm(int32_t window) { return std::sqrt(55000.0f / static_cast<float>(window)); }
@@ -79,6 +82,12 @@ struct fs_index {
     bool ready = false;         // operand tables built (false after a failed re-conversion)
     float row_limit_sq = 0.f;   // squared norm of the longest scaled row of the index
     int32_t operand_bits = 8;   // 16: fp16 operands, 8: fp8 e4m3 operands (default)
+    int32_t prefilter_auto = 0; // 1: prefilter_dims == 0 picks the kept columns by energy share; 0: keeps all
+    int32_t prefilter_dims = 0; // FS_OPT_PREFILTER_DIMS: embedding columns kept in the operand rows (0 = auto)
+    int32_t kept_dims = 0;      // columns actually kept (<= dim), in the order of `perm`
+    int32_t* perm = nullptr;    // [dim] source column of operand element c: columns by descending energy
+    double* col_energy = nullptr;  // [dim] sum of squares per column over the table and the script extras
+    double kept_energy = 1.0;   // share of the table's energy in the kept columns
     int64_t n_extra_rows = 0;
     double threshold = 0.1;
     float scale = 1.f;
@@ -86,10 +95,10 @@ struct fs_index {
 
     float* table32 = nullptr;
     __half* table16 = nullptr;
-    float2* table_sq = nullptr;
+    float4* table_sq = nullptr;   // per row (norm^2, kept rounding error^2, dropped^2, -) of the scaled row
     float* sx32 = nullptr;
     __half* sx16 = nullptr;
-    float2* sx_sq = nullptr;
+    float4* sx_sq = nullptr;
 
     int32_t* script_tok = nullptr;
     int64_t n_script_tok = 0;
@@ -97,9 +106,9 @@ struct fs_index {
     int32_t n_scripts = 0;
     int64_t n_script_windows = 0;
     __half* script_emb = nullptr;
-    float2* script_tok_sq = nullptr;
-    float2* script_norm = nullptr;      // (B_j, D_j) per script window start
-    float2* script_norm_min = nullptr;  // (min B, max D) over 32 columns
+    float4* script_tok_sq = nullptr;
+    float4* script_norm = nullptr;      // (B_j, D_j, H_j) per script window start
+    float4* script_norm_min = nullptr;  // (min B, max D, max H) over 32 columns
     int32_t tiles_n = 0;
     CUtensorMap map_script;
     CUtensorMap map_script128;  // boxes of 128 rows (E = 6: no halo rows)
@@ -112,15 +121,15 @@ struct fs_index {
     int64_t emb_cap = 0;  // elements of fan_emb
     __half* fan_emb = nullptr;
     int64_t sq_cap = 0;
-    float2* fan_tok_sq = nullptr;
+    float4* fan_tok_sq = nullptr;
     int64_t thr_cap = 0;
-    float2* fan_thr = nullptr;  // (A_i, C_i) per fan window start
+    float4* fan_thr = nullptr;  // (A_i, C_i, G_i) per fan window start
     int64_t cand_cap = 0;
     fs_pair* cand = nullptr;
     int64_t fx_cap = 0;  // fan extra rows
     __half* fx16 = nullptr;
     int64_t fxsq_cap = 0;
-    float2* fx_sq = nullptr;
+    float4* fx_sq = nullptr;
 
     // staging of the _host entry points
     cudaStream_t stream = nullptr;
@@ -135,6 +144,26 @@ struct fs_index {
     int64_t h_pair_cap = 0;
     fs_pair* h_pair = nullptr;
     unsigned long long* h_counters = nullptr;
+
+    // fs_search_submit / fs_search_collect: kSlots batches in flight.  A slot owns the device copies of
+    // its inputs and its outputs; the workspace above is shared (the kernels of consecutive batches
+    // are ordered on `stream`).  Inputs travel on `stream_in`, match lists on `stream_out`, so the H2D
+    // of batch k+1 and the D2H of batch k-1 run under the distance kernel of batch k.
+    struct Slot {
+        bool busy = false;
+        int64_t tok_cap = 0, off_cap = 0, extra_cap = 0, out_cap = 0;
+        int32_t* d_tok = nullptr;
+        int64_t* d_off = nullptr;
+        float* d_extra = nullptr;
+        fs_match* d_out = nullptr;
+        unsigned long long* d_counters = nullptr;
+        long long* h_counters = nullptr;  // page-locked
+        int64_t cap = 0;
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    };
+    static constexpr int kSlots = 2;
+    Slot slots[kSlots];
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
 
     // LSH emulation (parity mode)
     double* lsh_normals = nullptr;
@@ -182,7 +211,7 @@ int fs_index_destroy(fs_index* idx) {
                     idx->script_norm, idx->hash_table, idx->fan_emb, idx->fan_tok_sq, idx->fan_thr,
                     idx->cand,    idx->fx16,      idx->fx_sq,      idx->h_tok,      idx->h_off,
                     idx->h_extra, idx->h_out,     idx->h_pair,     idx->h_counters,
-                    idx->lsh_normals, idx->script_norm_min};
+                    idx->lsh_normals, idx->script_norm_min, idx->perm, idx->col_energy};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (idx->ev_created) {
@@ -191,8 +220,75 @@ int fs_index_destroy(fs_index* idx) {
             cudaEventDestroy(idx->ev_stop[i]);
         }
     }
+    for (auto& sl : idx->slots) {
+        void* q[] = {sl.d_tok, sl.d_off, sl.d_extra, sl.d_out, sl.d_counters};
+        for (void* p : q)
+            if (p) cudaFree(p);
+        if (sl.h_counters) cudaFreeHost(sl.h_counters);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
     if (idx->stream) cudaStreamDestroy(idx->stream);
+    if (idx->stream_in) cudaStreamDestroy(idx->stream_in);
+    if (idx->stream_out) cudaStreamDestroy(idx->stream_out);
     delete idx;
+    return FS_OK;
+}
+
+// Which embedding columns the operand rows keep (FS_OPT_PREFILTER_DIMS).  The columns are ordered by
+// their energy over the index's table and script extras (a permutation: every dot product is
+// unchanged), the first `kept_dims` enter the operand rows, and what a window holds in the dropped
+// ones is bounded per pair by |f_drop| |s_drop| in the pre-filter threshold (window_norm_kernel), so
+// the candidates stay a guaranteed superset whatever is dropped: fewer K-steps per tile for a wider
+// threshold.  0 = automatic (see kAutoKeepEnergy).
+static int choose_kept_columns(fs_index* idx) {
+    cudaStream_t st = idx->stream;
+    const int32_t dim = idx->dim;
+    int r;
+    std::vector<double> energy(static_cast<size_t>(dim), 0.0);
+    if (!idx->perm) {
+        if ((r = dev_alloc(&idx->perm, dim)) != FS_OK) return r;
+        if ((r = dev_alloc(&idx->col_energy, dim)) != FS_OK) return r;
+    }
+    FS_CUDA_CHECK(cudaMemsetAsync(idx->col_energy, 0, sizeof(double) * dim, st));
+    if ((r = launch_column_energy(idx->table32, idx->n_base, dim, idx->col_energy, st)) != FS_OK) return r;
+    if ((r = launch_column_energy(idx->sx32, idx->n_sx, dim, idx->col_energy, st)) != FS_OK) return r;
+    FS_CUDA_CHECK(cudaMemcpyAsync(energy.data(), idx->col_energy, sizeof(double) * dim, cudaMemcpyDeviceToHost, st));
+    FS_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<int32_t> perm(static_cast<size_t>(dim));
+    for (int32_t c = 0; c < dim; ++c) perm[c] = c;
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return energy[a] > energy[b]; });
+    double total = 0.0;
+    for (double e : energy) total += e;
+    const int32_t kstep = idx->operand_bits == 8 ? 2 * kUmmaK : kUmmaK;
+    int32_t kept = dim;
+    if (idx->prefilter_dims > 0) {
+        kept = idx->prefilter_dims < dim ? idx->prefilter_dims : dim;
+    } else if (idx->prefilter_auto && total > 0.0 && dim > 4 * kstep) {
+        // automatic: whole 128-byte chunks of operand row (the unit the stage ring and the L2 -> SM
+        // stream move), as few as keep kAutoKeepEnergy of the energy; never more than the embedding has
+        const int32_t chunk = idx->operand_bits == 8 ? 2 * kChunkK : kChunkK;
+        double run = 0.0;
+        int32_t need = dim;
+        for (int32_t c = 0; c < dim; ++c) {
+            run += energy[perm[c]];
+            if (run >= kAutoKeepEnergy * total) {
+                need = c + 1;
+                break;
+            }
+        }
+        kept = static_cast<int32_t>(round_up(need, chunk));
+        if (kept > dim) kept = dim;
+    }
+    if (kept < 1) kept = 1;
+    if (kept >= dim)  // nothing dropped: keep the table's own column order
+        for (int32_t c = 0; c < dim; ++c) perm[c] = c;
+    idx->kept_dims = kept;
+    double kept_e = 0.0;
+    for (int32_t c = 0; c < kept; ++c) kept_e += energy[perm[c]];
+    idx->kept_energy = total > 0.0 ? kept_e / total : 1.0;
+    FS_CUDA_CHECK(cudaMemcpyAsync(idx->perm, perm.data(), sizeof(int32_t) * dim, cudaMemcpyHostToDevice, st));
+    FS_CUDA_CHECK(cudaStreamSynchronize(st));
     return FS_OK;
 }
 
@@ -208,7 +304,9 @@ static int prepare_operands(fs_index* idx) {
     idx->ready = false;
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     FS_CUDA_CHECK(cudaDeviceSynchronize());
-    idx->dim_pad_elems = static_cast<int32_t>(round_up(idx->dim, f8 ? 2 * kUmmaK : kUmmaK));  // K of one tcgen05.mma
+    int r;
+    if ((r = choose_kept_columns(idx)) != FS_OK) return r;
+    idx->dim_pad_elems = static_cast<int32_t>(round_up(idx->kept_dims, f8 ? 2 * kUmmaK : kUmmaK));  // K of one tcgen05.mma
     idx->dim_pad = f8 ? idx->dim_pad_elems / 2 : idx->dim_pad_elems;
     if (!idx->diag_user) {
         // Default diagonal factor (all variants are parity-tested and selectable).  E = 6 runs one MMA
@@ -229,7 +327,6 @@ static int prepare_operands(fs_index* idx) {
         if (q) cudaFree(q);
     idx->table16 = idx->sx16 = idx->script_emb = idx->fan_emb = idx->fx16 = nullptr;
     idx->emb_cap = idx->tok_cap = idx->fx_cap = 0;
-    int r;
     if ((r = dev_alloc(&idx->table16, idx->n_base * idx->dim_pad)) != FS_OK) return r;
     if ((r = dev_alloc(&idx->sx16, idx->n_sx * idx->dim_pad)) != FS_OK) return r;
     if ((r = dev_alloc(&idx->script_emb, idx->n_script_tok * idx->dim_pad)) != FS_OK) return r;
@@ -257,11 +354,11 @@ static int prepare_operands(fs_index* idx) {
     idx->row_limit_sq = (h_norm_sq > 0.f && std::isfinite(h_norm_sq))
                             ? h_norm_sq * idx->scale * idx->scale * 1.0001f
                             : 0.f;
-    if ((r = launch_convert_rows(idx->table32, idx->n_base, idx->dim, idx->dim_pad, idx->scale, f8, 0.f,
-                                 idx->table16, idx->table_sq, st)) != FS_OK)
+    if ((r = launch_convert_rows(idx->table32, idx->n_base, idx->dim, idx->dim_pad, idx->kept_dims, idx->perm,
+                                 idx->scale, f8, 0.f, idx->table16, idx->table_sq, st)) != FS_OK)
         return r;
-    if ((r = launch_convert_rows(idx->sx32, idx->n_sx, idx->dim, idx->dim_pad, idx->scale, f8, 0.f,
-                                 idx->sx16, idx->sx_sq, st)) != FS_OK)
+    if ((r = launch_convert_rows(idx->sx32, idx->n_sx, idx->dim, idx->dim_pad, idx->kept_dims, idx->perm,
+                                 idx->scale, f8, 0.f, idx->sx16, idx->sx_sq, st)) != FS_OK)
         return r;
     const int64_t n_pad = static_cast<int64_t>(idx->tiles_n) * kBlockN;
     GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16, idx->sx_sq,
@@ -269,7 +366,7 @@ static int prepare_operands(fs_index* idx) {
     if ((r = launch_gather(idx->script_tok, idx->n_script_tok, src, idx->dim_pad, idx->script_emb,
                            idx->script_tok_sq, idx->sm_count, st)) != FS_OK)
         return r;
-    FS_CUDA_CHECK(cudaMemsetAsync(idx->script_tok_sq + idx->n_script_tok, 0, sizeof(float2) * 8, st));
+    FS_CUDA_CHECK(cudaMemsetAsync(idx->script_tok_sq + idx->n_script_tok, 0, sizeof(float4) * 8, st));
     unsigned long long* d_cnt = idx->h_counters;
     FS_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
     const float coef = static_cast<float>(1.0 - idx->threshold - kEpsAccum);
@@ -361,6 +458,14 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     } while (0)
 
     FS_TRY_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
+    FS_TRY_CUDA(cudaStreamCreateWithFlags(&idx->stream_in, cudaStreamNonBlocking));
+    FS_TRY_CUDA(cudaStreamCreateWithFlags(&idx->stream_out, cudaStreamNonBlocking));
+    for (auto& sl : idx->slots) {
+        FS_TRY_CUDA(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+        FS_TRY_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+        FS_TRY(dev_alloc(&sl.d_counters, FS_CNT_COUNT));
+        FS_TRY_CUDA(cudaMallocHost(reinterpret_cast<void**>(&sl.h_counters), sizeof(long long) * FS_CNT_COUNT));
+    }
     cudaStream_t st = idx->stream;
     for (int i = 0; i < kTimingRing; ++i) {
         FS_TRY_CUDA(cudaEventCreate(&idx->ev_start[i]));
@@ -463,6 +568,18 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             idx->operand_bits = static_cast<int32_t>(value);
             return prepare_operands(idx);
         }
+        case FS_OPT_PREFILTER_DIMS: {
+            if (value < -1 || value > idx->dim) {
+                set_error("pre-filter dimensions must be -1 (automatic), 0 (all) or 1..dim");
+                return FS_E_INVALID;
+            }
+            const int32_t want_auto = value == -1 ? 1 : 0;
+            const int32_t want_dims = value > 0 ? static_cast<int32_t>(value) : 0;
+            if (want_auto == idx->prefilter_auto && want_dims == idx->prefilter_dims) return FS_OK;
+            idx->prefilter_auto = want_auto;
+            idx->prefilter_dims = want_dims;
+            return prepare_operands(idx);
+        }
         case FS_OPT_GRID_LIMIT:
             idx->grid_limit = static_cast<int32_t>(value < 0 ? 0 : value);
             return FS_OK;
@@ -509,6 +626,8 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
         case 8: return idx->pack;
         case 11: return idx->operand_bits;
         case 12: return idx->tile_group;
+        case 13: return idx->kept_dims;
+        case 14: return static_cast<int64_t>(idx->kept_energy * 1e6);  // share of the energy kept, ppm
         default: return -1;
     }
 }
@@ -574,14 +693,14 @@ int check_batch(const fs_index* idx, const BatchArgs& a, const char* who) {
 
 // gather + window thresholds of one batch into the index workspace
 int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned long long* counters,
-                __half* emb_out, float2* thr_out, int64_t thr_pad) {
+                __half* emb_out, float4* thr_out, int64_t thr_pad) {
     int r;
     if (a.n_extra > 0) {
         if ((r = dev_grow(&idx->fx16, &idx->fx_cap, a.n_extra * idx->dim_pad)) != FS_OK) return r;
         if ((r = dev_grow(&idx->fx_sq, &idx->fxsq_cap, a.n_extra)) != FS_OK) return r;
-        if ((r = launch_convert_rows(a.extra, a.n_extra, idx->dim, idx->dim_pad, idx->scale,
-                                     idx->operand_bits == 8, idx->row_limit_sq, idx->fx16, idx->fx_sq,
-                                     st)) != FS_OK)
+        if ((r = launch_convert_rows(a.extra, a.n_extra, idx->dim, idx->dim_pad, idx->kept_dims, idx->perm,
+                                     idx->scale, idx->operand_bits == 8, idx->row_limit_sq, idx->fx16,
+                                     idx->fx_sq, st)) != FS_OK)
             return r;
     }
     GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16,  idx->sx_sq,
@@ -590,7 +709,7 @@ int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned lon
                            st)) != FS_OK)
         return r;
     // zero the halo so the window sums never read stale squares
-    FS_CUDA_CHECK(cudaMemsetAsync(idx->fan_tok_sq + a.n_tok, 0, sizeof(float2) * 8, st));
+    FS_CUDA_CHECK(cudaMemsetAsync(idx->fan_tok_sq + a.n_tok, 0, sizeof(float4) * 8, st));
     // fan side of the pre-filter bound: (|f|, |f - qf|) per window (window_norm_kernel)
     return launch_window_norm(idx->fan_tok_sq, a.n_tok, a.off, static_cast<int32_t>(a.n_works),
                               idx->window, 0.0f, false, thr_out, thr_pad,
@@ -677,6 +796,7 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     rp.out = out;
     rp.out_cap = cap;
     rp.match_counter = counters + FS_CNT_MATCHES;
+    rp.overflow = counters + FS_CNT_OVERFLOW;
     if ((r = launch_rescore(rp, idx->sm_count, st)) != FS_OK) return r;
     if (idx->lsh_tables > 0) {
         LshParams lp{};
@@ -740,6 +860,101 @@ int fs_search_csr_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n
                         nullptr, 0, reinterpret_cast<unsigned long long*>(counters));
 }
 
+// Enqueue one host batch into a free slot: inputs H2D on stream_in, the kernels on `stream` behind
+// whatever is already queued there, the counters D2H into the slot's page-locked words.  No
+// synchronisation with the device unless a buffer has to grow.
+static int submit_slot(fs_index* idx, const BatchArgs& h, int64_t cap, int32_t* ticket) {
+    int r;
+    int s = -1;
+    for (int k = 0; k < fs_index::kSlots; ++k)
+        if (!idx->slots[k].busy) {
+            s = k;
+            break;
+        }
+    if (s < 0) {
+        set_error("fs_search_submit: %d batches are already in flight; collect one first", fs_index::kSlots);
+        return FS_E_INVALID;
+    }
+    fs_index::Slot& sl = idx->slots[s];
+    // the workspace of the shared pipeline must not be re-allocated under a batch in flight:
+    // run_pipeline's own reserve (dev_grow) synchronises the device before it frees anything
+    if ((r = dev_grow(&sl.d_tok, &sl.tok_cap, h.n_tok + 8)) != FS_OK) return r;
+    if ((r = dev_grow(&sl.d_off, &sl.off_cap, h.n_works + 1)) != FS_OK) return r;
+    if ((r = dev_grow(&sl.d_extra, &sl.extra_cap, h.n_extra * idx->dim)) != FS_OK) return r;
+    if ((r = dev_grow(&sl.d_out, &sl.out_cap, cap)) != FS_OK) return r;
+    cudaStream_t in = idx->stream_in, st = idx->stream;
+    if (h.n_tok)
+        FS_CUDA_CHECK(cudaMemcpyAsync(sl.d_tok, h.tok, sizeof(int32_t) * h.n_tok, cudaMemcpyHostToDevice, in));
+    // ids read past the end of the batch by the last (invalid) windows must stay harmless
+    FS_CUDA_CHECK(cudaMemsetAsync(sl.d_tok + h.n_tok, 0xFF, sizeof(int32_t) * 8, in));
+    FS_CUDA_CHECK(cudaMemcpyAsync(sl.d_off, h.off, sizeof(int64_t) * (h.n_works + 1), cudaMemcpyHostToDevice, in));
+    if (h.n_extra)
+        FS_CUDA_CHECK(cudaMemcpyAsync(sl.d_extra, h.extra, sizeof(float) * h.n_extra * idx->dim,
+                                      cudaMemcpyHostToDevice, in));
+    FS_CUDA_CHECK(cudaEventRecord(sl.ev_in, in));
+    FS_CUDA_CHECK(cudaStreamWaitEvent(st, sl.ev_in, 0));
+    BatchArgs d{sl.d_tok, h.n_tok, sl.d_off, h.n_works, sl.d_extra, h.n_extra};
+    if ((r = run_pipeline(idx, st, d, Mode::kSearch, sl.d_out, cap, nullptr, 0, nullptr, 0, sl.d_counters)) != FS_OK)
+        return r;
+    FS_CUDA_CHECK(cudaMemcpyAsync(sl.h_counters, sl.d_counters, sizeof(int64_t) * FS_CNT_COUNT,
+                                  cudaMemcpyDeviceToHost, st));
+    FS_CUDA_CHECK(cudaEventRecord(sl.ev_done, st));
+    sl.cap = cap;
+    sl.busy = true;
+    *ticket = s;
+    return FS_OK;
+}
+
+static int collect_slot(fs_index* idx, int32_t ticket, fs_match* out, int64_t cap, int64_t* counters) {
+    fs_index::Slot& sl = idx->slots[ticket];
+    FS_CUDA_CHECK(cudaEventSynchronize(sl.ev_done));
+    sl.busy = false;
+    for (int k = 0; k < FS_CNT_COUNT; ++k) counters[k] = sl.h_counters[k];
+    const int64_t n_match = counters[FS_CNT_MATCHES];
+    int64_t n_copy = n_match < cap ? n_match : cap;
+    if (n_copy > sl.cap) n_copy = sl.cap;
+    if (n_copy > 0) {
+        // on its own stream: the next batch's kernels are already queued on `stream`
+        FS_CUDA_CHECK(cudaMemcpyAsync(out, sl.d_out, sizeof(fs_match) * n_copy, cudaMemcpyDeviceToHost,
+                                      idx->stream_out));
+        FS_CUDA_CHECK(cudaStreamSynchronize(idx->stream_out));
+    }
+    if (counters[FS_CNT_OVERFLOW] & FS_OVERFLOW_CANDIDATES) {
+        set_error("candidate buffer overflow: %lld candidates, capacity %lld; fs_index_reserve more",
+                  static_cast<long long>(counters[FS_CNT_CANDIDATES]), static_cast<long long>(idx->cand_cap));
+        return FS_E_OVERFLOW;
+    }
+    if (n_match > cap || n_match > sl.cap) {
+        set_error("match buffer overflow: %lld matches, capacity %lld", static_cast<long long>(n_match),
+                  static_cast<long long>(cap < sl.cap ? cap : sl.cap));
+        return FS_E_OVERFLOW;
+    }
+    return FS_OK;
+}
+
+int fs_search_submit(fs_index* idx, const int32_t* tok, int64_t n_tok, const int64_t* off, int64_t n_works,
+                     const float* extra, int64_t n_extra, int64_t cap, int32_t* ticket) {
+    BatchArgs h{tok, n_tok, off, n_works, extra, n_extra};
+    int r = check_batch(idx, h, "fs_search_submit");
+    if (r != FS_OK) return r;
+    if (!ticket || cap < 0) {
+        set_error("fs_search_submit: invalid output arguments");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    return submit_slot(idx, h, cap, ticket);
+}
+
+int fs_search_collect(fs_index* idx, int32_t ticket, fs_match* out, int64_t cap, int64_t* counters) {
+    if (!idx || ticket < 0 || ticket >= fs_index::kSlots || !idx->slots[ticket].busy || !counters || cap < 0 ||
+        (cap > 0 && !out)) {
+        set_error("fs_search_collect: invalid argument (unknown or already collected ticket?)");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    return collect_slot(idx, ticket, out, cap, counters);
+}
+
 int fs_search_csr_host(fs_index* idx, const int32_t* tok, int64_t n_tok, const int64_t* off,
                        int64_t n_works, const float* extra, int64_t n_extra, fs_match* out,
                        int64_t cap, int64_t* counters) {
@@ -751,35 +966,9 @@ int fs_search_csr_host(fs_index* idx, const int32_t* tok, int64_t n_tok, const i
         return FS_E_INVALID;
     }
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
-    BatchArgs d;
-    if ((r = stage_host_batch(idx, h, &d)) != FS_OK) return r;
-    if ((r = dev_grow(&idx->h_out, &idx->h_out_cap, cap)) != FS_OK) return r;
-    cudaStream_t st = idx->stream;
-    if ((r = run_pipeline(idx, st, d, Mode::kSearch, idx->h_out, cap, nullptr, 0, nullptr, 0,
-                          idx->h_counters)) != FS_OK)
-        return r;
-    FS_CUDA_CHECK(cudaMemcpyAsync(counters, idx->h_counters, sizeof(int64_t) * FS_CNT_COUNT,
-                                  cudaMemcpyDeviceToHost, st));
-    FS_CUDA_CHECK(cudaStreamSynchronize(st));
-    const int64_t n_match = counters[FS_CNT_MATCHES];
-    const int64_t n_copy = n_match < cap ? n_match : cap;
-    if (n_copy > 0) {
-        FS_CUDA_CHECK(cudaMemcpyAsync(out, idx->h_out, sizeof(fs_match) * n_copy,
-                                      cudaMemcpyDeviceToHost, st));
-        FS_CUDA_CHECK(cudaStreamSynchronize(st));
-    }
-    if (counters[FS_CNT_CANDIDATES] > idx->cand_cap) {
-        set_error("candidate buffer overflow: %lld candidates, capacity %lld; fs_index_reserve more",
-                  static_cast<long long>(counters[FS_CNT_CANDIDATES]),
-                  static_cast<long long>(idx->cand_cap));
-        return FS_E_OVERFLOW;
-    }
-    if (n_match > cap) {
-        set_error("match buffer overflow: %lld matches, capacity %lld", static_cast<long long>(n_match),
-                  static_cast<long long>(cap));
-        return FS_E_OVERFLOW;
-    }
-    return FS_OK;
+    int32_t ticket = -1;
+    if ((r = submit_slot(idx, h, cap, &ticket)) != FS_OK) return r;
+    return collect_slot(idx, ticket, out, cap, counters);
 }
 
 int fs_exact_join_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n_tok,
@@ -849,7 +1038,7 @@ int fs_stage_embed_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t 
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     if ((r = fs_index_reserve(idx, n_tok, idx->cand_cap > 0 ? idx->cand_cap : 1024)) != FS_OK) return r;
     return embed_batch(idx, static_cast<cudaStream_t>(stream), a, nullptr,
-                       static_cast<__half*>(emb_out), reinterpret_cast<float2*>(thr_out), n_tok);
+                       static_cast<__half*>(emb_out), reinterpret_cast<float4*>(thr_out), n_tok);
 }
 
 int fs_stage_dots_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n_tok,

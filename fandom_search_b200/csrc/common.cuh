@@ -51,7 +51,7 @@ constexpr int kProducerWarp = kEpiWarps;               // single-thread roles ge
 constexpr int kMmaWarp = kEpiWarps + 1;                // warp ids (scheduler priority)
 constexpr int kDistThreads = 32 * (kEpiWarps + 2);     // 576
 constexpr int kHaloCols = kBlockN + 8;
-constexpr int kNormTileBytes = kAccumStages * kHaloCols * 8;               // 4224: (B, D) per column
+constexpr int kNormTileBytes = kAccumStages * kHaloCols * 16;              // 8448: (B, D, H, -) per column
 // E = 6 (one MMA shift, no row offsets inside a stage): the four 32-lane TMEM quarters of a tile
 // hold OVERLAPPING fan rows, quarter q = rows [27 q, 27 q + 32) of the tile (four TMA boxes of 32
 // rows), so every quarter sums its own diagonals -- no boundary rows to publish, no boundary
@@ -78,8 +78,8 @@ __host__ __device__ constexpr int dist_stage_bytes(bool pair, bool ares) {
     return ares ? kStageABytes : (pair ? 2 * kStageABytes : kStageBytes);
 }
 __host__ __device__ constexpr int dist_stages(int diag, bool pair, bool ares) {
-    (void)diag;
-    return ares ? 7 : (pair ? 6 : 4);
+    // (E < 6 keeps boundary rows and the tile's bounds in shared memory: one stage less)
+    return ares ? (diag == 6 ? 7 : 6) : (pair ? (diag == 6 ? 6 : 5) : (diag == 3 ? 3 : 4));
 }
 // per published boundary row and 32-column chunk, the maximum of the row over the chunk's 40 loaded
 // columns (one half; 8 chunks per tile, two buffers): lets the boundary pass reject a chunk at once
@@ -91,17 +91,20 @@ __host__ __device__ constexpr int dist_smem_bytes(int diag, bool pair, bool ares
            1024 /*align slack*/ + 256 /*barriers*/ + dist_pub_bytes(diag) + kNormTileBytes +
            dist_rowmax_bytes(diag);
 }
-static_assert(dist_smem_bytes(1, false, false) <= 232448 && dist_smem_bytes(3, true, false) <= 232448 &&
+static_assert(dist_smem_bytes(2, false, false) <= 232448 && dist_smem_bytes(3, false, false) <= 232448 &&
+                  dist_smem_bytes(2, true, false) <= 232448 && dist_smem_bytes(2, true, true) <= 232448 &&
+                  dist_smem_bytes(1, false, false) <= 232448 && dist_smem_bytes(3, true, false) <= 232448 &&
                   dist_smem_bytes(6, true, false) <= 232448 && dist_smem_bytes(6, false, false) <= 232448 &&
                   dist_smem_bytes(3, true, true) <= 232448 && dist_smem_bytes(6, true, true) <= 232448 &&
                   dist_smem_bytes(1, true, true) <= 232448,
               "distance kernel exceeds the 227 KB shared memory limit");
 
 struct DistParams {
-    // pre-filter: keep (i, j) iff acc_ij > A_i * B_j - C_i * D_j  (window_norm_kernel, embed.cu)
-    const float2* fan_ac;       // [Mpad]  (A_i, C_i) = (|fan window|, |its rounding error|), NaN when invalid
-    const float2* script_bd;    // [Npad]  (B_j, D_j) = ((1-thr-eps)|s| - err, |s| + err), NaN when invalid
-    const float2* script_mm32;  // [Npad]  (min B, max D) over columns j .. j+31
+    // pre-filter: keep (i, j) iff acc_ij > A_i * B_j - C_i * D_j - G_i * H_j  (window_norm_kernel, embed.cu)
+    const float4* fan_ac;       // [Mpad]  (A_i, C_i, G_i) = (|fan window|, |its rounding error|, |its dropped
+                                //         elements|), NaN when invalid
+    const float4* script_bd;    // [Npad]  (B_j, D_j, H_j) = ((1-thr-eps)|s| - err, |s| + err, |dropped|), NaN when invalid
+    const float4* script_mm32;  // [Npad]  (min B, max D, max H) over columns j .. j+31
     int64_t n_fan_tok;        // rows of the fan token matrix (M)
     int64_t n_script_tok;     // rows of the script token matrix (N)
     int32_t chunks;           // ceil(dim_pad / 64) 64-column chunks
@@ -149,6 +152,7 @@ struct RescoreParams {
     fs_match* out;
     int64_t out_cap;
     unsigned long long* match_counter;
+    unsigned long long* overflow;  // FS_OVERFLOW_* bits (counters + FS_CNT_OVERFLOW)
 };
 
 struct LshParams {
@@ -171,32 +175,35 @@ struct LshParams {
 // Operand rows are raw bytes: fp16 (2 B per element) or fp8 e4m3 (1 B per element); the plumbing
 // counts a row in 2-byte units ("dim_pad": fp16 elements, or fp8 elements / 2), so the gather, the
 // tensor maps (plain byte movers) and the 128-byte chunking are the same for both.
-// *_sq: per row (squared norm of the scaled fp32 row, squared norm of its rounding error).
+// *_sq: per row (squared norm of the scaled fp32 row, squared norm of the rounding error of its kept
+// elements, squared norm of its dropped elements, unused).
 struct GatherSources {
     const __half* base16;
-    const float2* base_sq;
+    const float4* base_sq;
     int64_t n_base;
     const __half* sx16;  // script extras
-    const float2* sx_sq;
+    const float4* sx_sq;
     int64_t n_sx;
     const __half* fx16;  // fan extras of this batch
-    const float2* fx_sq;
+    const float4* fx_sq;
     int64_t n_fx;
 };
 
 int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad, int32_t box_rows);
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, const CUtensorMap& map_script,
                     const CUtensorMap& map_script128, const DistParams& p, int grid_limit, cudaStream_t stream);
-int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
-                        bool f8, float limit_sq, __half* dst, float2* sq, cudaStream_t stream);
+int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, int32_t kept,
+                        const int32_t* perm, float scale, bool f8, float limit_sq, __half* dst, float4* sq,
+                        cudaStream_t stream);
+int launch_column_energy(const float* src, int64_t n_rows, int32_t dim, double* energy, cudaStream_t stream);
 int launch_rownorm_max(const float* src, int64_t n_rows, int32_t dim, unsigned int* out, cudaStream_t stream);
 int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t stream);
 int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,
-                  __half* emb, float2* tok_sq, int sm_count, cudaStream_t stream);
-int launch_window_norm(const float2* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
-                       int32_t window, float coef, bool script_side, float2* out, int64_t n_pad,
+                  __half* emb, float4* tok_sq, int sm_count, cudaStream_t stream);
+int launch_window_norm(const float4* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
+                       int32_t window, float coef, bool script_side, float4* out, int64_t n_pad,
                        unsigned long long* window_counter, cudaStream_t stream);
-int launch_sliding_minmax32(const float2* src, float2* dst, int64_t n, cudaStream_t stream);
+int launch_sliding_minmax32(const float4* src, float4* dst, int64_t n, cudaStream_t stream);
 int launch_rescore(const RescoreParams& p, int sm_count, cudaStream_t stream);
 int launch_lsh(const LshParams& p, int sm_count, cudaStream_t stream);
 int launch_hash_build(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,

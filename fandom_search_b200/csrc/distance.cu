@@ -27,6 +27,7 @@
 // cursor; they are re-scored in float64 afterwards.
 #include "common.cuh"
 
+#include <mutex>
 #include <type_traits>
 
 #ifdef FS_TIMELINE
@@ -262,7 +263,7 @@ template <int kDiag, bool kDump, int kPack, bool kPair>
 __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t m0, const int32_t n0,
                                               const int as, const uint32_t tfull_addr, const uint32_t tempty_addr,
                                               const uint32_t aphase, const uint32_t tmem_base, float* halo,
-                                              float2* norm_tile, __half* rowmax, const int warp, const int lane,
+                                              float4* norm_tile, __half* rowmax, const int warp, const int lane,
                                               const int tl_tile = 0) {
     (void)tl_tile;
     constexpr bool kOverlap = kDiag == 6;  // lane quarters hold overlapping fan rows: nothing crosses quarters
@@ -287,15 +288,17 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     const int32_t gi = m0 + row;
     const bool row_ok = kOverlap ? lane < kQuarterRows6 : row < kMStep;
     const float kNaN = __int_as_float(0x7fc00000);
-    // (A_i, C_i) of this lane's fan window (padded to a tile multiple); NaN = never a candidate
-    const float2 ac = row_ok ? __ldg(p.fan_ac + gi) : make_float2(kNaN, kNaN);
+    // (A_i, C_i, G_i) of this lane's fan window (padded to a tile multiple); NaN = never a candidate
+    const float4 ac = row_ok ? __ldg(p.fan_ac + gi) : make_float4(kNaN, kNaN, kNaN, 0.f);
+    // pre-filter bound of this lane's row against script-side (B, D, H): A B - C D - G H
+    auto bound_of = [&](float a, const float4& bd) { return fmaf(-ac.z, bd.z, fmaf(-ac.y, bd.y, a * bd.x)); };
     // rows whose sum needs another warp's rows are finished in the boundary pass
     const float a_main = (kDiag > 1 && lane >= kTail0) ? kNaN : ac.x;
     // E > 1: (B_j, D_j) of this tile staged once in smem, NaN baked in for the E-1 columns that
     // belong to the next tile
-    float2* ns_tile = norm_tile + as * kHaloCols;
+    float4* ns_tile = norm_tile + as * kHaloCols;
     if (kDiag > 1 && !kOverlap && epi_tid < kHaloCols)
-        ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.script_bd + n0 + epi_tid) : make_float2(kNaN, kNaN);
+        ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.script_bd + n0 + epi_tid) : make_float4(kNaN, kNaN, kNaN, 0.f);
     mbar_wait_warp(tfull_addr, aphase, 0);
     tc_fence_after();
     FS_TL(2 + warp, tl_tile, 1);
@@ -312,7 +315,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
             const int halo_off = (group * kEpiCols + 64 < kBlockN) ? 64 : 56;  // (see load_chunk below)
             tmem_ld_32x72(taddr, taddr + halo_off, q);
         }
-        float2 mm2[2];
+        float4 mm2[2];
         mm2[0] = __ldg(p.script_mm32 + n0 + group * kEpiCols);
         mm2[1] = __ldg(p.script_mm32 + n0 + group * kEpiCols + 32);
         tmem_ld_wait();
@@ -339,7 +342,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
             const uint32_t b01 = h2_add(m, __shfl_down_sync(0xffffffffu, m, 1));
             const uint32_t bsum =
                 h2_add(h2_add(b01, __shfl_down_sync(0xffffffffu, b01, 2)), __shfl_down_sync(0xffffffffu, b01, 4));
-            const float thr_chunk = fmaf(-ac.y, mm2[ch].y, a_main * mm2[ch].x);
+            const float thr_chunk = bound_of(a_main, mm2[ch]);
             if (!__any_sync(0xffffffffu, h2_lo(bsum) > thr_chunk || h2_hi(bsum) > thr_chunk)) continue;
             uint32_t pk[20], o16[16];
 #pragma unroll
@@ -350,9 +353,9 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                 const int32_t gj0 = n0 + c0;
 #pragma unroll
                 for (int x = 0; x < 32; ++x) {
-                    const float2 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float2(kNaN, kNaN);
+                    const float4 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float4(kNaN, kNaN, kNaN, 0.f);
                     const float v = (x & 1) ? h2_hi(o16[x >> 1]) : h2_lo(o16[x >> 1]);
-                    if (v > fmaf(-ac.y, bd.y, a_main * bd.x)) {
+                    if (v > bound_of(a_main, bd)) {
                         const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                         if (slot < static_cast<unsigned long long>(p.cand_cap)) {
                             p.cand[slot].fan_pos = gi;
@@ -385,7 +388,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
         __syncwarp();
         // prefetch the chunk's (min B, max D): the latency hides behind the TMEM load.  (Fetching it
         // one tile ahead in the caller changed nothing and cost 8 live registers -> spills.)
-        const float2 mm = kDump ? make_float2(0.f, 0.f) : __ldg(p.script_mm32 + n0 + c0);
+        const float4 mm = kDump ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(p.script_mm32 + n0 + c0);
         if (!kHalf) load_chunk(ch);
         tmem_ld_wait();
         uint32_t pk[20];
@@ -421,7 +424,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
         }
         const int32_t gj0 = n0 + c0;
         // smallest pre-filter bound of the chunk for this lane's row (NaN: row not decided here)
-        const float thr_chunk = fmaf(-ac.y, mm.y, a_main * mm.x);
+        const float thr_chunk = bound_of(a_main, mm);
         if (kHalf && !kDump) {
             // Cheap rejection before any diagonal sum.  With m(l) = max over the 40 loaded columns of
             // row l,  out[lane][x] = sum_d a[lane+d][x+d] <= sum_d m(lane+d): one HMNMX2 tree and E-1
@@ -496,8 +499,8 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
             if (mx > thr_chunk) {
 #pragma unroll
                 for (int x = 0; x < 32; ++x) {
-                    const float2 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float2(kNaN, kNaN);
-                    if (out_val(x) > fmaf(-ac.y, bd.y, a_main * bd.x)) {
+                    const float4 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float4(kNaN, kNaN, kNaN, 0.f);
+                    if (out_val(x) > bound_of(a_main, bd)) {
                         const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                         if (slot < static_cast<unsigned long long>(p.cand_cap)) {
                             p.cand[slot].fan_pos = gi;
@@ -523,11 +526,12 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     if (kDiag > 1 && !kOverlap) {
         // boundary rows: tail rows of quarters 0..2 (quarter 3's belong to the next tile)
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        float a_l[kEdge > 0 ? kEdge : 1], c_l[kEdge > 0 ? kEdge : 1];  // (kDiag == 1 never gets here)
+        float a_l[kEdge > 0 ? kEdge : 1], c_l[kEdge > 0 ? kEdge : 1], g_l[kEdge > 0 ? kEdge : 1];  // (kDiag == 1 never gets here)
 #pragma unroll
         for (int tr = 0; tr < kEdge; ++tr) {
             a_l[tr] = __shfl_sync(0xffffffffu, ac.x, kTail0 + tr);
             c_l[tr] = __shfl_sync(0xffffffffu, ac.y, kTail0 + tr);
+            g_l[tr] = __shfl_sync(0xffffffffu, ac.z, kTail0 + tr);
         }
         if (quarter < 3) {
 #pragma unroll
@@ -538,7 +542,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                 // row maxima (summed in the order of `v` below: fp32 addition is monotone), against
                 // the chunk's smallest pre-filter bound -- the same rejection as in the main pass
                 float rmx[2 * (kEdge > 0 ? kEdge : 1)];  // row maxima: tail rows of this quarter, head rows of the next
-                float2 mm = make_float2(0.f, 0.f);
+                float4 mm = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (kHalf && !kDump) {
 #pragma unroll
                     for (int s2 = 0; s2 < kEdge; ++s2) {
@@ -555,7 +559,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                         float bsum = 0.f;
 #pragma unroll
                         for (int d = 0; d < kDiag; ++d) bsum += rmx[tr + d];
-                        if (!(bsum > fmaf(-c_l[tr], mm.y, a_l[tr] * mm.x))) continue;
+                        if (!(bsum > fmaf(-g_l[tr], mm.z, fmaf(-c_l[tr], mm.y, a_l[tr] * mm.x)))) continue;
                     }
                     float v = 0.f;
 #pragma unroll
@@ -575,7 +579,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                     if (kDump) {
                         if (gr < p.n_fan_tok && c < kNStep && n0 + c < p.dump_ld)
                             p.dump[static_cast<int64_t>(gr) * p.dump_ld + n0 + c] = v;
-                    } else if (v > fmaf(-c_l[tr], ns_tile[c].y, a_l[tr] * ns_tile[c].x)) {
+                    } else if (v > fmaf(-g_l[tr], ns_tile[c].z, fmaf(-c_l[tr], ns_tile[c].y, a_l[tr] * ns_tile[c].x))) {
                         const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                         if (slot < static_cast<unsigned long long>(p.cand_cap)) {
                             p.cand[slot].fan_pos = gr;
@@ -636,7 +640,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
-    float2* norm_tile = reinterpret_cast<float2*>(halo + dist_pub_bytes(kDiag) / 4);
+    float4* norm_tile = reinterpret_cast<float4*>(halo + dist_pub_bytes(kDiag) / 4);
     __half* rowmax_base = reinterpret_cast<__half*>(norm_tile + kAccumStages * kHaloCols);
 
     // Warp roles.  The warp scheduler prefers the HIGHEST warp id among eligible warps, so the
@@ -1047,15 +1051,23 @@ template <int kDiag, bool kPair, bool kARes, int kPack, bool kF8 = false>
 static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_fan32,
                              const CUtensorMap& map_script, const CUtensorMap& map_script128, const DistParams& p,
                              int grid, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           dist_smem_bytes(kDiag, kPair, kARes)));
-        FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair, kARes, kPack, kF8>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           dist_smem_bytes(kDiag, kPair, kARes)));
-        attr_set = true;
+    // The shared-memory attribute belongs to the (function, DEVICE) pair: one bit per device ordinal,
+    // under a lock (indexes on several GPUs may live in one process and be driven from several threads).
+    {
+        static std::mutex mu;
+        static uint64_t configured = 0;
+        int dev = 0;
+        FS_CUDA_CHECK(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 64 || !((configured >> dev) & 1ull)) {
+            FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, false, kPair, kARes, kPack, kF8>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               dist_smem_bytes(kDiag, kPair, kARes)));
+            FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel<kDiag, true, kPair, kARes, kPack, kF8>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               dist_smem_bytes(kDiag, kPair, kARes)));
+            if (dev < 64) configured |= 1ull << dev;
+        }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));

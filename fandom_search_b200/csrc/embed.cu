@@ -11,24 +11,35 @@
 
 namespace fs {
 
-// fp32 rows -> scaled operand rows (fp16, or fp8 e4m3 when kF8) padded to the row length, plus
-// per row the squared norm of the scaled fp32 row and the squared norm of its rounding error
-// (one warp per row).  Used once for the base table and per batch for OOV extras.
+// fp32 rows -> scaled operand rows (fp16, or fp8 e4m3 when kF8) padded to the row length, plus per
+// row (squared norm of the scaled fp32 row, squared norm of the rounding error of its KEPT elements,
+// squared norm of its DROPPED elements); one warp per row.  Used once for the base table and per
+// batch for OOV extras.
+//
+// Kept / dropped elements (pre-filter dimensions): operand element c is source column perm[c]; only
+// the first `kept` columns of that order enter the operand row, the remaining dim - kept are left
+// to the bound  |f_drop . s_drop| <= |f_drop| |s_drop|  of the distance epilogue (window_norm_kernel).
+// perm orders the columns by their energy over the index's table, so the dropped ones weigh least.
 template <bool kF8>
 __global__ void convert_rows_kernel(const float* __restrict__ src, int64_t n_rows, int32_t dim,
-                                    int32_t n_elems, float scale, float limit_sq, void* __restrict__ dst,
-                                    float2* __restrict__ sq) {
+                                    int32_t n_elems, int32_t kept, const int32_t* __restrict__ perm,
+                                    float scale, float limit_sq, void* __restrict__ dst,
+                                    float4* __restrict__ sq) {
     const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
     const float* s = src + row * dim;
-    float acc = 0.f;
+    float acc = 0.f, drop = 0.f;
     for (int c = lane; c < dim; c += 32) {
-        const float v = s[c] * scale;
+        const float v = s[__ldg(perm + c)] * scale;
         acc = fmaf(v, v, acc);
+        if (c >= kept) drop = fmaf(v, v, drop);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        drop += __shfl_xor_sync(0xffffffffu, drop, o);
+    }
     // A per-batch row longer than the longest row of the index would overflow the fp16 range of
     // the epilogue sums: its operand is shrunk to the limit and its error set to +inf, which turns
     // every window it belongs to into an unconditional candidate (decided by the float64 rescoring
@@ -37,7 +48,7 @@ __global__ void convert_rows_kernel(const float* __restrict__ src, int64_t n_row
     const float shrink = clamp ? sqrtf(limit_sq / acc) : 1.f;
     float err = 0.f;
     for (int c = lane; c < n_elems; c += 32) {
-        const float v = c < dim ? s[c] * scale : 0.f;
+        const float v = c < kept ? s[__ldg(perm + c)] * scale : 0.f;
         float back;
         if (kF8) {
             const __nv_fp8_storage_t q = __nv_cvt_float_to_fp8(v * shrink, __NV_SATFINITE, __NV_E4M3);
@@ -52,7 +63,20 @@ __global__ void convert_rows_kernel(const float* __restrict__ src, int64_t n_row
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
-    if (lane == 0) sq[row] = make_float2(acc, clamp ? INFINITY : err);
+    if (lane == 0) sq[row] = make_float4(acc, clamp ? INFINITY : err, drop, 0.f);
+}
+
+// energy[c] += sum over rows of src[row][c]^2 (which columns the pre-filter may drop)
+__global__ void column_energy_kernel(const float* __restrict__ src, int64_t n_rows, int32_t dim,
+                                     double* __restrict__ energy) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= dim) return;
+    double acc = 0.0;
+    for (int64_t r = blockIdx.y; r < n_rows; r += gridDim.y) {
+        const float v = src[r * dim + c];
+        if (isfinite(v)) acc += static_cast<double>(v) * v;
+    }
+    atomicAdd(energy + c, acc);
 }
 
 // max over rows of the squared row norm (global fp8 scale); atomicMax on the bit pattern
@@ -91,9 +115,9 @@ constexpr int kGatherUnroll = 4;
 
 __device__ __forceinline__ int4 gather_chunk(const GatherSources& src, const int4* base16,
                                              const int4* sx16, const int4* fx16, int64_t id,
-                                             int32_t chunks16, int32_t c, float2* sq) {
+                                             int32_t chunks16, int32_t c, float4* sq) {
     int4 v = make_int4(0, 0, 0, 0);  // unknown ids embed as the zero vector
-    *sq = make_float2(0.f, 0.f);
+    *sq = make_float4(0.f, 0.f, 0.f, 0.f);
     if (id >= 0 && id < src.n_base) {
         v = __ldg(base16 + id * chunks16 + c);
         if (c == 0) *sq = __ldg(src.base_sq + id);
@@ -110,7 +134,7 @@ __device__ __forceinline__ int4 gather_chunk(const GatherSources& src, const int
 __global__ void __launch_bounds__(256)
 gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSources src,
               int32_t chunks16 /* dim_pad*2/16 */, int4* __restrict__ emb,
-              float2* __restrict__ tok_sq) {
+              float4* __restrict__ tok_sq) {
     const int64_t total = n_tok * chunks16;
     const int4* base16 = reinterpret_cast<const int4*>(src.base16);
     const int4* sx16 = reinterpret_cast<const int4*>(src.sx16);
@@ -125,7 +149,7 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
     int32_t c0 = static_cast<int32_t>(g0 - t0 * chunks16);
     while (g0 < total) {
         int4 v[kGatherUnroll];
-        float2 sq[kGatherUnroll];
+        float4 sq[kGatherUnroll];
         int64_t t[kGatherUnroll];
         int32_t c[kGatherUnroll];
         int64_t id[kGatherUnroll];
@@ -156,20 +180,23 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
     }
 }
 
-// Per window start t, with n = sqrt(sum_{k<w} tok_sq[t+k].x) (norm of the scaled fp32 window) and
-// e = sqrt(sum tok_sq[t+k].y) (norm of the rounding error of its operand rows):
-//   fan side    out[t] = (n, e)                    = (A_i, C_i)
-//   script side out[t] = (coef * n - e, n + e)     = (B_j, D_j),  coef = 1 - thr - eps
-// when the window lies inside its CSR row, else (NaN, NaN) -- every comparison with NaN is false,
+// Per window start t, with n = sqrt(sum_{k<w} tok_sq[t+k].x) (norm of the scaled fp32 window),
+// e = sqrt(sum tok_sq[t+k].y) (norm of the rounding error of its operand rows) and g = sqrt(sum
+// tok_sq[t+k].z) (norm of the elements the operand rows drop):
+//   fan side    out[t] = (n, e, g)                     = (A_i, C_i, G_i)
+//   script side out[t] = (coef * n - e, n + e, g)      = (B_j, D_j, H_j),  coef = 1 - thr - eps
+// when the window lies inside its CSR row, else NaN -- every comparison with NaN is false,
 // whatever the sign of the other factor.  The distance epilogue keeps a pair iff
-//   acc_ij > A_i * B_j - C_i * D_j.
-// With qf, qs the rounded windows:  qf.qs >= f.s - |f - qf| |qs| - |f| |s - qs|  and  |qs| <= n_s + e_s,
+//   acc_ij > A_i * B_j - C_i * D_j - G_i * H_j.
+// With qf, qs the rounded kept parts of the windows:
+//   f.s = qf.qs + (f_kept - qf).qs + f_kept.(s_kept - qs) + f_drop.s_drop
+//   => qf.qs >= f.s - |f_kept - qf| |qs| - |f| |s_kept - qs| - |f_drop| |s_drop|,  |qs| <= n_s + e_s,
 // so every pair with f.s > (1 - thr) |f||s| passes: each window carries its own measured slack and a
-// badly represented window (rows that underflow the operand format) only widens its own row/column.
-// out is padded with (NaN, NaN) up to n_pad.
-__global__ void window_norm_kernel(const float2* __restrict__ tok_sq, int64_t n_tok,
+// badly represented window (rows that underflow the operand format, or whose weight sits in the
+// dropped elements) only widens its own row/column.  out is padded with NaN up to n_pad.
+__global__ void window_norm_kernel(const float4* __restrict__ tok_sq, int64_t n_tok,
                                    const int64_t* __restrict__ off, int32_t n_rows, int32_t window,
-                                   float coef, int script_side, float2* __restrict__ out, int64_t n_pad,
+                                   float coef, int script_side, float4* __restrict__ out, int64_t n_pad,
                                    unsigned long long* window_counter) {
     __shared__ int32_t row_hint;
     const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x;
@@ -179,18 +206,19 @@ __global__ void window_norm_kernel(const float2* __restrict__ tok_sq, int64_t n_
     unsigned int valid = 0;
     if (t < n_pad) {
         const float nan = __int_as_float(0x7fc00000);
-        float2 r = make_float2(nan, nan);
+        float4 r = make_float4(nan, nan, nan, 0.f);
         if (t < n_tok) {
             const int32_t row = csr_row_from_hint(off, n_rows, t, row_hint);
             if (t + window <= __ldg(off + row + 1)) {
-                float s = 0.f, e = 0.f;
+                float s = 0.f, e = 0.f, g = 0.f;
                 for (int k = 0; k < window; ++k) {
-                    const float2 q = tok_sq[t + k];
+                    const float4 q = tok_sq[t + k];
                     s += q.x;
                     e += q.y;
+                    g += q.z;
                 }
-                const float n = sqrtf(s), en = sqrtf(e);
-                r = script_side ? make_float2(coef * n - en, n + en) : make_float2(n, en);
+                const float n = sqrtf(s), en = sqrtf(e), gn = sqrtf(g);
+                r = script_side ? make_float4(coef * n - en, n + en, gn, 0.f) : make_float4(n, en, gn, 0.f);
                 valid = 1;
             }
         }
@@ -202,39 +230,49 @@ __global__ void window_norm_kernel(const float2* __restrict__ tok_sq, int64_t n_
     }
 }
 
-// dst[j] = (min B[j .. j+31], max D[j .. j+31]) over the valid (non-NaN) entries, clamped at n: lets
-// the distance epilogue reject a whole 32-column chunk with one compare of its largest accumulator
-// (A * minB - C * maxD <= A * B_j - C * D_j for A, C, D >= 0).  No valid entry: (+inf, 0).
-__global__ void sliding_minmax32_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int64_t n) {
+// dst[j] = (min B, max D, max H) over the valid (non-NaN) entries j .. j+31, clamped at n: lets the
+// distance epilogue reject a whole 32-column chunk with one compare of its largest accumulator
+// (A minB - C maxD - G maxH <= A B_j - C D_j - G H_j for A, C, D, G, H >= 0).  No valid entry: (+inf, 0, 0).
+__global__ void sliding_minmax32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n) {
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    float mn = INFINITY, mx = 0.f;
+    float mn = INFINITY, mx = 0.f, mh = 0.f;
     for (int k = 0; k < 32 && j + k < n; ++k) {
-        const float2 v = src[j + k];
+        const float4 v = src[j + k];
         mn = fminf(mn, v.x);  // fminf / fmaxf return the non-NaN operand
         mx = fmaxf(mx, v.y);
+        mh = fmaxf(mh, v.z);
     }
-    dst[j] = make_float2(mn, mx);
+    dst[j] = make_float4(mn, mx, mh, 0.f);
 }
 
-int launch_sliding_minmax32(const float2* src, float2* dst, int64_t n, cudaStream_t stream) {
+int launch_sliding_minmax32(const float4* src, float4* dst, int64_t n, cudaStream_t stream) {
     if (n <= 0) return FS_OK;
     sliding_minmax32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }
 
-int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, float scale,
-                        bool f8, float limit_sq, __half* dst, float2* sq, cudaStream_t stream) {
+int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, int32_t kept,
+                        const int32_t* perm, float scale, bool f8, float limit_sq, __half* dst, float4* sq,
+                        cudaStream_t stream) {
     if (n_rows <= 0) return FS_OK;
     const int threads = 256;
     const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
     if (f8)
         convert_rows_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-            src, n_rows, dim, 2 * dim_pad, scale, limit_sq, dst, sq);
+            src, n_rows, dim, 2 * dim_pad, kept, perm, scale, limit_sq, dst, sq);
     else
         convert_rows_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-            src, n_rows, dim, dim_pad, scale, limit_sq, dst, sq);
+            src, n_rows, dim, dim_pad, kept, perm, scale, limit_sq, dst, sq);
+    FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
+int launch_column_energy(const float* src, int64_t n_rows, int32_t dim, double* energy, cudaStream_t stream) {
+    if (n_rows <= 0) return FS_OK;
+    const dim3 grid(static_cast<unsigned>((dim + 127) / 128), static_cast<unsigned>(n_rows < 256 ? n_rows : 256));
+    column_energy_kernel<<<grid, 128, 0, stream>>>(src, n_rows, dim, energy);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }
@@ -258,7 +296,7 @@ int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t s
 }
 
 int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,
-                  __half* emb, float2* tok_sq, int sm_count, cudaStream_t stream) {
+                  __half* emb, float4* tok_sq, int sm_count, cudaStream_t stream) {
     if (n_tok <= 0) return FS_OK;
     const int32_t chunks16 = dim_pad * 2 / 16;
     const int64_t total = n_tok * chunks16;
@@ -272,8 +310,8 @@ int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, i
     return FS_OK;
 }
 
-int launch_window_norm(const float2* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
-                       int32_t window, float coef, bool script_side, float2* out, int64_t n_pad,
+int launch_window_norm(const float4* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
+                       int32_t window, float coef, bool script_side, float4* out, int64_t n_pad,
                        unsigned long long* window_counter, cudaStream_t stream) {
     if (n_pad <= 0) return FS_OK;
     const int threads = 256;

@@ -418,9 +418,30 @@ int64_t fs_records_best(const fs_match* matches, const int32_t* tie, int64_t n, 
                         int64_t n_script_words, int32_t* out_work, int32_t* out_word,
                         int32_t* out_window_ix, int32_t* out_match_ix, double* out_distance,
                         int32_t* out_lev, int64_t cap_out) {
+    return fs_records_best_mt(matches, tie, n, window, topk, text, tok_start, tok_end, tok_off, n_works,
+                              script_blob, script_word_off, n_script_words, out_work, out_word, out_window_ix,
+                              out_match_ix, out_distance, out_lev, cap_out, 1);
+}
+
+// The same with `n_threads` host threads: works are independent (a window never leaves its work), so
+// the position-sorted match list is cut at work boundaries into contiguous ranges of about equal
+// length, every thread runs the single-pass algorithm on its range into its own buffers, and the
+// buffers are concatenated in range order -- the rows come out sorted by (work, word) as before.
+int64_t fs_records_best_mt(const fs_match* matches, const int32_t* tie, int64_t n, int32_t window,
+                           int32_t topk, const char* text, const int64_t* tok_start,
+                           const int64_t* tok_end, const int64_t* tok_off, int64_t n_works,
+                           const char* script_blob, const int64_t* script_word_off,
+                           int64_t n_script_words, int32_t* out_work, int32_t* out_word,
+                           int32_t* out_window_ix, int32_t* out_match_ix, double* out_distance,
+                           int32_t* out_lev, int64_t cap_out, int32_t n_threads) {
     if (n < 0 || window < 1 || topk < 1 || (n > 0 && (!matches || !text || !tok_start || !tok_end ||
                                                      !tok_off || !script_blob || !script_word_off))) {
         fs::set_error("fs_records_best: invalid argument");
+        return INT64_MIN;
+    }
+    constexpr int kRing = 8;
+    if (window > kRing) {
+        fs::set_error("fs_records_best: window > 8");
         return INT64_MIN;
     }
     std::vector<int64_t> order(static_cast<size_t>(n));
@@ -436,90 +457,114 @@ int64_t fs_records_best(const fs_match* matches, const int32_t* tie, int64_t n, 
         if (tx != ty) return tx < ty;
         return x.script_pos < y.script_pos;
     });
+    struct Row {
+        int32_t work, word, window_ix, match_ix, lev;
+        double distance;
+    };
     // A fan word at global position `pos` receives records from the windows starting at
     // pos-w+1 .. pos, which arrive here in ascending order: a ring of 8 >= w open positions is
     // enough, and every position below the current window start is final and can be emitted --
     // no hash map, no final sort (rows come out ordered by position = by (work, word)).
-    struct Best {
-        int64_t pos;
-        double combined;
-        double distance;
-        int32_t window_ix, match_ix, lev;
-    };
-    constexpr int kRing = 8;
-    if (window > kRing) {
-        fs::set_error("fs_records_best: window > 8");
-        return INT64_MIN;
-    }
-    Best ring[kRing];
-    for (auto& e : ring) e.pos = -1;
-    int64_t rows = 0, w = 0;
-    auto emit = [&](const Best& bb) {
-        if (rows < cap_out) {
+    auto process = [&](int64_t r_begin, int64_t r_end, std::vector<Row>& rows_out) {
+        struct Best {
+            int64_t pos;
+            double combined;
+            double distance;
+            int32_t window_ix, match_ix, lev;
+        };
+        Best ring[kRing];
+        for (auto& e : ring) e.pos = -1;
+        int64_t w = 0;
+        auto emit = [&](const Best& bb) {
             while (w + 1 < n_works && tok_off[w + 1] <= bb.pos) ++w;
-            out_work[rows] = static_cast<int32_t>(w);
-            out_word[rows] = static_cast<int32_t>(bb.pos - tok_off[w]);
-            out_window_ix[rows] = bb.window_ix;
-            out_match_ix[rows] = bb.match_ix;
-            out_distance[rows] = bb.distance;
-            out_lev[rows] = bb.lev;
+            rows_out.push_back(Row{static_cast<int32_t>(w), static_cast<int32_t>(bb.pos - tok_off[w]), bb.window_ix,
+                                   bb.match_ix, bb.lev, bb.distance});
+        };
+        auto flush_below = [&](int64_t limit) {  // emit open positions < limit in ascending order
+            int64_t lo = INT64_MAX;
+            for (const auto& e : ring)
+                if (e.pos >= 0 && e.pos < lo) lo = e.pos;
+            if (lo == INT64_MAX) return;
+            if (limit - lo > kRing) limit = lo + kRing;  // open positions span less than the ring
+            for (int64_t pos = lo; pos < limit; ++pos) {
+                Best& e = ring[pos % kRing];
+                if (e.pos == pos) {
+                    emit(e);
+                    e.pos = -1;
+                }
+            }
+        };
+        std::string fan_ctx, match_str;
+        int64_t run_start = r_begin, cur_p = -1;
+        for (int64_t r = r_begin; r < r_end; ++r) {
+            const fs_match& m = matches[order[r]];
+            if (r > r_begin && matches[order[r - 1]].fan_pos != m.fan_pos) run_start = r;
+            if (r - run_start >= topk) continue;  // NearestFilter(10)
+            if (m.script_pos < 0 || m.script_pos + window > n_script_words) continue;
+            if (m.fan_pos != cur_p) {  // positions before this window start are final
+                flush_below(m.fan_pos);
+                cur_p = m.fan_pos;
+            }
+            // str(list of Token) vs str(Span): "[a, b, c]" vs "a b c"  (search.py:123,189)
+            fan_ctx.assign("[");
+            match_str.clear();
+            for (int k = 0; k < window; ++k) {
+                const int64_t t = static_cast<int64_t>(m.fan_pos) + k;
+                if (k) {
+                    fan_ctx.append(", ");
+                    match_str.push_back(' ');
+                }
+                fan_ctx.append(text + tok_start[t], static_cast<size_t>(tok_end[t] - tok_start[t]));
+                const int64_t a = script_word_off[m.script_pos + k];
+                match_str.append(script_blob + a, static_cast<size_t>(script_word_off[m.script_pos + k + 1] - a));
+            }
+            fan_ctx.push_back(']');
+            const int32_t lev = fs_levenshtein_utf8(match_str.data(), static_cast<int64_t>(match_str.size()),
+                                                    fan_ctx.data(), static_cast<int64_t>(fan_ctx.size()));
+            const double combined = m.distance * lev;
+            for (int k = 0; k < window; ++k) {
+                const int64_t pos = static_cast<int64_t>(m.fan_pos) + k;
+                Best& e = ring[pos % kRing];
+                if (e.pos != pos) {
+                    e = Best{pos, combined, m.distance, k, m.script_pos, lev};
+                } else if (combined < e.combined) {  // first minimal record wins ties
+                    e = Best{pos, combined, m.distance, k, m.script_pos, lev};
+                }
+            }
         }
-        ++rows;
+        flush_below(INT64_MAX);
     };
-    auto flush_below = [&](int64_t limit) {  // emit open positions < limit in ascending order
-        int64_t lo = INT64_MAX;
-        for (const auto& e : ring)
-            if (e.pos >= 0 && e.pos < lo) lo = e.pos;
-        if (lo == INT64_MAX) return;
-        if (limit - lo > kRing) limit = lo + kRing;  // open positions span less than the ring
-        for (int64_t pos = lo; pos < limit; ++pos) {
-            Best& e = ring[pos % kRing];
-            if (e.pos == pos) {
-                emit(e);
-                e.pos = -1;
-            }
-        }
-    };
-    std::string fan_ctx, match_str;
-    int64_t run_start = 0, cur_p = -1;
-    for (int64_t r = 0; r < n; ++r) {
-        const fs_match& m = matches[order[r]];
-        if (r > 0 && matches[order[r - 1]].fan_pos != m.fan_pos) run_start = r;
-        if (r - run_start >= topk) continue;  // NearestFilter(10)
-        if (m.script_pos < 0 || m.script_pos + window > n_script_words) continue;
-        if (m.fan_pos != cur_p) {  // positions before this window start are final
-            flush_below(m.fan_pos);
-            cur_p = m.fan_pos;
-        }
-        // str(list of Token) vs str(Span): "[a, b, c]" vs "a b c"  (search.py:123,189)
-        fan_ctx.assign("[");
-        match_str.clear();
-        for (int k = 0; k < window; ++k) {
-            const int64_t t = static_cast<int64_t>(m.fan_pos) + k;
-            if (k) {
-                fan_ctx.append(", ");
-                match_str.push_back(' ');
-            }
-            fan_ctx.append(text + tok_start[t], static_cast<size_t>(tok_end[t] - tok_start[t]));
-            const int64_t a = script_word_off[m.script_pos + k];
-            match_str.append(script_blob + a, static_cast<size_t>(script_word_off[m.script_pos + k + 1] - a));
-        }
-        fan_ctx.push_back(']');
-        const int32_t lev = fs_levenshtein_utf8(match_str.data(), static_cast<int64_t>(match_str.size()),
-                                                fan_ctx.data(), static_cast<int64_t>(fan_ctx.size()));
-        const double combined = m.distance * lev;
-        for (int k = 0; k < window; ++k) {
-            const int64_t pos = static_cast<int64_t>(m.fan_pos) + k;
-            Best& e = ring[pos % kRing];
-            if (e.pos != pos) {
-                e = Best{pos, combined, m.distance, k, m.script_pos, lev};
-            } else if (combined < e.combined) {  // first minimal record wins ties
-                e = Best{pos, combined, m.distance, k, m.script_pos, lev};
-            }
-        }
+    // ranges of the sorted list, cut where the work changes
+    if (n_threads < 1) n_threads = 1;
+    if (n < 4096) n_threads = 1;
+    std::vector<int64_t> cut(1, 0);
+    for (int t = 1; t < n_threads; ++t) {
+        int64_t r = n * t / n_threads;
+        if (r <= cut.back()) continue;
+        while (r < n && matches[order[r]].work == matches[order[r - 1]].work) ++r;
+        if (r > cut.back() && r < n) cut.push_back(r);
     }
-    flush_below(INT64_MAX);
+    cut.push_back(n);
+    const int64_t n_ranges = static_cast<int64_t>(cut.size()) - 1;
+    std::vector<std::vector<Row>> parts(static_cast<size_t>(n_ranges));
+    parallel_for(n_ranges, static_cast<int>(n_ranges), [&](int64_t k) {
+        parts[static_cast<size_t>(k)].reserve(static_cast<size_t>((cut[k + 1] - cut[k]) * 2 + 16));
+        process(cut[k], cut[k + 1], parts[static_cast<size_t>(k)]);
+    });
+    int64_t rows = 0;
+    for (const auto& part : parts) rows += static_cast<int64_t>(part.size());
     if (rows > cap_out) return -rows;
+    int64_t o = 0;
+    for (const auto& part : parts)
+        for (const Row& r : part) {
+            out_work[o] = r.work;
+            out_word[o] = r.word;
+            out_window_ix[o] = r.window_ix;
+            out_match_ix[o] = r.match_ix;
+            out_distance[o] = r.distance;
+            out_lev[o] = r.lev;
+            ++o;
+        }
     return rows;
 }
 

@@ -74,13 +74,12 @@ lsh_first_table_kernel(const LshParams p) {
 int launch_lsh(const LshParams& p, int sm_count, cudaStream_t stream) {
     const int wd = p.window * p.dim;
     const size_t smem = sizeof(double) * 2 * wd + 2 * static_cast<size_t>(p.n_tables) * p.n_bits + 16;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    // the attribute belongs to the (function, device) pair and the call is cheap: set it on the
+    // current device before every launch that needs more than the default 48 KB
+    if (smem > 48 * 1024)
         FS_CUDA_CHECK(cudaFuncSetAttribute(lsh_first_table_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem)));
-        configured = smem;
-    }
     lsh_first_table_kernel<<<sm_count * 4, kLshThreads, smem, stream>>>(p);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;

@@ -32,7 +32,12 @@ __global__ void rescore_kernel(const RescoreParams p) {
     const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     unsigned long long n = p.counters[FS_CNT_CANDIDATES];
-    if (n > static_cast<unsigned long long>(p.cand_cap)) n = p.cand_cap;
+    if (n > static_cast<unsigned long long>(p.cand_cap)) {
+        // pairs were lost in the pre-filter's compaction: tell the caller (the host entry points turn
+        // this into FS_E_OVERFLOW, a device-pointer caller reads the bit once its stream has drained)
+        if (warp_global == 0 && lane == 0) atomicOr(p.overflow, static_cast<unsigned long long>(FS_OVERFLOW_CANDIDATES));
+        n = p.cand_cap;
+    }
     for (int64_t c = warp_global; c < static_cast<int64_t>(n); c += n_warps) {
         const fs_pair pr = p.cand[c];
         double sf = 0.0, ss = 0.0;
@@ -79,6 +84,8 @@ __global__ void rescore_kernel(const RescoreParams p) {
                 m.work = csr_row_of(p.fan_off, p.n_works, pr.fan_pos);
                 m.flags = same ? FS_MATCH_EXACT : 0u;
                 p.out[slot] = m;
+            } else {
+                atomicOr(p.overflow, static_cast<unsigned long long>(FS_OVERFLOW_MATCHES));
             }
         }
     }

@@ -58,7 +58,8 @@ class DeviceIndex:
         for env, opt in (("FANDOM_SEARCH_DIAG", nt.FS_OPT_DIAG), ("FANDOM_SEARCH_CTA_PAIR", nt.FS_OPT_CTA_PAIR),
                          ("FANDOM_SEARCH_A_RESIDENT", nt.FS_OPT_A_RESIDENT),
                          ("FANDOM_SEARCH_PACKED_SHUFFLE", nt.FS_OPT_PACKED_SHUFFLE),
-                         ("FANDOM_SEARCH_OPERAND_BITS", nt.FS_OPT_OPERAND_BITS)):
+                         ("FANDOM_SEARCH_OPERAND_BITS", nt.FS_OPT_OPERAND_BITS),
+                         ("FANDOM_SEARCH_PREFILTER_DIMS", nt.FS_OPT_PREFILTER_DIMS)):
             v = os.environ.get(env)
             if v not in (None, ""):
                 self.set_option(opt, int(v))
@@ -78,7 +79,7 @@ class DeviceIndex:
     # -- knobs ------------------------------------------------------------
     def set_option(self, option, value):
         nt.check(self._lib.fs_index_set_option(self._h, option, value))
-        if option == nt.FS_OPT_OPERAND_BITS:      # the index was re-converted
+        if option in (nt.FS_OPT_OPERAND_BITS, nt.FS_OPT_PREFILTER_DIMS):      # the index was re-converted
             self.dim_pad = int(self._lib.fs_index_get_info(self._h, 1))
             self.scale = float(self._lib.fs_index_scale(self._h))
 
@@ -90,6 +91,11 @@ class DeviceIndex:
     def info(self, what):
         """fs_index_get_info(what) (see include/fandom_search.h)."""
         return int(self._lib.fs_index_get_info(self._h, what))
+
+    @property
+    def kept_dims(self):
+        """Embedding columns the pre-filter's operand rows keep (FS_OPT_PREFILTER_DIMS)."""
+        return int(self._lib.fs_index_get_info(self._h, 13))
 
     @property
     def diag(self):
@@ -133,7 +139,7 @@ class DeviceIndex:
         return tok, off, extra
 
     def search_host(self, tok, off, extra=None, cap=None, out=None):
-        """tok/off: host CSR batch.  Returns (matches[MATCH_DTYPE], counters[int64 x4])."""
+        """tok/off: host CSR batch.  Returns (matches[MATCH_DTYPE], counters[int64 x FS_CNT_COUNT])."""
         tok, off, extra = self._host_batch(tok, off, extra, self.dim)
         if cap is None:
             cap = max(4096, tok.shape[0] // 8)
@@ -146,8 +152,7 @@ class DeviceIndex:
                 off.shape[0] - 1, nt.ptr(extra) if extra.shape[0] else None, extra.shape[0],
                 nt.ptr(out), cap, nt.ptr(counters))
             if st == nt.FS_E_OVERFLOW:
-                cand_cap = int(self._lib.fs_index_get_info(self._h, 3))
-                if counters[nt.FS_CNT_CANDIDATES] > cand_cap:
+                if counters[nt.FS_CNT_OVERFLOW] & nt.FS_OVERFLOW_CANDIDATES:
                     self.reserve(tok.shape[0], int(counters[nt.FS_CNT_CANDIDATES]) * 5 // 4 + 1024)
                     # the match count of an overflowed candidate list is a lower bound
                     cap = max(cap, int(counters[nt.FS_CNT_CANDIDATES]))
@@ -157,6 +162,35 @@ class DeviceIndex:
                 continue
             nt.check(st)
             return out[:counters[nt.FS_CNT_MATCHES]], counters
+
+    def search_submit(self, tok, off, extra=None, cap=None):
+        """Asynchronous form of search_host (fs_search_submit): enqueues the batch and returns a
+        ticket at once; up to two batches may be in flight.  The ticket keeps the host arrays alive
+        (the copies run asynchronously from them; pass page-locked arrays for true DMA)."""
+        tok, off, extra = self._host_batch(tok, off, extra, self.dim)
+        if cap is None:
+            cap = max(4096, tok.shape[0] // 8)
+        t = ctypes.c_int32(-1)
+        nt.check(self._lib.fs_search_submit(
+            self._h, nt.ptr(tok) if tok.size else None, tok.shape[0], nt.ptr(off), off.shape[0] - 1,
+            nt.ptr(extra) if extra.shape[0] else None, extra.shape[0], cap, ctypes.byref(t)))
+        return {'ticket': t.value, 'tok': tok, 'off': off, 'extra': extra, 'cap': cap}
+
+    def search_collect(self, ticket, out=None):
+        """Wait for one submitted batch: (matches[MATCH_DTYPE], counters).  A batch whose buffers
+        overflowed is searched again synchronously with larger ones (rare: the first clusters of a run)."""
+        cap = ticket['cap']
+        if out is None or out.shape[0] < cap:
+            out = np.empty(cap, dtype=nt.MATCH_DTYPE)
+        counters = np.zeros(nt.FS_CNT_COUNT, dtype=np.int64)
+        st = self._lib.fs_search_collect(self._h, ticket['ticket'], nt.ptr(out), cap, nt.ptr(counters))
+        if st == nt.FS_E_OVERFLOW:
+            grow = max(int(counters[nt.FS_CNT_CANDIDATES]), int(counters[nt.FS_CNT_MATCHES])) * 5 // 4 + 1024
+            if counters[nt.FS_CNT_OVERFLOW] & nt.FS_OVERFLOW_CANDIDATES:
+                self.reserve(ticket['tok'].shape[0], grow)
+            return self.search_host(ticket['tok'], ticket['off'], ticket['extra'], cap=max(cap, grow))
+        nt.check(st)
+        return out[:counters[nt.FS_CNT_MATCHES]], counters
 
     def exact_join_host(self, tok, off, cap=None):
         tok, off, _ = self._host_batch(tok, off, None, self.dim)
@@ -212,7 +246,8 @@ class DeviceIndex:
             emb = torch.empty((n, self.dim_pad), dtype=torch.uint8, device=tok_t.device)
         else:
             emb = torch.empty((n, self.dim_pad), dtype=torch.float16, device=tok_t.device)
-        thr = torch.empty((n, 2), dtype=torch.float32, device=tok_t.device)   # (|window|, |rounding error|)
+        # (|window|, |rounding error of the kept columns|, |dropped columns|, 0)
+        thr = torch.empty((n, 4), dtype=torch.float32, device=tok_t.device)
         nt.check(self._lib.fs_stage_embed_dev(
             self._h, self._stream(stream), nt.ptr(tok_t), n, nt.ptr(off_t), off_t.numel() - 1,
             nt.ptr(extra_t), 0 if extra_t is None else extra_t.shape[0], nt.ptr(emb), nt.ptr(thr)))

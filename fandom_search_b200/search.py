@@ -348,7 +348,17 @@ class AnnIndexSearch(object):
 
     def search_prepared(self, prep):
         """GPU stage: one C-ABI call for the cluster (search.py:169-184 for every work)."""
-        matches, counters = self.engine.index.search_host(prep['tok'], prep['offs'], prep['extra'])
+        return self.collect_prepared(prep, self.submit_prepared(prep))
+
+    def submit_prepared(self, prep):
+        """Enqueue the cluster on the GPU and return at once (fs_search_submit; two clusters may be
+        in flight, so the next one is already queued while this one is searched)."""
+        return self.engine.index.search_submit(prep['tok'], prep['offs'], prep['extra'])
+
+    def collect_prepared(self, prep, ticket):
+        """Wait for a submitted cluster: (matches, first LSH table or None)."""
+        matches, counters = self.engine.index.search_collect(ticket)
+        ticket.clear()
         if prep.get('pin') is not None:
             # the token ids are on the device now: the page-locked buffer goes back to the pool
             _PINNED_TOKENS.give_back(prep.pop('pin'))
@@ -661,18 +671,29 @@ def analyze(args,
     switch_interval = sys.getswitchinterval()
     sys.setswitchinterval(2e-4)
     try:
-        with ThreadPoolExecutor(max_workers=1) as prep_pool, ThreadPoolExecutor(max_workers=1) as post_pool:
+        with ThreadPoolExecutor(max_workers=1) as prep_pool, ThreadPoolExecutor(max_workers=2) as post_pool:
             pending = prep_pool.submit(ann_index.prepare, mine[0][1]) if mine else None
-            in_flight = collections.deque()      # at most two clusters' buffers are alive at a time
+            on_gpu = collections.deque()         # clusters submitted to the GPU, oldest first (<= 2)
+            in_flight = collections.deque()      # records/CSV stages running (a few clusters' buffers alive)
+
+            def collect_oldest():
+                i0, prep0, ticket0 = on_gpu.popleft()
+                found = ann_index.collect_prepared(prep0, ticket0)
+                in_flight.append(post_pool.submit(finish, i0, prep0, found))
+                while len(in_flight) > 3:
+                    in_flight.popleft().result()
+
             for k, (i, fan_cluster) in enumerate(mine):
                 print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
                 prep = pending.result()
                 pending = prep_pool.submit(ann_index.prepare, mine[k + 1][1]) if k + 1 < len(mine) else None
-                found = ann_index.search_prepared(prep)
-                in_flight.append(post_pool.submit(finish, i, prep, found))
-                del prep, found
-                while len(in_flight) > 2:
-                    in_flight.popleft().result()
+                # the GPU always holds the next cluster: submit this one BEFORE waiting for the previous
+                on_gpu.append((i, prep, ann_index.submit_prepared(prep)))
+                del prep
+                if len(on_gpu) == 2:
+                    collect_oldest()
+            while on_gpu:
+                collect_oldest()
             while in_flight:
                 in_flight.popleft().result()
     finally:

@@ -88,9 +88,9 @@ class Vocab:
     def encode_files(self, paths, threads=None):
         if threads is None:
             # leave two cores to the thread that drives the GPU and to the post-processing thread:
-            # with every core tokenising, the kernel launches of the search call queue up behind them
-            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4
-            threads = max(1, min(16, cores) - 2)
+            # with every core tokenising, the kernel launches of the search call queue up behind them;
+            # under torchrun the node's cores are shared between the ranks (LOCAL_WORLD_SIZE)
+            threads = host_threads()
         arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
         h = self._lib.fs_batch_encode_files(self._h, arr, len(paths), threads)
         if not h:
@@ -172,7 +172,19 @@ class Batch:
             pass
 
 
-def records_best(matches, tie, window, topk, batch, script_blob, script_off):
+def host_threads(reserve=2, limit=16):
+    """Host threads one rank may use for a native stage: the cores this process may run on, shared
+    between the ranks of the node (LOCAL_WORLD_SIZE under torchrun), minus `reserve` cores for the
+    threads that drive the GPU and write the CSVs."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+    try:
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    except ValueError:
+        local_world = 1
+    return max(1, min(limit, cores // local_world) - reserve)
+
+
+def records_best(matches, tie, window, topk, batch, script_blob, script_off, threads=None):
     """Native search.py:182-226 core.  Returns dict of arrays (work, word, window_ix, match_ix,
     distance, lev) for the winning record of every matched fan word, sorted by (work, word)."""
     lib = nt.load()
@@ -186,13 +198,14 @@ def records_best(matches, tie, window, topk, batch, script_blob, script_off):
                "window_ix": np.empty(cap, np.int32), "match_ix": np.empty(cap, np.int32),
                "distance": np.empty(cap, np.float64), "lev": np.empty(cap, np.int32)}
         text = np.ascontiguousarray(batch.text)
-        rows = lib.fs_records_best(
+        rows = lib.fs_records_best_mt(
             nt.ptr(matches) if n else None, nt.ptr(tie_arr) if tie_arr is not None and n else None, n,
             window, topk, nt.ptr(text) if len(text) else None, nt.ptr(np.ascontiguousarray(batch.tok_start)),
             nt.ptr(np.ascontiguousarray(batch.tok_end)), nt.ptr(np.ascontiguousarray(batch.tok_off)),
             len(batch.tok_off) - 1, script_blob, nt.ptr(script_off), len(script_off) - 1,
             nt.ptr(out["work"]), nt.ptr(out["word"]), nt.ptr(out["window_ix"]), nt.ptr(out["match_ix"]),
-            nt.ptr(out["distance"]), nt.ptr(out["lev"]), cap)
+            nt.ptr(out["distance"]), nt.ptr(out["lev"]), cap,
+            host_threads(limit=8) if threads is None else threads)
         if rows < 0 and rows > -(1 << 62):
             cap = -rows
             continue

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define FS_ABI_VERSION 1
+#define FS_ABI_VERSION 2
 
 typedef enum fs_status {
     FS_OK = 0,
@@ -83,8 +83,14 @@ enum {
     FS_CNT_MATCHES = 1,    /* pairs with float64 distance < threshold                */
     FS_CNT_EXACT = 2,      /* pairs emitted by the hash-join                         */
     FS_CNT_WINDOWS = 3,    /* fan windows searched = sum max(T_i - w + 1, 0)         */
-    FS_CNT_COUNT = 4
+    FS_CNT_OVERFLOW = 4,   /* FS_OVERFLOW_* bits, written on the device by the search entry
+                              points: how a caller of the stream-ordered "_dev" variants
+                              learns that a buffer was too small                     */
+    FS_CNT_COUNT = 5
 };
+#define FS_OVERFLOW_CANDIDATES 1 /* the internal candidate buffer overflowed (pairs were lost):
+                                    fs_index_reserve more candidates and search again        */
+#define FS_OVERFLOW_MATCHES 2    /* more matches than `cap`: counters[FS_CNT_MATCHES] says how many */
 
 /* Options for fs_index_set_option. */
 enum {
@@ -109,6 +115,12 @@ enum {
                                     an epilogue warp loads both of its 32-column chunks at once, hands
                                     the accumulator back, takes the row maxima on the fp32 values and
                                     packs to fp16x2 only the chunks that survive the bound          */
+    FS_OPT_PREFILTER_DIMS = 11,  /* embedding columns kept in the operand rows of the tensor-core pre-filter:
+                                    0 = all (default), -1 = automatic (whole 128-byte chunks holding ~5/6
+                                    of the table's energy), n = the n columns of largest energy.  What a
+                                    window holds in the dropped columns enters its pre-filter threshold as
+                                    |f_drop| |s_drop|, so the candidates stay a guaranteed superset and the
+                                    float64 decision is unchanged.  Re-converts the index.             */
     FS_OPT_DIAG = 4              /* 1 (dense), 2, 3 or 6: the tensor cores accumulate window/E shifts
                                     and the epilogue adds E diagonal neighbours (same products,
                                     E-fold fewer tensor-core flops)                            */
@@ -149,7 +161,8 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value);
  * FS_MATCH_LSH_SHIFT.  n_tables = 0 switches the mode off. */
 int fs_index_set_lsh(fs_index* idx, const double* normals, int32_t n_tables, int32_t n_bits);
 /* what = 0: script windows, 1: dim_pad, 2: SM count, 3: candidate capacity, 4: shifts per stage,
- * 5: diagonal factor, 6: CTA pair, 7: A-resident, 8: pack level, 11: operand bits, 12: tile-group bits */
+ * 5: diagonal factor, 6: CTA pair, 7: A-resident, 8: pack level, 11: operand bits, 12: tile-group bits,
+ * 13: embedding columns kept by the pre-filter, 14: share of the table's energy they hold (ppm) */
 int64_t fs_index_get_info(const fs_index* idx, int32_t what);
 
 /*
@@ -163,7 +176,9 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what);
  *   counters   [FS_CNT_COUNT] int64
  *
  * Returns FS_E_OVERFLOW (host variant only) when counters[FS_CNT_MATCHES] > cap or
- * the internal candidate buffer overflowed; the first `cap` slots are valid.
+ * the internal candidate buffer overflowed; the first `cap` slots are valid.  The "_dev"
+ * variant cannot return what the device has not computed yet: once its stream has drained the
+ * caller MUST test counters[FS_CNT_OVERFLOW] (FS_OVERFLOW_* bits, set on the device).
  */
 int fs_search_csr_dev(fs_index* idx, void* stream,
                       const int32_t* tok, int64_t n_tok,
@@ -175,6 +190,23 @@ int fs_search_csr_host(fs_index* idx,
                        const int64_t* off, int64_t n_works,
                        const float* extra, int64_t n_extra,
                        fs_match* out, int64_t cap, int64_t* counters);
+
+/*
+ * Asynchronous form of fs_search_csr_host: up to two batches in flight per index.
+ * fs_search_submit enqueues the host -> device copies (page-locked `tok`/`off`/`extra` make them
+ * true DMA; the buffers must stay valid and unchanged until the matching collect returns), the
+ * kernels and the counter read-back, and returns at once with a ticket; fs_search_collect waits for
+ * that batch only, copies its matches out (on a stream of its own, under the next batch's kernels)
+ * and reports overflow exactly like fs_search_csr_host.  Replaces the blocking pool.map of
+ * search.py:381-386 by a pipeline: while batch k is searched, batch k+1 is already queued and the
+ * host works on the records of batch k-1.  Tickets are collected in any order, each once.
+ */
+int fs_search_submit(fs_index* idx,
+                     const int32_t* tok, int64_t n_tok,
+                     const int64_t* off, int64_t n_works,
+                     const float* extra, int64_t n_extra,
+                     int64_t cap, int32_t* ticket);
+int fs_search_collect(fs_index* idx, int32_t ticket, fs_match* out, int64_t cap, int64_t* counters);
 
 /* Exact 6-gram hash-join only (the distance-0 special case). */
 int fs_exact_join_dev(fs_index* idx, void* stream,
@@ -191,8 +223,9 @@ int fs_exact_join_host(fs_index* idx,
  * one kernel at a time.  All pointers are DEVICE pointers.
  */
 /* token gather + window norms: emb_out [n_tok, dim_pad] operand rows (e4m3 bytes, or fp16);
- * thr_out [n_tok][2] float = per window start (norm of the scaled window, norm of the rounding
- * error of its operand rows), NaN where the window leaves its work */
+ * thr_out [n_tok][4] float = per window start (norm of the scaled window, norm of the rounding
+ * error of its operand rows, norm of the columns the operand rows drop, 0), NaN where the window
+ * leaves its work */
 int fs_stage_embed_dev(fs_index* idx, void* stream,
                        const int32_t* tok, int64_t n_tok,
                        const int64_t* off, int64_t n_works,
@@ -276,6 +309,15 @@ int64_t fs_records_best(const fs_match* matches, const int32_t* tie, int64_t n, 
                         int64_t n_script_words, int32_t* out_work, int32_t* out_word,
                         int32_t* out_window_ix, int32_t* out_match_ix, double* out_distance,
                         int32_t* out_lev, int64_t cap_out);
+/* The same on n_threads host threads (works are independent: the position-sorted match list is cut
+ * at work boundaries); identical output. */
+int64_t fs_records_best_mt(const fs_match* matches, const int32_t* tie, int64_t n, int32_t window,
+                           int32_t topk, const char* text, const int64_t* tok_start,
+                           const int64_t* tok_end, const int64_t* tok_off, int64_t n_works,
+                           const char* script_blob, const int64_t* script_word_off,
+                           int64_t n_script_words, int32_t* out_work, int32_t* out_word,
+                           int32_t* out_window_ix, int32_t* out_match_ix, double* out_distance,
+                           int32_t* out_lev, int64_t cap_out, int32_t n_threads);
 
 /* CSV text of the winning records (arrays as returned by fs_records_best): the rows of
  * search.py:206-217 exactly as csv.writer(...).writerows writes them (search.py:331-334: excel

@@ -244,6 +244,7 @@ class OracleIndex(object):
     def _neighbours_dense(self, fan_win):
         thr = self.distance_threshold
         out = {}
+        self.last_all_pairs = []
         if fan_win.shape[0] == 0 or self.n_script_windows == 0:
             return out
         fan_unit = unit_rows(fan_win)
@@ -264,6 +265,8 @@ class OracleIndex(object):
                 for t in tables:
                     out.setdefault(fan_ix, []).append((d[i, j], t, j))
         res = {}
+        # (kept for the parity tests: every pair under the threshold, before the top-10 cut)
+        self.last_all_pairs = [(fan_ix, j, dist) for fan_ix in sorted(out) for dist, t, j in out[fan_ix]]
         for fan_ix, cands in out.items():
             cands.sort()                       # (distance, first table, insertion order) == stable sort
             res[fan_ix] = [(j, dist) for dist, t, j in cands[:10]]   # NearestFilter(10)
@@ -311,6 +314,14 @@ class OracleIndex(object):
         with open(filename, encoding='utf8') as f:
             fan = tokenize(f.read())
         return self.search_words(fan, filename)
+
+    def all_pairs_words(self, fan):
+        """Every (fan_ix, match_ix, distance) with distance < threshold, BEFORE the top-10 cut of
+        NearestFilter: the full float64 match set of search.py:176-184 under exhaustive candidates
+        (dense engine only) -- what the GPU path's match list must equal pair for pair."""
+        assert self.engine_kind == "dense" and self.mode == "exhaustive"
+        self._neighbours_dense(windows_of(self.lexicon.vectors(fan), self.window_size))
+        return list(self.last_all_pairs)
 
     def pairs_words(self, fan):
         """All (fan_ix, match_ix, distance) under the threshold after the top-10 filter."""

@@ -75,6 +75,12 @@ class NumpyIndex:
         counters[nt.FS_CNT_WINDOWS] = len(fpos)
         return m, counters
 
+    def search_submit(self, tok, off, extra=None, cap=None):
+        return {'result': self.search_host(tok, off, extra)}
+
+    def search_collect(self, ticket, out=None):
+        return ticket['result']
+
     def exact_join_host(self, tok, off, cap=None):
         tok = np.asarray(tok, np.int64)
         off = np.asarray(off, np.int64)

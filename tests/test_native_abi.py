@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libfandom_search.so does not export %s" % n
     assert set(names) == set(nt.SIGNATURES), set(names) ^ set(nt.SIGNATURES)
-    assert lib.fs_abi_version() == 1
+    assert lib.fs_abi_version() == 2
 
 
 def test_struct_layout_matches_header():

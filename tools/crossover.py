@@ -23,7 +23,7 @@ def main():
         idx = DeviceIndex(lex.table_all, script)
         tok_t, off_t, _ = idx.to_device(tok, off)
         out_t = torch.empty(24 << 20, dtype=torch.uint8, device="cuda")
-        cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
+        cnt_t = torch.zeros(nt.FS_CNT_COUNT, dtype=torch.int64, device="cuda")
         idx.reserve(len(tok), 1 << 20)
         res = {"dim": d, "default_diag": idx.diag}
         for e in (3, 6):

@@ -109,7 +109,7 @@ def main():
         idx2.set_option(nt.FS_OPT_SHIFTS_PER_STAGE, S)
         tok_t, off_t, _ = idx2.to_device(tok_f3, off2)
         out_t = torch.empty(24 << 20, dtype=torch.uint8, device="cuda")
-        cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
+        cnt_t = torch.zeros(nt.FS_CNT_COUNT, dtype=torch.int64, device="cuda")
         for it in range(3):
             if it == 1:
                 idx2.timing_reset()

@@ -68,7 +68,7 @@ def main():
     res["memset_same_bytes"] = {"ms": ms, "gbs": buf.numel() / ms / 1e6}
     del buf
     out_t = torch.empty((1 << 22, 2), dtype=torch.int32, device="cuda")
-    cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
+    cnt_t = torch.zeros(nt.FS_CNT_COUNT, dtype=torch.int64, device="cuda")
     ms = timeit(lambda: idx.exact_join_dev(tok_t, off_t, out_t, cnt_t))
     n_pairs = int(cnt_t.cpu()[nt.FS_CNT_EXACT])
     windows = int(np.maximum(np.diff(off) - 5, 0).sum())

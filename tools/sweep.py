@@ -43,7 +43,7 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
     tok_t = torch.randint(0, vocab, (int(off[-1]),), generator=g, device="cuda", dtype=torch.int32)
     off_t = torch.from_numpy(off).cuda()
     out_t = torch.empty(24 << 16, dtype=torch.uint8, device="cuda")
-    cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
+    cnt_t = torch.zeros(nt.FS_CNT_COUNT, dtype=torch.int64, device="cuda")
     idx.reserve(int(off[-1]), 1 << 16)
     idx.search_dev(tok_t, off_t, None, out_t, cnt_t)   # warm-up
     idx.search_dev(tok_t, off_t, None, out_t, cnt_t)

@@ -37,7 +37,7 @@ def main():
     tok_t = torch.randint(0, vocab, (int(off[-1]),), generator=g, device="cuda", dtype=torch.int32)
     off_t = torch.from_numpy(off).cuda()
     out_t = torch.empty(24 << 16, dtype=torch.uint8, device="cuda")
-    cnt_t = torch.zeros(4, dtype=torch.int64, device="cuda")
+    cnt_t = torch.zeros(nt.FS_CNT_COUNT, dtype=torch.int64, device="cuda")
     idx.reserve(int(off[-1]), 1 << 16)
     for _ in range(3):
         idx.search_dev(tok_t, off_t, None, out_t, cnt_t)
