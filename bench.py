@@ -512,6 +512,7 @@ def run_native_arm(args):
                                      "fp16 tcgen05 pre-filter (fp32 accumulate, slack 4e-3) + float64 rescoring"),
                        "candidates_per_step": int(counters[0][nt.FS_CNT_CANDIDATES]),
                        "matches_per_step": int(counters[0][nt.FS_CNT_MATCHES]),
+                       "kept_dims": index.kept_dims,
                        "kernel": "diagonal factor E=%d, cta_group::%d" % (diag, 2 if index.cta_pair else 1)},
             "clocks": clocks,
             "e2e": {"value": total_windows / (e2e_ms * 1e-3), "unit": UNIT,

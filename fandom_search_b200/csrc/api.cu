@@ -107,8 +107,8 @@ struct fs_index {
     int64_t n_script_windows = 0;
     __half* script_emb = nullptr;
     float4* script_tok_sq = nullptr;
-    float4* script_norm = nullptr;      // (B_j, D_j, H_j) per script window start
-    float4* script_norm_min = nullptr;  // (min B, max D, max H) over 32 columns
+    float2* script_norm = nullptr;      // (B_j, half2(D_j, H_j)) per script window start
+    float2* script_norm_min = nullptr;  // (min B, half2(max D, max H)) over 32 columns
     int32_t tiles_n = 0;
     CUtensorMap map_script;
     CUtensorMap map_script128;  // boxes of 128 rows (E = 6: no halo rows)
@@ -123,7 +123,7 @@ struct fs_index {
     int64_t sq_cap = 0;
     float4* fan_tok_sq = nullptr;
     int64_t thr_cap = 0;
-    float4* fan_thr = nullptr;  // (A_i, C_i, G_i) per fan window start
+    float2* fan_thr = nullptr;  // (A_i, half2(C_i, G_i)) per fan window start
     int64_t cand_cap = 0;
     fs_pair* cand = nullptr;
     int64_t fx_cap = 0;  // fan extra rows
@@ -371,8 +371,8 @@ static int prepare_operands(fs_index* idx) {
     FS_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
     const float coef = static_cast<float>(1.0 - idx->threshold - kEpsAccum);
     if ((r = launch_window_norm(idx->script_tok_sq, idx->n_script_tok, idx->script_off, idx->n_scripts,
-                                idx->window, coef, true, idx->script_norm, n_pad, d_cnt + FS_CNT_WINDOWS,
-                                st)) != FS_OK)
+                                idx->window, coef, true, idx->script_norm, nullptr, n_pad,
+                                d_cnt + FS_CNT_WINDOWS, st)) != FS_OK)
         return r;
     if ((r = launch_sliding_minmax32(idx->script_norm, idx->script_norm_min, n_pad, st)) != FS_OK) return r;
     unsigned long long h_cnt[FS_CNT_COUNT];
@@ -693,7 +693,7 @@ int check_batch(const fs_index* idx, const BatchArgs& a, const char* who) {
 
 // gather + window thresholds of one batch into the index workspace
 int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned long long* counters,
-                __half* emb_out, float4* thr_out, int64_t thr_pad) {
+                __half* emb_out, float2* thr_out, float4* thr_plain, int64_t thr_pad) {
     int r;
     if (a.n_extra > 0) {
         if ((r = dev_grow(&idx->fx16, &idx->fx_cap, a.n_extra * idx->dim_pad)) != FS_OK) return r;
@@ -712,7 +712,7 @@ int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned lon
     FS_CUDA_CHECK(cudaMemsetAsync(idx->fan_tok_sq + a.n_tok, 0, sizeof(float4) * 8, st));
     // fan side of the pre-filter bound: (|f|, |f - qf|) per window (window_norm_kernel)
     return launch_window_norm(idx->fan_tok_sq, a.n_tok, a.off, static_cast<int32_t>(a.n_works),
-                              idx->window, 0.0f, false, thr_out, thr_pad,
+                              idx->window, 0.0f, false, thr_out, thr_plain, thr_pad,
                               counters ? counters + FS_CNT_WINDOWS : nullptr, st);
 }
 
@@ -736,7 +736,7 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
                   static_cast<long long>(a.n_tok), static_cast<long long>(idx->tok_cap));
         return FS_E_INVALID;
     }
-    if ((r = embed_batch(idx, st, a, counters, idx->fan_emb, idx->fan_thr, thr_pad)) != FS_OK) return r;
+    if ((r = embed_batch(idx, st, a, counters, idx->fan_emb, idx->fan_thr, nullptr, thr_pad)) != FS_OK) return r;
 
     CUtensorMap map_fan;
     if ((r = make_token_map(&map_fan, idx->fan_emb, a.n_tok, idx->dim_pad, kBoxRows)) != FS_OK) return r;
@@ -1037,8 +1037,13 @@ int fs_stage_embed_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t 
     }
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     if ((r = fs_index_reserve(idx, n_tok, idx->cand_cap > 0 ? idx->cand_cap : 1024)) != FS_OK) return r;
-    return embed_batch(idx, static_cast<cudaStream_t>(stream), a, nullptr,
-                       static_cast<__half*>(emb_out), reinterpret_cast<float4*>(thr_out), n_tok);
+    // (the packed bounds go to the workspace the search would use; the caller gets the plain values)
+    if (n_tok > idx->thr_cap) {
+        set_error("fs_stage_embed_dev: internal workspace too small");
+        return FS_E_INVALID;
+    }
+    return embed_batch(idx, static_cast<cudaStream_t>(stream), a, nullptr, static_cast<__half*>(emb_out),
+                       idx->fan_thr, reinterpret_cast<float4*>(thr_out), n_tok);
 }
 
 int fs_stage_dots_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n_tok,

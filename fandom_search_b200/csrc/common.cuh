@@ -51,7 +51,7 @@ constexpr int kProducerWarp = kEpiWarps;               // single-thread roles ge
 constexpr int kMmaWarp = kEpiWarps + 1;                // warp ids (scheduler priority)
 constexpr int kDistThreads = 32 * (kEpiWarps + 2);     // 576
 constexpr int kHaloCols = kBlockN + 8;
-constexpr int kNormTileBytes = kAccumStages * kHaloCols * 16;              // 8448: (B, D, H, -) per column
+constexpr int kNormTileBytes = kAccumStages * kHaloCols * 8;               // 4224: (B, half2(D, H)) per column
 // E = 6 (one MMA shift, no row offsets inside a stage): the four 32-lane TMEM quarters of a tile
 // hold OVERLAPPING fan rows, quarter q = rows [27 q, 27 q + 32) of the tile (four TMA boxes of 32
 // rows), so every quarter sums its own diagonals -- no boundary rows to publish, no boundary
@@ -78,8 +78,8 @@ __host__ __device__ constexpr int dist_stage_bytes(bool pair, bool ares) {
     return ares ? kStageABytes : (pair ? 2 * kStageABytes : kStageBytes);
 }
 __host__ __device__ constexpr int dist_stages(int diag, bool pair, bool ares) {
-    // (E < 6 keeps boundary rows and the tile's bounds in shared memory: one stage less)
-    return ares ? (diag == 6 ? 7 : 6) : (pair ? (diag == 6 ? 6 : 5) : (diag == 3 ? 3 : 4));
+    (void)diag;
+    return ares ? 7 : (pair ? 6 : 4);
 }
 // per published boundary row and 32-column chunk, the maximum of the row over the chunk's 40 loaded
 // columns (one half; 8 chunks per tile, two buffers): lets the boundary pass reject a chunk at once
@@ -91,20 +91,20 @@ __host__ __device__ constexpr int dist_smem_bytes(int diag, bool pair, bool ares
            1024 /*align slack*/ + 256 /*barriers*/ + dist_pub_bytes(diag) + kNormTileBytes +
            dist_rowmax_bytes(diag);
 }
-static_assert(dist_smem_bytes(2, false, false) <= 232448 && dist_smem_bytes(3, false, false) <= 232448 &&
-                  dist_smem_bytes(2, true, false) <= 232448 && dist_smem_bytes(2, true, true) <= 232448 &&
-                  dist_smem_bytes(1, false, false) <= 232448 && dist_smem_bytes(3, true, false) <= 232448 &&
+static_assert(dist_smem_bytes(1, false, false) <= 232448 && dist_smem_bytes(3, true, false) <= 232448 &&
                   dist_smem_bytes(6, true, false) <= 232448 && dist_smem_bytes(6, false, false) <= 232448 &&
                   dist_smem_bytes(3, true, true) <= 232448 && dist_smem_bytes(6, true, true) <= 232448 &&
                   dist_smem_bytes(1, true, true) <= 232448,
               "distance kernel exceeds the 227 KB shared memory limit");
 
 struct DistParams {
-    // pre-filter: keep (i, j) iff acc_ij > A_i * B_j - C_i * D_j - G_i * H_j  (window_norm_kernel, embed.cu)
-    const float4* fan_ac;       // [Mpad]  (A_i, C_i, G_i) = (|fan window|, |its rounding error|, |its dropped
-                                //         elements|), NaN when invalid
-    const float4* script_bd;    // [Npad]  (B_j, D_j, H_j) = ((1-thr-eps)|s| - err, |s| + err, |dropped|), NaN when invalid
-    const float4* script_mm32;  // [Npad]  (min B, max D, max H) over columns j .. j+31
+    // pre-filter: keep (i, j) iff acc_ij > A_i * B_j - C_i * D_j - G_i * H_j  (window_norm_kernel, embed.cu).
+    // The two slack factors of a side travel as ONE register, half2 rounded UP (a larger slack only
+    // widens the superset): the epilogue's live state is what it was with two terms.
+    const float2* fan_ac;       // [Mpad]  (A_i, half2(C_i, G_i)) = (|fan window|, (|its rounding error|, |its dropped
+                                //         elements|)), A = NaN when invalid
+    const float2* script_bd;    // [Npad]  (B_j, half2(D_j, H_j)) = ((1-thr-eps)|s| - err, (|s| + err, |dropped|)), B = NaN when invalid
+    const float2* script_mm32;  // [Npad]  (min B, half2(max D, max H)) over columns j .. j+31
     int64_t n_fan_tok;        // rows of the fan token matrix (M)
     int64_t n_script_tok;     // rows of the script token matrix (N)
     int32_t chunks;           // ceil(dim_pad / 64) 64-column chunks
@@ -201,9 +201,9 @@ int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t s
 int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,
                   __half* emb, float4* tok_sq, int sm_count, cudaStream_t stream);
 int launch_window_norm(const float4* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
-                       int32_t window, float coef, bool script_side, float4* out, int64_t n_pad,
-                       unsigned long long* window_counter, cudaStream_t stream);
-int launch_sliding_minmax32(const float4* src, float4* dst, int64_t n, cudaStream_t stream);
+                       int32_t window, float coef, bool script_side, float2* out, float4* out_plain,
+                       int64_t n_pad, unsigned long long* window_counter, cudaStream_t stream);
+int launch_sliding_minmax32(const float2* src, float2* dst, int64_t n, cudaStream_t stream);
 int launch_rescore(const RescoreParams& p, int sm_count, cudaStream_t stream);
 int launch_lsh(const LshParams& p, int sm_count, cudaStream_t stream);
 int launch_hash_build(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,

@@ -263,7 +263,7 @@ template <int kDiag, bool kDump, int kPack, bool kPair>
 __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t m0, const int32_t n0,
                                               const int as, const uint32_t tfull_addr, const uint32_t tempty_addr,
                                               const uint32_t aphase, const uint32_t tmem_base, float* halo,
-                                              float4* norm_tile, __half* rowmax, const int warp, const int lane,
+                                              float2* norm_tile, __half* rowmax, const int warp, const int lane,
                                               const int tl_tile = 0) {
     (void)tl_tile;
     constexpr bool kOverlap = kDiag == 6;  // lane quarters hold overlapping fan rows: nothing crosses quarters
@@ -288,17 +288,23 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     const int32_t gi = m0 + row;
     const bool row_ok = kOverlap ? lane < kQuarterRows6 : row < kMStep;
     const float kNaN = __int_as_float(0x7fc00000);
-    // (A_i, C_i, G_i) of this lane's fan window (padded to a tile multiple); NaN = never a candidate
-    const float4 ac = row_ok ? __ldg(p.fan_ac + gi) : make_float4(kNaN, kNaN, kNaN, 0.f);
-    // pre-filter bound of this lane's row against script-side (B, D, H): A B - C D - G H
-    auto bound_of = [&](float a, const float4& bd) { return fmaf(-ac.z, bd.z, fmaf(-ac.y, bd.y, a * bd.x)); };
+    // (A_i, half2(C_i, G_i)) of this lane's fan window (padded to a tile multiple); NaN = never a candidate
+    const float2 ac = row_ok ? __ldg(p.fan_ac + gi) : make_float2(kNaN, kNaN);
+    // pre-filter bound of a fan row (a, half2(c, g)) against script-side (B, half2(D, H)): a B - c D - g H
+    auto bound_row = [](float a, float cg, const float2& bd) {
+        const uint32_t u = __float_as_uint(cg), v = __float_as_uint(bd.y);
+        const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&u));
+        const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&v));
+        return fmaf(-x.y, y.y, fmaf(-x.x, y.x, a * bd.x));
+    };
+    auto bound_of = [&](float a, const float2& bd) { return bound_row(a, ac.y, bd); };
     // rows whose sum needs another warp's rows are finished in the boundary pass
     const float a_main = (kDiag > 1 && lane >= kTail0) ? kNaN : ac.x;
     // E > 1: (B_j, D_j) of this tile staged once in smem, NaN baked in for the E-1 columns that
     // belong to the next tile
-    float4* ns_tile = norm_tile + as * kHaloCols;
+    float2* ns_tile = norm_tile + as * kHaloCols;
     if (kDiag > 1 && !kOverlap && epi_tid < kHaloCols)
-        ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.script_bd + n0 + epi_tid) : make_float4(kNaN, kNaN, kNaN, 0.f);
+        ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.script_bd + n0 + epi_tid) : make_float2(kNaN, kNaN);
     mbar_wait_warp(tfull_addr, aphase, 0);
     tc_fence_after();
     FS_TL(2 + warp, tl_tile, 1);
@@ -315,7 +321,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
             const int halo_off = (group * kEpiCols + 64 < kBlockN) ? 64 : 56;  // (see load_chunk below)
             tmem_ld_32x72(taddr, taddr + halo_off, q);
         }
-        float4 mm2[2];
+        float2 mm2[2];
         mm2[0] = __ldg(p.script_mm32 + n0 + group * kEpiCols);
         mm2[1] = __ldg(p.script_mm32 + n0 + group * kEpiCols + 32);
         tmem_ld_wait();
@@ -353,7 +359,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                 const int32_t gj0 = n0 + c0;
 #pragma unroll
                 for (int x = 0; x < 32; ++x) {
-                    const float4 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float4(kNaN, kNaN, kNaN, 0.f);
+                    const float2 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float2(kNaN, kNaN);
                     const float v = (x & 1) ? h2_hi(o16[x >> 1]) : h2_lo(o16[x >> 1]);
                     if (v > bound_of(a_main, bd)) {
                         const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
@@ -388,7 +394,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
         __syncwarp();
         // prefetch the chunk's (min B, max D): the latency hides behind the TMEM load.  (Fetching it
         // one tile ahead in the caller changed nothing and cost 8 live registers -> spills.)
-        const float4 mm = kDump ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(p.script_mm32 + n0 + c0);
+        const float2 mm = kDump ? make_float2(0.f, 0.f) : __ldg(p.script_mm32 + n0 + c0);
         if (!kHalf) load_chunk(ch);
         tmem_ld_wait();
         uint32_t pk[20];
@@ -499,7 +505,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
             if (mx > thr_chunk) {
 #pragma unroll
                 for (int x = 0; x < 32; ++x) {
-                    const float4 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float4(kNaN, kNaN, kNaN, 0.f);
+                    const float2 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float2(kNaN, kNaN);
                     if (out_val(x) > bound_of(a_main, bd)) {
                         const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                         if (slot < static_cast<unsigned long long>(p.cand_cap)) {
@@ -526,12 +532,11 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     if (kDiag > 1 && !kOverlap) {
         // boundary rows: tail rows of quarters 0..2 (quarter 3's belong to the next tile)
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        float a_l[kEdge > 0 ? kEdge : 1], c_l[kEdge > 0 ? kEdge : 1], g_l[kEdge > 0 ? kEdge : 1];  // (kDiag == 1 never gets here)
+        float a_l[kEdge > 0 ? kEdge : 1], c_l[kEdge > 0 ? kEdge : 1];  // (kDiag == 1 never gets here)
 #pragma unroll
         for (int tr = 0; tr < kEdge; ++tr) {
             a_l[tr] = __shfl_sync(0xffffffffu, ac.x, kTail0 + tr);
-            c_l[tr] = __shfl_sync(0xffffffffu, ac.y, kTail0 + tr);
-            g_l[tr] = __shfl_sync(0xffffffffu, ac.z, kTail0 + tr);
+            c_l[tr] = __shfl_sync(0xffffffffu, ac.y, kTail0 + tr);  // half2(C, G) of that row
         }
         if (quarter < 3) {
 #pragma unroll
@@ -542,7 +547,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                 // row maxima (summed in the order of `v` below: fp32 addition is monotone), against
                 // the chunk's smallest pre-filter bound -- the same rejection as in the main pass
                 float rmx[2 * (kEdge > 0 ? kEdge : 1)];  // row maxima: tail rows of this quarter, head rows of the next
-                float4 mm = make_float4(0.f, 0.f, 0.f, 0.f);
+                float2 mm = make_float2(0.f, 0.f);
                 if (kHalf && !kDump) {
 #pragma unroll
                     for (int s2 = 0; s2 < kEdge; ++s2) {
@@ -559,7 +564,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                         float bsum = 0.f;
 #pragma unroll
                         for (int d = 0; d < kDiag; ++d) bsum += rmx[tr + d];
-                        if (!(bsum > fmaf(-g_l[tr], mm.z, fmaf(-c_l[tr], mm.y, a_l[tr] * mm.x)))) continue;
+                        if (!(bsum > bound_row(a_l[tr], c_l[tr], mm))) continue;
                     }
                     float v = 0.f;
 #pragma unroll
@@ -579,7 +584,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                     if (kDump) {
                         if (gr < p.n_fan_tok && c < kNStep && n0 + c < p.dump_ld)
                             p.dump[static_cast<int64_t>(gr) * p.dump_ld + n0 + c] = v;
-                    } else if (v > fmaf(-g_l[tr], ns_tile[c].z, fmaf(-c_l[tr], ns_tile[c].y, a_l[tr] * ns_tile[c].x))) {
+                    } else if (v > bound_row(a_l[tr], c_l[tr], ns_tile[c])) {
                         const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
                         if (slot < static_cast<unsigned long long>(p.cand_cap)) {
                             p.cand[slot].fan_pos = gr;
@@ -640,7 +645,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
     uint32_t* tmem_slot_ptr =
         reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
-    float4* norm_tile = reinterpret_cast<float4*>(halo + dist_pub_bytes(kDiag) / 4);
+    float2* norm_tile = reinterpret_cast<float2*>(halo + dist_pub_bytes(kDiag) / 4);
     __half* rowmax_base = reinterpret_cast<__half*>(norm_tile + kAccumStages * kHaloCols);
 
     // Warp roles.  The warp scheduler prefers the HIGHEST warp id among eligible warps, so the

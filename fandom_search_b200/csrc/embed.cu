@@ -186,7 +186,8 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
 //   fan side    out[t] = (n, e, g)                     = (A_i, C_i, G_i)
 //   script side out[t] = (coef * n - e, n + e, g)      = (B_j, D_j, H_j),  coef = 1 - thr - eps
 // when the window lies inside its CSR row, else NaN -- every comparison with NaN is false,
-// whatever the sign of the other factor.  The distance epilogue keeps a pair iff
+// whatever the sign of the other factor; stored as (x, half2(y, z)), the halves rounded UP
+// (pack_bound).  The distance epilogue keeps a pair iff
 //   acc_ij > A_i * B_j - C_i * D_j - G_i * H_j.
 // With qf, qs the rounded kept parts of the windows:
 //   f.s = qf.qs + (f_kept - qf).qs + f_kept.(s_kept - qs) + f_drop.s_drop
@@ -194,9 +195,16 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
 // so every pair with f.s > (1 - thr) |f||s| passes: each window carries its own measured slack and a
 // badly represented window (rows that underflow the operand format, or whose weight sits in the
 // dropped elements) only widens its own row/column.  out is padded with NaN up to n_pad.
+// (x, half2(y, z)) with the halves rounded towards +inf (a slack factor may only grow)
+__device__ __forceinline__ float2 pack_bound(float x, float y, float z) {
+    const __half2 h = __halves2half2(__float2half_ru(y), __float2half_ru(z));
+    return make_float2(x, __uint_as_float(*reinterpret_cast<const uint32_t*>(&h)));
+}
+
 __global__ void window_norm_kernel(const float4* __restrict__ tok_sq, int64_t n_tok,
                                    const int64_t* __restrict__ off, int32_t n_rows, int32_t window,
-                                   float coef, int script_side, float4* __restrict__ out, int64_t n_pad,
+                                   float coef, int script_side, float2* __restrict__ out,
+                                   float4* __restrict__ out_plain, int64_t n_pad,
                                    unsigned long long* window_counter) {
     __shared__ int32_t row_hint;
     const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x;
@@ -222,7 +230,8 @@ __global__ void window_norm_kernel(const float4* __restrict__ tok_sq, int64_t n_
                 valid = 1;
             }
         }
-        out[t] = r;
+        out[t] = pack_bound(r.x, r.y, r.z);
+        if (out_plain) out_plain[t] = r;  // (tests: the unrounded values)
     }
     if (window_counter) {
         const unsigned int n = __reduce_add_sync(0xffffffffu, valid);
@@ -230,23 +239,25 @@ __global__ void window_norm_kernel(const float4* __restrict__ tok_sq, int64_t n_
     }
 }
 
-// dst[j] = (min B, max D, max H) over the valid (non-NaN) entries j .. j+31, clamped at n: lets the
-// distance epilogue reject a whole 32-column chunk with one compare of its largest accumulator
-// (A minB - C maxD - G maxH <= A B_j - C D_j - G H_j for A, C, D, G, H >= 0).  No valid entry: (+inf, 0, 0).
-__global__ void sliding_minmax32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n) {
+// dst[j] = (min B, half2(max D, max H)) over the valid (B not NaN) entries j .. j+31, clamped at n: lets
+// the distance epilogue reject a whole 32-column chunk with one compare of its largest accumulator
+// (A minB - C maxD - G maxH <= A B_j - C D_j - G H_j for A, C, D, G, H >= 0).  No valid entry: (+inf, (0, 0)).
+__global__ void sliding_minmax32_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int64_t n) {
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    float mn = INFINITY, mx = 0.f, mh = 0.f;
+    float mn = INFINITY;
+    __half2 mx = __float2half2_rn(0.f);
     for (int k = 0; k < 32 && j + k < n; ++k) {
-        const float4 v = src[j + k];
-        mn = fminf(mn, v.x);  // fminf / fmaxf return the non-NaN operand
-        mx = fmaxf(mx, v.y);
-        mh = fmaxf(mh, v.z);
+        const float2 v = src[j + k];
+        if (v.x != v.x) continue;  // invalid window: its halves are NaN too
+        mn = fminf(mn, v.x);
+        const uint32_t u = __float_as_uint(v.y);
+        mx = __hmax2(mx, *reinterpret_cast<const __half2*>(&u));
     }
-    dst[j] = make_float4(mn, mx, mh, 0.f);
+    dst[j] = make_float2(mn, __uint_as_float(*reinterpret_cast<const uint32_t*>(&mx)));
 }
 
-int launch_sliding_minmax32(const float4* src, float4* dst, int64_t n, cudaStream_t stream) {
+int launch_sliding_minmax32(const float2* src, float2* dst, int64_t n, cudaStream_t stream) {
     if (n <= 0) return FS_OK;
     sliding_minmax32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
     FS_CUDA_CHECK(cudaGetLastError());
@@ -311,13 +322,13 @@ int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, i
 }
 
 int launch_window_norm(const float4* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
-                       int32_t window, float coef, bool script_side, float4* out, int64_t n_pad,
-                       unsigned long long* window_counter, cudaStream_t stream) {
+                       int32_t window, float coef, bool script_side, float2* out, float4* out_plain,
+                       int64_t n_pad, unsigned long long* window_counter, cudaStream_t stream) {
     if (n_pad <= 0) return FS_OK;
     const int threads = 256;
     const int64_t blocks = (n_pad + threads - 1) / threads;
     window_norm_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
-        tok_sq, n_tok, off, n_rows, window, coef, script_side ? 1 : 0, out, n_pad, window_counter);
+        tok_sq, n_tok, off, n_rows, window, coef, script_side ? 1 : 0, out, out_plain, n_pad, window_counter);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }

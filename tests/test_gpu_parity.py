@@ -148,6 +148,9 @@ def test_gather_is_bit_exact_and_norms_match():
     # per window: (norm of the scaled window, norm of its fp16 rounding error), NaN where the window
     # leaves its work
     thr = thr.cpu().numpy()
+    assert thr.shape[1] == 4 and np.all(thr[:, 3] == 0)
+    assert np.all(thr[np.isfinite(thr[:, 2]), 2] == 0)      # nothing dropped: every column is kept
+    thr = thr[:, :2]
     x = allrows.astype(np.float64) * float(scale)
     back = (allrows * scale).astype(np.float16).astype(np.float64)
     sq = (x[tok] ** 2).sum(axis=1)
