@@ -52,7 +52,11 @@ static int dev_alloc(T** p, int64_t count) {
 template <typename T>
 static int dev_grow(T** p, int64_t* cap, int64_t need) {
     if (need <= *cap && *p) return FS_OK;
-    int64_t ncap = *cap > 0 ? *cap : need;  // first allocation is exact, growth is geometric
+    // Growing a buffer synchronises the device (a batch may be in flight): leave headroom from the
+    // first allocation on, so that clusters a few percent larger than the first do not stall the
+    // pipeline; later growth is geometric.  (Requests of at most 64 Ki elements stay exact: tests
+    // size candidate buffers tightly on purpose.)
+    int64_t ncap = *cap > 0 ? *cap : (need > (1 << 16) ? need + need / 4 : need);
     while (ncap < need) ncap += ncap / 2 + 1024;
     if (*p) {
         cudaDeviceSynchronize();
@@ -82,7 +86,7 @@ struct fs_index {
     bool ready = false;         // operand tables built (false after a failed re-conversion)
     float row_limit_sq = 0.f;   // squared norm of the longest scaled row of the index
     int32_t operand_bits = 8;   // 16: fp16 operands, 8: fp8 e4m3 operands (default)
-    int32_t prefilter_auto = 0; // 1: prefilter_dims == 0 picks the kept columns by energy share; 0: keeps all
+    int32_t prefilter_auto = 1; // 1 (default): the kept columns are chosen by energy share; 0: prefilter_dims (0 = all)
     int32_t prefilter_dims = 0; // FS_OPT_PREFILTER_DIMS: embedding columns kept in the operand rows (0 = auto)
     int32_t kept_dims = 0;      // columns actually kept (<= dim), in the order of `perm`
     int32_t* perm = nullptr;    // [dim] source column of operand element c: columns by descending energy

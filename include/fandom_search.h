@@ -116,8 +116,9 @@ enum {
                                     the accumulator back, takes the row maxima on the fp32 values and
                                     packs to fp16x2 only the chunks that survive the bound          */
     FS_OPT_PREFILTER_DIMS = 11,  /* embedding columns kept in the operand rows of the tensor-core pre-filter:
-                                    0 = all (default), -1 = automatic (whole 128-byte chunks holding ~5/6
-                                    of the table's energy), n = the n columns of largest energy.  What a
+                                    -1 = automatic (default: whole 128-byte chunks of operand row holding
+                                    ~5/6 of the table's energy: 256 of 300, 640 of 768), 0 = all, n = the
+                                    n columns of largest energy.  What a
                                     window holds in the dropped columns enters its pre-filter threshold as
                                     |f_drop| |s_drop|, so the candidates stay a guaranteed superset and the
                                     float64 decision is unchanged.  Re-converts the index.             */

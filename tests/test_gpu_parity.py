@@ -27,8 +27,12 @@ def _device_index(*a, bits=16, **kw):
     test_library_defaults): the stage-level expectations below are written for fp16."""
     from fandom_search_b200.engine import DeviceIndex
     idx = DeviceIndex(*a, **kw)
-    if bits is not None and idx.operand_bits != bits:
-        idx.set_option(nt.FS_OPT_OPERAND_BITS, bits)
+    if bits is not None:
+        # ... and for operand rows that keep every embedding column (the library default drops the
+        # lowest-energy ones, see test_prefilter_columns_*)
+        idx.set_option(nt.FS_OPT_PREFILTER_DIMS, 0)
+        if idx.operand_bits != bits:
+            idx.set_option(nt.FS_OPT_OPERAND_BITS, bits)
     return idx
 
 
@@ -176,13 +180,14 @@ def test_library_defaults():
     idx = _device_index(table, script, extra=sx, bits=None)
     assert idx.operand_bits == 8 and idx.diag == 6 and idx.cta_pair == 1 and idx.info(7) == 1 and idx.info(8) == 2
     assert idx.info(12) == 7          # grouped stages + early accumulator release + one-pass epilogue
+    assert idx.kept_dims == 256 and idx.dim_pad == 256      # two 128-byte chunks of the 300 columns
     want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
     got, _ = idx.search_host(tok, off, fx)
     assert _pairs(got) == _pairs(want)
     idx.close()
     table, sx, fx, script, tok, off = _case(3, dim=768)
     idx = _device_index(table, script, extra=sx, bits=None)
-    assert idx.operand_bits == 8 and idx.diag == 6
+    assert idx.operand_bits == 8 and idx.diag == 6 and idx.kept_dims == 640
     idx.close()
 
 
