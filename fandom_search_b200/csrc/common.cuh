@@ -86,16 +86,27 @@ __host__ __device__ constexpr int dist_stages(int diag, bool pair, bool ares) {
 __host__ __device__ constexpr int dist_rowmax_bytes(int diag) {
     return diag == 6 ? 0 : 2 * 4 * dist_pub_slots(diag) * 8 * 2;
 }
+constexpr int kMmStageBytes = kEpiWarps * 8 * 8;  // per epilogue warp: two buffers of four chunk bounds
 __host__ __device__ constexpr int dist_smem_bytes(int diag, bool pair, bool ares) {
     return (ares ? kAResBytes : 0) + dist_stages(diag, pair, ares) * dist_stage_bytes(pair, ares) +
            1024 /*align slack*/ + 256 /*barriers*/ + dist_pub_bytes(diag) + kNormTileBytes +
-           dist_rowmax_bytes(diag);
+           dist_rowmax_bytes(diag) + (diag == 6 ? kMmStageBytes : 0);
 }
 static_assert(dist_smem_bytes(1, false, false) <= 232448 && dist_smem_bytes(3, true, false) <= 232448 &&
                   dist_smem_bytes(6, true, false) <= 232448 && dist_smem_bytes(6, false, false) <= 232448 &&
                   dist_smem_bytes(3, true, true) <= 232448 && dist_smem_bytes(6, true, true) <= 232448 &&
                   dist_smem_bytes(1, true, true) <= 232448,
               "distance kernel exceeds the 227 KB shared memory limit");
+
+// bit 4 of FS_OPT_TILE_GROUP with the one-pass epilogue (E = 6, fp16x2 sums, bit 2): the epilogue whose
+// per-tile bounds are prefetched (distance.cu, epilogue_onepass_loop); bit 3 on top of it: two sets of
+// 8 epilogue warps drain alternate tiles
+__host__ __device__ constexpr bool dist_prefetch_epilogue(int diag, int pack, bool dump, int group_bits) {
+    return diag == 6 && pack == 2 && !dump && (group_bits & 4) != 0 && (group_bits & 16) != 0;
+}
+__host__ __device__ constexpr bool dist_alt_sets(int diag, int pack, bool dump, int group_bits) {
+    return dist_prefetch_epilogue(diag, pack, dump, group_bits) && (group_bits & 8) != 0;
+}
 
 struct DistParams {
     // pre-filter: keep (i, j) iff acc_ij > A_i * B_j - C_i * D_j - G_i * H_j  (window_norm_kernel, embed.cu).

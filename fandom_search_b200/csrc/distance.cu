@@ -227,6 +227,13 @@ struct TileWalk {
         um = tn > 0 ? static_cast<int32_t>(begin / tn) : 0;
         un = tn > 0 ? static_cast<int32_t>(begin - static_cast<int64_t>(um) * tn) : 0;
     }
+    // first script column of the tile `skip` (0 or 1) positions after the one next() would return, or -1
+    __device__ __forceinline__ int32_t peek_n0(int skip) const {
+        if (left <= skip) return -1;
+        int32_t u = un + skip;
+        if (u >= tn) u -= tn;
+        return u * (kBlockN - (kDiag - 1));
+    }
     __device__ __forceinline__ bool next(Tile& out) {
         if (left <= 0) return false;
         out.m0 = static_cast<int32_t>(kPair ? 2 * um + cta_rank : um) * dist_m_step(kDiag);
@@ -599,6 +606,165 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-pass epilogue of E = 6 (fp16x2 sums) with nothing but the accumulator on a warp's critical
+// path (FS_OPT_TILE_GROUP bit 4).  A clock64 timeline of the 16-warp epilogue
+// (profiles/r02_timeline_*.txt) showed what a tile cost each warp: ~250 clk waiting for (A, C, G) of its
+// fan row, ~450 clk for the two chunk bounds (min B, max D|H) -- both L2 round trips, the L1 is all
+// shared memory here -- ~30 clk for the TMEM load itself, ~500 clk of arithmetic, and that the MMA
+// issuer idled 1000 clk per tile waiting for the accumulator to come back: the epilogue warps, not
+// the tensor pipe and not the TMEM port, paced the kernel.  Here
+//   * (A, C, G) stay in registers for the whole sweep over the script (the fan tile changes every
+//     tiles_n tiles),
+//   * the chunk bounds of the NEXT tile are copied into a private shared-memory slot by cp.async while
+//     this tile is processed (no register is held across the 72 accumulator registers),
+//   * kAlt (bit 3): warps 0..7 drain the even tiles of the CTA and warps 8..15 the odd ones, two
+//     64-column passes each, so that one set's arithmetic runs under the other set's loads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <bool kPair, bool kAlt>
+__device__ __forceinline__ void epilogue_onepass_loop(const DistParams& p, TileWalk<6, kPair>& walk,
+                                                      const uint32_t tfull0, const uint32_t tempty0,
+                                                      const uint32_t tmem_base, float2* mm_stage, const int warp,
+                                                      const int lane) {
+    constexpr int kNStep = kBlockN - 5;
+    constexpr int kPasses = kAlt ? 2 : 1;
+    constexpr int kVals = 2 * kPasses;  // chunk bounds of this warp per tile
+    const int quarter = warp & 3;
+    const int set = kAlt ? warp >> 3 : 0;
+    const int group0 = kAlt ? ((warp >> 2) & 1) * 2 : warp >> 2;
+    const int row = quarter * kQuarterRows6 + lane;
+    const bool lane_ok = lane < kQuarterRows6;
+    const float kNaN = __int_as_float(0x7fc00000);
+    float2* my = mm_stage + warp * 8;  // two buffers of (up to) four chunk bounds
+    const uint32_t my_s = smem_u32(my);
+    auto bound_row = [](float a, float cg, const float2& bd) {
+        const uint32_t u = __float_as_uint(cg), v = __float_as_uint(bd.y);
+        const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&u));
+        const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&v));
+        return fmaf(-x.y, y.y, fmaf(-x.x, y.x, a * bd.x));
+    };
+    auto prefetch = [&](int32_t n0, int buf) {
+        if (lane < kVals)
+            cp_async_8(my_s + static_cast<uint32_t>((buf * 4 + lane) * 8),
+                       p.script_mm32 + n0 + (group0 + (lane >> 1)) * kEpiCols + (lane & 1) * 32);
+    };
+    int buf = 0;
+    {
+        const int32_t n_first = walk.peek_n0(kAlt ? set : 0);
+        if (n_first >= 0) prefetch(n_first, 0);
+    }
+    uint32_t aphase = 0;
+    int as = kAlt ? set : 0;
+    int32_t ac_m0 = -1;
+    float2 ac = make_float2(kNaN, kNaN);
+    Tile tile;
+    int tl_tile = -1;
+    while (walk.next(tile)) {
+        ++tl_tile;
+        if (kAlt && (tl_tile & 1) != set) continue;
+        FS_TL(2 + warp, tl_tile, 0);
+        cp_async_wait_all();  // this tile's bounds have landed (they were requested a tile ago)
+        __syncwarp();
+        {
+            const int32_t n_next = walk.peek_n0(kAlt ? 1 : 0);
+            if (n_next >= 0) prefetch(n_next, buf ^ 1);
+        }
+        const int32_t gi = tile.m0 + row;
+        if (tile.m0 != ac_m0) {  // new fan tile: once per sweep over the script
+            ac = lane_ok ? __ldg(p.fan_ac + gi) : make_float2(kNaN, kNaN);
+            ac_m0 = tile.m0;
+        }
+        const uint32_t tfull_addr = tfull0 + 8u * as, tempty_addr = tempty0 + 8u * as;
+        mbar_wait_warp(tfull_addr, aphase, 0);
+        tc_fence_after();
+        FS_TL(2 + warp, tl_tile, 1);
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass) {
+            const int group = group0 + pass;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
+            uint32_t q[72];
+            {
+                // the 8 halo columns of the LAST group lie outside the tile: any readable columns do
+                // (they only enter outputs >= kNStep, which carry NaN bounds)
+                const int halo_off = (group * kEpiCols + 64 < kBlockN) ? 64 : 56;
+                tmem_ld_32x72(taddr, taddr + halo_off, q);
+            }
+            float thr_ch[2];
+            thr_ch[0] = bound_row(ac.x, ac.y, my[buf * 4 + 2 * pass]);
+            thr_ch[1] = bound_row(ac.x, ac.y, my[buf * 4 + 2 * pass + 1]);
+            FS_TL(2 + warp, tl_tile, 4 + 3 * pass);
+            tmem_ld_wait();
+            FS_TL(2 + warp, tl_tile, 5 + 3 * pass);
+            if (pass == kPasses - 1) {  // the warp's last accumulator column is in registers
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (kPair)
+                        mbar_arrive_leader(tempty_addr);
+                    else
+                        mbar_arrive(tempty_addr);
+                }
+            }
+            auto f = [&](int i) { return __uint_as_float(q[i]); };
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int b = 32 * ch;
+                float ma = f(b), mb = f(b + 16), mc = f(b + 24);
+#pragma unroll
+                for (int k = 1; k < 16; ++k) ma = fmaxf(ma, f(b + k));   // columns 0..15
+#pragma unroll
+                for (int k = 17; k < 24; ++k) mb = fmaxf(mb, f(b + k));  // columns 16..23
+#pragma unroll
+                for (int k = 25; k < 40; ++k) mc = fmaxf(mc, f(b + k));  // columns 24..39
+                const uint32_t m = pack_h2(fmaxf(ma, mb), fmaxf(mb, mc));
+                const uint32_t b01 = h2_add(m, __shfl_down_sync(0xffffffffu, m, 1));
+                const uint32_t bsum =
+                    h2_add(h2_add(b01, __shfl_down_sync(0xffffffffu, b01, 2)), __shfl_down_sync(0xffffffffu, b01, 4));
+                const float thr_chunk = thr_ch[ch];
+                if (!__any_sync(0xffffffffu, h2_lo(bsum) > thr_chunk || h2_hi(bsum) > thr_chunk)) continue;
+                uint32_t pk[20], o16[16];
+#pragma unroll
+                for (int k = 0; k < 20; ++k) pk[k] = pack_h2(f(b + 2 * k), f(b + 2 * k + 1));
+                const float mx = diag6_half(pk, o16);
+                if (mx > thr_chunk) {
+                    const int c0 = group * kEpiCols + b;
+                    const int32_t gj0 = tile.n0 + c0;
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) {
+                        const float2 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float2(kNaN, kNaN);
+                        const float v = (x & 1) ? h2_hi(o16[x >> 1]) : h2_lo(o16[x >> 1]);
+                        if (v > bound_row(ac.x, ac.y, bd)) {
+                            const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
+                            if (slot < static_cast<unsigned long long>(p.cand_cap)) {
+                                p.cand[slot].fan_pos = gi;
+                                p.cand[slot].script_pos = gj0 + x;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        FS_TL(2 + warp, tl_tile, 2);
+        buf ^= 1;
+        if (kAlt) {
+            aphase ^= 1u;  // the set always drains accumulator stage `set`
+        } else if (++as == kAccumStages) {
+            as = 0;
+            aphase ^= 1u;
+        }
+        FS_TL(2 + warp, tl_tile, 3);
+    }
+    cp_async_wait_all();
+}
+
 // kDiag = E: the MMAs accumulate only the shifts {0, E, 2E, ...} (w/E of them) and the epilogue
 // adds E diagonal neighbours, out[i][j] = sum_{d<E} acc[i+d][j+d].  E = 1 is the plain dense
 // contraction.  E > 1 re-uses every partial sum for E windows (w/E times fewer tensor-core
@@ -647,6 +813,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
     float* halo = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
     float2* norm_tile = reinterpret_cast<float2*>(halo + dist_pub_bytes(kDiag) / 4);
     __half* rowmax_base = reinterpret_cast<__half*>(norm_tile + kAccumStages * kHaloCols);
+    float2* mm_stage = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(rowmax_base) + dist_rowmax_bytes(kDiag));
 
     // Warp roles.  The warp scheduler prefers the HIGHEST warp id among eligible warps, so the
     // two single-thread roles that everything else waits for get the two highest ids: with
@@ -666,7 +833,7 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
         }
         for (int s = 0; s < kAccumStages; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), kPair ? 2 * kEpiWarps : kEpiWarps);
+            mbar_init(tempty_bar(s), (kPair ? 2 : 1) * (dist_alt_sets(kDiag, kPack, kDump, p.group) ? kEpiWarps / 2 : kEpiWarps));
         }
         mbar_init(afull_bar, 1);
         mbar_init(aempty_bar, 1);
@@ -981,6 +1148,15 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
         // kPack == 2: two half-precision boundary-row buffers, one per accumulator stage
         constexpr bool kHalfRows = kPack == 2 && (kDiag == 6 || kDiag == 3 || kDiag == 2);
         int tl_tile = -1;
+        if (kDiag == 6 && dist_prefetch_epilogue(kDiag, kPack, kDump, p.group)) {
+            if (kDiag == 6) {  // (the walk's type)
+                auto& walk6 = reinterpret_cast<TileWalk<6, kPair>&>(walk);
+                if (dist_alt_sets(kDiag, kPack, kDump, p.group))
+                    epilogue_onepass_loop<kPair, true>(p, walk6, tfull_bar(0), tempty_bar(0), tmem_base, mm_stage, warp, lane);
+                else
+                    epilogue_onepass_loop<kPair, false>(p, walk6, tfull_bar(0), tempty_bar(0), tmem_base, mm_stage, warp, lane);
+            }
+        } else
         while (walk.next(tile)) {
             ++tl_tile;
             FS_TL(2 + warp, tl_tile, 0);

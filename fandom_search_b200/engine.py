@@ -59,7 +59,8 @@ class DeviceIndex:
                          ("FANDOM_SEARCH_A_RESIDENT", nt.FS_OPT_A_RESIDENT),
                          ("FANDOM_SEARCH_PACKED_SHUFFLE", nt.FS_OPT_PACKED_SHUFFLE),
                          ("FANDOM_SEARCH_OPERAND_BITS", nt.FS_OPT_OPERAND_BITS),
-                         ("FANDOM_SEARCH_PREFILTER_DIMS", nt.FS_OPT_PREFILTER_DIMS)):
+                         ("FANDOM_SEARCH_PREFILTER_DIMS", nt.FS_OPT_PREFILTER_DIMS),
+                         ("FANDOM_SEARCH_TILE_GROUP", nt.FS_OPT_TILE_GROUP)):
             v = os.environ.get(env)
             if v not in (None, ""):
                 self.set_option(opt, int(v))

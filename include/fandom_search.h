@@ -114,7 +114,12 @@ enum {
                                     last column is packed, before the sums; bit 2 (default on, E = 6):
                                     an epilogue warp loads both of its 32-column chunks at once, hands
                                     the accumulator back, takes the row maxima on the fp32 values and
-                                    packs to fp16x2 only the chunks that survive the bound          */
+                                    packs to fp16x2 only the chunks that survive the bound; bit 4
+                                    (default off, with bit 2): the fan row's bound stays in registers
+                                    over the sweep of the script and the chunk bounds of the next tile
+                                    are prefetched into shared memory by cp.async (no L2 round trip on
+                                    the epilogue's critical path); bit 3 (default off, with bit 4): two
+                                    sets of 8 epilogue warps drain alternate tiles                    */
     FS_OPT_PREFILTER_DIMS = 11,  /* embedding columns kept in the operand rows of the tensor-core pre-filter:
                                     -1 = automatic (default: whole 128-byte chunks of operand row holding
                                     ~5/6 of the table's energy: 256 of 300, 640 of 768), 0 = all, n = the
