@@ -23,9 +23,12 @@ FS_CNT_MATCHES = 1
 FS_CNT_EXACT = 2
 FS_CNT_WINDOWS = 3
 FS_CNT_OVERFLOW = 4
-FS_CNT_COUNT = 5
+FS_CNT_ROWS = 5
+FS_CNT_COUNT = 6
 FS_OVERFLOW_CANDIDATES = 1
 FS_OVERFLOW_MATCHES = 2
+FS_OVERFLOW_ROWS = 4
+FS_OVERFLOW_TEXT = 8
 
 FS_OPT_SHIFTS_PER_STAGE = 1
 FS_OPT_GRID_LIMIT = 3
@@ -44,7 +47,10 @@ FS_MATCH_LSH_SHIFT = 8
 MATCH_DTYPE = np.dtype([("fan_pos", "<i4"), ("script_pos", "<i4"), ("distance", "<f8"),
                         ("work", "<i4"), ("flags", "<u4")], align=True)
 PAIR_DTYPE = np.dtype([("fan_pos", "<i4"), ("script_pos", "<i4")], align=True)
-assert MATCH_DTYPE.itemsize == 24 and PAIR_DTYPE.itemsize == 8
+# struct fs_row {int32 work, word, window_ix, match_ix; double distance; int32 lev, reserved;}
+ROW_DTYPE = np.dtype([("work", "<i4"), ("word", "<i4"), ("window_ix", "<i4"), ("match_ix", "<i4"),
+                      ("distance", "<f8"), ("lev", "<i4"), ("reserved", "<i4")], align=True)
+assert MATCH_DTYPE.itemsize == 24 and PAIR_DTYPE.itemsize == 8 and ROW_DTYPE.itemsize == 32
 
 # every symbol include/fandom_search.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
@@ -65,6 +71,10 @@ SIGNATURES = {
     "fs_search_csr_host": (ctypes.c_int, [_vp] + _BATCHX + [_vp, _i64, _vp]),
     "fs_search_submit": (ctypes.c_int, [_vp] + _BATCHX + [_i64, ctypes.POINTER(_i32)]),
     "fs_search_collect": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp]),
+    "fs_index_set_script_text": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, _i64]),
+    "fs_search_submit_rows": (ctypes.c_int, [_vp] + _BATCHX + [_vp, _i64, _vp, _vp, _i32, _i64, _i64,
+                                                               ctypes.POINTER(_i32)]),
+    "fs_search_collect_rows": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp]),
     "fs_exact_join_dev": (ctypes.c_int, [_vp, _vp] + _BATCH + [_vp, _i64, _vp]),
     "fs_exact_join_host": (ctypes.c_int, [_vp] + _BATCH + [_vp, _i64, _vp]),
     "fs_stage_embed_dev": (ctypes.c_int, [_vp, _vp] + _BATCHX + [_vp, _vp]),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfandom_search.so")
-SOURCES = ["api.cu", "distance.cu", "embed.cu", "rescore.cu", "hashjoin.cu", "lsh.cu", "aggregate.cu", "host_text.cpp", "host_pipeline.cpp"]
+SOURCES = ["api.cu", "distance.cu", "embed.cu", "rescore.cu", "hashjoin.cu", "lsh.cu", "aggregate.cu", "postprocess.cu", "host_text.cpp", "host_pipeline.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

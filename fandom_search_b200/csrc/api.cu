@@ -163,11 +163,29 @@ struct fs_index {
         unsigned long long* d_counters = nullptr;
         long long* h_counters = nullptr;  // page-locked
         int64_t cap = 0;
+        // device-side post-processing (fs_search_submit_rows): verbatim token texts and the rows
+        bool with_rows = false;
+        int64_t text_cap = 0, tstart_cap = 0, tlen_cap = 0, rows_buf_cap = 0, rows_cap = 0;
+        uint8_t* d_text = nullptr;
+        uint32_t* d_tstart = nullptr;
+        uint16_t* d_tlen = nullptr;
+        fs_row* d_rows = nullptr;
         cudaEvent_t ev_in = nullptr, ev_done = nullptr;
     };
     static constexpr int kSlots = 2;
     Slot slots[kSlots];
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
+
+    // script words for the device-side Levenshtein, and the post-processing workspace (shared by the
+    // slots: the kernels of consecutive batches are ordered on `stream`)
+    uint8_t* script_text = nullptr;
+    int64_t* script_word_off = nullptr;
+    int64_t n_script_words = 0;
+    int64_t pp_tok_cap = 0, pp_match_cap = 0, pp_blocks_cap = 0;
+    int32_t *pp_head = nullptr, *pp_winner = nullptr, *pp_next = nullptr, *pp_lev = nullptr, *pp_rank = nullptr,
+            *pp_block_count = nullptr;
+    unsigned long long *pp_best_key = nullptr, *pp_best_tie = nullptr;
+    int64_t* pp_block_off = nullptr;
 
     // LSH emulation (parity mode)
     double* lsh_normals = nullptr;
@@ -217,7 +235,10 @@ int fs_index_destroy(fs_index* idx) {
                     idx->script_norm, idx->hash_table, idx->fan_emb, idx->fan_tok_sq, idx->fan_thr,
                     idx->cand,    idx->fx16,      idx->fx_sq,      idx->h_tok,      idx->h_off,
                     idx->h_extra, idx->h_out,     idx->h_pair,     idx->h_counters,
-                    idx->lsh_normals, idx->script_norm_min, idx->perm, idx->col_energy};
+                    idx->lsh_normals, idx->script_norm_min, idx->perm, idx->col_energy,
+                    idx->script_text, idx->script_word_off, idx->pp_head, idx->pp_winner, idx->pp_next,
+                    idx->pp_lev, idx->pp_rank, idx->pp_block_count, idx->pp_best_key, idx->pp_best_tie,
+                    idx->pp_block_off};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (idx->ev_created) {
@@ -227,7 +248,7 @@ int fs_index_destroy(fs_index* idx) {
         }
     }
     for (auto& sl : idx->slots) {
-        void* q[] = {sl.d_tok, sl.d_off, sl.d_extra, sl.d_out, sl.d_counters};
+        void* q[] = {sl.d_tok, sl.d_off, sl.d_extra, sl.d_out, sl.d_counters, sl.d_text, sl.d_tstart, sl.d_tlen, sl.d_rows};
         for (void* p : q)
             if (p) cudaFree(p);
         if (sl.h_counters) cudaFreeHost(sl.h_counters);
@@ -869,7 +890,17 @@ int fs_search_csr_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n
 // Enqueue one host batch into a free slot: inputs H2D on stream_in, the kernels on `stream` behind
 // whatever is already queued there, the counters D2H into the slot's page-locked words.  No
 // synchronisation with the device unless a buffer has to grow.
-static int submit_slot(fs_index* idx, const BatchArgs& h, int64_t cap, int32_t* ticket) {
+struct TextArgs {  // verbatim token texts of a batch (fs_search_submit_rows); text == nullptr: none
+    const char* text = nullptr;
+    int64_t text_bytes = 0;
+    const uint32_t* tok_start = nullptr;
+    const uint16_t* tok_len = nullptr;
+    int32_t lsh_filter = 0;
+    int64_t cap_rows = 0;
+};
+
+static int submit_slot(fs_index* idx, const BatchArgs& h, int64_t cap, int32_t* ticket,
+                       const TextArgs& tx = TextArgs()) {
     int r;
     int s = -1;
     for (int k = 0; k < fs_index::kSlots; ++k)
@@ -888,7 +919,66 @@ static int submit_slot(fs_index* idx, const BatchArgs& h, int64_t cap, int32_t* 
     if ((r = dev_grow(&sl.d_off, &sl.off_cap, h.n_works + 1)) != FS_OK) return r;
     if ((r = dev_grow(&sl.d_extra, &sl.extra_cap, h.n_extra * idx->dim)) != FS_OK) return r;
     if ((r = dev_grow(&sl.d_out, &sl.out_cap, cap)) != FS_OK) return r;
+    const bool with_rows = tx.text != nullptr || tx.cap_rows > 0;
+    if (with_rows) {
+        if ((r = dev_grow(&sl.d_text, &sl.text_cap, tx.text_bytes + 16)) != FS_OK) return r;
+        if ((r = dev_grow(&sl.d_tstart, &sl.tstart_cap, h.n_tok + 8)) != FS_OK) return r;
+        if ((r = dev_grow(&sl.d_tlen, &sl.tlen_cap, h.n_tok + 8)) != FS_OK) return r;
+        if ((r = dev_grow(&sl.d_rows, &sl.rows_buf_cap, tx.cap_rows)) != FS_OK) return r;
+        if (idx->pp_tok_cap < h.n_tok + 8) {  // the four per-position arrays grow together
+            void* old[] = {idx->pp_head, idx->pp_winner, idx->pp_best_key, idx->pp_best_tie};
+            for (void* q : old)
+                if (q) {
+                    cudaDeviceSynchronize();
+                    cudaFree(q);
+                }
+            idx->pp_head = idx->pp_winner = nullptr;
+            idx->pp_best_key = idx->pp_best_tie = nullptr;
+            idx->pp_tok_cap = 0;
+            const int64_t want = h.n_tok + h.n_tok / 4 + 1024;
+            if ((r = dev_alloc(&idx->pp_head, want)) != FS_OK) return r;
+            if ((r = dev_alloc(&idx->pp_winner, want)) != FS_OK) return r;
+            if ((r = dev_alloc(&idx->pp_best_key, want)) != FS_OK) return r;
+            if ((r = dev_alloc(&idx->pp_best_tie, want)) != FS_OK) return r;
+            idx->pp_tok_cap = want;
+        }
+        if (idx->pp_match_cap < cap) {
+            void* old[] = {idx->pp_next, idx->pp_lev, idx->pp_rank};
+            for (void* q : old)
+                if (q) {
+                    cudaDeviceSynchronize();
+                    cudaFree(q);
+                }
+            idx->pp_next = idx->pp_lev = idx->pp_rank = nullptr;
+            const int64_t want = cap + cap / 4 + 1024;
+            if ((r = dev_alloc(&idx->pp_next, want)) != FS_OK) return r;
+            if ((r = dev_alloc(&idx->pp_lev, want)) != FS_OK) return r;
+            if ((r = dev_alloc(&idx->pp_rank, want)) != FS_OK) return r;
+            idx->pp_match_cap = want;
+        }
+        const int64_t nb = postprocess_scan_blocks(h.n_tok) + 1;
+        if (idx->pp_blocks_cap < nb) {
+            void* old[] = {idx->pp_block_count, idx->pp_block_off};
+            for (void* q : old)
+                if (q) {
+                    cudaDeviceSynchronize();
+                    cudaFree(q);
+                }
+            idx->pp_block_count = nullptr;
+            idx->pp_block_off = nullptr;
+            const int64_t want = nb + nb / 4 + 64;
+            if ((r = dev_alloc(&idx->pp_block_count, want)) != FS_OK) return r;
+            if ((r = dev_alloc(&idx->pp_block_off, want)) != FS_OK) return r;
+            idx->pp_blocks_cap = want;
+        }
+    }
     cudaStream_t in = idx->stream_in, st = idx->stream;
+    if (with_rows && h.n_tok) {
+        if (tx.text_bytes)
+            FS_CUDA_CHECK(cudaMemcpyAsync(sl.d_text, tx.text, static_cast<size_t>(tx.text_bytes), cudaMemcpyHostToDevice, in));
+        FS_CUDA_CHECK(cudaMemcpyAsync(sl.d_tstart, tx.tok_start, sizeof(uint32_t) * h.n_tok, cudaMemcpyHostToDevice, in));
+        FS_CUDA_CHECK(cudaMemcpyAsync(sl.d_tlen, tx.tok_len, sizeof(uint16_t) * h.n_tok, cudaMemcpyHostToDevice, in));
+    }
     if (h.n_tok)
         FS_CUDA_CHECK(cudaMemcpyAsync(sl.d_tok, h.tok, sizeof(int32_t) * h.n_tok, cudaMemcpyHostToDevice, in));
     // ids read past the end of the batch by the last (invalid) windows must stay harmless
@@ -902,12 +992,67 @@ static int submit_slot(fs_index* idx, const BatchArgs& h, int64_t cap, int32_t* 
     BatchArgs d{sl.d_tok, h.n_tok, sl.d_off, h.n_works, sl.d_extra, h.n_extra};
     if ((r = run_pipeline(idx, st, d, Mode::kSearch, sl.d_out, cap, nullptr, 0, nullptr, 0, sl.d_counters)) != FS_OK)
         return r;
+    if (with_rows && h.n_tok > 0 && idx->n_script_tok > 0) {
+        PostParams pp{};
+        pp.matches = sl.d_out;
+        pp.counters = sl.d_counters;
+        pp.match_cap = cap;
+        pp.n_tok = static_cast<int32_t>(h.n_tok);
+        pp.window = idx->window;
+        pp.topk = 10;  // NearestFilter(10), search.py:119-120
+        pp.lsh = tx.lsh_filter ? 1 : 0;
+        pp.fan_off = sl.d_off;
+        pp.n_works = static_cast<int32_t>(h.n_works);
+        pp.fan_text = sl.d_text;
+        pp.tok_start = sl.d_tstart;
+        pp.tok_len = sl.d_tlen;
+        pp.script_text = idx->script_text;
+        pp.script_word_off = idx->script_word_off;
+        pp.n_script_words = idx->n_script_words;
+        pp.head = idx->pp_head;
+        pp.next = idx->pp_next;
+        pp.m_lev = idx->pp_lev;
+        pp.m_rank = idx->pp_rank;
+        pp.best_key = idx->pp_best_key;
+        pp.best_tie = idx->pp_best_tie;
+        pp.winner = idx->pp_winner;
+        pp.block_count = idx->pp_block_count;
+        pp.block_off = idx->pp_block_off;
+        pp.rows = sl.d_rows;
+        pp.rows_cap = tx.cap_rows;
+        pp.overflow = sl.d_counters + FS_CNT_OVERFLOW;
+        if ((r = launch_postprocess(pp, idx->sm_count, st)) != FS_OK) return r;
+    }
     FS_CUDA_CHECK(cudaMemcpyAsync(sl.h_counters, sl.d_counters, sizeof(int64_t) * FS_CNT_COUNT,
                                   cudaMemcpyDeviceToHost, st));
     FS_CUDA_CHECK(cudaEventRecord(sl.ev_done, st));
     sl.cap = cap;
+    sl.with_rows = with_rows;
+    sl.rows_cap = tx.cap_rows;
     sl.busy = true;
     *ticket = s;
+    return FS_OK;
+}
+
+static int collect_slot_rows(fs_index* idx, int32_t ticket, fs_row* out, int64_t cap, int64_t* counters) {
+    fs_index::Slot& sl = idx->slots[ticket];
+    FS_CUDA_CHECK(cudaEventSynchronize(sl.ev_done));
+    for (int k = 0; k < FS_CNT_COUNT; ++k) counters[k] = sl.h_counters[k];
+    const int64_t flags = counters[FS_CNT_OVERFLOW];
+    if ((flags & (FS_OVERFLOW_CANDIDATES | FS_OVERFLOW_MATCHES | FS_OVERFLOW_TEXT | FS_OVERFLOW_ROWS)) ||
+        counters[FS_CNT_ROWS] > cap) {
+        // the ticket stays valid: the caller may still fetch the raw matches (fs_search_collect)
+        set_error("device post-processing incomplete (overflow bits %lld, %lld rows for %lld slots)",
+                  static_cast<long long>(flags), static_cast<long long>(counters[FS_CNT_ROWS]),
+                  static_cast<long long>(cap));
+        return FS_E_OVERFLOW;
+    }
+    sl.busy = false;
+    const int64_t n = counters[FS_CNT_ROWS];
+    if (n > 0) {
+        FS_CUDA_CHECK(cudaMemcpyAsync(out, sl.d_rows, sizeof(fs_row) * n, cudaMemcpyDeviceToHost, idx->stream_out));
+        FS_CUDA_CHECK(cudaStreamSynchronize(idx->stream_out));
+    }
     return FS_OK;
 }
 
@@ -949,6 +1094,65 @@ int fs_search_submit(fs_index* idx, const int32_t* tok, int64_t n_tok, const int
     }
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     return submit_slot(idx, h, cap, ticket);
+}
+
+int fs_index_set_script_text(fs_index* idx, const char* blob, const int64_t* word_off, int64_t n_words) {
+    if (!idx || !word_off || n_words != idx->n_script_tok || (n_words > 0 && !blob) || word_off[0] != 0) {
+        set_error("fs_index_set_script_text: one word per script token is expected");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    FS_CUDA_CHECK(cudaDeviceSynchronize());
+    if (idx->script_text) cudaFree(idx->script_text);
+    if (idx->script_word_off) cudaFree(idx->script_word_off);
+    idx->script_text = nullptr;
+    idx->script_word_off = nullptr;
+    idx->n_script_words = 0;
+    int r;
+    if ((r = dev_alloc(&idx->script_text, word_off[n_words] + 16)) != FS_OK) return r;
+    if ((r = dev_alloc(&idx->script_word_off, n_words + 1)) != FS_OK) return r;
+    if (word_off[n_words] > 0)
+        FS_CUDA_CHECK(cudaMemcpy(idx->script_text, blob, static_cast<size_t>(word_off[n_words]), cudaMemcpyHostToDevice));
+    FS_CUDA_CHECK(cudaMemcpy(idx->script_word_off, word_off, sizeof(int64_t) * (n_words + 1), cudaMemcpyHostToDevice));
+    idx->n_script_words = n_words;
+    return FS_OK;
+}
+
+int fs_search_submit_rows(fs_index* idx, const int32_t* tok, int64_t n_tok, const int64_t* off, int64_t n_works,
+                          const float* extra, int64_t n_extra, const char* text, int64_t text_bytes,
+                          const uint32_t* tok_start, const uint16_t* tok_len, int32_t lsh_filter,
+                          int64_t cap_matches, int64_t cap_rows, int32_t* ticket) {
+    BatchArgs h{tok, n_tok, off, n_works, extra, n_extra};
+    int r = check_batch(idx, h, "fs_search_submit_rows");
+    if (r != FS_OK) return r;
+    if (!ticket || cap_matches < 0 || cap_rows < 0 || text_bytes < 0 || text_bytes >= (1ll << 32) ||
+        (n_tok > 0 && (!tok_start || !tok_len)) || (text_bytes > 0 && !text)) {
+        set_error("fs_search_submit_rows: invalid argument (batch text must stay below 4 GiB)");
+        return FS_E_INVALID;
+    }
+    if (idx->n_scripts != 1 || idx->n_script_words != idx->n_script_tok) {
+        set_error("fs_search_submit_rows: a single-script index with fs_index_set_script_text is required");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    TextArgs tx;
+    tx.text = text ? text : "";
+    tx.text_bytes = text_bytes;
+    tx.tok_start = tok_start;
+    tx.tok_len = tok_len;
+    tx.lsh_filter = lsh_filter;
+    tx.cap_rows = cap_rows > 0 ? cap_rows : 1;
+    return submit_slot(idx, h, cap_matches, ticket, tx);
+}
+
+int fs_search_collect_rows(fs_index* idx, int32_t ticket, fs_row* out, int64_t cap, int64_t* counters) {
+    if (!idx || ticket < 0 || ticket >= fs_index::kSlots || !idx->slots[ticket].busy ||
+        !idx->slots[ticket].with_rows || !counters || cap < 0 || (cap > 0 && !out)) {
+        set_error("fs_search_collect_rows: invalid argument (not a ticket of fs_search_submit_rows?)");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    return collect_slot_rows(idx, ticket, out, cap, counters);
 }
 
 int fs_search_collect(fs_index* idx, int32_t ticket, fs_match* out, int64_t cap, int64_t* counters) {

@@ -166,6 +166,37 @@ struct RescoreParams {
     unsigned long long* overflow;  // FS_OVERFLOW_* bits (counters + FS_CNT_OVERFLOW)
 };
 
+// device-side post-processing of the match list (postprocess.cu)
+struct PostParams {
+    const fs_match* matches;
+    unsigned long long* counters;  // reads FS_CNT_MATCHES, writes FS_CNT_ROWS
+    int64_t match_cap;
+    int32_t n_tok, window, topk, lsh;
+    const int64_t* fan_off;
+    int32_t n_works;
+    // fan tokens: bytes of token t = fan_text[tok_start[t] .. + tok_len[t])
+    const uint8_t* fan_text;
+    const uint32_t* tok_start;
+    const uint16_t* tok_len;
+    // script words (lower-cased): bytes of word j = script_text[script_word_off[j] .. script_word_off[j+1])
+    const uint8_t* script_text;
+    const int64_t* script_word_off;
+    int64_t n_script_words;
+    // workspace
+    int32_t* head;                 // [n_tok] first match of the window starting here
+    int32_t* next;                 // [match_cap]
+    int32_t* m_lev;                // [match_cap] -1 = dropped
+    int32_t* m_rank;               // [match_cap]
+    unsigned long long* best_key;  // [n_tok] minimal combined distance (order-preserving bits)
+    unsigned long long* best_tie;  // [n_tok] first inserted among the minimal records
+    int32_t* winner;               // [n_tok] winning match, -1 = none
+    int32_t* block_count;          // [ceil(n_tok / 1024)]
+    int64_t* block_off;
+    fs_row* rows;
+    int64_t rows_cap;
+    unsigned long long* overflow;
+};
+
 struct LshParams {
     fs_match* matches;
     const unsigned long long* match_counter;
@@ -217,6 +248,8 @@ int launch_window_norm(const float4* tok_sq, int64_t n_tok, const int64_t* off, 
 int launch_sliding_minmax32(const float2* src, float2* dst, int64_t n, cudaStream_t stream);
 int launch_rescore(const RescoreParams& p, int sm_count, cudaStream_t stream);
 int launch_lsh(const LshParams& p, int sm_count, cudaStream_t stream);
+int launch_postprocess(const PostParams& p, int sm_count, cudaStream_t stream);
+int64_t postprocess_scan_blocks(int64_t n_tok);
 int launch_hash_build(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,
                       int32_t window, unsigned long long* table, uint32_t slots,
                       cudaStream_t stream);

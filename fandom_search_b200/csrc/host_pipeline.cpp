@@ -153,6 +153,8 @@ struct fs_batch {
     RawArray<int32_t> tok;            // [T] row id, or -(1+u) for the u-th unique OOV string
     RawArray<int64_t> tok_start;      // [T] byte offsets into text
     RawArray<int64_t> tok_end;        // [T]
+    RawArray<uint32_t> tok_start32;   // [T] the same offsets and lengths in the compact form the device
+    RawArray<uint16_t> tok_len16;     // [T] takes (fs_search_submit_rows); lengths clamped at 65535
     std::vector<int64_t> oov_start;   // [U] one representative span per unique OOV string
     std::vector<int64_t> oov_end;     // [U]
     std::vector<int32_t> file_status; // [n_files] 0 ok, 1 unreadable
@@ -276,6 +278,8 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
     b->tok.alloc(static_cast<size_t>(T));
     b->tok_start.alloc(static_cast<size_t>(T));
     b->tok_end.alloc(static_cast<size_t>(T));
+    b->tok_start32.alloc(static_cast<size_t>(T));
+    b->tok_len16.alloc(static_cast<size_t>(T));
     // Out-of-vocabulary tokens are collected per file while the text is hot in the tokenising thread's
     // cache: (token index, length, key) with key = the bytes themselves for words of <= 8 bytes, else
     // their 64-bit hash.  The serial pass below then only walks these compact lists.
@@ -292,6 +296,8 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
         int32_t* tok = b->tok.data();
         int64_t* st = b->tok_start.data();
         int64_t* en = b->tok_end.data();
+        uint32_t* st32 = b->tok_start32.data();
+        uint16_t* len16 = b->tok_len16.data();
         std::vector<OovTok>& oov = oov_of_file[static_cast<size_t>(k)];
         int64_t i = 0;
         while (i < len) {
@@ -304,6 +310,8 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
             tok[o] = row;
             st[o] = base + s;
             en[o] = base + i;
+            st32[o] = static_cast<uint32_t>(base + s);
+            len16[o] = static_cast<uint16_t>(n > 65535 ? 65535 : n);
             if (row < 0) {
                 uint64_t key;
                 if (n <= 8) {
@@ -396,6 +404,8 @@ void* fs_batch_array(fs_batch* b, int32_t which) {
         case 6: return b->oov_start.data();
         case 7: return b->oov_end.data();
         case 8: return b->file_status.data();
+        case 9: return b->tok_start32.data();
+        case 10: return b->tok_len16.data();
         default: return nullptr;
     }
 }

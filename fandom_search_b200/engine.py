@@ -193,6 +193,56 @@ class DeviceIndex:
         nt.check(st)
         return out[:counters[nt.FS_CNT_MATCHES]], counters
 
+    # -- search + records on the device ------------------------------
+    def set_script_text(self, blob, word_off):
+        """Register the lower-cased script words (utf-8 blob + offsets, one word per script token)
+        for the device-side Levenshtein of fs_search_submit_rows."""
+        word_off = np.ascontiguousarray(word_off, dtype=np.int64)
+        nt.check(self._lib.fs_index_set_script_text(self._h, blob, nt.ptr(word_off), word_off.shape[0] - 1))
+        self._script_text_set = True
+
+    @property
+    def device_records(self):
+        return bool(getattr(self, "_script_text_set", False))
+
+    def search_submit_rows(self, tok, off, extra, text, tok_start32, tok_len16, lsh_filter=False,
+                           cap=None, cap_rows=None):
+        """fs_search_submit_rows: like search_submit, plus the verbatim token texts of the batch;
+        the matching search_collect_rows returns the WINNING ROWS (top-10 per window, Levenshtein,
+        per-word argmin done on the GPU)."""
+        tok, off, extra = self._host_batch(tok, off, extra, self.dim)
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        tok_start32 = np.ascontiguousarray(tok_start32, dtype=np.uint32)
+        tok_len16 = np.ascontiguousarray(tok_len16, dtype=np.uint16)
+        hint = getattr(self, "_cap_hint", (0, 0))
+        if cap is None:
+            cap = max(4096, tok.shape[0] // 8, hint[0])
+        if cap_rows is None:
+            cap_rows = max(4096, tok.shape[0] // 4, hint[1])
+        t = ctypes.c_int32(-1)
+        nt.check(self._lib.fs_search_submit_rows(
+            self._h, nt.ptr(tok) if tok.size else None, tok.shape[0], nt.ptr(off), off.shape[0] - 1,
+            nt.ptr(extra) if extra.shape[0] else None, extra.shape[0],
+            nt.ptr(text) if text.size else None, text.shape[0], nt.ptr(tok_start32) if tok.size else None,
+            nt.ptr(tok_len16) if tok.size else None, 1 if lsh_filter else 0, cap, cap_rows, ctypes.byref(t)))
+        return {'ticket': t.value, 'tok': tok, 'off': off, 'extra': extra, 'cap': cap, 'cap_rows': cap_rows,
+                'text': (text, tok_start32, tok_len16)}
+
+    def search_collect_rows(self, ticket):
+        """(rows[ROW_DTYPE] sorted by (work, word), counters), or (None, None) when the device could
+        not finish the records (a buffer overflowed, or a window text was too long for the device
+        Levenshtein): the ticket is then still open for search_collect (raw matches)."""
+        cap = ticket['cap_rows']
+        out = np.empty(cap, dtype=nt.ROW_DTYPE)
+        counters = np.zeros(nt.FS_CNT_COUNT, dtype=np.int64)
+        st = self._lib.fs_search_collect_rows(self._h, ticket['ticket'], nt.ptr(out), cap, nt.ptr(counters))
+        if st == nt.FS_E_OVERFLOW:
+            self._cap_hint = (int(counters[nt.FS_CNT_MATCHES]) * 5 // 4 + 1024,
+                              int(counters[nt.FS_CNT_ROWS]) * 5 // 4 + 1024)
+            return None, counters
+        nt.check(st)
+        return out[:counters[nt.FS_CNT_ROWS]], counters
+
     def exact_join_host(self, tok, off, cap=None):
         tok, off, _ = self._host_batch(tok, off, None, self.dim)
         if cap is None:

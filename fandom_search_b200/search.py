@@ -203,6 +203,19 @@ def _device_ordinal():
     return 0
 
 
+class DeviceRows(object):
+    """Winning records of one cluster as the device returned them (fs_row array, sorted by
+    (work, word)), presented as the arrays fs_records_best yields."""
+
+    def __init__(self, rows):
+        self.rows = rows
+        self.best = {k: numpy.ascontiguousarray(rows[k]) for k in
+                     ('work', 'word', 'window_ix', 'match_ix', 'distance', 'lev')}
+
+    def __len__(self):
+        return len(self.rows)
+
+
 class ScriptEngine(object):
     """Returned by build_lsh_engine: the device-resident script index (replaces the nearpy
     Engine of search.py:118-123).  The per-window `neighbours(v)` seam of nearpy is replaced
@@ -242,6 +255,15 @@ def build_lsh_engine(orig, window_size, number_of_hashes, hash_dimensions,
     engine = ScriptEngine(index, lsh)
     engine.script_tok = script_tok
     engine.n_script_extra = n_sx
+    # single script: the records (top-10, Levenshtein, per-word argmin; search.py:182-226) are made on
+    # the device right behind the search -- FANDOM_SEARCH_DEVICE_RECORDS=0 keeps them on the host
+    single = script_offsets is None or len(script_offsets) == 2
+    if (single and hasattr(index, 'set_script_text') and len(words) > 0
+            and os.environ.get('FANDOM_SEARCH_DEVICE_RECORDS', '1') != '0'):
+        enc = [w.encode('utf-8') for w in words]
+        off = numpy.zeros(len(enc) + 1, dtype=numpy.int64)
+        numpy.cumsum([len(e) for e in enc], out=off[1:])
+        index.set_script_text(b''.join(enc), off)
     return engine
 
 
@@ -300,7 +322,10 @@ class AnnIndexSearch(object):
 
     def search_many(self, filenames):
         """Record lists (one per file, each sorted) for a cluster of works."""
-        return self.run_prepared(self.prepare(filenames))
+        prep = self.prepare(filenames)
+        if len(self.script_filenames) != 1:
+            return self.run_prepared(prep)
+        return self.records_prepared(prep, *self.collect_prepared(prep, self.submit_prepared(prep, rows=True)))
 
     def prepare(self, filenames):
         """Host stage before the GPU: read + tokenise + row ids -> CSR batch (search.py:164-169).
@@ -350,14 +375,34 @@ class AnnIndexSearch(object):
         """GPU stage: one C-ABI call for the cluster (search.py:169-184 for every work)."""
         return self.collect_prepared(prep, self.submit_prepared(prep))
 
-    def submit_prepared(self, prep):
+    def submit_prepared(self, prep, rows=False):
         """Enqueue the cluster on the GPU and return at once (fs_search_submit; two clusters may be
-        in flight, so the next one is already queued while this one is searched)."""
-        return self.engine.index.search_submit(prep['tok'], prep['offs'], prep['extra'])
+        in flight, so the next one is already queued while this one is searched).  rows=True: the
+        records are made on the device too (fs_search_submit_rows) when the index supports it."""
+        index = self.engine.index
+        batch = prep['batch']
+        if (rows and getattr(index, 'device_records', False) and getattr(batch, 'tok_start32', None) is not None
+                and len(batch.text) < (1 << 32)):
+            return index.search_submit_rows(prep['tok'], prep['offs'], prep['extra'], batch.text,
+                                            batch.tok_start32, batch.tok_len16,
+                                            lsh_filter=self.engine.lsh is not None)
+        return index.search_submit(prep['tok'], prep['offs'], prep['extra'])
 
     def collect_prepared(self, prep, ticket):
-        """Wait for a submitted cluster: (matches, first LSH table or None)."""
-        matches, counters = self.engine.index.search_collect(ticket)
+        """Wait for a submitted cluster: (matches, first LSH table or None) -- or, for a cluster
+        submitted with rows=True, (DeviceRows, None): the winning rows, made on the device."""
+        index = self.engine.index
+        if 'cap_rows' in ticket:
+            rows, counters = index.search_collect_rows(ticket)
+            if rows is not None:
+                ticket.clear()
+                if prep.get('pin') is not None:
+                    _PINNED_TOKENS.give_back(prep.pop('pin'))
+                    prep['tok'] = None
+                self._windows_processed += int(counters[nt.FS_CNT_WINDOWS])
+                return DeviceRows(rows), None
+            # the device could not finish the records of this cluster: raw matches, host records
+        matches, counters = index.search_collect(ticket)
         ticket.clear()
         if prep.get('pin') is not None:
             # the token ids are on the device now: the page-locked buffer goes back to the pool
@@ -377,6 +422,14 @@ class AnnIndexSearch(object):
         if len(self.script_filenames) != 1:
             raise ValueError("several scripts are indexed: use records_prepared_scripts")
         return self._records(prep['filenames'], prep['batch'], matches, first_table)
+
+    def _best(self, batch, matches, first_table):
+        """Winning records as arrays: straight from the device (DeviceRows) or made natively on the
+        host from the match list (fs_records_best_mt)."""
+        if isinstance(matches, DeviceRows):
+            return matches.best
+        blob, soff = self._script_text()
+        return _text.records_best(matches, first_table, self.window_size, 10, batch, blob, soff)
 
     def records_prepared_scripts(self, prep, matches, first_table=None):
         """One record-set list per indexed script: what separate reference runs, one per script,
@@ -425,7 +478,7 @@ class AnnIndexSearch(object):
         if len(matches) == 0:
             return b''
         blob, soff = self._script_text()
-        best = _text.records_best(matches, first_table, self.window_size, 10, batch, blob, soff)
+        best = self._best(batch, matches, first_table)
         orth, cblob, coff, cnone, scene, snone = self._script_columns()
         return _text.records_format_csv(best, filenames, batch, blob, soff, orth, cblob, coff, cnone,
                                         scene, snone, word_base)
@@ -436,8 +489,7 @@ class AnnIndexSearch(object):
         out = [[] for _ in filenames]
         if len(matches) == 0:
             return out
-        blob, soff = self._script_text()
-        best = _text.records_best(matches, first_table, self.window_size, 10, batch, blob, soff)
+        best = self._best(batch, matches, first_table)
         tok_off = batch.tok_off
         work = best['work'].tolist()
         word = best['word'].tolist()
@@ -688,7 +740,7 @@ def analyze(args,
                 prep = pending.result()
                 pending = prep_pool.submit(ann_index.prepare, mine[k + 1][1]) if k + 1 < len(mine) else None
                 # the GPU always holds the next cluster: submit this one BEFORE waiting for the previous
-                on_gpu.append((i, prep, ann_index.submit_prepared(prep)))
+                on_gpu.append((i, prep, ann_index.submit_prepared(prep, rows=True)))
                 del prep
                 if len(on_gpu) == 2:
                     collect_oldest()

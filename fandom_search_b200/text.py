@@ -61,7 +61,8 @@ def _view(ptr, count, dtype):
     if count == 0 or not ptr:
         return np.zeros(0, dtype=dtype)
     ctype = {np.dtype(np.int64): ctypes.c_int64, np.dtype(np.int32): ctypes.c_int32,
-             np.dtype(np.uint8): ctypes.c_uint8}[np.dtype(dtype)]
+             np.dtype(np.uint8): ctypes.c_uint8, np.dtype(np.uint32): ctypes.c_uint32,
+             np.dtype(np.uint16): ctypes.c_uint16}[np.dtype(dtype)]
     return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(count,))
 
 
@@ -124,6 +125,8 @@ class Batch:
         self.tok = _view(arr(3), n_tok, np.int32)
         self.tok_start = _view(arr(4), n_tok, np.int64)
         self.tok_end = _view(arr(5), n_tok, np.int64)
+        self.tok_start32 = _view(arr(9), n_tok, np.uint32)     # compact form for the device-side records
+        self.tok_len16 = _view(arr(10), n_tok, np.uint16)
         self.oov_start = _view(arr(6), n_oov, np.int64)
         self.oov_end = _view(arr(7), n_oov, np.int64)
         status = _view(arr(8), n_files, np.int32)
@@ -144,6 +147,8 @@ class Batch:
         if len(flat):
             self.tok_start[1:] = np.cumsum(lens[:-1] + 1)
         self.tok_end = self.tok_start + lens
+        self.tok_start32 = self.tok_start.astype(np.uint32)
+        self.tok_len16 = np.minimum(lens, 65535).astype(np.uint16)
         self.text = np.frombuffer(b" ".join(flat), dtype=np.uint8)
         self.tok_off = np.zeros(len(lists) + 1, dtype=np.int64)
         np.cumsum([len(ws) for ws in lists], out=self.tok_off[1:])
@@ -162,6 +167,7 @@ class Batch:
     def close(self):
         if self._h:
             self.text = self.tok = self.tok_start = self.tok_end = self.tok_off = None
+            self.tok_start32 = self.tok_len16 = None
             self._lib.fs_batch_destroy(self._h)
             self._h = None
 

@@ -71,6 +71,20 @@ typedef struct fs_match {
  * nearpy index would never have compared that pair). */
 #define FS_MATCH_LSH_SHIFT 8
 
+/* One winning record of the device-side post-processing (fs_search_submit_rows): the fan word
+ * `word` of work `work` is best covered by the fan window that starts `window_ix` words before it,
+ * matched with the script window starting at `match_ix`.  The CSV row of search.py:206-217 follows
+ * from these six values (fs_records_format_csv). */
+typedef struct fs_row {
+    int32_t work;      /* CSR row (fanwork)                                             */
+    int32_t word;      /* FAN_WORK_WORD_INDEX                                           */
+    int32_t window_ix; /* position of the word inside the winning window (0 .. w-1)     */
+    int32_t match_ix;  /* first script word of the matched script window               */
+    double distance;   /* BEST_MATCH_DISTANCE                                           */
+    int32_t lev;       /* BEST_LEVENSHTEIN_DISTANCE                                     */
+    int32_t reserved;
+} fs_row;
+
 /* One exact 6-gram hit of the hash-join kernel. */
 typedef struct fs_pair {
     int32_t fan_pos;
@@ -86,11 +100,16 @@ enum {
     FS_CNT_OVERFLOW = 4,   /* FS_OVERFLOW_* bits, written on the device by the search entry
                               points: how a caller of the stream-ordered "_dev" variants
                               learns that a buffer was too small                     */
-    FS_CNT_COUNT = 5
+    FS_CNT_ROWS = 5,       /* winning rows of the device-side post-processing            */
+    FS_CNT_COUNT = 6
 };
 #define FS_OVERFLOW_CANDIDATES 1 /* the internal candidate buffer overflowed (pairs were lost):
                                     fs_index_reserve more candidates and search again        */
 #define FS_OVERFLOW_MATCHES 2    /* more matches than `cap`: counters[FS_CNT_MATCHES] says how many */
+#define FS_OVERFLOW_ROWS 4       /* more winning rows than `cap_rows`: counters[FS_CNT_ROWS] says how many */
+#define FS_OVERFLOW_TEXT 8       /* a window text too long for the device Levenshtein (a token of 64 KiB,
+                                    or both strings above 250 code points): the rows are incomplete, do
+                                    this batch's records on the host (fs_records_best_mt)               */
 
 /* Options for fs_index_set_option. */
 enum {
@@ -214,6 +233,32 @@ int fs_search_submit(fs_index* idx,
                      int64_t cap, int32_t* ticket);
 int fs_search_collect(fs_index* idx, int32_t ticket, fs_match* out, int64_t cap, int64_t* counters);
 
+/*
+ * Search + post-processing on the device: top-10 per fan window
+ * (NearestFilter(10)), Levenshtein of "[t0, ..., t5]" vs "s0 ... s5", six records per pair and the
+ * per-word argmin with first-inserted ties (search.py:182-226) run on the GPU right behind the
+ * float64 rescoring; only the winning rows come back, sorted by (work, word) -- the output of
+ * fs_records_best on the same matches, bit for bit.
+ *
+ * fs_index_set_script_text registers the lower-cased script words (once per index):
+ *   blob, word_off [n_words + 1]   n_words must equal the index's script token count
+ * fs_search_submit_rows takes, besides the CSR batch, the verbatim token texts of the batch:
+ *   text [text_bytes], tok_start [n_tok] uint32, tok_len [n_tok] uint16 (fs_batch arrays 0, 9, 10)
+ *   lsh_filter != 0: LSH-emulation mode -- pairs that share no table are dropped and the first
+ *   shared table orders equal distances, as in the reference's candidate order
+ * Single-script indexes only.  FS_OVERFLOW_ROWS / FS_OVERFLOW_TEXT are reported like the other
+ * overflow bits; on either the ticket can still be collected with fs_search_collect (raw matches).
+ */
+int fs_index_set_script_text(fs_index* idx, const char* blob, const int64_t* word_off, int64_t n_words);
+int fs_search_submit_rows(fs_index* idx,
+                          const int32_t* tok, int64_t n_tok,
+                          const int64_t* off, int64_t n_works,
+                          const float* extra, int64_t n_extra,
+                          const char* text, int64_t text_bytes,
+                          const uint32_t* tok_start, const uint16_t* tok_len,
+                          int32_t lsh_filter, int64_t cap_matches, int64_t cap_rows, int32_t* ticket);
+int fs_search_collect_rows(fs_index* idx, int32_t ticket, fs_row* out, int64_t cap, int64_t* counters);
+
 /* Exact 6-gram hash-join only (the distance-0 special case). */
 int fs_exact_join_dev(fs_index* idx, void* stream,
                       const int32_t* tok, int64_t n_tok,
@@ -301,7 +346,9 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
 void fs_batch_destroy(fs_batch* b);
 int64_t fs_batch_info(const fs_batch* b, int32_t what);  /* 0 files, 1 tokens, 2 unique OOV, 3 text bytes */
 /* 0 text(char) 1 file_off(i64[files+1]) 2 tok_off(i64[files+1]) 3 tok(i32[T]) 4 tok_start(i64[T])
- * 5 tok_end(i64[T]) 6 oov_start(i64[U]) 7 oov_end(i64[U]) 8 file_status(i32[files]); valid until destroy */
+ * 5 tok_end(i64[T]) 6 oov_start(i64[U]) 7 oov_end(i64[U]) 8 file_status(i32[files])
+ * 9 tok_start32(u32[T]) 10 tok_len16(u16[T], clamped at 65535: what fs_search_submit_rows takes);
+ * valid until destroy */
 void* fs_batch_array(fs_batch* b, int32_t which);
 
 /* Top-k per fan window (NearestFilter(10)), Levenshtein of "[t0, ..., t5]" vs "s0 ... s5"
