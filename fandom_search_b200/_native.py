@@ -75,6 +75,7 @@ SIGNATURES = {
     "fs_search_submit_rows": (ctypes.c_int, [_vp] + _BATCHX + [_vp, _i64, _vp, _vp, _i32, _i64, _i64,
                                                                ctypes.POINTER(_i32)]),
     "fs_search_collect_rows": (ctypes.c_int, [_vp, _i32, _vp, _i64, _vp]),
+    "fs_index_set_reuse_histogram": (ctypes.c_int, [_vp, _vp, _vp, _i32]),
     "fs_exact_join_dev": (ctypes.c_int, [_vp, _vp] + _BATCH + [_vp, _i64, _vp]),
     "fs_exact_join_host": (ctypes.c_int, [_vp] + _BATCH + [_vp, _i64, _vp]),
     "fs_stage_embed_dev": (ctypes.c_int, [_vp, _vp] + _BATCHX + [_vp, _vp]),

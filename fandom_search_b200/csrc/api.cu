@@ -187,6 +187,11 @@ struct fs_index {
     unsigned long long *pp_best_key = nullptr, *pp_best_tie = nullptr;
     int64_t* pp_block_off = nullptr;
 
+    // per-script-word reuse histogram accumulated from the device rows (caller-owned device buffers)
+    unsigned long long* hist_counts = nullptr;
+    const double* hist_thresholds = nullptr;
+    int32_t hist_n_thr = 0;
+
     // LSH emulation (parity mode)
     double* lsh_normals = nullptr;
     int32_t lsh_tables = 0, lsh_bits = 0;
@@ -1022,6 +1027,11 @@ static int submit_slot(fs_index* idx, const BatchArgs& h, int64_t cap, int32_t* 
         pp.rows_cap = tx.cap_rows;
         pp.overflow = sl.d_counters + FS_CNT_OVERFLOW;
         if ((r = launch_postprocess(pp, idx->sm_count, st)) != FS_OK) return r;
+        if (idx->hist_counts &&
+            (r = launch_reuse_histogram_rows(sl.d_rows, sl.d_counters, tx.cap_rows, idx->hist_thresholds,
+                                             idx->hist_n_thr, idx->n_script_tok, idx->hist_counts, idx->sm_count,
+                                             st)) != FS_OK)
+            return r;
     }
     FS_CUDA_CHECK(cudaMemcpyAsync(sl.h_counters, sl.d_counters, sizeof(int64_t) * FS_CNT_COUNT,
                                   cudaMemcpyDeviceToHost, st));
@@ -1115,6 +1125,19 @@ int fs_index_set_script_text(fs_index* idx, const char* blob, const int64_t* wor
         FS_CUDA_CHECK(cudaMemcpy(idx->script_text, blob, static_cast<size_t>(word_off[n_words]), cudaMemcpyHostToDevice));
     FS_CUDA_CHECK(cudaMemcpy(idx->script_word_off, word_off, sizeof(int64_t) * (n_words + 1), cudaMemcpyHostToDevice));
     idx->n_script_words = n_words;
+    return FS_OK;
+}
+
+int fs_index_set_reuse_histogram(fs_index* idx, int64_t* counts_dev, const double* thresholds_dev, int32_t n_thr) {
+    if (!idx || n_thr < 0 || (n_thr > 0 && (!counts_dev || !thresholds_dev))) {
+        set_error("fs_index_set_reuse_histogram: invalid argument");
+        return FS_E_INVALID;
+    }
+    FS_CUDA_CHECK(cudaSetDevice(idx->device));
+    FS_CUDA_CHECK(cudaStreamSynchronize(idx->stream));
+    idx->hist_counts = n_thr > 0 ? reinterpret_cast<unsigned long long*>(counts_dev) : nullptr;
+    idx->hist_thresholds = n_thr > 0 ? thresholds_dev : nullptr;
+    idx->hist_n_thr = n_thr;
     return FS_OK;
 }
 

@@ -249,6 +249,9 @@ int launch_sliding_minmax32(const float2* src, float2* dst, int64_t n, cudaStrea
 int launch_rescore(const RescoreParams& p, int sm_count, cudaStream_t stream);
 int launch_lsh(const LshParams& p, int sm_count, cudaStream_t stream);
 int launch_postprocess(const PostParams& p, int sm_count, cudaStream_t stream);
+int launch_reuse_histogram_rows(const fs_row* rows, const unsigned long long* counters, int64_t rows_cap,
+                                const double* thresholds, int32_t n_thr, int64_t n_words,
+                                unsigned long long* counts, int sm_count, cudaStream_t stream);
 int64_t postprocess_scan_blocks(int64_t n_tok);
 int launch_hash_build(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,
                       int32_t window, unsigned long long* table, uint32_t slots,

@@ -470,7 +470,7 @@ class AnnIndexSearch(object):
             self._script_cols = (orth, b''.join(enc), coff, cnone, scene, snone)
         return self._script_cols
 
-    def records_text_prepared(self, prep, matches, first_table=None, word_base=0):
+    def records_text_prepared(self, prep, matches, first_table=None, word_base=0, on_best=None):
         """CSV text (utf-8 bytes) of the cluster's records: byte for byte what
         write_records(records_prepared(...)) puts in the batch file, formatted natively
         (fs_records_format_csv) without building per-row Python objects."""
@@ -479,6 +479,8 @@ class AnnIndexSearch(object):
             return b''
         blob, soff = self._script_text()
         best = self._best(batch, matches, first_table)
+        if on_best is not None:
+            on_best(matches, best)
         orth, cblob, coff, cnone, scene, snone = self._script_columns()
         return _text.records_format_csv(best, filenames, batch, blob, soff, orth, cblob, coff, cnone,
                                         scene, snone, word_base)
@@ -680,7 +682,8 @@ def analyze(args,
             number_of_hashes=15,
             hash_dimensions=14,
             distance_threshold=0.1,
-            chunk_size=500):
+            chunk_size=500,
+            reuse_histogram=None):
     # search.py:336-399.  Listing, seeded shuffle, sub-sampling, clustering and file names are
     # the reference's; the per-cluster pool.map becomes one batched GPU search.  Under
     # torchrun (WORLD_SIZE > 1) cluster i is searched by rank i % WORLD_SIZE on its own GPU,
@@ -706,6 +709,24 @@ def analyze(args,
     global _ANN_INDEX
     _ANN_INDEX = ann_index
 
+    # Optional (reuse_histogram=True / a path, or FANDOM_SEARCH_REUSE_HISTOGRAM): the
+    # per-script-word reuse counts of `ao3.py format` (ao3.py:351-363,407-411), accumulated on the GPU
+    # from the winning rows while the search runs, summed over the ranks with one all_reduce and
+    # written next to the aggregate as match-{w}gram-YYYYMMDD[-k]-reuse.csv
+    if reuse_histogram is None:
+        reuse_histogram = os.environ.get('FANDOM_SEARCH_REUSE_HISTOGRAM') or None
+    hist = None
+    if reuse_histogram:
+        from .aggregate import ReuseHistogram
+        hist = ReuseHistogram(len(ann_index.word_lowercase), device=_device_ordinal())
+        if getattr(ann_index.engine.index, 'device_records', False):
+            hist.attach(ann_index.engine.index)
+
+    def count_host_records(found0, best):
+        # clusters whose records the device made are counted by the device itself
+        if hist is not None and not isinstance(found0, DeviceRows):
+            hist.add_best(best)
+
     # Three overlapped stages per cluster: (1) native read + tokenise + encode of the NEXT
     # cluster, (2) the GPU search of this one, (3) records + batch CSV of the PREVIOUS one.
     # ctypes releases the GIL inside the native calls, so plain threads are enough.
@@ -714,7 +735,8 @@ def analyze(args,
 
     def finish(i, prep, found):
         # rows are formatted ONCE, natively; the aggregate is assembled from the batch files
-        _write_text(ann_index.records_text_prepared(prep, *found), batch_filename.format(i))
+        _write_text(ann_index.records_text_prepared(prep, *found, on_best=count_host_records),
+                    batch_filename.format(i))
         return i
 
     import collections
@@ -751,11 +773,15 @@ def analyze(args,
     finally:
         sys.setswitchinterval(switch_interval)
 
+    if hist is not None:
+        hist.detach()
     if world > 1:
         # every rank has written its own batch files (same directory, one node): rank 0 only has
         # to wait for them -- no record ever crosses ranks
         from .parallel import barrier
         barrier()
+        if hist is not None:
+            hist.all_reduce()       # the one collective of the path: [n_script_words, 11] int64
         if rank != 0:
             return
 
@@ -768,6 +794,10 @@ def analyze(args,
         name_check = filename_base.format(today_str)
     # header row (search.py:367) + the rows of every cluster in cluster order (search.py:388),
     # streamed from the batch files: memory stays flat however large the corpus is
+    if hist is not None:
+        hist_name = reuse_histogram if isinstance(reuse_histogram, str) and reuse_histogram not in ('1', 'true', 'True') \
+            else name_check[:-4] + '-reuse.csv'
+        hist.write_csv(hist_name, ann_index.word_lowercase)
     import shutil
     with open(name_check, 'wb') as out:
         out.write(format_records([new_record_structure['fields']]).encode('utf-8'))

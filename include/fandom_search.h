@@ -258,6 +258,12 @@ int fs_search_submit_rows(fs_index* idx,
                           const uint32_t* tok_start, const uint16_t* tok_len,
                           int32_t lsh_filter, int64_t cap_matches, int64_t cap_rows, int32_t* ticket);
 int fs_search_collect_rows(fs_index* idx, int32_t ticket, fs_row* out, int64_t cap, int64_t* counters);
+/* Accumulate the per-script-word reuse histogram (see fs_reuse_histogram_dev below) from the winning
+ * rows of every fs_search_submit_rows batch, on the device, before the rows are copied out:
+ * counts_dev [n_script_tok, n_thr] int64 and thresholds_dev [n_thr] double are DEVICE buffers owned by
+ * the caller (zero the counts first); n_thr = 0 switches it off.  A batch that ends with an overflow
+ * bit set is not counted (the caller redoes it on the host and counts it there). */
+int fs_index_set_reuse_histogram(fs_index* idx, int64_t* counts_dev, const double* thresholds_dev, int32_t n_thr);
 
 /* Exact 6-gram hash-join only (the distance-0 special case). */
 int fs_exact_join_dev(fs_index* idx, void* stream,

@@ -182,3 +182,50 @@ def test_texts_too_long_for_the_device_fall_back_to_the_host_records(tmp_path):
         assert got == normalise(index.search_many([fan_path])[0])
     finally:
         search.set_pipeline(None)
+
+
+def test_reuse_histogram_from_device_rows_equals_format_data(golden_dir, tmp_path, monkeypatch):
+    """analyze(reuse_histogram=True): the table the device accumulates from its winning rows ==
+    the thresholded group-by of the reference's `ao3.py format` (ao3.py:351-363,407-411, restated
+    with the same pandas calls) applied to the reference's golden match CSV."""
+    import argparse
+    import pandas as pd
+    from fandom_search_b200.aggregate import COLUMN_NAMES
+    search.set_pipeline(search.Pipeline(
+        Lexicon.from_npz(os.path.join(golden_dir, "lexicon.npz"), hash_fn=py_hash_seed0)))
+    try:
+        listing = open(os.path.join(golden_dir, "listing.txt")).read().split()
+        real_listdir = os.listdir
+        monkeypatch.setattr(os, "listdir", lambda d: list(listing) if str(d) == "fanworks" else real_listdir(d))
+        monkeypatch.chdir(tmp_path)
+        os.symlink(os.path.join(golden_dir, "fanworks"), "fanworks")
+        os.symlink(os.path.join(golden_dir, "script.txt"), "script.txt")
+        args = argparse.Namespace(fan_works="fanworks", script="script.txt", skip_works=-1, num_works=-1)
+        search.analyze(args, chunk_size=16, reuse_histogram=True)
+        got = pd.read_csv(glob.glob("match-6gram-2*-reuse.csv")[0], index_col='ORIGINAL_SCRIPT_WORD_INDEX')
+        # --- the reference's own statements (ao3.py:351-363, 407-411) on the reference's golden CSV
+        matches = pd.read_csv(os.path.join(golden_dir, "golden_exhaustive.csv"))
+        name = 'Frequency of Reuse (Exact Matches)'
+        matches_thresh = matches.assign(**{name: matches.BEST_COMBINED_DISTANCE <= 0})
+        thresholds = [0.05, 0.1, 0.15, 0.2, 0.25, 0.3, 0.35, 0.4, 0.45, 0.5]
+        threshname = ['Frequency of Reuse (0-{})'.format(str(t)) for t in thresholds]
+        for thresh, name in zip(thresholds, threshname):
+            matches_thresh = matches_thresh.assign(**{name: matches.BEST_COMBINED_DISTANCE <= thresh})
+        threshname = ['Frequency of Reuse (Exact Matches)'] + threshname
+        want = matches_thresh.groupby('ORIGINAL_SCRIPT_WORD_INDEX').aggregate({n: 'sum' for n in threshname})
+        want = want.reindex(got.index, fill_value=0)
+        assert threshname == COLUMN_NAMES
+        exact = 'Frequency of Reuse (Exact Matches)'
+        for col in threshname:
+            if col == exact:
+                continue
+            assert (got[col].to_numpy() == want[col].to_numpy().astype(np.int64)).all(), col
+        # exact reuse has BEST_COMBINED_DISTANCE = +-1e-16 float noise in the reference itself
+        # (distance = 1 - dot(u, u)); "<= 0" is therefore only comparable up to that noise: every
+        # row the reference counts as exact must be one that is exact here within 1e-12
+        near = matches.BEST_COMBINED_DISTANCE.abs() < 1e-12
+        upper = matches[near].groupby('ORIGINAL_SCRIPT_WORD_INDEX').size().reindex(got.index, fill_value=0)
+        assert (got[exact].to_numpy() <= upper.to_numpy()).all() and got[exact].sum() > 0
+        assert got[threshname[1]].sum() > 0 and (got[threshname].to_numpy()[:, 1:] >= got[threshname].to_numpy()[:, :-1]).all()
+    finally:
+        search.set_pipeline(None)
