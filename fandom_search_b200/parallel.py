@@ -10,6 +10,16 @@ record lists to rank 0 with gather_object.)
 import os
 
 
+def device_ordinal():
+    """The CUDA device of this process -- the ONE place that decides it: FANDOM_SEARCH_DEVICE if
+    set, else LOCAL_RANK (torchrun), else 0."""
+    for key in ('FANDOM_SEARCH_DEVICE', 'LOCAL_RANK'):
+        v = os.environ.get(key)
+        if v not in (None, ''):
+            return int(v)
+    return 0
+
+
 def init_process_group():
     """Initialise torch.distributed from the torchrun environment if needed.
     Returns (rank, world).  nccl when CUDA is available, gloo otherwise (CPU tests)."""
@@ -21,7 +31,7 @@ def init_process_group():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', '29531')
         if torch.cuda.is_available():
-            local = int(os.environ.get('LOCAL_RANK', str(rank)) or 0)
+            local = device_ordinal()
             torch.cuda.set_device(local)
             dist.init_process_group('nccl', rank=rank, world_size=world,
                                     device_id=torch.device('cuda', local))
@@ -44,6 +54,44 @@ def barrier():
 
 def cluster_owner(cluster_index, world):
     return cluster_index % world
+
+
+def assign_clusters(sizes, world, policy=None):
+    """Owner rank of every cluster.  policy 'balanced' (default under FANDOM_SEARCH_BALANCE unset):
+    longest-processing-time greedy on the cluster sizes (bytes of text ~ tokens ~ windows), so that a
+    corpus whose cluster count is not a multiple of the world size, or whose clusters differ in size,
+    does not leave a tail on one GPU; 'roundrobin': cluster i -> rank i % world.
+    Deterministic: every rank computes the same table from the same sizes."""
+    if policy is None:
+        policy = os.environ.get('FANDOM_SEARCH_BALANCE', 'balanced')
+    n = len(sizes)
+    if world <= 1:
+        return [0] * n
+    if policy == 'roundrobin':
+        return [cluster_owner(i, world) for i in range(n)]
+    if policy != 'balanced':
+        raise ValueError("FANDOM_SEARCH_BALANCE must be 'balanced' or 'roundrobin'")
+    load = [0] * world
+    owner = [0] * n
+    for i in sorted(range(n), key=lambda k: (-int(sizes[k]), k)):
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += int(sizes[i])
+    return owner
+
+
+def any_rank_failed(failed):
+    """True on every rank if `failed` is true on any (one small all_reduce): a rank that hit an
+    error must not leave the others waiting at the barrier until the collective times out."""
+    import torch
+    import torch.distributed as dist
+    rank, world = init_process_group()
+    if world <= 1:
+        return bool(failed)
+    dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+    flag = torch.tensor([1 if failed else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    return bool(int(flag.item()))
 
 
 def gather_cluster_records(my_records, rank, world):

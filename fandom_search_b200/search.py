@@ -117,9 +117,26 @@ def get_spacy_model():
             raise RuntimeError(
                 "no lexicon configured: set FANDOM_SEARCH_LEXICON to a lexicon .npz exported "
                 "from the spaCy vectors table (Lexicon.from_spacy) or call search.set_pipeline()")
-        hash_fn = py_hash_seed0 if os.environ.get('FANDOM_SEARCH_OOV_HASH') == 'seed0' else None
-        _SPACY_MODEL = Pipeline(Lexicon.from_npz(path, hash_fn=hash_fn))
+        _SPACY_MODEL = Pipeline(Lexicon.from_npz(path, hash_fn=_default_oov_hash()))
     return _SPACY_MODEL
+
+
+def _default_oov_hash():
+    """The hash of the out-of-vocabulary rule (search.py:79-83).  The reference uses the builtin str
+    hash, randomised per INTERPRETER: its four workers are forked from one process and share it.
+    Ranks under torchrun are separate interpreters -- with the builtin hash every rank would build
+    different OOV pseudo-vectors and an N-GPU run would differ from a 1-GPU run.  So: seed0 (the
+    PYTHONHASHSEED=0 hash, identical everywhere) when asked for, or when WORLD_SIZE > 1 and the
+    environment does not pin PYTHONHASHSEED itself; the builtin hash otherwise."""
+    choice = os.environ.get('FANDOM_SEARCH_OOV_HASH')
+    if choice == 'seed0':
+        return py_hash_seed0
+    if choice in (None, ''):
+        world = int(os.environ.get('WORLD_SIZE', '1') or 1)
+        pinned = os.environ.get('PYTHONHASHSEED', '') not in ('', 'random')
+        if world > 1 and not pinned:
+            return py_hash_seed0
+    return None
 
 
 def sp_parse_chunks(txt, size=100000):
@@ -196,11 +213,8 @@ _PINNED_TOKENS = _PinnedTokens()
 
 
 def _device_ordinal():
-    for key in ('FANDOM_SEARCH_DEVICE', 'LOCAL_RANK'):
-        v = os.environ.get(key)
-        if v not in (None, ''):
-            return int(v)
-    return 0
+    from .parallel import device_ordinal
+    return device_ordinal()
 
 
 class DeviceRows(object):
@@ -671,6 +685,13 @@ def analyze_scripts(args, scripts, window_size=6, number_of_hashes=15, hash_dime
         write_records(accumulated, name)
 
 
+def _file_size(path):
+    try:
+        return os.path.getsize(path)
+    except OSError:
+        return 0
+
+
 def _dist_env():
     world = int(os.environ.get('WORLD_SIZE', '1') or 1)
     rank = int(os.environ.get('RANK', '0') or 0)
@@ -704,6 +725,9 @@ def analyze(args,
     batch_filename = filename_base.format('-batch-{}.csv')
 
     rank, world = _dist_env()
+    if world > 1:
+        from .parallel import init_process_group
+        init_process_group()
     ann_index = AnnIndexSearch(original_script_markup, window_size, number_of_hashes,
                                hash_dimensions, distance_threshold)
     global _ANN_INDEX
@@ -731,7 +755,14 @@ def analyze(args,
     # cluster, (2) the GPU search of this one, (3) records + batch CSV of the PREVIOUS one.
     # ctypes releases the GIL inside the native calls, so plain threads are enough.
     from concurrent.futures import ThreadPoolExecutor
-    mine = [(i, c) for i, c in enumerate(fan_clusters, start=start) if i % world == rank]
+    if world > 1:
+        # cluster -> rank: balanced on the bytes of text per cluster, the same table on every rank
+        from .parallel import assign_clusters
+        sizes = [sum(_file_size(f) for f in c) for c in fan_clusters]
+        owner = assign_clusters(sizes, world)
+    else:
+        owner = [0] * len(fan_clusters)
+    mine = [(i, c) for i, c in enumerate(fan_clusters, start=start) if owner[i - start] == rank]
 
     def finish(i, prep, found):
         # rows are formatted ONCE, natively; the aggregate is assembled from the batch files
@@ -744,6 +775,7 @@ def analyze(args,
     # interval it would wait that long behind the Python parts of the two helper threads.
     switch_interval = sys.getswitchinterval()
     sys.setswitchinterval(2e-4)
+    failure = None
     try:
         with ThreadPoolExecutor(max_workers=1) as prep_pool, ThreadPoolExecutor(max_workers=2) as post_pool:
             pending = prep_pool.submit(ann_index.prepare, mine[0][1]) if mine else None
@@ -770,8 +802,20 @@ def analyze(args,
                 collect_oldest()
             while in_flight:
                 in_flight.popleft().result()
+    except Exception as exc:     # noqa: BLE001 -- reported to every rank below, then re-raised
+        if world <= 1:
+            raise
+        failure = exc
     finally:
         sys.setswitchinterval(switch_interval)
+    if world > 1:
+        # a rank that failed (unreadable file, out of memory, ...) tells the others instead of leaving
+        # them at the barrier until the collective times out
+        from .parallel import any_rank_failed
+        if any_rank_failed(failure is not None):
+            if failure is not None:
+                raise failure
+            raise RuntimeError("another rank failed while searching its clusters; see its log")
 
     if hist is not None:
         hist.detach()

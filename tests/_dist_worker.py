@@ -24,6 +24,10 @@ def main():
     os.listdir = lambda d: list(listing) if str(d) == "fanworks" else real_listdir(d)
     os.chdir(workdir)
     args = argparse.Namespace(fan_works="fanworks", script="script.txt", skip_works=-1, num_works=-1)
+    if os.environ.get('FS_TEST_FAIL_RANK') == os.environ.get('RANK'):
+        def broken(self, filenames):
+            raise OSError("simulated unreadable fanwork on rank %s" % os.environ.get('RANK'))
+        search.AnnIndexSearch.prepare = broken
     search.analyze(args, chunk_size=16)
     import torch.distributed as dist
     if dist.is_initialized():

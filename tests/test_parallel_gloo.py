@@ -60,10 +60,19 @@ def _run_world(golden_dir, tmp_path, world, real):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
-    # each rank announced only its own clusters
+    # each rank announced only its own clusters: the balanced table every rank computes from the
+    # bytes of text per cluster (parallel.assign_clusters)
+    import random
+    listing = open(os.path.join(golden_dir, "listing.txt")).read().split()
+    files = [os.path.join(golden_dir, "fanworks", f) for f in listing]
+    random.seed(4815162342)
+    random.shuffle(files)
+    sizes = [sum(os.path.getsize(f) for f in files[i:i + 16]) for i in range(0, len(files), 16)]
+    owner = parallel.assign_clusters(sizes, world)
+    assert len(sizes) == 3 and sorted(set(owner)) == list(range(min(world, 3)))
     for rank, o in enumerate(outs):
         seen = [int(l.split()[2]) for l in o.splitlines() if l.startswith("Processing cluster")]
-        assert seen == [i for i in range(3) if i % world == rank]
+        assert seen == [i for i in range(3) if owner[i] == rank]
     aggs = glob.glob(str(tmp_path / "match-6gram-2*.csv"))
     assert len(aggs) == 1                                   # only rank 0 writes the aggregate
     got = read_csv(aggs[0])
@@ -78,3 +87,55 @@ def _run_world(golden_dir, tmp_path, world, real):
 
 def test_cluster_owner_is_round_robin():
     assert [parallel.cluster_owner(i, 4) for i in range(9)] == [0, 1, 2, 3, 0, 1, 2, 3, 0]
+    assert parallel.assign_clusters([5] * 9, 4, policy='roundrobin') == [0, 1, 2, 3, 0, 1, 2, 3, 0]
+
+
+def test_balanced_assignment_leaves_no_tail():
+    # equal clusters: the same loads as round robin; a short last cluster and one heavy cluster: LPT
+    assert sorted(parallel.assign_clusters([7] * 8, 4)) == [0, 0, 1, 1, 2, 2, 3, 3]
+    sizes = [10, 10, 10, 10, 10, 10, 10, 10, 3]          # 9 clusters on 4 ranks
+    owner = parallel.assign_clusters(sizes, 4)
+    load = [sum(s for s, o in zip(sizes, owner) if o == r) for r in range(4)]
+    assert max(load) == 23 and max(load) - min(load) <= 3 and len(owner) == 9
+    rr = [sum(s for i, s in enumerate(sizes) if i % 4 == r) for r in range(4)]
+    assert max(rr) == 23                                  # here round robin happens to be as good ...
+    sizes = [30, 5, 5, 5, 30, 5, 5, 5]                    # ... here it puts both heavy clusters on rank 0
+    owner = parallel.assign_clusters(sizes, 4)
+    load = [sum(s for s, o in zip(sizes, owner) if o == r) for r in range(4)]
+    assert max(load) == 30 and max(sum(s for i, s in enumerate(sizes) if i % 4 == r) for r in range(4)) == 60
+    assert parallel.assign_clusters(sizes, 4) == owner and parallel.assign_clusters(sizes, 1) == [0] * 8
+
+
+def test_oov_hash_is_rank_independent_under_torchrun(monkeypatch):
+    from fandom_search_b200 import search
+    from fandom_search_b200.lexicon import py_hash_seed0
+    monkeypatch.delenv("FANDOM_SEARCH_OOV_HASH", raising=False)
+    monkeypatch.delenv("PYTHONHASHSEED", raising=False)
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    assert search._default_oov_hash() is None                 # one interpreter: the builtin hash, as the reference
+    monkeypatch.setenv("WORLD_SIZE", "8")
+    assert search._default_oov_hash() is py_hash_seed0        # separate interpreters: one hash for all ranks
+    monkeypatch.setenv("PYTHONHASHSEED", "123")
+    assert search._default_oov_hash() is None                 # the environment pinned the builtin hash itself
+    monkeypatch.setenv("FANDOM_SEARCH_OOV_HASH", "seed0")
+    assert search._default_oov_hash() is py_hash_seed0
+
+
+def test_a_failing_rank_stops_the_others(golden_dir, tmp_path):
+    """One rank cannot read its cluster: every rank must end with an error promptly (the failure is
+    all_reduced before the barrier) instead of hanging until the collective times out."""
+    os.symlink(os.path.join(golden_dir, "fanworks"), tmp_path / "fanworks")
+    os.symlink(os.path.join(golden_dir, "script.txt"), tmp_path / "script.txt")
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES="", FS_TEST_FAIL_RANK="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_dist_worker.py"),
+                                       golden_dir, str(tmp_path)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert procs[0].returncode != 0 and procs[1].returncode != 0
+    assert "simulated unreadable fanwork" in outs[1]
+    assert "another rank failed" in outs[0]
+    assert not glob.glob(str(tmp_path / "match-6gram-2*.csv"))       # no aggregate from a failed run
