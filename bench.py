@@ -17,14 +17,19 @@ Numbers on the JSON line
   e2e       the same K steps through the host-buffer C-ABI call the drop-in search.py makes
             (fs_search_csr_host): pinned host CSR -> H2D, search, matches -> D2H, every step
   roofline  distance kernel only, mean launch time from CUDA events recorded on the launching
-            stream inside the timed region; peak = MEASURED_PEAKS.json (sustained cuBLAS bf16).
-            `achieved` counts the tensor-core flops the kernel EXECUTES, 2*(6/E)*300*24995 per
-            window (nominal d): with the diagonal factor E = 3 the tensor cores accumulate 2 of
-            the 6 window shifts and the epilogue adds 3 diagonal neighbours, so the same
-            products cost E times fewer tensor flops.  Per SURVEY 8d the two numbers are kept
-            apart: `frac` is a tensor-pipe roofline fraction (useful flops only; `issued_tflops`
-            adds the flops spent on tile overlap and row padding); `algorithmic_advantage` =
-            windows/s / (peak / F_dense), F_dense = 2*(6*300)*24995, is NOT a roofline fraction
+            stream inside the timed region.  `achieved` counts the USEFUL tensor flops of the
+            diagonal formulation, 2*(6/E)*300*Ns per window (nominal d, E = 6: one window shift on the
+            tensor cores, six diagonal neighbours added in the epilogue); `issued_tflops` is what the
+            MMAs really execute (tile overlap, and only the KEPT embedding columns -- the pre-filter
+            drops the lowest-energy columns and carries them as a per-window bound, so issued can be
+            BELOW useful).  peak = fp8 GEMM measured in this run (MEASURED_PEAKS.json has bf16 only),
+            clocks sampled around that measurement too.  `stages` holds the HBM-bound kernels (token
+            gather + window norms, exact 6-gram hash-join) with achieved GB/s against MEASURED_PEAKS'
+            hbm_gbs.  `traffic` is a STATIC number from the committed ncu capture, labelled as such.
+            `algorithmic_advantage` = windows/s / (peak / F_dense) is NOT a roofline fraction.
+  pipeline  files -> CSVs through the drop-in search.analyze under the same launch (every rank
+            tokenises, searches and writes the clusters it owns; wall-clock, max over ranks)
+  check     the reference's golden corpus searched across the ranks of THIS launch == golden CSV
   cpu_baseline  the oracle's port of the reference algorithm (per-window LSH loop over the nearpy
             stand-in) on a bounded sample of the same workload, on this box's host cores
 """
@@ -277,6 +282,22 @@ def cpu_exhaustive_gemm(lex, script, cores, budget_s=6.0):
                       "script windows prebuilt, not timed" % (works, windows, dt, pairs)}
 
 
+def shared_config(n_script_windows, step_windows, world):
+    """The `config` object of BOTH arms (the driver compares them): the workload, nothing about how an
+    arm computes it."""
+    return {"workload": WORKLOAD, "script_windows": int(n_script_windows),
+            "windows_per_step_per_gpu": int(step_windows),
+            "step": "one cluster of %d fanworks per GPU" % WORKS_PER_STEP,
+            "parallelism": "work-sharded x%d, script index replicated" % world,
+            "threshold": 0.1, "window": WINDOW, "dim": DIM}
+
+
+def nominal_step_windows(lex, script):
+    """Windows of cluster 0 (the same synthetic works for both arms)."""
+    _, off = make_cluster(lex, script, 0)
+    return int(np.maximum(np.diff(off) - (WINDOW - 1), 0).sum())
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0") or 0)
     if rank != 0:
@@ -296,16 +317,18 @@ def run_reference_arm(args):
         windows += n
         seconds += dt
     value = windows / seconds if seconds > 0 else 0.0
-    sample = ("%d steps x %d synthetic fanworks of the C2 workload (%d windows) vs the 25000-token script; "
-              "oracle port of search.py:163-226 over the nearpy stand-in, seeded LSH 15x14 bits, "
-              "whitespace tokeniser (faster than spaCy), index build %.1f s not timed"
-              % (args.steps, works_per_step, windows, ref.index_build_s))
+    sample = ("each step a bounded sample of the workload: %d synthetic fanworks (one per host core) of the C2 "
+              "cluster, %d steps, %d windows in all, vs the 25000-token script; oracle port of search.py:163-226 "
+              "over the nearpy stand-in (seeded LSH 15x14 bits, all %d host cores, one process each; the reference "
+              "itself uses 4), whitespace tokeniser and index build (%.1f s) not timed -- both flatter the CPU"
+              % (works_per_step, args.steps, windows, procs, ref.index_build_s))
+    step_windows = nominal_step_windows(lex, script)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * seconds / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "step": "bounded sample: %d fanworks per step" % works_per_step},
+        "config": shared_config(len(script) - WINDOW + 1, step_windows, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -317,6 +340,175 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------
+def _write_works(job):
+    """(pool worker) write the synthetic fanworks ids[...] of the pipeline corpus."""
+    from fandom_search_b200 import synth
+    lex, script, fan_dir, ids = _PIPE_STATE
+    n = 0
+    for k in job:
+        tok, _ = synth.make_fanwork_tokens(lex, script, k)
+        with open(os.path.join(fan_dir, "%07d.txt" % k), "w", encoding="utf-8") as f:
+            f.write(synth.fanwork_text(lex, tok))
+        n += max(len(tok) - (WINDOW - 1), 0)
+    return n
+
+
+_PIPE_STATE = None
+
+
+def run_pipeline(lex, script, works_total, rank, world, local, barrier, all_sum, all_max):
+    """files -> CSVs through the drop-in search.analyze, sharded over the ranks of this launch."""
+    global _PIPE_STATE
+    import shutil
+    import torch
+    from fandom_search_b200 import search, synth
+    from fandom_search_b200.lexicon import Lexicon, py_hash_seed0
+    root = os.path.join(tempfile.gettempdir(), "fs_bench_pipeline_%s" % os.environ.get("MASTER_PORT", str(os.getpid())))
+    fan_dir, out_dir = os.path.join(root, "fanworks"), os.path.join(root, "out")
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+        os.makedirs(fan_dir)
+        os.makedirs(out_dir)
+        lex.save(os.path.join(root, "lexicon.npz"))
+        synth.write_markup_script(lex, script, os.path.join(root, "script.txt"))
+    barrier()
+    t0 = time.perf_counter()
+    mine = list(range(rank, works_total, world))           # every rank writes its share of the files
+    procs = max(1, min(16, host_cores() // max(world, 1)))
+    _PIPE_STATE = (lex, script, fan_dir, None)
+    jobs = [mine[j::procs * 4] for j in range(procs * 4)]
+    with multiprocessing.get_context("fork").Pool(processes=procs) as pool:
+        my_windows = sum(pool.map(_write_works, [j for j in jobs if j], chunksize=1))
+    gen_s = time.perf_counter() - t0
+    barrier()
+    total_windows = all_sum(float(my_windows))
+    search.set_pipeline(search.Pipeline(Lexicon.from_npz(os.path.join(root, "lexicon.npz"), hash_fn=py_hash_seed0)))
+    cwd = os.getcwd()
+    os.chdir(out_dir)
+    ns = argparse.Namespace(fan_works=fan_dir, script=os.path.join(root, "script.txt"), skip_works=-1, num_works=-1)
+    try:
+        barrier()
+        t0 = time.perf_counter()
+        with open(os.devnull, "w") as null, _stdout_to(null):
+            search.analyze(ns)
+        torch.cuda.synchronize()
+        mine_s = time.perf_counter() - t0
+        barrier()
+        total_s = all_max(mine_s)
+        rows = 0
+        if rank == 0:
+            import glob
+            agg = glob.glob(os.path.join(out_dir, "match-6gram-2*.csv"))
+            rows = sum(1 for _ in open(agg[0])) - 1 if agg else -1
+    finally:
+        os.chdir(cwd)
+        search.set_pipeline(None)
+    barrier()
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+    return {"value": total_windows / total_s, "unit": UNIT, "works": works_total, "windows": int(total_windows),
+            "seconds": total_s, "csv_rows": rows,
+            "what": "plaintext fanwork files -> match CSVs through search.analyze (native read + tokenise + encode, "
+                    "GPU search with two clusters in flight, records on the device, native CSV text, aggregate), "
+                    "script parse and index build included; wall clock, max over ranks",
+            "host_threads_per_rank": __import__("fandom_search_b200.text", fromlist=["x"]).host_threads(),
+            "corpus_generation_s": gen_s}
+
+
+class _stdout_to:
+    """analyze prints one line per cluster (as the reference does): keep them off the JSON line."""
+
+    def __init__(self, target):
+        self.target = target
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(self.target.fileno(), 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def run_golden_check(rank, world, barrier):
+    """The reference's golden corpus (tests/golden: 40 works, 3 clusters of 16) searched by the ranks
+    of this launch through search.analyze; rank 0 compares the aggregate with the CSV the unmodified
+    reference wrote.  Proves the SHARDED product path, not only concurrent kernels."""
+    import glob
+    import shutil
+    import torch
+    from fandom_search_b200 import search
+    from fandom_search_b200.lexicon import Lexicon, py_hash_seed0
+    golden = os.path.join(ROOT, "tests", "golden")
+    root = os.path.join(tempfile.gettempdir(), "fs_bench_check_%s" % os.environ.get("MASTER_PORT", str(os.getpid())))
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+        os.makedirs(root)
+        os.symlink(os.path.join(golden, "fanworks"), os.path.join(root, "fanworks"))
+        os.symlink(os.path.join(golden, "script.txt"), os.path.join(root, "script.txt"))
+    barrier()
+    listing = open(os.path.join(golden, "listing.txt")).read().split()
+    real_listdir = os.listdir
+    os.listdir = lambda d: list(listing) if str(d) == "fanworks" else real_listdir(d)
+    search.set_pipeline(search.Pipeline(Lexicon.from_npz(os.path.join(golden, "lexicon.npz"), hash_fn=py_hash_seed0)))
+    cwd = os.getcwd()
+    os.chdir(root)
+    result = {"corpus": "tests/golden (40 works, 3 clusters of 16, written by the unmodified reference over the shims)"}
+    try:
+        ns = argparse.Namespace(fan_works="fanworks", script="script.txt", skip_works=-1, num_works=-1)
+        with open(os.devnull, "w") as null, _stdout_to(null):
+            search.analyze(ns, chunk_size=16)
+        torch.cuda.synchronize()
+        barrier()
+        if rank == 0:
+            from tests.util import compare_records, read_csv
+            got = read_csv(glob.glob("match-6gram-2*.csv")[0])
+            want = read_csv(os.path.join(golden, "golden_exhaustive.csv"))
+            ties = compare_records(got, want, tol=1e-12, basename=False)
+            same_order = [(r[0], r[1]) for r in got] == [(r[0], r[1]) for r in want]
+            result.update({"rows": len(got), "identical": bool(same_order), "exact_reuse_alternates": ties,
+                           "ranks": world})
+    except AssertionError as exc:
+        result.update({"identical": False, "error": str(exc)[:300]})
+    finally:
+        os.chdir(cwd)
+        os.listdir = real_listdir
+        search.set_pipeline(None)
+    barrier()
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+    return result
+
+
+def time_stages(index, dev_in, reps=5):
+    """CUDA-event times of the HBM-bound stages on torch's current stream (they are launched on the
+    stream they are given): token gather + window norms, exact 6-gram hash-join."""
+    import torch
+    from fandom_search_b200 import _native as nt
+    tok_t, off_t, _ = dev_in
+    n_tok = tok_t.numel()
+    pairs = torch.empty((1 << 20, 2), dtype=torch.int32, device=tok_t.device)
+    cnt = torch.zeros(nt.FS_CNT_COUNT, dtype=torch.int64, device=tok_t.device)
+    out = {}
+    for name, fn in (("gather", lambda: index.stage_embed(tok_t, off_t)),
+                     ("hash_join", lambda: index.exact_join_dev(tok_t, off_t, pairs, cnt))):
+        fn()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        out[name] = best
+    return out, n_tok
+
+
 def run_native_arm(args):
     import torch
     import torch.distributed as dist
@@ -352,13 +544,25 @@ def run_native_arm(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    def all_reduce(x, op):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t[0])
+
+    def all_sum(x):
+        return all_reduce(x, dist.ReduceOp.SUM)
+
+    def all_max(x):
+        return all_reduce(x, dist.ReduceOp.MAX)
+
     lex = make_lexicon()
     script = synth.make_script_tokens(lex, SCRIPT_TOKENS).astype(np.int32)
     index = DeviceIndex(lex.table_all, script, window=WINDOW, threshold=0.1, device=local)
     n_script_windows = index.n_script_windows
 
-    # distinct clusters per rank; a handful are generated and cycled (each step's fp16 token
-    # matrix is 1.6 GB, far larger than the 126 MB L2, so nothing carries over between steps)
+    # distinct clusters per rank; a handful are generated and cycled (each step's operand token
+    # matrix is 0.6 GB, far larger than the 126 MB L2, so nothing carries over between steps)
     n_distinct = max(1, min(args.steps + args.warmup, args.distinct))
     clusters = [make_cluster(lex, script, rank * 1000 + c) for c in range(n_distinct)]
     max_tok = max(len(t) for t, _ in clusters)
@@ -414,7 +618,7 @@ def run_native_arm(args):
     counters = cnt_t.cpu().numpy()
     for c in range(min(n_distinct, args.steps + args.warmup)):
         assert counters[c][nt.FS_CNT_WINDOWS] == windows_of[c], "window count mismatch"
-        assert counters[c][nt.FS_CNT_MATCHES] <= cap and counters[c][nt.FS_CNT_CANDIDATES] <= (1 << 20)
+        assert counters[c][nt.FS_CNT_OVERFLOW] == 0, "a buffer overflowed inside the timed region"
 
     # ---- e2e: host buffers through the C-ABI call of the drop-in --------------------------------
     for s in range(min(args.warmup, 2)):
@@ -433,25 +637,29 @@ def run_native_arm(args):
               for s in range(args.steps))
 
     # ---- reduce over ranks: max time, summed windows ------------------------------------------
-    stats = torch.tensor([elapsed_ms, e2e_s * 1e3, float(step_windows)], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        elapsed_ms, e2e_ms, total_windows = float(mx[0]), float(mx[1]), float(sm[2])
-    else:
-        e2e_ms, total_windows = e2e_s * 1e3, float(step_windows)
+    elapsed_ms = all_max(elapsed_ms)
+    e2e_ms = all_max(e2e_s * 1e3)
+    total_windows = all_sum(float(step_windows))
+
+    # ---- HBM-bound stages (rank 0's cluster 0) ------------------------------------------------------
+    stage_ms, stage_tok = time_stages(index, dev_in[0])
 
     peaks = measured_peaks()
     bits = index.operand_bits
+    peak_clocks = None
     if bits == 8:
         # the driver-written file has no fp8 figure: measure the fp8 GEMM on this box (after the
-        # timed regions), else take twice the measured bf16 figures (the nominal fp8:bf16 ratio)
-        fp8 = measure_fp8_peak(dev) if rank == 0 else None
+        # timed regions, clocks sampled the same way), else take twice the measured bf16 figures
+        fp8 = None
+        if rank == 0:
+            ps = ClockSampler(local)
+            ps.start()
+            fp8 = measure_fp8_peak(dev)
+            peak_clocks = ps.stop()
         if fp8:
             roof = {"sustained": fp8["sustained"], "burst": fp8["burst"],
-                    "kind": "fp8 e4m3 cuBLASLt GEMM measured in this run (torch._scaled_mm 8192^3, sustained 2 s)"}
+                    "kind": "fp8 e4m3 cuBLASLt GEMM measured BY THIS RUN after the timed regions "
+                            "(torch._scaled_mm 8192^3, sustained 2 s); MEASURED_PEAKS.json holds bf16 only"}
         else:
             roof = {"sustained": 2 * peaks["sustained"], "burst": 2 * peaks["burst"],
                     "kind": "2 x %s sustained bf16 cuBLAS (fp8 GEMM not measurable here)" % peaks["source"]}
@@ -465,19 +673,47 @@ def run_native_arm(args):
     launch_s = kernel_ms / max(launches, 1) * 1e-3
     achieved_tflops = f_exec * win_per_launch / launch_s / 1e12 if launches else 0.0
     dense_equiv_tflops = f_dense * win_per_launch / launch_s / 1e12 if launches else 0.0
-    # tensor-core flops the kernel ISSUES per useful (executed) flop: tiles overlap by E-1 rows and
-    # columns (E = 6: 108 of 128 rows, overlapping TMEM lane quarters), rows are padded to the K-step
+    # tensor-core flops the kernel ISSUES per useful flop: tiles overlap by E-1 rows and columns (E = 6:
+    # 108 of 128 rows, overlapping TMEM lane quarters) and the operand rows hold dim_pad elements (the
+    # kept columns of the pre-filter, padded to the K-step) instead of the nominal d
     m_eff = (108.0 if diag == 6 else 129.0 - diag) / 128.0
     n_eff = (257.0 - diag) / 256.0
     k_eff = float(DIM) / float(index.info(1))
     issue_factor = 1.0 / (m_eff * n_eff * k_eff)
-    traffic = None
+    traffic, traffic_source = None, None
     prof = os.path.join(ROOT, "profiles", "distance_kernel_ncu_summary.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            summary = json.load(open(prof))
+            traffic = summary.get("dram_bytes_per_launch")
+            traffic_source = ("STATIC: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full "
+                              "capture %s (not measured by this run)" % summary.get("capture", "profiles/"))
         except Exception:
             traffic = None
+    row_bytes = index.dim_pad if bits == 8 else 2 * index.dim_pad
+    gather_bytes = stage_tok * (4 + row_bytes + 16)      # id read, operand row + (norm, error, dropped) written
+    join_bytes = stage_tok * 4                           # every id read once (windows staged in shared memory)
+    stages = {
+        "gather+window_norms": {"bound": "hbm", "ms": stage_ms["gather"],
+                                "achieved": gather_bytes / (stage_ms["gather"] * 1e-3) / 1e9, "unit": "GB/s",
+                                "peak": peaks["hbm_gbs"], "frac": gather_bytes / (stage_ms["gather"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                "bytes": "tokens x (4 B id + %d B operand row + 16 B norms)" % row_bytes},
+        "hash_join": {"bound": "hbm (in practice issue/latency)", "ms": stage_ms["hash_join"],
+                      "achieved": join_bytes / (stage_ms["hash_join"] * 1e-3) / 1e9, "unit": "GB/s",
+                      "peak": peaks["hbm_gbs"], "frac": join_bytes / (stage_ms["hash_join"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "bytes": "tokens x 4 B id"},
+    }
+
+    # ---- files -> CSV through search.analyze, and the golden corpus across the ranks -----------------
+    kept_dims, cta_pair, group_bits = index.kept_dims, index.cta_pair, index.info(12)
+    index.close()
+    del dev_in, out_t
+    torch.cuda.empty_cache()
+    pipeline = check = None
+    if not args.no_pipeline:
+        works_total = args.pipeline_works if args.pipeline_works > 0 else 12500 * world
+        pipeline = run_pipeline(lex, script, works_total, rank, world, local, barrier, all_sum, all_max)
+        check = run_golden_check(rank, world, barrier)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -501,38 +737,42 @@ def run_native_arm(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f8e4m3" if bits == 8 else "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "script_windows": n_script_windows,
-                       "windows_per_step_per_gpu": step_windows // max(args.steps, 1),
-                       "parallelism": "work-sharded x%d, script index replicated" % world,
-                       "l2": "inputs larger than L2 (%.1f GB %s token matrix per step)"
-                             % ((0.8, "fp8") if bits == 8 else (1.6, "fp16")),
-                       "precision": ("fp8 e4m3 tcgen05 pre-filter (fp32 accumulate; every window's measured rounding "
-                                     "error is in its threshold: guaranteed superset) + float64 rescoring"
-                                     if bits == 8 else
-                                     "fp16 tcgen05 pre-filter (fp32 accumulate, slack 4e-3) + float64 rescoring"),
-                       "candidates_per_step": int(counters[0][nt.FS_CNT_CANDIDATES]),
-                       "matches_per_step": int(counters[0][nt.FS_CNT_MATCHES]),
-                       "kept_dims": index.kept_dims,
-                       "kernel": "diagonal factor E=%d, cta_group::%d" % (diag, 2 if index.cta_pair else 1)},
+            "config": shared_config(n_script_windows, nominal_step_windows(lex, script), world),
+            "details": {"l2": "inputs larger than L2 (%.2f GB %s token matrix per step)"
+                              % (max_tok * row_bytes / 1e9, "fp8" if bits == 8 else "fp16"),
+                        "precision": ("fp8 e4m3 tcgen05 pre-filter over the %d highest-energy embedding columns of %d (fp32 "
+                                      "accumulate; every window's measured rounding error and dropped-column norm are in "
+                                      "its threshold: guaranteed superset) + float64 rescoring from the fp32 rows"
+                                      % (kept_dims, DIM) if bits == 8 else
+                                      "fp16 tcgen05 pre-filter (fp32 accumulate) + float64 rescoring"),
+                        "candidates_per_step": int(counters[0][nt.FS_CNT_CANDIDATES]),
+                        "matches_per_step": int(counters[0][nt.FS_CNT_MATCHES]),
+                        "kept_dims": kept_dims,
+                        "kernel": "diagonal factor E=%d, cta_group::%d, tile-group bits %d"
+                                  % (diag, 2 if cta_pair else 1, group_bits)},
             "clocks": clocks,
             "e2e": {"value": total_windows / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1)},
             "gpu_launches": 4 * args.steps * world,
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": roof["sustained"],
                          "unit": "TFLOP/s", "frac": achieved_tflops / roof["sustained"],
-                         "traffic": traffic, "peak_kind": roof["kind"],
+                         "traffic": traffic, "traffic_source": traffic_source,
+                         "peak_kind": roof["kind"], "peak_clocks": peak_clocks,
                          "frac_of_burst": achieved_tflops / roof["burst"],
                          "bf16_sustained_peak": peaks["sustained"],
                          "frac_of_bf16_sustained": achieved_tflops / peaks["sustained"],
                          "kernel": "distance_kernel", "kernel_ms_per_launch": kernel_ms / max(launches, 1),
                          "kernel_share_of_step": kernel_ms / elapsed_ms if elapsed_ms else None,
-                         "flop_per_window_executed": f_exec, "flop_per_window_dense": f_dense,
-                         "diagonal_factor": diag, "cta_pair": index.cta_pair,
+                         "flop_per_window_useful": f_exec, "flop_per_window_dense": f_dense,
+                         "diagonal_factor": diag, "cta_pair": cta_pair,
                          "dense_equivalent_tflops": dense_equiv_tflops,
                          "algorithmic_advantage": dense_equiv_tflops / roof["sustained"],
                          "issued_tflops": achieved_tflops * issue_factor,
                          "issued_frac": achieved_tflops * issue_factor / roof["sustained"],
-                         "useful_share_of_issued": 1.0 / issue_factor},
+                         "useful_per_issued": 1.0 / issue_factor,
+                         "stages": stages},
+            "pipeline": pipeline,
+            "check": check,
             "cpu_baseline": cpu_baseline,
             "cpu_exhaustive_gemm": cpu_exhaustive,
         }
@@ -550,6 +790,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic clusters cycled per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the files -> CSV run and the golden check")
+    ap.add_argument("--pipeline-works", type=int, default=0,
+                    help="fanworks of the files -> CSV run over all ranks (default 12500 per GPU)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
