@@ -393,8 +393,18 @@ def run_pipeline(lex, script, works_total, rank, world, local, barrier, all_sum,
             search.analyze(ns)
         torch.cuda.synchronize()
         mine_s = time.perf_counter() - t0
+        st = dict(search.ANALYZE_STATS)
         barrier()
         total_s = all_max(mine_s)
+        # steady state of this rank: from the first cluster collected to the last one collected
+        col = st.get('collected', [])
+        steady = (col[-1][2] - col[0][2]) / (col[-1][1] - col[0][1]) if len(col) > 2 else 0.0
+        steady_all = all_sum(steady)
+        phases = {"script parse + index build": st.get('index_ready', 0) - st.get('start', 0),
+                  "until the first cluster is collected": (col[0][1] - st['index_ready']) if col else None,
+                  "first to last cluster collected": (col[-1][1] - col[0][1]) if col else None,
+                  "last records + batch CSVs": st.get('searched', 0) - (col[-1][1] if col else 0),
+                  "barrier + aggregate CSV": st.get('end', 0) - st.get('searched', 0)}
         rows = 0
         if rank == 0:
             import glob
@@ -408,6 +418,9 @@ def run_pipeline(lex, script, works_total, rank, world, local, barrier, all_sum,
         shutil.rmtree(root, ignore_errors=True)
     return {"value": total_windows / total_s, "unit": UNIT, "works": works_total, "windows": int(total_windows),
             "seconds": total_s, "csv_rows": rows,
+            "steady_state": {"value": steady_all, "unit": UNIT,
+                             "what": "windows between the first and the last cluster collected / that time, summed over ranks"},
+            "rank0_phases_s": phases,
             "what": "plaintext fanwork files -> match CSVs through search.analyze (native read + tokenise + encode, "
                     "GPU search with two clusters in flight, records on the device, native CSV text, aggregate), "
                     "script parse and index build included; wall clock, max over ranks",
@@ -711,7 +724,7 @@ def run_native_arm(args):
     torch.cuda.empty_cache()
     pipeline = check = None
     if not args.no_pipeline:
-        works_total = args.pipeline_works if args.pipeline_works > 0 else 12500 * world
+        works_total = args.pipeline_works if args.pipeline_works > 0 else 25000 * world
         pipeline = run_pipeline(lex, script, works_total, rank, world, local, barrier, all_sum, all_max)
         check = run_golden_check(rank, world, barrier)
 

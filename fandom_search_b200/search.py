@@ -41,6 +41,9 @@ from .lexicon import Lexicon, py_hash_seed0
 
 _SPACY_MODEL = None
 _ANN_INDEX = None
+# wall-clock marks of the last analyze() of this process (time.perf_counter): start, index_ready,
+# collected[(cluster, t, windows so far)], searched, end -- read by bench.py / tools/pipeline_bench.py
+ANALYZE_STATS = {}
 
 # search.py:20-37 -- the CSV schema is the drop-in contract
 new_record_structure = {
@@ -709,6 +712,10 @@ def analyze(args,
     # the reference's; the per-cluster pool.map becomes one batched GPU search.  Under
     # torchrun (WORLD_SIZE > 1) cluster i is searched by rank i % WORLD_SIZE on its own GPU,
     # each rank writes its own batch files and rank 0 writes the aggregate in cluster order.
+    import time
+    stats = {'start': time.perf_counter(), 'collected': []}
+    ANALYZE_STATS.clear()
+    ANALYZE_STATS.update(stats)
     fan_work_directory = args.fan_works
     original_script_markup = args.script
     subsample_start = 0 if args.skip_works < 0 else args.skip_works
@@ -732,6 +739,7 @@ def analyze(args,
                                hash_dimensions, distance_threshold)
     global _ANN_INDEX
     _ANN_INDEX = ann_index
+    ANALYZE_STATS['index_ready'] = time.perf_counter()
 
     # Optional (reuse_histogram=True / a path, or FANDOM_SEARCH_REUSE_HISTOGRAM): the
     # per-script-word reuse counts of `ao3.py format` (ao3.py:351-363,407-411), accumulated on the GPU
@@ -785,6 +793,7 @@ def analyze(args,
             def collect_oldest():
                 i0, prep0, ticket0 = on_gpu.popleft()
                 found = ann_index.collect_prepared(prep0, ticket0)
+                ANALYZE_STATS['collected'].append((i0, time.perf_counter(), ann_index.windows_processed))
                 in_flight.append(post_pool.submit(finish, i0, prep0, found))
                 while len(in_flight) > 3:
                     in_flight.popleft().result()
@@ -802,6 +811,7 @@ def analyze(args,
                 collect_oldest()
             while in_flight:
                 in_flight.popleft().result()
+        ANALYZE_STATS['searched'] = time.perf_counter()
     except Exception as exc:     # noqa: BLE001 -- reported to every rank below, then re-raised
         if world <= 1:
             raise
@@ -827,6 +837,7 @@ def analyze(args,
         if hist is not None:
             hist.all_reduce()       # the one collective of the path: [n_script_words, 11] int64
         if rank != 0:
+            ANALYZE_STATS['end'] = time.perf_counter()
             return
 
     i = 0
@@ -848,3 +859,4 @@ def analyze(args,
         for ci in range(start, start + len(fan_clusters)):
             with open(batch_filename.format(ci), 'rb') as part:
                 shutil.copyfileobj(part, out, 1 << 22)
+    ANALYZE_STATS['end'] = time.perf_counter()

@@ -112,10 +112,11 @@ def test_quotation_heavy_corpus(tmp_path):
 
 
 def _tiny_case(tmp_path, fan_words, script_words, extra_keys=()):
-    """A lexicon whose keys are exactly the given words (random rows; extra_keys = (key, same-row-as)),
+    """A lexicon whose keys are the given words (random rows) plus extra_keys = (key, same-row-as),
     one script line and one fanwork."""
     rng = np.random.default_rng(3)
-    words = sorted(set(script_words) | set(w for w in fan_words if not w.startswith("OOV")))
+    aliased = {k for k, _ in extra_keys}
+    words = sorted(set(script_words) | set(w for w in fan_words if w not in aliased))
     keys = list(words)
     rows = list(range(len(words)))
     for key, same_as in extra_keys:
@@ -137,7 +138,7 @@ def test_unicode_tokens_and_levenshtein_over_code_points(tmp_path):
     script_words = ["café", "日本語", "naïve", "😀x", "plain", "zürich", "añb", "end", "of", "line", "here", "now"]
     fan_words = ["before", "Café", "日本語", "naïve", "😀x", "plain", "zürich", "añb", "END", "of", "line", "after", "x"]
     lex_path, script_path, fan_path = _tiny_case(
-        tmp_path, [w for w in fan_words if w not in ("Café", "END")], script_words,
+        tmp_path, fan_words, script_words,
         extra_keys=(("Café", "café"), ("END", "end"), ("before", "café"), ("after", "now"), ("x", "now")))
     search.set_pipeline(search.Pipeline(Lexicon.from_npz(lex_path, hash_fn=py_hash_seed0)))
     try:
@@ -164,7 +165,7 @@ def test_texts_too_long_for_the_device_fall_back_to_the_host_records(tmp_path):
     script_words = ["a", "b", "c", "d", "e", "f"] + mid + ["g", "h"]
     fan_words = ["q", "a", "b", "c", "d", "e", long_tok, "r"] + mid + ["s"]
     lex_path, script_path, fan_path = _tiny_case(
-        tmp_path, [w for w in fan_words if w != long_tok], script_words,
+        tmp_path, fan_words, script_words,
         extra_keys=((long_tok, "f"), ("q", "g"), ("r", "h"), ("s", "g")))
     search.set_pipeline(search.Pipeline(Lexicon.from_npz(lex_path, hash_fn=py_hash_seed0)))
     try:
