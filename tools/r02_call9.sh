@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 ( timeout 1200 python -m pytest tests -m gpu -q -x ) > gpurun_out/r02_c9_pytest.log 2>&1
 tail -12 gpurun_out/r02_c9_pytest.log
-( time timeout 900 python bench.py ) > gpurun_out/r02_c9_bench.json 2> gpurun_out/r02_c9_bench.err
+( time timeout 1200 python bench.py ) > gpurun_out/r02_c9_bench.json 2> gpurun_out/r02_c9_bench.err
 tail -5 gpurun_out/r02_c9_bench.err
 python - <<'PY'
 import json
