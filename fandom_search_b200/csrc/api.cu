@@ -1,6 +1,7 @@
 // C ABI of the reuse-search hot path (see include/fandom_search.h).
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -616,7 +617,7 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             idx->grid_limit = static_cast<int32_t>(value < 0 ? 0 : value);
             return FS_OK;
         case FS_OPT_TILE_GROUP:
-            idx->tile_group = static_cast<int32_t>(value & 31);
+            idx->tile_group = static_cast<int32_t>(value & 127);  // (bits 5, 6: floor probes of a -DFS_FLOOR_PROBE build)
             return FS_OK;
         default:
             set_error("unknown option %d", option);
@@ -791,6 +792,12 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.pack = idx->pack;
     p.shifts_per_stage = idx->shifts_per_stage > 0 ? idx->shifts_per_stage : idx->window / idx->diag;
     p.group = idx->tile_group;
+    {
+        // 2: every lane of an epilogue warp waits on the accumulator barrier itself (try_wait with a
+        // suspend hint) -- 11 % faster than one polling lane + __syncwarp (profiles/r02_sweep_wait_modes.jsonl)
+        static const int wait_mode = getenv("FS_DEBUG_WAIT") ? atoi(getenv("FS_DEBUG_WAIT")) : 2;
+        p.wait_mode = wait_mode;
+    }
     p.tiles_m = tiles_m;
     p.tiles_n = tiles_n;
     p.cand = (mode == Mode::kCandidates) ? cand_out : idx->cand;

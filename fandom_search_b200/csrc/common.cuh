@@ -129,6 +129,7 @@ struct DistParams {
     int32_t shifts_per_stage; // S: MMA shifts served by one smem stage (divides window/E)
     int32_t group;            // 1: (A-resident, E = 6, chunks <= kGroupMaxChunks) all chunks of a script tile
                               //    land on ONE barrier and are issued as one block of MMAs
+    int32_t wait_mode;        // experiment switch of the barrier waits (FS_DEBUG_WAIT; see mbar_wait_mode)
     int32_t tiles_m, tiles_n;
     fs_pair* cand;            // candidate output
     int64_t cand_cap;
@@ -307,6 +308,71 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, ui
     if ((threadIdx.x & 31) == 0) {
         while (!mbar_try_wait(bar, parity)) {
             if (backoff_ns) __nanosleep(backoff_ns);
+        }
+    }
+    __syncwarp();
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or `ns`
+// have passed -- no issue slots and no polling traffic while parked
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking probe of a phase (no hardware parking at all)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// experiment switch of the epilogue's accumulator wait (DistParams::wait_mode & 15, FS_DEBUG_WAIT):
+//  0 one polling lane on try_wait, then the warp (the round-1 form)   1 the same, napping 40 ns
+//  2 every lane parked on try_wait with a 4 us hint                   3 one lane parked with the hint, then the warp
+//  8 one lane spinning on test_wait, then the warp                    9 every lane spinning on test_wait
+// 10 one lane on try_wait with a 100 ns hint, then the warp          11 every lane on try_wait with a 100 ns hint
+__device__ __forceinline__ void mbar_wait_mode(uint32_t bar, uint32_t parity, int mode) {
+    if (mode == 2 || mode == 11) {
+        const uint32_t ns = mode == 2 ? 4000u : 100u;
+        while (!mbar_try_wait_hint(bar, parity, ns)) {
+        }
+        return;
+    }
+    if (mode == 9) {
+        while (!mbar_test_wait(bar, parity)) {
+        }
+        return;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mode == 3 || mode == 10) {
+            const uint32_t ns = mode == 3 ? 4000u : 100u;
+            while (!mbar_try_wait_hint(bar, parity, ns)) {
+            }
+        } else if (mode == 8) {
+            while (!mbar_test_wait(bar, parity)) {
+            }
+        } else {
+            while (!mbar_try_wait(bar, parity)) {
+                if (mode == 1) __nanosleep(40);
+            }
         }
     }
     __syncwarp();

@@ -312,7 +312,7 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
     float2* ns_tile = norm_tile + as * kHaloCols;
     if (kDiag > 1 && !kOverlap && epi_tid < kHaloCols)
         ns_tile[epi_tid] = epi_tid < kNStep ? __ldg(p.script_bd + n0 + epi_tid) : make_float2(kNaN, kNaN);
-    mbar_wait_warp(tfull_addr, aphase, 0);
+    mbar_wait_mode(tfull_addr, aphase, p.wait_mode & 15);
     tc_fence_after();
     FS_TL(2 + warp, tl_tile, 1);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
@@ -331,7 +331,9 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
         float2 mm2[2];
         mm2[0] = __ldg(p.script_mm32 + n0 + group * kEpiCols);
         mm2[1] = __ldg(p.script_mm32 + n0 + group * kEpiCols + 32);
+        FS_TL(2 + warp, tl_tile, 4);
         tmem_ld_wait();
+        FS_TL(2 + warp, tl_tile, 5);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -682,7 +684,7 @@ __device__ __forceinline__ void epilogue_onepass_loop(const DistParams& p, TileW
             ac_m0 = tile.m0;
         }
         const uint32_t tfull_addr = tfull0 + 8u * as, tempty_addr = tempty0 + 8u * as;
-        mbar_wait_warp(tfull_addr, aphase, 0);
+        mbar_wait_mode(tfull_addr, aphase, p.wait_mode & 15);
         tc_fence_after();
         FS_TL(2 + warp, tl_tile, 1);
 #pragma unroll
@@ -691,6 +693,9 @@ __device__ __forceinline__ void epilogue_onepass_loop(const DistParams& p, TileW
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                    static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
             uint32_t q[72];
+#ifdef FS_FLOOR_PROBE
+            if (!(p.group & 64))  // (probe build: bit 6 = no TMEM load at all, the accumulator is handed straight back)
+#endif
             {
                 // the 8 halo columns of the LAST group lie outside the tile: any readable columns do
                 // (they only enter outputs >= kNStep, which carry NaN bounds)
@@ -714,6 +719,9 @@ __device__ __forceinline__ void epilogue_onepass_loop(const DistParams& p, TileW
                 }
             }
             auto f = [&](int i) { return __uint_as_float(q[i]); };
+#ifdef FS_FLOOR_PROBE
+            if (p.group & 96) continue;  // (probe build: bit 5 = load and release only, no arithmetic)
+#endif
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const int b = 32 * ch;
@@ -1000,7 +1008,15 @@ distance_kernel(const __grid_constant__ CUtensorMap map_fan, const __grid_consta
             }
             // (every lane polls, no naps: this wait is on the accumulator round trip -- one polling
             // lane napping 20 ns cost 10 %, profiles/r01_sweep_early.jsonl)
-            mbar_wait_all(tempty_bar(as), aphase ^ 1u);
+            if (p.wait_mode & 16) {
+                while (!mbar_try_wait_hint(tempty_bar(as), aphase ^ 1u, 100u)) {
+                }
+            } else if (p.wait_mode & 32) {
+                while (!mbar_test_wait(tempty_bar(as), aphase ^ 1u)) {
+                }
+            } else {
+                mbar_wait_all(tempty_bar(as), aphase ^ 1u);
+            }
             tc_fence_after();
             FS_TL(1, tl_tile, 1);
             const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBlockN);
