@@ -203,9 +203,9 @@ struct fs_index {
     int32_t ares = 1;              // A-resident variant of the pair kernel (used when the row fits: <= 640 B)
     int32_t pack = 2;              // epilogue diagonal sums: 0 fp32 shuffles, 1 fp16x2 shuffles, 2 fp16x2 arithmetic
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
-    int32_t tile_group = 7;        // FS_OPT_TILE_GROUP: bit 0 grouped stages, bit 1 early TMEM release, bit 2 one-pass epilogue,
-                                   // bit 4 prefetched bounds, bit 3 alternating epilogue warp sets (both off: measured slower
-                                   // under the power cap, profiles/r02_sweep_epilogue_variants.jsonl)
+    int32_t tile_group = 39;       // FS_OPT_TILE_GROUP: bit 0 grouped stages, bit 1 early TMEM release, bit 2 one-pass epilogue,
+                                   // bit 5 second-level rejection; bit 4 prefetched bounds and bit 3 alternating epilogue warp
+                                   // sets are off (measured slower, profiles/r02_sweep_epilogue_variants.jsonl)
     int32_t grid_limit = 0;
 
     // timing ring
@@ -617,7 +617,7 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             idx->grid_limit = static_cast<int32_t>(value < 0 ? 0 : value);
             return FS_OK;
         case FS_OPT_TILE_GROUP:
-            idx->tile_group = static_cast<int32_t>(value & 127);  // (bits 5, 6: floor probes of a -DFS_FLOOR_PROBE build)
+            idx->tile_group = static_cast<int32_t>(value & 511);  // (bits 7, 8: floor probes of a -DFS_FLOOR_PROBE build)
             return FS_OK;
         default:
             set_error("unknown option %d", option);

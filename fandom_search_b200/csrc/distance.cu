@@ -359,6 +359,32 @@ __device__ __forceinline__ void epilogue_tile(const DistParams& p, const int32_t
                 h2_add(h2_add(b01, __shfl_down_sync(0xffffffffu, b01, 2)), __shfl_down_sync(0xffffffffu, b01, 4));
             const float thr_chunk = bound_of(a_main, mm2[ch]);
             if (!__any_sync(0xffffffffu, h2_lo(bsum) > thr_chunk || h2_hi(bsum) > thr_chunk)) continue;
+            if (p.group & 32) {
+                // Second level (FS_OPT_TILE_GROUP bit 5), for the few chunks the 24-column bound lets through:
+                // the same bound over four spans of 8 outputs -- outputs [8 s, 8 s + 8) only read columns
+                // [8 s, 8 s + 13) -- summed with the same association.  On text that shares its frequent words
+                // with the script a row maximum over 13 columns is far less often a full token match than one
+                // over 24, so most of these chunks stop here (~45 instructions) instead of running the diagonal
+                // sum (~300) -- and a warp that does not run it does not fall a tile behind the others.
+                float n0 = f(b), n1 = f(b + 8), n2 = f(b + 16), n3 = f(b + 24);
+#pragma unroll
+                for (int k = 1; k < 13; ++k) {
+                    n0 = fmaxf(n0, f(b + k));
+                    n1 = fmaxf(n1, f(b + 8 + k));
+                    n2 = fmaxf(n2, f(b + 16 + k));
+                    n3 = fmaxf(n3, f(b + 24 + k));
+                }
+                const uint32_t u01 = pack_h2(n0, n1), u23 = pack_h2(n2, n3);
+                const uint32_t v01 = h2_add(u01, __shfl_down_sync(0xffffffffu, u01, 1));
+                const uint32_t v23 = h2_add(u23, __shfl_down_sync(0xffffffffu, u23, 1));
+                const uint32_t s01 =
+                    h2_add(h2_add(v01, __shfl_down_sync(0xffffffffu, v01, 2)), __shfl_down_sync(0xffffffffu, v01, 4));
+                const uint32_t s23 =
+                    h2_add(h2_add(v23, __shfl_down_sync(0xffffffffu, v23, 2)), __shfl_down_sync(0xffffffffu, v23, 4));
+                if (!__any_sync(0xffffffffu, h2_lo(s01) > thr_chunk || h2_hi(s01) > thr_chunk ||
+                                                 h2_lo(s23) > thr_chunk || h2_hi(s23) > thr_chunk))
+                    continue;
+            }
             uint32_t pk[20], o16[16];
 #pragma unroll
             for (int k = 0; k < 20; ++k) pk[k] = pack_h2(f(b + 2 * k), f(b + 2 * k + 1));
@@ -694,7 +720,7 @@ __device__ __forceinline__ void epilogue_onepass_loop(const DistParams& p, TileW
                                    static_cast<uint32_t>(as * kBlockN + group * kEpiCols);
             uint32_t q[72];
 #ifdef FS_FLOOR_PROBE
-            if (!(p.group & 64))  // (probe build: bit 6 = no TMEM load at all, the accumulator is handed straight back)
+            if (!(p.group & 256))  // (probe build: bit 8 = no TMEM load at all, the accumulator is handed straight back)
 #endif
             {
                 // the 8 halo columns of the LAST group lie outside the tile: any readable columns do
@@ -720,7 +746,7 @@ __device__ __forceinline__ void epilogue_onepass_loop(const DistParams& p, TileW
             }
             auto f = [&](int i) { return __uint_as_float(q[i]); };
 #ifdef FS_FLOOR_PROBE
-            if (p.group & 96) continue;  // (probe build: bit 5 = load and release only, no arithmetic)
+            if (p.group & 384) continue;  // (probe build: bit 7 = load and release only, no arithmetic)
 #endif
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {

@@ -70,7 +70,10 @@ class Token(object):
     def __init__(self, text):
         self.text = text
 
-    is_space = False
+    @property
+    def is_space(self):
+        # spaCy's Token.is_space: the token consists of whitespace characters only
+        return self.text.isspace()
 
     @property
     def orth_(self):
@@ -99,7 +102,28 @@ class Pipeline(object):
 
     def __init__(self, lexicon, tokenizer=None):
         self.lexicon = lexicon
+        if tokenizer == 'rules':
+            tokenizer = _text.tokenize_rules
         self.tokenizer = tokenizer or _text.tokenize
+        self._warned_glued = False
+
+    def check_tokens(self, words, where):
+        """The default tokeniser splits on whitespace only (what pre-tokenised / cleaned corpora
+        need).  Raw prose then keeps its punctuation glued to the words ('Hello,' / "don't"), those
+        tokens miss the lexicon, become 3-hot OOV vectors, and the matches silently diverge from a
+        reference run with spaCy: say so, once, loudly."""
+        if self._warned_glued or self.tokenizer is not _text.tokenize:
+            return
+        share = _text.glued_punctuation_share(words)
+        if share > 0.02:
+            self._warned_glued = True
+            import warnings
+            warnings.warn(
+                "%s: %.0f %% of the tokens carry leading/trailing punctuation -- this looks like raw prose, "
+                "and the default tokeniser splits on whitespace only (no spaCy here). Results will differ from "
+                "the reference's spaCy tokenisation; pass a spaCy-compatible `tokenizer=` to search.Pipeline "
+                "(or FANDOM_SEARCH_TOKENIZER=rules for the built-in approximation)." % (where, 100 * share),
+                RuntimeWarning, stacklevel=3)
 
     def __call__(self, text):
         return [Token(w) for w in self.tokenizer(text)]
@@ -120,7 +144,8 @@ def get_spacy_model():
             raise RuntimeError(
                 "no lexicon configured: set FANDOM_SEARCH_LEXICON to a lexicon .npz exported "
                 "from the spaCy vectors table (Lexicon.from_spacy) or call search.set_pipeline()")
-        _SPACY_MODEL = Pipeline(Lexicon.from_npz(path, hash_fn=_default_oov_hash()))
+        _SPACY_MODEL = Pipeline(Lexicon.from_npz(path, hash_fn=_default_oov_hash()),
+                                tokenizer=os.environ.get('FANDOM_SEARCH_TOKENIZER') or None)
     return _SPACY_MODEL
 
 
@@ -326,12 +351,12 @@ class AnnIndexSearch(object):
 
     # -- host side of one batch --------------------------------------------
     def _tokenize_file(self, filename):
-        # search.py:164-166.  Returns the token TEXTS (no per-token objects on the fast path).
-        # The reference tokenises >=100k-character texts in pieces cut at spaces
-        # (sp_parse_chunks); a whitespace tokeniser yields the same stream for the whole text.
+        # search.py:164-166: the text goes through sp_parse_chunks (>= 100k characters: pieces cut at
+        # spaces, search.py:47-63) and the is_space tokens are dropped, exactly as the reference does
+        # with whatever tokeniser the pipeline holds.  Returns the token TEXTS.
         with open(filename, encoding='utf8') as fan_file:
             fan = fan_file.read()
-        return self.spacy_model.tokenizer(fan)
+        return [str(t) for ch in sp_parse_chunks(fan) for t in ch if not t.is_space]
 
     def search(self, filename):
         # search.py:163-226 for one work
@@ -354,6 +379,9 @@ class AnnIndexSearch(object):
             if getattr(self.spacy_model, '_vocab', None) is None:
                 self.spacy_model._vocab = _text.Vocab(lex)
             batch = self.spacy_model._vocab.encode_files(filenames)
+            if not self.spacy_model._warned_glued and len(batch.tok):
+                n = min(int(batch.tok_off[-1]), 2000)
+                self.spacy_model.check_tokens([batch.token_text(i) for i in range(n)], filenames[0])
             tok, pin = _PINNED_TOKENS.take(batch.tok)              # private, page-locked copy
             offs = numpy.array(batch.tok_off, dtype=numpy.int64)
             extra = None

@@ -30,6 +30,76 @@ def tokenize(text):
     return [data[s:e].decode("utf-8") for s, e in zip(starts.tolist(), ends.tolist())]
 
 
+# ---------------------------------------------------------------------------------------------
+# rule tokeniser: an APPROXIMATION of spaCy's English tokeniser (search.py:43-44 loads
+# en_core_web_md with everything but the tokeniser disabled).  spaCy is not installed in the build
+# image, so these rules are written from its documented behaviour (whitespace split, then prefix /
+# suffix / infix punctuation and the common English contractions) and are NOT validated against it:
+# CSV parity with a reference run holds for pre-tokenised text (tokens separated by spaces, which is
+# what the whitespace tokeniser assumes); for raw prose pass the real thing as `tokenizer=`.
+# ---------------------------------------------------------------------------------------------
+import re  # noqa: E402
+
+_PREFIX = re.compile(r"""^(?:\.\.\.|--+|[\[\](){}<>"'`“”‘’«»¡¿$£€#*_~|/\\,;:!?…-])""")
+_SUFFIX = re.compile(r"""(?:\.\.\.|--+|[\[\](){}<>"'`“”‘’«»,;:!?…%*_~|/\\-]|(?<=[0-9a-zA-Z)\]"'’”])\.)$""")
+_ABBREV = re.compile(r"^(?:[A-Za-z]\.){2,}$|^(?:Mr|Mrs|Ms|Dr|Prof|St|Jr|Sr|vs|etc|e\.g|i\.e)\.$")
+_CONTRACTION = re.compile(r"^(.+?)(n't|n’t|'s|’s|'re|’re|'ve|’ve|'ll|’ll|'d|’d|'m|’m)$", re.IGNORECASE)
+_INFIX = re.compile(r"(?<=[A-Za-z])(--+|—|–|\.\.\.|…|/)(?=[A-Za-z])")
+
+
+def _split_word(word, out):
+    prefixes, suffixes = [], []
+    while word:
+        if _ABBREV.match(word):
+            break
+        m = _PREFIX.match(word)
+        if m and len(word) > len(m.group(0)):
+            prefixes.append(m.group(0))
+            word = word[len(m.group(0)):]
+            continue
+        m = _SUFFIX.search(word)
+        if m and len(word) > len(m.group(0)):
+            suffixes.append(m.group(0))
+            word = word[:-len(m.group(0))]
+            continue
+        break
+    out.extend(prefixes)
+    if word:
+        m = _CONTRACTION.match(word)
+        if m:
+            if m.group(2).lower() in ("n't", "n’t") and m.group(1).lower() == "ca":
+                out.extend([m.group(1), m.group(2)])          # can't -> ca n't
+            else:
+                out.extend([m.group(1), m.group(2)])
+        else:
+            pieces = _INFIX.split(word)
+            out.extend(p for p in pieces if p)
+    out.extend(reversed(suffixes))
+
+
+def tokenize_rules(text):
+    """Whitespace split + punctuation / contraction rules (see the note above): 'Hello, world!' ->
+    Hello , world ! ; "don't" -> do n't ; "it's" -> it 's ; 'U.S.' and 'Mr.' stay whole."""
+    out = []
+    for word in text.split():
+        _split_word(word, out)
+    return out
+
+
+def glued_punctuation_share(words, sample=2000):
+    """Share of (a sample of) tokens that start or end with punctuation although they contain
+    letters or digits: raw prose through the whitespace tokeniser looks like this ('Hello,' /
+    '"Why?'), pre-tokenised text does not."""
+    n = bad = 0
+    for w in words[:sample]:
+        if len(w) < 2 or not any(c.isalnum() for c in w):
+            continue
+        n += 1
+        if not (w[0].isalnum() and w[-1].isalnum()):
+            bad += 1
+    return bad / n if n else 0.0
+
+
 _ID_CACHE = {}
 
 

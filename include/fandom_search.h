@@ -133,7 +133,9 @@ enum {
                                     last column is packed, before the sums; bit 2 (default on, E = 6):
                                     an epilogue warp loads both of its 32-column chunks at once, hands
                                     the accumulator back, takes the row maxima on the fp32 values and
-                                    packs to fp16x2 only the chunks that survive the bound; bit 4
+                                    packs to fp16x2 only the chunks that survive the bound; bit 5
+                                    (default on, with bit 2): a chunk that survives is bounded again over
+                                    four spans of 8 outputs before the diagonal sum is run; bit 4
                                     (default off, with bit 2): the fan row's bound stays in registers
                                     over the sweep of the script and the chunk bounds of the next tile
                                     are prefetched into shared memory by cp.async (no L2 round trip on

@@ -179,7 +179,7 @@ def test_library_defaults():
     table, sx, fx, script, tok, off = _case(5)
     idx = _device_index(table, script, extra=sx, bits=None)
     assert idx.operand_bits == 8 and idx.diag == 6 and idx.cta_pair == 1 and idx.info(7) == 1 and idx.info(8) == 2
-    assert idx.info(12) == 7          # grouped stages + early accumulator release + one-pass epilogue
+    assert idx.info(12) == 39         # grouped stages + early accumulator release + one-pass epilogue
     assert idx.kept_dims == 256 and idx.dim_pad == 256      # two 128-byte chunks of the 300 columns
     want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
     got, _ = idx.search_host(tok, off, fx)
@@ -383,7 +383,7 @@ def test_grouped_stages_and_early_release(dim):
     table, sx, fx, script, tok, off = _case(11, dim=dim, works=(900, 3, 0, 6, 1400, 700))
     want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
     dots = {}
-    for group in (0, 1, 2, 3, 4, 7, 20, 23, 28, 31):
+    for group in (0, 1, 2, 3, 4, 7, 39, 20, 23, 28, 31, 55):
         for grid in (0, 4):
             idx = _f8_index(table, script, sx, 6)
             idx.set_option(nt.FS_OPT_A_RESIDENT, 1)

@@ -358,3 +358,68 @@ def test_records_best_against_python_restatement():
         got={(int(a),int(b)):(float(d)*int(l),float(d),int(k),int(mi),int(l)) for a,b,k,mi,d,l in zip(best['work'],best['word'],best['window_ix'],best['match_ix'],best['distance'],best['lev'])}
         assert list(got)==sorted(got), "order"
         assert got==want, (trial, len(got), len(want))
+
+
+def _raw_and_pretokenised(golden_dir, tmp_path):
+    """A fanwork written as raw prose (punctuation glued to the words, a contraction, a newline)
+    and the same token stream written pre-tokenised (single spaces)."""
+    from fandom_search_b200 import text
+    script_words = [r[0] for r in search.load_markup_script(os.path.join(golden_dir, "script.txt"))[1:]]
+    q = script_words[20:34]
+    raw = ('Before, "%s %s %s %s %s %s %s!" she said; it isn\'t\n(%s %s %s %s %s %s %s)... After--end.'
+           % tuple(q[:14]))
+    raw_path = tmp_path / "raw.txt"
+    raw_path.write_text(raw, encoding="utf-8")
+    toks = text.tokenize_rules(raw)
+    pre_path = tmp_path / "pre.txt"
+    pre_path.write_text(" ".join(toks), encoding="utf-8")
+    return str(raw_path), str(pre_path), toks
+
+
+def test_custom_tokenizer_with_punctuation(monkeypatch, golden_dir, tmp_path):
+    """tokenizer= (here the built-in rule tokeniser; in production spaCy's): the file goes through
+    sp_parse_chunks and the is_space filter like in the reference (search.py:164-166), punctuation
+    becomes tokens of its own, and the records equal those of the same token stream pre-tokenised."""
+    from fandom_search_b200 import text
+    monkeypatch.setattr(engine_mod, "DeviceIndex", NumpyIndex)
+    lex = Lexicon.from_npz(os.path.join(golden_dir, "lexicon.npz"), hash_fn=py_hash_seed0)
+    script = os.path.join(golden_dir, "script.txt")
+    try:
+        search.set_pipeline(search.Pipeline(lex))
+        raw_path, pre_path, toks = _raw_and_pretokenised(golden_dir, tmp_path)
+        assert "," in toks and "n't" in toks and '"' in toks and "..." in toks and "--" in toks
+        want = search.AnnIndexSearch(script, 6, 15, 14, 0.1).search(pre_path)
+        # a tokeniser that also yields whitespace tokens (as spaCy does for newlines): they are dropped
+        noisy = lambda s: [t for w in text.tokenize_rules(s) for t in (w, " ")] + ["\n"]
+        for tok in (text.tokenize_rules, "rules", noisy):
+            search.set_pipeline(search.Pipeline(lex, tokenizer=tok))
+            got = search.AnnIndexSearch(script, 6, 15, 14, 0.1).search(raw_path)
+            assert len(got) == len(want) > 0
+            for g, w in zip(normalise(got), normalise(want)):
+                assert g[1:] == w[1:]                          # everything but the file name
+        # the default whitespace tokeniser on the raw prose: punctuation stays glued, fewer matches,
+        # and the pipeline says so
+        search.set_pipeline(search.Pipeline(lex))
+        with pytest.warns(RuntimeWarning, match="punctuation"):
+            glued = search.AnnIndexSearch(script, 6, 15, 14, 0.1).search(raw_path)
+        assert len(glued) < len(want)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")                     # pre-tokenised text: no warning
+            search.set_pipeline(search.Pipeline(lex))
+            search.AnnIndexSearch(script, 6, 15, 14, 0.1).search(pre_path)
+    finally:
+        search.set_pipeline(None)
+
+
+def test_rule_tokeniser_examples():
+    from fandom_search_b200 import text
+    assert text.tokenize_rules('Hello, world!') == ['Hello', ',', 'world', '!']
+    assert text.tokenize_rules("I don't know; it's \"fine\"...") == \
+        ['I', 'do', "n't", 'know', ';', 'it', "'s", '"', 'fine', '"', '...']
+    assert text.tokenize_rules("The U.S. and Mr. Smith (really) can't go--now.") == \
+        ['The', 'U.S.', 'and', 'Mr.', 'Smith', '(', 'really', ')', 'ca', "n't", 'go', '--', 'now', '.']
+    assert text.tokenize_rules("  spaced\tout\n\ntext  ") == ['spaced', 'out', 'text']
+    assert text.tokenize_rules("") == [] and text.tokenize_rules("...") == ['...']
+    assert text.glued_punctuation_share('Hello, world! said "Bob" and left.'.split()) > 0.5
+    assert text.glued_punctuation_share('w00012 w00013 the of'.split()) == 0.0
