@@ -57,8 +57,41 @@ DIM = 300
 SCRIPT_TOKENS = 25000
 WORKS_PER_STEP = 500
 VOCAB = 50000
+N_SCRIPTS = 1
+CONFIG = "C2"
 WORKLOAD = ("C2: synthetic fanworks (~5k tokens, Zipf + planted reuse) vs one feature-length script "
             "(25000 tokens), d=300, w=6, thr=0.1; step = one cluster of 500 fanworks")
+
+
+def select_config(name):
+    """BASELINE.json configs beside the headline one (C2): the same arms, kernel-level numbers only
+    (the files -> CSV run and the CPU baseline stay with C2)."""
+    global CONFIG, DIM, SCRIPT_TOKENS, N_SCRIPTS, WORKS_PER_STEP, WORKLOAD
+    CONFIG = name
+    if name == "C2":
+        return
+    if name == "C1":
+        SCRIPT_TOKENS = 10000
+        WORKLOAD = ("C1: 500 synthetic fanworks (~5k tokens, Zipf + planted reuse) vs one ~10k-word script, "
+                    "d=300, w=6, thr=0.1; step = the cluster of 500 fanworks")
+    elif name == "C4":
+        N_SCRIPTS = 8
+        WORKLOAD = ("C4: synthetic fanworks (~5k tokens) vs a batch of 8 feature-length scripts searched in one pass "
+                    "(8 x 25000 tokens, windows never straddle scripts), d=300, w=6, thr=0.1; step = one cluster of 500 fanworks")
+    elif name == "D768":
+        DIM = 768
+        WORKLOAD = ("C5 corner d=768: synthetic fanworks (~5k tokens) vs one 25000-token script at embedding "
+                    "dimension 768, w=6, thr=0.1; step = one cluster of 500 fanworks")
+    else:
+        raise SystemExit("unknown --config %s" % name)
+
+
+def make_script(lex):
+    """Script token ids (all scripts concatenated) and their CSR offsets."""
+    from fandom_search_b200 import synth
+    parts = [synth.make_script_tokens(lex, SCRIPT_TOKENS, seed=1003 + 31 * k) for k in range(N_SCRIPTS)]
+    off = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64)
+    return np.concatenate(parts).astype(np.int32), off
 
 
 def host_cores():
@@ -289,7 +322,7 @@ def shared_config(n_script_windows, step_windows, world):
             "windows_per_step_per_gpu": int(step_windows),
             "step": "one cluster of %d fanworks per GPU" % WORKS_PER_STEP,
             "parallelism": "work-sharded x%d, script index replicated" % world,
-            "threshold": 0.1, "window": WINDOW, "dim": DIM}
+            "threshold": 0.1, "window": WINDOW, "dim": DIM, "scripts": N_SCRIPTS}
 
 
 def nominal_step_windows(lex, script):
@@ -305,6 +338,9 @@ def run_reference_arm(args):
     procs = max(1, host_cores())
     lex = make_lexicon()
     from fandom_search_b200 import synth
+    if N_SCRIPTS != 1:
+        raise SystemExit("bench.py --impl reference: the reference searches one script per run (C4 is a "
+                         "multi-script pass of this repo only)")
     script = synth.make_script_tokens(lex, SCRIPT_TOKENS)
     ref = CpuReference(lex, script, procs)
     works_per_step = procs
@@ -570,14 +606,17 @@ def run_native_arm(args):
         return all_reduce(x, dist.ReduceOp.MAX)
 
     lex = make_lexicon()
-    script = synth.make_script_tokens(lex, SCRIPT_TOKENS).astype(np.int32)
-    index = DeviceIndex(lex.table_all, script, window=WINDOW, threshold=0.1, device=local)
+    script, script_off = make_script(lex)
+    index = DeviceIndex(lex.table_all, script, script_off=script_off, window=WINDOW, threshold=0.1, device=local)
     n_script_windows = index.n_script_windows
+    if CONFIG != "C2":
+        args.no_pipeline = True
+        args.no_cpu_baseline = True
 
     # distinct clusters per rank; a handful are generated and cycled (each step's operand token
     # matrix is 0.6 GB, far larger than the 126 MB L2, so nothing carries over between steps)
     n_distinct = max(1, min(args.steps + args.warmup, args.distinct))
-    clusters = [make_cluster(lex, script, rank * 1000 + c) for c in range(n_distinct)]
+    clusters = [make_cluster(lex, script[:SCRIPT_TOKENS], rank * 1000 + c) for c in range(n_distinct)]
     max_tok = max(len(t) for t, _ in clusters)
     index.reserve(max_tok, 1 << 20)
     cap = 1 << 20
@@ -750,7 +789,7 @@ def run_native_arm(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f8e4m3" if bits == 8 else "f16", "data": "synthetic",
-            "config": shared_config(n_script_windows, nominal_step_windows(lex, script), world),
+            "config": shared_config(n_script_windows, nominal_step_windows(lex, script[:SCRIPT_TOKENS]), world),
             "details": {"l2": "inputs larger than L2 (%.2f GB %s token matrix per step)"
                               % (max_tok * row_bytes / 1e9, "fp8" if bits == 8 else "fp16"),
                         "precision": ("fp8 e4m3 tcgen05 pre-filter over the %d highest-energy embedding columns of %d (fp32 "
@@ -802,11 +841,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic clusters cycled per rank")
+    ap.add_argument("--config", default="C2", choices=["C2", "C1", "C4", "D768"],
+                    help="BASELINE.json workload (default C2, the headline; the others report kernel-level numbers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the files -> CSV run and the golden check")
     ap.add_argument("--pipeline-works", type=int, default=0,
                     help="fanworks of the files -> CSV run over all ranks (default 12500 per GPU)")
     args = ap.parse_args()
+    select_config(args.config)
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
     if args.impl == "reference":

@@ -18,7 +18,10 @@ from fandom_search_b200 import _native as nt
 from fandom_search_b200.engine import DeviceIndex
 
 
-def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, pack=None, clocks=False, bits=8, group=None):
+def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, pack=None, clocks=False, bits=8, group=None,
+             total_windows=None):
+    """total_windows: search that many fan windows by re-launching over the SAME device buffer of nf
+    windows (the 1e8 / 1e9 points of BASELINE.json configs[4]: a fixed device buffer, many launches)."""
     table = rng.standard_normal((vocab, d), dtype=np.float32)
     script = rng.integers(0, vocab, ns + 5).astype(np.int32)
     idx = DeviceIndex(table, script, window=6, threshold=0.1)
@@ -54,17 +57,27 @@ def run_case(nf, ns, d, reps, rng, vocab=50000, works_len=5000, diag=1, pair=0, 
         from bench import ClockSampler
         sampler = ClockSampler(0)
         sampler.start()
+    if total_windows:
+        reps = max(1, int(round(total_windows / nf)))
     idx.timing_reset()
-    for _ in range(reps):
-        idx.search_dev(tok_t, off_t, None, out_t, cnt_t)
-    torch.cuda.synchronize()
-    ms, n = idx.timing_read()
+    ms, n = 0.0, 0
+    done = 0
+    while done < reps:       # (the library keeps the events of the last 256 launches)
+        burst = min(200, reps - done)
+        idx.timing_reset()
+        for _ in range(burst):
+            idx.search_dev(tok_t, off_t, None, out_t, cnt_t)
+        torch.cuda.synchronize()
+        b_ms, b_n = idx.timing_read()
+        ms += b_ms
+        n += b_n
+        done += burst
     clk = sampler.stop() if sampler else None
     windows = int(cnt_t.cpu()[nt.FS_CNT_WINDOWS])
     per = ms / n * 1e-3
     m_step = 108 if diag == 6 else 129 - diag      # E = 6: overlapping lane quarters
     exec_factor = (6 // diag) * (128.0 * 256.0) / (m_step * (257 - diag))
-    res = {"bits": bits, "candidates": int(cnt_t.cpu()[nt.FS_CNT_CANDIDATES]), "matches": int(cnt_t.cpu()[nt.FS_CNT_MATCHES]),
+    res = {"launches": n, "total_fan_windows": windows * n, "kept_dims": idx.kept_dims, "bits": bits, "candidates": int(cnt_t.cpu()[nt.FS_CNT_CANDIDATES]), "matches": int(cnt_t.cpu()[nt.FS_CNT_MATCHES]),
            "diag": diag, "pair": pair, "pack": pack, "group": group, "fan_windows": windows, "script_windows": idx.n_script_windows, "dim": d, "dim_pad": idx.dim_pad,
            "kernel_ms": ms / n, "windows_per_s": windows / per, "clocks": clk,
            "tflops_dense_nominal": 2.0 * 6 * d * idx.n_script_windows * windows / per / 1e12,
@@ -87,12 +100,20 @@ def main():
     ap.add_argument("--pack", type=int, default=None)
     ap.add_argument("--group", type=int, default=None, help="FS_OPT_TILE_GROUP for --one (default: library default)")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--big", action="store_true",
+                    help="the 1e8 and 1e9 fan-window points of the C5 grid, default kernel, through a fixed 1e7-window device buffer")
     args = ap.parse_args()
     rng = np.random.default_rng(0)
     if args.one:
         diag, nf, ns, d = args.one
         print(json.dumps(run_case(nf, ns, d, args.reps, rng, diag=diag, pair=args.pair, pack=args.pack,
                                   bits=args.bits, group=args.group, clocks=True)), flush=True)
+        return
+    if args.big:
+        for d in (300, 768):
+            for ns in (1000, 10000, 100000):
+                for total in (100_000_000, 1_000_000_000):
+                    print(json.dumps(run_case(10_000_000, ns, d, 1, rng, diag=None, total_windows=total, clocks=True)), flush=True)
         return
     if args.defaults:
         for d in (300, 768):
