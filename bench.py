@@ -764,6 +764,12 @@ def run_native_arm(args):
     pipeline = check = None
     if not args.no_pipeline:
         works_total = args.pipeline_works if args.pipeline_works > 0 else 25000 * world
+        try:        # ~35 KB of text per work: stay well inside the scratch space of the box
+            import shutil as _sh
+            free = _sh.disk_usage(tempfile.gettempdir()).free
+            works_total = int(max(2000 * world, min(works_total, free * 0.4 / 36000)))
+        except OSError:
+            pass
         pipeline = run_pipeline(lex, script, works_total, rank, world, local, barrier, all_sum, all_max)
         check = run_golden_check(rank, world, barrier)
 

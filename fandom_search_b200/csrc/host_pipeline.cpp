@@ -8,6 +8,7 @@
 //                (search.py:182-226), leaving only string formatting to Python
 //
 // No GPU code here; everything is exposed through the same C ABI.
+#include <emmintrin.h>
 #include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -22,6 +23,7 @@
 #include <atomic>
 #include <charconv>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -133,16 +135,65 @@ struct fs_vocab {
 // ---------------------------------------------------------------------------------------
 // encoded batch of files
 // ---------------------------------------------------------------------------------------
+// Batch buffers are recycled: a cluster needs ~100 MB of them (text, ids, offsets), a fresh
+// allocation of that size comes from mmap and costs a page fault per 4 KB on first touch (a quarter of
+// the tokenising time), and a run allocates the same sizes cluster after cluster.
+namespace {
+struct BlockPool {
+    std::mutex mu;
+    std::vector<std::pair<void*, size_t>> blocks;  // free blocks
+    size_t held = 0;
+    static constexpr size_t kMaxHeld = size_t(3) << 30;
+    void* take(size_t bytes, size_t* cap) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            size_t best = blocks.size();
+            for (size_t i = 0; i < blocks.size(); ++i)
+                if (blocks[i].second >= bytes && blocks[i].second <= 2 * bytes + (1 << 20) &&
+                    (best == blocks.size() || blocks[i].second < blocks[best].second))
+                    best = i;
+            if (best != blocks.size()) {
+                void* p = blocks[best].first;
+                *cap = blocks[best].second;
+                held -= blocks[best].second;
+                blocks.erase(blocks.begin() + static_cast<long>(best));
+                return p;
+            }
+        }
+        *cap = bytes + bytes / 8 + 4096;  // headroom: the next cluster is a few percent larger or smaller
+        return malloc(*cap);
+    }
+    void give(void* p, size_t cap) {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (held + cap <= kMaxHeld && blocks.size() < 64) {
+                blocks.emplace_back(p, cap);
+                held += cap;
+                return;
+            }
+        }
+        free(p);
+    }
+};
+BlockPool g_pool;
+}  // namespace
+
 template <typename T>
-struct RawArray {  // uninitialised storage (no zero fill, no page touching before the writers)
-    std::unique_ptr<T[]> p;
-    size_t n = 0;
+struct RawArray {  // uninitialised, recycled storage (no zero fill, no page touching before the writers)
+    T* p = nullptr;
+    size_t n = 0, cap_bytes = 0;
+    RawArray() = default;
+    RawArray(const RawArray&) = delete;
+    RawArray& operator=(const RawArray&) = delete;
+    ~RawArray() { g_pool.give(p, cap_bytes); }
     void alloc(size_t count) {
-        p.reset(new T[count > 0 ? count : 1]);
+        g_pool.give(p, cap_bytes);
+        p = static_cast<T*>(g_pool.take((count > 0 ? count : 1) * sizeof(T), &cap_bytes));
         n = count;
     }
-    T* data() { return p.get(); }
-    const T* data() const { return p.get(); }
+    T* data() { return p; }
+    const T* data() const { return p; }
     size_t size() const { return n; }
 };
 
@@ -175,15 +226,62 @@ void parallel_for(int64_t n, int n_threads, F&& body) {
     for (auto& t : th) t.join();
 }
 
+// Whitespace classes of 64 bytes at once (SSE2, part of every x86-64): bit i = text[i] is ' ' or
+// 9..13.  The caller guarantees 64 readable bytes at p (the batch text buffer carries that slack).
+inline uint64_t ws_mask64(const char* p) {
+    const __m128i sp = _mm_set1_epi8(' '), nine = _mm_set1_epi8(9), four = _mm_set1_epi8(4);
+    uint64_t m = 0;
+    for (int k = 0; k < 4; ++k) {
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p + 16 * k));
+        const __m128i t = _mm_sub_epi8(c, nine);
+        const __m128i in_range = _mm_cmpeq_epi8(_mm_min_epu8(t, four), t);  // 9 <= c <= 13 (unsigned)
+        const __m128i w = _mm_or_si128(in_range, _mm_cmpeq_epi8(c, sp));
+        m |= static_cast<uint64_t>(static_cast<uint32_t>(_mm_movemask_epi8(w))) << (16 * k);
+    }
+    return m;
+}
+
+// whitespace mask of the block at text + i, with everything at or beyond `len` counted as whitespace
+inline uint64_t ws_block(const char* text, int64_t i, int64_t len) {
+    uint64_t ws = ws_mask64(text + i);
+    if (len - i < 64) ws |= ~0ull << (len - i);
+    return ws;
+}
+
 inline int64_t count_tokens(const char* text, int64_t len) {
     int64_t n = 0;
-    bool in_tok = false;
-    for (int64_t i = 0; i < len; ++i) {
-        const bool ws = is_ws(static_cast<unsigned char>(text[i]));
-        n += (!ws && !in_tok);
-        in_tok = !ws;
+    uint64_t prev_ws = 1;  // the position before the text counts as whitespace
+    for (int64_t i = 0; i < len; i += 64) {
+        const uint64_t ws = ws_block(text, i, len);
+        n += __builtin_popcountll(~ws & ((ws << 1) | prev_ws));  // token starts
+        prev_ws = ws >> 63;
     }
     return n;
+}
+
+// calls emit(start, end) for every maximal run of non-whitespace bytes of text[0, len)
+template <typename F>
+inline void for_each_token(const char* text, int64_t len, F&& emit) {
+    bool in_tok = false;
+    int64_t s = 0;
+    for (int64_t blk = 0; blk < len; blk += 64) {
+        const uint64_t ws = ws_block(text, blk, len);
+        int pos = 0;
+        while (pos < 64) {
+            const uint64_t m = (in_tok ? ws : ~ws) & (~0ull << pos);
+            if (!m) break;
+            const int b = __builtin_ctzll(m);
+            if (!in_tok) {
+                s = blk + b;
+                in_tok = true;
+            } else {
+                emit(s, blk + b);
+                in_tok = false;
+            }
+            pos = b + 1;
+        }
+    }
+    if (in_tok) emit(s, len);
 }
 
 }  // namespace
@@ -250,8 +348,8 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
         sizes[k] = static_cast<int64_t>(st.st_size);
     });
     for (int64_t k = 0; k < n_files; ++k) b->file_off[k + 1] = b->file_off[k] + sizes[k];
-    b->text.alloc(static_cast<size_t>(b->file_off[n_files]) + 8);  // + slack for 8-byte key loads
-    memset(b->text.data() + b->file_off[n_files], 0, 8);
+    b->text.alloc(static_cast<size_t>(b->file_off[n_files]) + 72);  // + slack for 64-byte blocks and 8-byte key loads
+    memset(b->text.data() + b->file_off[n_files], ' ', 72);
     std::vector<int64_t> counts(n_files, 0);
     parallel_for(n_files, n_threads, [&](int64_t k) {
         if (b->file_status[k] || sizes[k] == 0) return;
@@ -299,12 +397,7 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
         uint32_t* st32 = b->tok_start32.data();
         uint16_t* len16 = b->tok_len16.data();
         std::vector<OovTok>& oov = oov_of_file[static_cast<size_t>(k)];
-        int64_t i = 0;
-        while (i < len) {
-            while (i < len && is_ws(static_cast<unsigned char>(text[i]))) ++i;
-            if (i >= len) break;
-            const int64_t s = i;
-            while (i < len && !is_ws(static_cast<unsigned char>(text[i]))) ++i;
+        for_each_token(text, len, [&](int64_t s, int64_t i) {
             const int64_t n = i - s;
             const int32_t row = v->find(text + s, n, true);  // -1 = OOV for now
             tok[o] = row;
@@ -315,7 +408,7 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
             if (row < 0) {
                 uint64_t key;
                 if (n <= 8) {
-                    memcpy(&key, text + s, 8);  // (the text buffer has 8 bytes of slack)
+                    memcpy(&key, text + s, 8);  // (the text buffer has slack behind its last byte)
                     if (n < 8) key &= (1ULL << (8 * n)) - 1;
                 } else {
                     key = hash_bytes(text + s, n);
@@ -323,7 +416,7 @@ fs_batch* fs_batch_encode_files(const fs_vocab* v, const char* const* paths, int
                 oov.push_back(OovTok{o, key, static_cast<int32_t>(n > INT32_MAX ? INT32_MAX : n)});
             }
             ++o;
-        }
+        });
     });
     lap("tokenise+lookup");
     // Serial pass over the OOV tokens only: number the unique strings in order of appearance (files in

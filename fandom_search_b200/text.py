@@ -257,7 +257,10 @@ def host_threads(reserve=2, limit=16):
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
     except ValueError:
         local_world = 1
-    return max(1, min(limit, cores // local_world) - reserve)
+    share = cores // local_world
+    if share <= 6:
+        reserve = min(reserve, 1)      # few cores per rank: the GPU-driving thread sleeps in its waits
+    return max(1, min(limit, share) - reserve)
 
 
 def records_best(matches, tie, window, topk, batch, script_blob, script_off, threads=None):
