@@ -767,7 +767,7 @@ def run_native_arm(args):
         try:        # ~35 KB of text per work: stay well inside the scratch space of the box
             import shutil as _sh
             free = _sh.disk_usage(tempfile.gettempdir()).free
-            works_total = int(max(2000 * world, min(works_total, free * 0.4 / 36000)))
+            works_total = int(max(2000 * world, min(works_total, free * 0.6 / 36000)))
         except OSError:
             pass
         pipeline = run_pipeline(lex, script, works_total, rank, world, local, barrier, all_sum, all_max)

@@ -794,8 +794,13 @@ def analyze(args,
     if world > 1:
         # cluster -> rank: balanced on the bytes of text per cluster, the same table on every rank
         from .parallel import assign_clusters
-        sizes = [sum(_file_size(f) for f in c) for c in fan_clusters]
-        owner = assign_clusters(sizes, world)
+        if len(fan_clusters) >= 8 * world and not os.environ.get('FANDOM_SEARCH_BALANCE'):
+            # many clusters per rank: round robin leaves a tail of at most one cluster in eight or more --
+            # not worth a stat() of every file on every rank (1 M files: seconds)
+            owner = assign_clusters([1] * len(fan_clusters), world, policy='roundrobin')
+        else:
+            sizes = [sum(_file_size(f) for f in c) for c in fan_clusters]
+            owner = assign_clusters(sizes, world)
     else:
         owner = [0] * len(fan_clusters)
     mine = [(i, c) for i, c in enumerate(fan_clusters, start=start) if owner[i - start] == rank]
