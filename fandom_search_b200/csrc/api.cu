@@ -117,6 +117,7 @@ struct fs_index {
     int32_t tiles_n = 0;
     CUtensorMap map_script;
     CUtensorMap map_script128;  // boxes of 128 rows (E = 6: no halo rows)
+    CUtensorMap map_script64;   // boxes of 64 rows (128-column tiles, distance_kernel_n128)
 
     unsigned long long* hash_table = nullptr;
     uint32_t hash_slots = 0;
@@ -415,6 +416,8 @@ static int prepare_operands(fs_index* idx) {
         if ((r = make_token_map(&idx->map_script, idx->script_emb, idx->n_script_tok, idx->dim_pad, kBoxRows)) != FS_OK)
             return r;
         if ((r = make_token_map(&idx->map_script128, idx->script_emb, idx->n_script_tok, idx->dim_pad, 128)) != FS_OK)
+            return r;
+        if ((r = make_token_map(&idx->map_script64, idx->script_emb, idx->n_script_tok, idx->dim_pad, 64)) != FS_OK)
             return r;
     }
     FS_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -810,7 +813,8 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     const int grid_limit = idx->grid_limit > 0 ? idx->grid_limit : idx->sm_count;
     const int slot = static_cast<int>(idx->ev_count % kTimingRing);
     FS_CUDA_CHECK(cudaEventRecord(idx->ev_start[slot], st));
-    if ((r = launch_distance(map_fan, map_fan32, idx->map_script, idx->map_script128, p, grid_limit, st)) != FS_OK)
+    if ((r = launch_distance(map_fan, map_fan32, idx->map_script, idx->map_script128, idx->map_script64, p, grid_limit,
+                             st)) != FS_OK)
         return r;
     FS_CUDA_CHECK(cudaEventRecord(idx->ev_stop[slot], st));
     idx->ev_count++;

@@ -234,7 +234,8 @@ struct GatherSources {
 
 int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad, int32_t box_rows);
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, const CUtensorMap& map_script,
-                    const CUtensorMap& map_script128, const DistParams& p, int grid_limit, cudaStream_t stream);
+                    const CUtensorMap& map_script128, const CUtensorMap& map_script64, const DistParams& p,
+                    int grid_limit, cudaStream_t stream);
 int launch_convert_rows(const float* src, int64_t n_rows, int32_t dim, int32_t dim_pad, int32_t kept,
                         const int32_t* perm, float scale, bool f8, float limit_sq, __half* dst, float4* sq,
                         cudaStream_t stream);

@@ -209,7 +209,7 @@ struct Tile {
     bool fan_last;
 };
 
-template <int kDiag, bool kPair>
+template <int kDiag, bool kPair, int kBN = kBlockN>
 struct TileWalk {
     int64_t left;
     int32_t um, un, tn;
@@ -232,12 +232,12 @@ struct TileWalk {
         if (left <= skip) return -1;
         int32_t u = un + skip;
         if (u >= tn) u -= tn;
-        return u * (kBlockN - (kDiag - 1));
+        return u * (kBN - (kDiag - 1));
     }
     __device__ __forceinline__ bool next(Tile& out) {
         if (left <= 0) return false;
         out.m0 = static_cast<int32_t>(kPair ? 2 * um + cta_rank : um) * dist_m_step(kDiag);
-        out.n0 = un * (kBlockN - (kDiag - 1));
+        out.n0 = un * (kBN - (kDiag - 1));
         out.fan_first = first || un == 0;
         --left;
         out.fan_last = left == 0 || un + 1 == tn;
@@ -1311,8 +1311,309 @@ static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_
     return FS_OK;
 }
 
+
+// =============================================================================================
+// distance_kernel_n128: the default configuration (E = 6, CTA pairs, resident fan tile, grouped
+// stages, one-pass fp16x2 epilogue, operand rows of at most two 128-byte chunks) re-cut for TWO
+// co-resident CTA pairs per TPC: script tiles of 128 columns, 8 epilogue warps, 256 TMEM columns
+// (two accumulator stages of 128) and ~100 KB of shared memory per CTA.
+//
+// Why.  Timelines and floor probes of the 256-column kernel (profiles/r02_timeline_*.txt,
+// r02_sweep_floor_probes.jsonl) showed a pipeline bound by LATENCY, not by any unit: from the
+// hand-back of an accumulator stage to its next hand-back pass ~3100 clk (MMA issue, ~1030 clk of
+// MMAs, the drain/commit latency of the tensor pipe, barrier wake-ups, the TMEM load, the remote
+// arrives), and with two stages a tile takes half of that -- the tile time follows
+// (T_mma + 2070) / 2 for 6, 8 and 10 MMAs per tile, the tensor pipe idles a third of the time and
+// an epilogue that does nothing is no faster.  All 512 TMEM columns are two stages of 256, so the
+// depth can only grow by narrowing the tile: two independent pipelines of 128-column tiles per SM
+// keep four accumulator stages in flight on the same tensor pipe.
+// =============================================================================================
+namespace n128 {
+constexpr int kBN = 128;                      // script windows per tile (UMMA N)
+constexpr int kEpi = 8;                       // epilogue warps: 4 TMEM lane quarters x 2 groups of 64 columns
+constexpr int kThreads = 32 * (kEpi + 2);     // + TMA producer + MMA issuer
+constexpr int kStages = 2;                    // accumulator stages of 128 columns
+constexpr int kTmem = 256;
+constexpr int kMaxChunks = 2;                 // operand rows of <= 256 bytes
+constexpr int kABytes = 4 * kOverlapBoxRows * 128;  // 16 KB: one 128-byte chunk of the 128-row fan tile
+constexpr int kBBytes = (kBN / 2) * 128;            // 8 KB: this CTA's 64 script rows of one chunk
+constexpr int kGroups = 4;                    // script tiles in flight in the ring
+__host__ __device__ constexpr int smem_bytes() {
+    return 1024 + kMaxChunks * kABytes + kGroups * kMaxChunks * kBBytes + 256 /*barriers*/;
+}
+static_assert(2 * (smem_bytes() + 1024) <= 233472, "two CTAs per SM must fit");
+}  // namespace n128
+
+template <bool kF8>
+__global__ void __launch_bounds__(n128::kThreads, 2)
+distance_kernel_n128(const __grid_constant__ CUtensorMap map_fan32, const __grid_constant__ CUtensorMap map_script64,
+                     const DistParams p) {
+    using namespace n128;
+    constexpr int kNStep = kBN - 5;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;   // resident fan tile
+    const uint32_t smem_b = smem_a + kMaxChunks * kABytes;           // ring of script tiles
+    const uint32_t bar_base = smem_b + kGroups * kMaxChunks * kBBytes;
+    auto full_bar = [&](int g) { return bar_base + 8u * g; };
+    auto empty_bar = [&](int g) { return bar_base + 8u * (kGroups + g); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kGroups + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kGroups + kStages + s); };
+    const uint32_t afull_bar = bar_base + 8u * (2 * kGroups + 2 * kStages);
+    const uint32_t aempty_bar = afull_bar + 8u;
+    const uint32_t tmem_slot = aempty_bar + 8u;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    constexpr int kProducerW = kEpi, kMmaW = kEpi + 1;
+
+    if (warp == kProducerW && lane == 0) {
+        tma_prefetch_desc(&map_fan32);
+        tma_prefetch_desc(&map_script64);
+        for (int g = 0; g < kGroups; ++g) {
+            mbar_init(full_bar(g), 1);
+            mbar_init(empty_bar(g), 1);
+        }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 2 * kEpi);
+        }
+        mbar_init(afull_bar, 1);
+        mbar_init(aempty_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == kMmaW) tmem_alloc_pair(tmem_slot, kTmem);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    TileWalk<6, true, kBN> walk(p, blockIdx.x / 2, gridDim.x / 2, cta_rank);
+    Tile tile;
+    const int chunks = p.chunks;
+
+    if (warp == kProducerW) {
+        // ------------------------------------------------------------ TMA producer
+        int grp = 0;
+        uint32_t gphase = 0, a_phase = 0;
+        while (walk.next(tile)) {
+            if (tile.fan_first) {
+                mbar_wait_warp(aempty_bar, a_phase ^ 1u, 64);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(afull_bar, 2 * chunks * kABytes);
+                    for (int c = 0; c < chunks; ++c)
+                        for (int q = 0; q < 4; ++q)
+                            tma_load_2d_pair(smem_a + c * kABytes + q * (kOverlapBoxRows * 128), &map_fan32, afull_bar,
+                                             c * kChunkK, tile.m0 + q * kQuarterRows6);
+                }
+                __syncwarp();
+                a_phase ^= 1u;
+            }
+            mbar_wait_warp(empty_bar(grp), gphase ^ 1u, 32);
+            if (elect_one()) {
+                if (leader) mbar_expect_tx(full_bar(grp), 2 * chunks * kBBytes);
+                for (int c = 0; c < chunks; ++c)
+                    tma_load_2d_pair(smem_b + (grp * kMaxChunks + c) * kBBytes, &map_script64, full_bar(grp), c * kChunkK,
+                                     tile.n0 + static_cast<int32_t>(cta_rank) * (kBN / 2));
+            }
+            __syncwarp();
+            if (++grp == kGroups) {
+                grp = 0;
+                gphase ^= 1u;
+            }
+        }
+    } else if (warp == kMmaW && leader) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = umma_idesc_f16(2 * kBlockM, kBN);
+        constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        int grp = 0, as = 0;
+        uint32_t gphase = 0, aphase = 0, a_phase = 0;
+        uint32_t group_en = 0;  // bit 4c+k: K-step k of chunk c exists
+        for (int c = 0; c < chunks; ++c)
+            group_en |= ((1u << (c == chunks - 1 ? p.last_chunk_ksteps : kChunkK / kUmmaK)) - 1u) << (4 * c);
+        const uint32_t a_lo = ((smem_a & 0x3FFFFu) >> 4) | (1u << 16);
+        while (walk.next(tile)) {
+            if (tile.fan_first) {
+                mbar_wait_warp(afull_bar, a_phase, 0);
+                a_phase ^= 1u;
+            }
+            mbar_wait_all(tempty_bar(as), aphase ^ 1u);
+            mbar_wait_all(full_bar(grp), gphase);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kBN);
+            const uint32_t b_src = smem_b + static_cast<uint32_t>(grp * kMaxChunks) * kBBytes;
+            const uint32_t b_lo = ((b_src & 0x3FFFFu) >> 4) | (1u << 16);
+            if (elect_one()) {
+#pragma unroll
+                for (int c = 0; c < kMaxChunks; ++c) {
+#pragma unroll
+                    for (int k = 0; k < kChunkK / kUmmaK; ++k) {
+                        const uint32_t a_off = static_cast<uint32_t>((c * kABytes + k * kUmmaK * 2) >> 4);
+                        const uint32_t b_off = static_cast<uint32_t>((c * kBBytes + k * kUmmaK * 2) >> 4);
+                        if (c == 0 && k == 0)
+                            umma_lohi<true, kF8>(tmem_d, a_lo, b_lo, kHi, idesc, 0u);
+                        else
+                            umma_lohi_pair_if<kF8>((group_en >> (4 * c + k)) & 1u, tmem_d, a_lo + a_off, b_lo + b_off,
+                                                   kHi, idesc, 1u);
+                    }
+                }
+                umma_commit_pair(empty_bar(grp));
+                umma_commit_pair(tfull_bar(as));
+                if (tile.fan_last) umma_commit_pair(aempty_bar);
+            }
+            __syncwarp();
+            if (++grp == kGroups) {
+                grp = 0;
+                gphase ^= 1u;
+            }
+            if (++as == kStages) {
+                as = 0;
+                aphase ^= 1u;
+            }
+        }
+    } else if (warp < kEpi) {
+        // ------------------------------------------------------------ epilogue (8 warps)
+        const int quarter = warp & 3;
+        const int group = warp >> 2;
+        const int row = quarter * kQuarterRows6 + lane;
+        const bool lane_ok = lane < kQuarterRows6;
+        const float kNaN = __int_as_float(0x7fc00000);
+        auto bound_row = [](float a, float cg, const float2& bd) {
+            const uint32_t u = __float_as_uint(cg), v = __float_as_uint(bd.y);
+            const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&u));
+            const float2 y = __half22float2(*reinterpret_cast<const __half2*>(&v));
+            return fmaf(-x.y, y.y, fmaf(-x.x, y.x, a * bd.x));
+        };
+        int as = 0;
+        uint32_t aphase = 0;
+        // (Keeping the fan row's bounds in registers over the sweep and prefetching the chunk bounds with
+        // cp.async -- the two L2 round trips of a warp's tile -- was measured here too: 134 M instead of 146 M
+        // windows/s, as in the 256-column kernel; profiles/r02_sweep_n128.jsonl.)
+        while (walk.next(tile)) {
+            const int32_t gi = tile.m0 + row;
+            const int32_t n0 = tile.n0;
+            const float2 ac = lane_ok ? __ldg(p.fan_ac + gi) : make_float2(kNaN, kNaN);
+            mbar_wait_mode(tfull_bar(as), aphase, p.wait_mode & 15);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                   static_cast<uint32_t>(as * kBN + group * kEpiCols);
+            uint32_t q[72];
+            // the 8 halo columns of the second group lie outside the tile: any readable columns do
+            // (they only enter outputs >= kNStep, which carry NaN bounds)
+            tmem_ld_32x72(taddr, taddr + (group == 0 ? 64 : 56), q);
+            float2 mm2[2];
+            mm2[0] = __ldg(p.script_mm32 + n0 + group * kEpiCols);
+            mm2[1] = __ldg(p.script_mm32 + n0 + group * kEpiCols + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty_bar(as));
+            auto f = [&](int i) { return __uint_as_float(q[i]); };
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int b = 32 * ch;
+                float ma = f(b), mb = f(b + 16), mc = f(b + 24);
+#pragma unroll
+                for (int k = 1; k < 16; ++k) ma = fmaxf(ma, f(b + k));   // columns 0..15
+#pragma unroll
+                for (int k = 17; k < 24; ++k) mb = fmaxf(mb, f(b + k));  // columns 16..23
+#pragma unroll
+                for (int k = 25; k < 40; ++k) mc = fmaxf(mc, f(b + k));  // columns 24..39
+                const uint32_t m = pack_h2(fmaxf(ma, mb), fmaxf(mb, mc));
+                const uint32_t b01 = h2_add(m, __shfl_down_sync(0xffffffffu, m, 1));
+                const uint32_t bsum =
+                    h2_add(h2_add(b01, __shfl_down_sync(0xffffffffu, b01, 2)), __shfl_down_sync(0xffffffffu, b01, 4));
+                const float thr_chunk = bound_row(ac.x, ac.y, mm2[ch]);
+                if (!__any_sync(0xffffffffu, h2_lo(bsum) > thr_chunk || h2_hi(bsum) > thr_chunk)) continue;
+                uint32_t pk[20], o16[16];
+#pragma unroll
+                for (int k = 0; k < 20; ++k) pk[k] = pack_h2(f(b + 2 * k), f(b + 2 * k + 1));
+                const float mx = diag6_half(pk, o16);
+                if (mx > thr_chunk) {
+                    const int c0 = group * kEpiCols + b;
+                    const int32_t gj0 = n0 + c0;
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) {
+                        const float2 bd = (c0 + x < kNStep) ? __ldg(p.script_bd + gj0 + x) : make_float2(kNaN, kNaN);
+                        const float v = (x & 1) ? h2_hi(o16[x >> 1]) : h2_lo(o16[x >> 1]);
+                        if (v > bound_row(ac.x, ac.y, bd)) {
+                            const unsigned long long slot = atomicAdd(p.counters + FS_CNT_CANDIDATES, 1ull);
+                            if (slot < static_cast<unsigned long long>(p.cand_cap)) {
+                                p.cand[slot].fan_pos = gi;
+                                p.cand[slot].script_pos = gj0 + x;
+                            }
+                        }
+                    }
+                }
+            }
+            if (++as == kStages) {
+                as = 0;
+                aphase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == kMmaW) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmem);
+    }
+}
+
+// usable when: fp8/fp16 operands in CTA pairs, E = 6 with the fp16x2 one-pass epilogue, resident fan
+// tile, operand rows of at most two 128-byte chunks, candidate search (no dense dump)
+static bool n128_applies(const DistParams& p) {
+    return p.pair && p.ares && p.diag == 6 && p.pack == 2 && !p.dump && (p.group & 5) == 5 && (p.group & 64) != 0 &&
+           p.chunks <= n128::kMaxChunks && p.window == 6;
+}
+
+template <bool kF8>
+static int launch_n128(const CUtensorMap& map_fan32, const CUtensorMap& map_script64, DistParams p, int grid_limit,
+                       cudaStream_t stream) {
+    p.tiles_n = static_cast<int32_t>((p.n_script_tok + (n128::kBN - 5) - 1) / (n128::kBN - 5));
+    const int64_t units_m = (p.tiles_m + 1) / 2;
+    const int64_t total = units_m * p.tiles_n;
+    if (total <= 0) return FS_OK;
+    {
+        static std::mutex mu;
+        static uint64_t configured = 0;
+        int dev = 0;
+        FS_CUDA_CHECK(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 64 || !((configured >> dev) & 1ull)) {
+            FS_CUDA_CHECK(cudaFuncSetAttribute(distance_kernel_n128<kF8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               n128::smem_bytes()));
+            if (dev < 64) configured |= 1ull << dev;
+        }
+    }
+    // two co-resident CTA pairs per TPC: twice as many clusters as the 256-column kernel
+    const int64_t clusters = grid_limit > 0 ? grid_limit : 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * (total < clusters ? total : clusters)));
+    cfg.blockDim = dim3(n128::kThreads);
+    cfg.dynamicSmemBytes = n128::smem_bytes();
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, distance_kernel_n128<kF8>, map_fan32, map_script64, p));
+    return FS_OK;
+}
+
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, const CUtensorMap& map_script,
-                    const CUtensorMap& map_script128, const DistParams& p, int grid_limit, cudaStream_t stream) {
+                    const CUtensorMap& map_script128, const CUtensorMap& map_script64, const DistParams& p,
+                    int grid_limit, cudaStream_t stream) {
+    if (n128_applies(p)) {
+        if (p.f8) return launch_n128<true>(map_fan32, map_script64, p, grid_limit, stream);
+        return launch_n128<false>(map_fan32, map_script64, p, grid_limit, stream);
+    }
     const int64_t units_m = p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m;
     const int64_t total = units_m * p.tiles_n;
     if (total <= 0) return FS_OK;

@@ -383,7 +383,7 @@ def test_grouped_stages_and_early_release(dim):
     table, sx, fx, script, tok, off = _case(11, dim=dim, works=(900, 3, 0, 6, 1400, 700))
     want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
     dots = {}
-    for group in (0, 1, 2, 3, 4, 7, 39, 20, 23, 28, 31, 55):
+    for group in (0, 1, 2, 3, 4, 7, 39, 20, 23, 28, 31, 55, 103, 71):
         for grid in (0, 4):
             idx = _f8_index(table, script, sx, 6)
             idx.set_option(nt.FS_OPT_A_RESIDENT, 1)
