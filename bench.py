@@ -729,7 +729,8 @@ def run_native_arm(args):
     # 108 of 128 rows, overlapping TMEM lane quarters) and the operand rows hold dim_pad elements (the
     # kept columns of the pre-filter, padded to the K-step) instead of the nominal d
     m_eff = (108.0 if diag == 6 else 129.0 - diag) / 128.0
-    n_eff = (257.0 - diag) / 256.0
+    n128 = index.info(15) == 1          # 128-column tiles (two CTA pairs per TPC): 123 of 128 columns
+    n_eff = 123.0 / 128.0 if n128 else (257.0 - diag) / 256.0
     k_eff = float(DIM) / float(index.info(1))
     issue_factor = 1.0 / (m_eff * n_eff * k_eff)
     traffic, traffic_source = None, None
@@ -758,6 +759,7 @@ def run_native_arm(args):
 
     # ---- files -> CSV through search.analyze, and the golden corpus across the ranks -----------------
     kept_dims, cta_pair, group_bits = index.kept_dims, index.cta_pair, index.info(12)
+    kernel_name = "distance_kernel_n128" if n128 else "distance_kernel"
     index.close()
     del dev_in, out_t
     torch.cuda.empty_cache()
@@ -819,7 +821,7 @@ def run_native_arm(args):
                          "frac_of_burst": achieved_tflops / roof["burst"],
                          "bf16_sustained_peak": peaks["sustained"],
                          "frac_of_bf16_sustained": achieved_tflops / peaks["sustained"],
-                         "kernel": "distance_kernel", "kernel_ms_per_launch": kernel_ms / max(launches, 1),
+                         "kernel": kernel_name, "kernel_ms_per_launch": kernel_ms / max(launches, 1),
                          "kernel_share_of_step": kernel_ms / elapsed_ms if elapsed_ms else None,
                          "flop_per_window_useful": f_exec, "flop_per_window_dense": f_dense,
                          "diagonal_factor": diag, "cta_pair": cta_pair,

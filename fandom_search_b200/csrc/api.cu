@@ -204,9 +204,10 @@ struct fs_index {
     int32_t ares = 1;              // A-resident variant of the pair kernel (used when the row fits: <= 640 B)
     int32_t pack = 2;              // epilogue diagonal sums: 0 fp32 shuffles, 1 fp16x2 shuffles, 2 fp16x2 arithmetic
     int32_t shifts_per_stage = 0;  // 0 = all MMA shifts of a chunk in one stage
-    int32_t tile_group = 39;       // FS_OPT_TILE_GROUP: bit 0 grouped stages, bit 1 early TMEM release, bit 2 one-pass epilogue,
-                                   // bit 5 second-level rejection; bit 4 prefetched bounds and bit 3 alternating epilogue warp
-                                   // sets are off (measured slower, profiles/r02_sweep_epilogue_variants.jsonl)
+    int32_t tile_group = 103;      // FS_OPT_TILE_GROUP: bit 0 grouped stages, bit 1 early TMEM release, bit 2 one-pass epilogue,
+                                   // bit 5 second-level rejection, bit 6 128-column tiles with two CTA pairs per TPC (rows of
+                                   // <= 256 bytes); bit 4 prefetched bounds and bit 3 alternating epilogue warp sets are off
+                                   // (measured slower, profiles/r02_sweep_epilogue_variants.jsonl)
     int32_t grid_limit = 0;
 
     // timing ring
@@ -666,6 +667,11 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
         case 12: return idx->tile_group;
         case 13: return idx->kept_dims;
         case 14: return static_cast<int64_t>(idx->kept_energy * 1e6);  // share of the energy kept, ppm
+        case 15:  // 1: the 128-column kernel (distance_kernel_n128) runs this configuration
+            return (idx->pair && idx->ares && idx->diag == 6 && idx->pack == 2 && (idx->tile_group & 69) == 69 &&
+                    (idx->dim_pad + kChunkK - 1) / kChunkK <= 2 && idx->window == 6)
+                       ? 1
+                       : 0;
         default: return -1;
     }
 }

@@ -135,7 +135,10 @@ enum {
                                     the accumulator back, takes the row maxima on the fp32 values and
                                     packs to fp16x2 only the chunks that survive the bound; bit 5
                                     (default on, with bit 2): a chunk that survives is bounded again over
-                                    four spans of 8 outputs before the diagonal sum is run; bit 4
+                                    four spans of 8 outputs before the diagonal sum is run; bit 6
+                                    (default on, with bits 0 and 2, operand rows of <= 256 bytes): script
+                                    tiles of 128 columns and two co-resident CTA pairs per TPC -- four
+                                    accumulator stages in flight per SM instead of two; bit 4
                                     (default off, with bit 2): the fan row's bound stays in registers
                                     over the sweep of the script and the chunk bounds of the next tile
                                     are prefetched into shared memory by cp.async (no L2 round trip on
@@ -189,7 +192,8 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value);
 int fs_index_set_lsh(fs_index* idx, const double* normals, int32_t n_tables, int32_t n_bits);
 /* what = 0: script windows, 1: dim_pad, 2: SM count, 3: candidate capacity, 4: shifts per stage,
  * 5: diagonal factor, 6: CTA pair, 7: A-resident, 8: pack level, 11: operand bits, 12: tile-group bits,
- * 13: embedding columns kept by the pre-filter, 14: share of the table's energy they hold (ppm) */
+ * 13: embedding columns kept by the pre-filter, 14: share of the table's energy they hold (ppm),
+ * 15: 1 when the 128-column kernel runs the current configuration */
 int64_t fs_index_get_info(const fs_index* idx, int32_t what);
 
 /*

@@ -179,7 +179,7 @@ def test_library_defaults():
     table, sx, fx, script, tok, off = _case(5)
     idx = _device_index(table, script, extra=sx, bits=None)
     assert idx.operand_bits == 8 and idx.diag == 6 and idx.cta_pair == 1 and idx.info(7) == 1 and idx.info(8) == 2
-    assert idx.info(12) == 39         # grouped stages + early accumulator release + one-pass epilogue
+    assert idx.info(12) == 103 and idx.info(15) == 1          # ... in 128-column tiles, two CTA pairs per TPC         # grouped stages + early accumulator release + one-pass epilogue
     assert idx.kept_dims == 256 and idx.dim_pad == 256      # two 128-byte chunks of the 300 columns
     want, _ = NumpyIndex(table, script, extra=sx).search_host(tok, off, fx)
     got, _ = idx.search_host(tok, off, fx)
@@ -187,7 +187,7 @@ def test_library_defaults():
     idx.close()
     table, sx, fx, script, tok, off = _case(3, dim=768)
     idx = _device_index(table, script, extra=sx, bits=None)
-    assert idx.operand_bits == 8 and idx.diag == 6 and idx.kept_dims == 640
+    assert idx.operand_bits == 8 and idx.diag == 6 and idx.kept_dims == 640 and idx.info(15) == 0
     idx.close()
 
 
