@@ -151,6 +151,32 @@ class Lexicon:
             out[i] = self.row_id(words[i])
         return out
 
+    def batch_oov(self, strings, n_fixed):
+        """Row ids and 3-hot rows for the unique out-of-vocabulary strings of ONE batch, without
+        registering them: a string the registry already knows below `n_fixed` (an OOV word of the
+        indexed script) keeps that id -- identical windows must have identical row ids -- every
+        other string gets a batch-local id n_fixed, n_fixed + 1, ... and its row in the returned
+        float32 [n_new, d] matrix.  The registry therefore holds script-side OOV words only, however
+        many fanworks (and misspellings) a run sees."""
+        ids = np.empty(len(strings), dtype=np.int32)
+        hot = []
+        known = self._oov_id
+        for k, w in enumerate(strings):
+            r = known.get(w)
+            if r is not None and r < n_fixed:
+                ids[k] = r
+            else:
+                ids[k] = n_fixed + len(hot)
+                hot.append(oov_indices(w, self.dim, self.hash_fn))
+        extra = None
+        if hot:
+            extra = np.zeros((len(hot), self.dim), dtype=np.float32)
+            h = np.array(hot, dtype=np.int64).reshape(len(hot), 3)
+            rows = np.arange(len(hot))
+            for c in range(3):
+                extra[rows, h[:, c]] = 1.0
+        return ids, extra
+
     def oov_rows(self, start=0, stop=None):
         """float32 [stop-start, d] 3-hot rows of the OOV registry slice."""
         hot = self._oov_hot[start:stop]

@@ -386,31 +386,31 @@ class AnnIndexSearch(object):
             offs = numpy.array(batch.tok_off, dtype=numpy.int64)
             extra = None
             if len(batch.oov_start):
-                # only the OOV positions are touched (a few % of the tokens): registry ids of the
-                # batch's unique OOV strings, then batch-local numbering of the fan-side OOV rows
-                oov_ids = numpy.array([lex.row_id(w) for w in batch.oov_strings()], dtype=numpy.int32)
+                # only the OOV positions are touched (a few % of the tokens).  The batch's unique OOV
+                # strings get the script's registered id when the script holds the same word, else a
+                # batch-local row -- nothing is added to the lexicon's registry (lexicon.batch_oov)
+                oov_ids, extra = lex.batch_oov(batch.oov_strings(), n_fixed)
                 pos = numpy.flatnonzero(tok < 0)
-                ids = oov_ids[-tok[pos] - 1]
-                is_new = ids >= n_fixed
-                if is_new.any():
-                    uniq, inv = numpy.unique(ids[is_new], return_inverse=True)
-                    ids[is_new] = (n_fixed + inv).astype(numpy.int32)
-                    extra = lex.oov_rows_at(uniq.astype(numpy.int64) - lex.n_rows)
-                tok[pos] = ids
+                tok[pos] = oov_ids[-tok[pos] - 1]
             return {'filenames': list(filenames), 'batch': batch, 'tok': tok, 'offs': offs, 'extra': extra,
                     'pin': pin}
         fans = [self._tokenize_file(fn) for fn in filenames]
         batch = _text.Batch.from_token_lists(fans)
-        tok = numpy.concatenate([lex.row_ids(f) for f in fans] +
-                                [numpy.zeros(0, numpy.int32)]).astype(numpy.int32)
+        if fans and not self.spacy_model._warned_glued:
+            self.spacy_model.check_tokens(fans[0][:2000], filenames[0])
+        words = [w for f in fans for w in f]
+        get = lex.key_to_row.get
+        tok = numpy.array([get(w, -1) for w in words], dtype=numpy.int32).reshape(-1)
         offs = numpy.array(batch.tok_off, dtype=numpy.int64)
-        # batch-local numbering of the fan-side OOV rows
+        # out-of-vocabulary words: the script's registered id or a batch-local row, never registered
         extra = None
-        is_new = tok >= n_fixed
-        if is_new.any():
-            uniq, inv = numpy.unique(tok[is_new], return_inverse=True)
-            tok[is_new] = (n_fixed + inv).astype(numpy.int32)
-            extra = lex.oov_rows_at(uniq.astype(numpy.int64) - lex.n_rows)
+        pos = numpy.flatnonzero(tok < 0)
+        if len(pos):
+            uniq = {}
+            for i in pos.tolist():
+                uniq.setdefault(words[i], len(uniq))
+            oov_ids, extra = lex.batch_oov(list(uniq), n_fixed)
+            tok[pos] = oov_ids[[uniq[words[i]] for i in pos.tolist()]]
         return {'filenames': list(filenames), 'batch': batch, 'tok': tok, 'offs': offs, 'extra': extra}
 
     def run_prepared(self, prep):

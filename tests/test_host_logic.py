@@ -423,3 +423,20 @@ def test_rule_tokeniser_examples():
     assert text.tokenize_rules("") == [] and text.tokenize_rules("...") == ['...']
     assert text.glued_punctuation_share('Hello, world! said "Bob" and left.'.split()) > 0.5
     assert text.glued_punctuation_share('w00012 w00013 the of'.split()) == 0.0
+
+
+def test_fan_side_oov_words_are_not_registered(cpu_device, golden_dir):
+    """Only the script's out-of-vocabulary words live in the lexicon's registry: searching works full
+    of unknown words must not grow it (a run over millions of fanworks sees millions of them)."""
+    idx = search.AnnIndexSearch(os.path.join(golden_dir, "script.txt"), 6, 15, 14, 0.1)
+    lex = search.get_spacy_model().lexicon
+    n_script_oov = lex.n_oov
+    assert n_script_oov > 0
+    files = sorted(glob.glob(os.path.join(golden_dir, "fanworks", "*.txt")))
+    first = normalise([r for s in idx.search_many(files) for r in s])
+    assert lex.n_oov == n_script_oov
+    again = normalise([r for s in idx.search_many(files[::-1]) for r in s])      # other batch order, same rows
+    assert sorted(map(tuple, again)) == sorted(map(tuple, first)) and lex.n_oov == n_script_oov
+    ids, extra = lex.batch_oov(["zzz-unknown", "zzz-unknown-2"], lex.n_rows + n_script_oov)
+    assert ids.tolist() == [lex.n_rows + n_script_oov, lex.n_rows + n_script_oov + 1] and extra.shape == (2, lex.dim)
+    assert 1 <= extra[0].sum() <= 3 and lex.n_oov == n_script_oov
