@@ -1491,10 +1491,15 @@ distance_kernel_n128(const __grid_constant__ CUtensorMap map_fan32, const __grid
         // (Keeping the fan row's bounds in registers over the sweep and prefetching the chunk bounds with
         // cp.async -- the two L2 round trips of a warp's tile -- was measured here too: 134 M instead of 146 M
         // windows/s, as in the 256-column kernel; profiles/r02_sweep_n128.jsonl.)
+        int32_t ac_m0 = -1;
+        float2 ac = make_float2(kNaN, kNaN);
         while (walk.next(tile)) {
             const int32_t gi = tile.m0 + row;
             const int32_t n0 = tile.n0;
-            const float2 ac = lane_ok ? __ldg(p.fan_ac + gi) : make_float2(kNaN, kNaN);
+            if (tile.m0 != ac_m0) {  // new fan tile: the row's bounds stay in registers over the sweep of the script
+                ac = lane_ok ? __ldg(p.fan_ac + gi) : make_float2(kNaN, kNaN);
+                ac_m0 = tile.m0;
+            }
             mbar_wait_mode(tfull_bar(as), aphase, p.wait_mode & 15);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
