@@ -890,6 +890,13 @@ def analyze(args,
     with open(name_check, 'wb') as out:
         out.write(format_records([new_record_structure['fields']]).encode('utf-8'))
         for ci in range(start, start + len(fan_clusters)):
-            with open(batch_filename.format(ci), 'rb') as part:
+            try:
+                part = open(batch_filename.format(ci), 'rb')
+            except FileNotFoundError:
+                raise RuntimeError(
+                    "%s is missing: under torchrun every rank writes the batch files of its clusters into "
+                    "the CURRENT DIRECTORY and rank 0 assembles the aggregate from them -- all ranks must "
+                    "run on one node (or share that directory)" % batch_filename.format(ci)) from None
+            with part:
                 shutil.copyfileobj(part, out, 1 << 22)
     ANALYZE_STATS['end'] = time.perf_counter()
