@@ -14,8 +14,9 @@ clusters (work-sharded, no data-path collective) -> weak scaling.
 Numbers on the JSON line
   value     windows/s with the cluster's CSR token arrays already resident in HBM, timed with
             CUDA events over exactly K steps (barrier + synchronize on both sides, max over ranks)
-  e2e       the same K steps through the host-buffer C-ABI call the drop-in search.py makes
-            (fs_search_csr_host): pinned host CSR -> H2D, search, matches -> D2H, every step
+  e2e       the same K steps through the host-buffer C-ABI calls the drop-in search.py makes
+            (fs_search_submit / fs_search_collect, two clusters in flight as in search.analyze):
+            pinned host CSR -> H2D, search, matches and counters -> D2H, every step
   roofline  distance kernel only, mean launch time from CUDA events recorded on the launching
             stream inside the timed region.  `achieved` counts the USEFUL tensor flops of the
             diagonal formulation, 2*(6/E)*300*Ns per window (nominal d, E = 6: one window shift on the
@@ -672,15 +673,30 @@ def run_native_arm(args):
         assert counters[c][nt.FS_CNT_WINDOWS] == windows_of[c], "window count mismatch"
         assert counters[c][nt.FS_CNT_OVERFLOW] == 0, "a buffer overflowed inside the timed region"
 
-    # ---- e2e: host buffers through the C-ABI call of the drop-in --------------------------------
+    # ---- e2e: host buffers through the C-ABI calls the drop-in makes --------------------------------
+    # fs_search_submit / fs_search_collect, as search.analyze drives them: the next cluster is submitted
+    # before the previous one is collected (two in flight), every step copies its CSR arrays host -> device
+    # from page-locked memory and its matches and counters device -> host
+    import collections
     for s in range(min(args.warmup, 2)):
         step_host(s)
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    in_flight = collections.deque()
+
+    def collect_one():
+        m, _ = index.search_collect(in_flight.popleft(), out=out_host)
+        return len(m) * nt.MATCH_DTYPE.itemsize + 8 * nt.FS_CNT_COUNT
+
     for s in range(args.steps):
-        n_match, _ = step_host(args.warmup + s)
-        d2h += n_match * nt.MATCH_DTYPE.itemsize + 8 * nt.FS_CNT_COUNT
+        c = (args.warmup + s) % n_distinct
+        tok_p, off_p = pinned[c]
+        in_flight.append(index.search_submit(tok_p.numpy(), off_p.numpy(), None, cap=cap))
+        if len(in_flight) == 2:
+            d2h += collect_one()
+    while in_flight:
+        d2h += collect_one()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
