@@ -542,8 +542,15 @@ def time_stages(index, dev_in, reps=5):
     pairs = torch.empty((1 << 20, 2), dtype=torch.int32, device=tok_t.device)
     cnt = torch.zeros(nt.FS_CNT_COUNT, dtype=torch.int64, device=tok_t.device)
     out = {}
+    # the join once more on 16 clusters in one launch (larger than L2): a cluster alone is 10 MB of ids
+    # and ~17 us, much of it launch and ramp
+    rep = 16
+    tok_big = tok_t.repeat(rep)
+    off_big = torch.cat([off_t[:1]] + [off_t[1:] + k * n_tok for k in range(rep)])
+    pairs_big = torch.empty((rep << 16, 2), dtype=torch.int32, device=tok_t.device)
     for name, fn in (("gather", lambda: index.stage_embed(tok_t, off_t)),
-                     ("hash_join", lambda: index.exact_join_dev(tok_t, off_t, pairs, cnt))):
+                     ("hash_join", lambda: index.exact_join_dev(tok_t, off_t, pairs, cnt)),
+                     ("hash_join_x16", lambda: index.exact_join_dev(tok_big, off_big, pairs_big, cnt))):
         fn()
         torch.cuda.synchronize()
         best = None
@@ -771,6 +778,11 @@ def run_native_arm(args):
                       "achieved": join_bytes / (stage_ms["hash_join"] * 1e-3) / 1e9, "unit": "GB/s",
                       "peak": peaks["hbm_gbs"], "frac": join_bytes / (stage_ms["hash_join"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
                       "bytes": "tokens x 4 B id"},
+        "hash_join_x16": {"bound": "hbm (in practice issue/L1)", "ms": stage_ms["hash_join_x16"],
+                          "achieved": 16 * join_bytes / (stage_ms["hash_join_x16"] * 1e-3) / 1e9, "unit": "GB/s",
+                          "peak": peaks["hbm_gbs"],
+                          "frac": 16 * join_bytes / (stage_ms["hash_join_x16"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "bytes": "16 clusters in one launch x tokens x 4 B id"},
     }
 
     # ---- files -> CSV through search.analyze, and the golden corpus across the ranks -----------------

@@ -120,6 +120,8 @@ struct fs_index {
     CUtensorMap map_script64;   // boxes of 64 rows (128-column tiles, distance_kernel_n128)
 
     unsigned long long* hash_table = nullptr;
+    uint32_t* hash_filter = nullptr;  // one bit per value of the top bits of the key hash (probe pre-test)
+    uint32_t hash_filter_bits = 0;
     uint32_t hash_slots = 0;
 
     // per-batch workspace
@@ -246,7 +248,7 @@ int fs_index_destroy(fs_index* idx) {
                     idx->lsh_normals, idx->script_norm_min, idx->perm, idx->col_energy,
                     idx->script_text, idx->script_word_off, idx->pp_head, idx->pp_winner, idx->pp_next,
                     idx->pp_lev, idx->pp_rank, idx->pp_block_count, idx->pp_best_key, idx->pp_best_tie,
-                    idx->pp_block_off};
+                    idx->pp_block_off, idx->hash_filter};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (idx->ev_created) {
@@ -540,12 +542,17 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     // operand rows (table, script extras, script token matrix), window norms, tensor map
     FS_TRY(prepare_operands(idx));
 
+    // load factor <= 1/16 up to 2^22 slots (32 MB of table, L2 resident), never above 1/2
     uint32_t slots = 1024;
-    while (slots < 2 * static_cast<uint64_t>(n_script_tok)) slots <<= 1;
+    while (slots < 2 * static_cast<uint64_t>(n_script_tok) ||
+           (slots < 16 * static_cast<uint64_t>(n_script_tok) && slots < (1u << 22)))
+        slots <<= 1;
     idx->hash_slots = slots;
     FS_TRY(dev_alloc(&idx->hash_table, slots));
+    idx->hash_filter_bits = hash_filter_bits(n_script_tok);
+    FS_TRY(dev_alloc(&idx->hash_filter, idx->hash_filter_bits / 32));
     FS_TRY(launch_hash_build(idx->script_tok, n_script_tok, idx->script_off, idx->n_scripts, window,
-                             idx->hash_table, slots, st));
+                             idx->hash_table, slots, idx->hash_filter, idx->hash_filter_bits, st));
     FS_TRY_CUDA(cudaStreamSynchronize(st));
 #undef FS_TRY
 #undef FS_TRY_CUDA
@@ -1238,7 +1245,8 @@ int fs_exact_join_dev(fs_index* idx, void* stream, const int32_t* tok, int64_t n
     unsigned long long* cnt = reinterpret_cast<unsigned long long*>(counters);
     FS_CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
     return launch_hash_probe(tok, n_tok, off, static_cast<int32_t>(n_works), idx->script_tok,
-                             idx->window, idx->hash_table, idx->hash_slots, out, cap,
+                             idx->window, idx->hash_table, idx->hash_slots, idx->hash_filter,
+                             idx->hash_filter_bits, out, cap,
                              cnt + FS_CNT_EXACT, idx->sm_count, st);
 }
 

@@ -255,13 +255,14 @@ int launch_reuse_histogram_rows(const fs_row* rows, const unsigned long long* co
                                 const double* thresholds, int32_t n_thr, int64_t n_words,
                                 unsigned long long* counts, int sm_count, cudaStream_t stream);
 int64_t postprocess_scan_blocks(int64_t n_tok);
+uint32_t hash_filter_bits(int64_t n_script_tok);
 int launch_hash_build(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,
-                      int32_t window, unsigned long long* table, uint32_t slots,
-                      cudaStream_t stream);
+                      int32_t window, unsigned long long* table, uint32_t slots, uint32_t* filter,
+                      uint32_t filter_bits, cudaStream_t stream);
 int launch_hash_probe(const int32_t* tok, int64_t n_tok, const int64_t* off, int32_t n_rows,
                       const int32_t* script_tok, int32_t window, const unsigned long long* table,
-                      uint32_t slots, fs_pair* out, int64_t cap, unsigned long long* counter,
-                      int sm_count, cudaStream_t stream);
+                      uint32_t slots, const uint32_t* filter, uint32_t filter_bits, fs_pair* out, int64_t cap,
+                      unsigned long long* counter, int sm_count, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
 // PTX wrappers

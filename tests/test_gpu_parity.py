@@ -472,6 +472,25 @@ def test_hash_join_is_bit_exact():
     idx.close()
 
 
+@pytest.mark.parametrize("window", [6, 4])
+def test_hash_join_with_heavy_collisions(window):
+    # a 3-word vocabulary: most script windows repeat many times (chains of equal keys in the
+    # table) and most fan windows hit several of them; window 4 runs the run-time-length kernel
+    rng = np.random.default_rng(77)
+    table = rng.standard_normal((3, 300)).astype(np.float32)
+    script = rng.integers(0, 3, 1500).astype(np.int32)
+    works = (700, 5, 0, 3000, 64)
+    off = np.concatenate([[0], np.cumsum(works)]).astype(np.int64)
+    tok = rng.integers(0, 3, int(off[-1])).astype(np.int32)
+    ref = NumpyIndex(table, script, window=window)
+    want, _ = ref.exact_join_host(tok, off)
+    idx = _device_index(table, script, window=window)
+    got, cnt = idx.exact_join_host(tok, off, cap=len(want) + 10)
+    assert cnt[nt.FS_CNT_EXACT] == len(want) > 5000
+    assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
+    idx.close()
+
+
 def test_ragged_and_empty_batches():
     table, sx, fx, script, _, _ = _case(9)
     idx = _device_index(table, script, extra=sx)
