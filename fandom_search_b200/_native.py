@@ -39,6 +39,7 @@ FS_OPT_PACKED_SHUFFLE = 7
 FS_OPT_OPERAND_BITS = 9
 FS_OPT_TILE_GROUP = 10
 FS_OPT_PREFILTER_DIMS = 11
+FS_OPT_FUSED_GATHER = 12
 
 FS_MATCH_EXACT = 1
 FS_MATCH_LSH_SHIFT = 8

@@ -31,6 +31,9 @@ constexpr int kTimingRing = 256;
 constexpr double kEpsAccum = 3.0e-3;
 // automatic choice of the pre-filter columns: keep this share of the table's energy (choose_kept_columns)
 constexpr double kAutoKeepEnergy = 0.83;
+// room for one batch's out-of-vocabulary rows behind the table (fused gather); batches with more fall back
+// to the materialised fan matrix
+constexpr int64_t kFusedExtraRows = 1 << 16;
 // largest scaled row norm of an fp8 table: window token dots, |sum| <= window * norm^2, must still
 // fit the fp16 range of the packed epilogue (norm = 95.7 for 6-gram windows)
 inline float f8_row_norm(int32_t window) { return std::sqrt(55000.0f / static_cast<float>(window)); }
@@ -99,6 +102,15 @@ struct fs_index {
     int64_t n_base = 0, n_sx = 0;
 
     float* table32 = nullptr;
+    // operand rows [table | script extras | room for one batch's fan extras]: ONE allocation, so that the
+    // distance kernel can fetch fan rows from it by token id (fused gather); table16, sx16 and fx_rows point
+    // into it
+    __half* rows16 = nullptr;
+    CUtensorMap map_rows;          // box {64 columns, 1 row}: TMA tile::gather4
+    int64_t n_table_rows = 0;      // n_base + n_sx + kFusedExtraRows
+    __half* fx_rows = nullptr;
+    int32_t fused_gather = 1;      // FS_OPT_FUSED_GATHER
+    int32_t last_fused = 0;        // the last search fetched its fan rows by fused gather
     __half* table16 = nullptr;
     float4* table_sq = nullptr;   // per row (norm^2, kept rounding error^2, dropped^2, -) of the scaled row
     float* sx32 = nullptr;
@@ -240,7 +252,7 @@ int fs_index_destroy(fs_index* idx) {
     if (!idx) return FS_OK;
     cudaSetDevice(idx->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {idx->table32, idx->table16,   idx->table_sq,   idx->sx32,       idx->sx16,
+    void* ptrs[] = {idx->table32, idx->rows16,    idx->table_sq,   idx->sx32,       nullptr,
                     idx->sx_sq,   idx->script_tok, idx->script_off, idx->script_emb, idx->script_tok_sq,
                     idx->script_norm, idx->hash_table, idx->fan_emb, idx->fan_tok_sq, idx->fan_thr,
                     idx->cand,    idx->fx16,      idx->fx_sq,      idx->h_tok,      idx->h_off,
@@ -359,13 +371,17 @@ static int prepare_operands(fs_index* idx) {
             idx->diag = idx->window % 3 == 0 ? 3 : (idx->window % 2 == 0 ? 2 : 1);
         idx->shifts_per_stage = 0;
     }
-    void* stale[] = {idx->table16, idx->sx16, idx->script_emb, idx->fan_emb, idx->fx16};
+    void* stale[] = {idx->rows16, idx->script_emb, idx->fan_emb, idx->fx16};
     for (void* q : stale)
         if (q) cudaFree(q);
-    idx->table16 = idx->sx16 = idx->script_emb = idx->fan_emb = idx->fx16 = nullptr;
+    idx->rows16 = idx->table16 = idx->sx16 = idx->fx_rows = idx->script_emb = idx->fan_emb = idx->fx16 = nullptr;
     idx->emb_cap = idx->tok_cap = idx->fx_cap = 0;
-    if ((r = dev_alloc(&idx->table16, idx->n_base * idx->dim_pad)) != FS_OK) return r;
-    if ((r = dev_alloc(&idx->sx16, idx->n_sx * idx->dim_pad)) != FS_OK) return r;
+    idx->n_table_rows = idx->n_base + idx->n_sx + kFusedExtraRows;
+    if ((r = dev_alloc(&idx->rows16, idx->n_table_rows * idx->dim_pad)) != FS_OK) return r;
+    idx->table16 = idx->rows16;
+    idx->sx16 = idx->table16 + idx->n_base * idx->dim_pad;
+    idx->fx_rows = idx->sx16 + idx->n_sx * idx->dim_pad;
+    if ((r = make_token_map(&idx->map_rows, idx->rows16, idx->n_table_rows, idx->dim_pad, 1)) != FS_OK) return r;
     if ((r = dev_alloc(&idx->script_emb, idx->n_script_tok * idx->dim_pad)) != FS_OK) return r;
     unsigned int* d_max = reinterpret_cast<unsigned int*>(idx->h_counters);
     FS_CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long) * FS_CNT_COUNT, st));
@@ -560,6 +576,20 @@ int fs_index_create(fs_index** out, int device, const float* table, int64_t n_ro
     return FS_OK;
 }
 
+// the configuration distance_kernel_n128 runs (fs_index_get_info 15) with the fused gather switched on
+static bool n128_config(const fs_index* idx) {
+    return idx->pair && idx->ares && idx->diag == 6 && idx->pack == 2 && (idx->tile_group & 69) == 69 &&
+           (idx->dim_pad + kChunkK - 1) / kChunkK <= 2 && idx->window == 6;
+}
+static bool fused_config(const fs_index* idx) { return idx->fused_gather && n128_config(idx); }
+
+static int grow_fan_matrix(fs_index* idx, int64_t max_tokens) {
+    int r;
+    if ((r = dev_grow(&idx->fan_emb, &idx->emb_cap, max_tokens * idx->dim_pad)) != FS_OK) return r;
+    idx->tok_cap = idx->emb_cap / idx->dim_pad;
+    return FS_OK;
+}
+
 int fs_index_reserve(fs_index* idx, int64_t max_tokens, int64_t max_candidates) {
     if (!idx || max_tokens < 0 || max_candidates < 0) {
         set_error("fs_index_reserve: invalid argument");
@@ -567,8 +597,8 @@ int fs_index_reserve(fs_index* idx, int64_t max_tokens, int64_t max_candidates) 
     }
     FS_CUDA_CHECK(cudaSetDevice(idx->device));
     int r;
-    if ((r = dev_grow(&idx->fan_emb, &idx->emb_cap, max_tokens * idx->dim_pad)) != FS_OK) return r;
-    idx->tok_cap = idx->emb_cap / idx->dim_pad;
+    // (the fan operand matrix is only needed when the fused gather does not apply: grown on demand there)
+    if (!fused_config(idx) && (r = grow_fan_matrix(idx, max_tokens)) != FS_OK) return r;
     if ((r = dev_grow(&idx->fan_tok_sq, &idx->sq_cap, max_tokens + 8)) != FS_OK) return r;
     // per-window bounds, padded to whole tiles of the SMALLEST row step any variant uses (E = 6: 108)
     if ((r = dev_grow(&idx->fan_thr, &idx->thr_cap, (max_tokens / dist_m_step(6) + 3) * kBlockM)) != FS_OK)
@@ -626,6 +656,9 @@ int fs_index_set_option(fs_index* idx, int32_t option, int64_t value) {
             idx->prefilter_dims = want_dims;
             return prepare_operands(idx);
         }
+        case FS_OPT_FUSED_GATHER:
+            idx->fused_gather = value != 0 ? 1 : 0;
+            return FS_OK;
         case FS_OPT_GRID_LIMIT:
             idx->grid_limit = static_cast<int32_t>(value < 0 ? 0 : value);
             return FS_OK;
@@ -675,10 +708,9 @@ int64_t fs_index_get_info(const fs_index* idx, int32_t what) {
         case 13: return idx->kept_dims;
         case 14: return static_cast<int64_t>(idx->kept_energy * 1e6);  // share of the energy kept, ppm
         case 15:  // 1: the 128-column kernel (distance_kernel_n128) runs this configuration
-            return (idx->pair && idx->ares && idx->diag == 6 && idx->pack == 2 && (idx->tile_group & 69) == 69 &&
-                    (idx->dim_pad + kChunkK - 1) / kChunkK <= 2 && idx->window == 6)
-                       ? 1
-                       : 0;
+            return n128_config(idx) ? 1 : 0;
+        case 16:  // 1: the last search fetched its fan rows by fused gather (no fan operand matrix)
+            return idx->last_fused;
         default: return -1;
     }
 }
@@ -743,22 +775,31 @@ int check_batch(const fs_index* idx, const BatchArgs& a, const char* who) {
 }
 
 // gather + window thresholds of one batch into the index workspace
+// emb_out == nullptr: fused gather -- the batch's extra rows are converted into the table's tail (a.n_extra <=
+// kFusedExtraRows) and only the per-token squares are gathered; the distance kernel fetches the rows itself
 int embed_batch(fs_index* idx, cudaStream_t st, const BatchArgs& a, unsigned long long* counters,
                 __half* emb_out, float2* thr_out, float4* thr_plain, int64_t thr_pad) {
     int r;
+    const bool fused = emb_out == nullptr;
+    __half* fx_dst = idx->fx_rows;
     if (a.n_extra > 0) {
-        if ((r = dev_grow(&idx->fx16, &idx->fx_cap, a.n_extra * idx->dim_pad)) != FS_OK) return r;
+        if (!fused) {
+            if ((r = dev_grow(&idx->fx16, &idx->fx_cap, a.n_extra * idx->dim_pad)) != FS_OK) return r;
+            fx_dst = idx->fx16;
+        }
         if ((r = dev_grow(&idx->fx_sq, &idx->fxsq_cap, a.n_extra)) != FS_OK) return r;
         if ((r = launch_convert_rows(a.extra, a.n_extra, idx->dim, idx->dim_pad, idx->kept_dims, idx->perm,
-                                     idx->scale, idx->operand_bits == 8, idx->row_limit_sq, idx->fx16,
+                                     idx->scale, idx->operand_bits == 8, idx->row_limit_sq, fx_dst,
                                      idx->fx_sq, st)) != FS_OK)
             return r;
     }
     GatherSources src{idx->table16, idx->table_sq, idx->n_base, idx->sx16,  idx->sx_sq,
-                      idx->n_sx,    idx->fx16,     idx->fx_sq,  a.n_extra};
-    if ((r = launch_gather(a.tok, a.n_tok, src, idx->dim_pad, emb_out, idx->fan_tok_sq, idx->sm_count,
-                           st)) != FS_OK)
-        return r;
+                      idx->n_sx,    fx_dst,        idx->fx_sq,  a.n_extra};
+    if (fused)
+        r = launch_gather_sq(a.tok, a.n_tok, src, idx->fan_tok_sq, idx->sm_count, st);
+    else
+        r = launch_gather(a.tok, a.n_tok, src, idx->dim_pad, emb_out, idx->fan_tok_sq, idx->sm_count, st);
+    if (r != FS_OK) return r;
     // zero the halo so the window sums never read stale squares
     FS_CUDA_CHECK(cudaMemsetAsync(idx->fan_tok_sq + a.n_tok, 0, sizeof(float4) * 8, st));
     // fan side of the pre-filter bound: (|f|, |f - qf|) per window (window_norm_kernel)
@@ -781,19 +822,11 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     const int64_t thr_pad = static_cast<int64_t>(tiles_m + 1) * kBlockM;
     int64_t want_cand = idx->cand_cap > 0 ? idx->cand_cap : (1 << 20);
     if ((r = fs_index_reserve(idx, a.n_tok, want_cand)) != FS_OK) return r;
-    if (thr_pad > idx->thr_cap || a.n_tok > idx->tok_cap) {  // the workspace must hold whole tiles
-        set_error("internal: workspace too small (%lld > %lld bounds, %lld > %lld tokens)",
-                  static_cast<long long>(thr_pad), static_cast<long long>(idx->thr_cap),
-                  static_cast<long long>(a.n_tok), static_cast<long long>(idx->tok_cap));
+    if (thr_pad > idx->thr_cap) {  // the workspace must hold whole tiles
+        set_error("internal: workspace too small (%lld > %lld bounds)", static_cast<long long>(thr_pad),
+                  static_cast<long long>(idx->thr_cap));
         return FS_E_INVALID;
     }
-    if ((r = embed_batch(idx, st, a, counters, idx->fan_emb, idx->fan_thr, nullptr, thr_pad)) != FS_OK) return r;
-
-    CUtensorMap map_fan;
-    if ((r = make_token_map(&map_fan, idx->fan_emb, a.n_tok, idx->dim_pad, kBoxRows)) != FS_OK) return r;
-    // E = 6 loads the fan tile as four overlapping boxes of 32 rows (common.cuh)
-    CUtensorMap map_fan32;
-    if ((r = make_token_map(&map_fan32, idx->fan_emb, a.n_tok, idx->dim_pad, kOverlapBoxRows)) != FS_OK) return r;
     DistParams p{};
     p.fan_ac = idx->fan_thr;
     p.script_bd = idx->script_norm;
@@ -823,6 +856,25 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.counters = counters;
     p.dump = (mode == Mode::kDots) ? dots : nullptr;
     p.dump_ld = dots_ld;
+
+    // Fused gather (the default kernel): the fan tile is fetched from the operand-row table by token id
+    // inside the distance kernel; otherwise the fan operand matrix is materialised first (gather_kernel).
+    const bool fused = idx->fused_gather && distance_uses_n128(p) && a.n_extra <= kFusedExtraRows;
+    idx->last_fused = fused ? 1 : 0;
+    CUtensorMap map_fan, map_fan32;
+    if (fused) {
+        if ((r = embed_batch(idx, st, a, counters, nullptr, idx->fan_thr, nullptr, thr_pad)) != FS_OK) return r;
+        p.fan_tok = a.tok;
+        p.n_valid_rows = static_cast<int32_t>(idx->n_base + idx->n_sx + a.n_extra);
+        p.n_table_rows = static_cast<int32_t>(idx->n_table_rows);
+        map_fan = map_fan32 = idx->map_rows;
+    } else {
+        if ((r = grow_fan_matrix(idx, a.n_tok)) != FS_OK) return r;
+        if ((r = embed_batch(idx, st, a, counters, idx->fan_emb, idx->fan_thr, nullptr, thr_pad)) != FS_OK) return r;
+        if ((r = make_token_map(&map_fan, idx->fan_emb, a.n_tok, idx->dim_pad, kBoxRows)) != FS_OK) return r;
+        // E = 6 loads the fan tile as four overlapping boxes of 32 rows (common.cuh)
+        if ((r = make_token_map(&map_fan32, idx->fan_emb, a.n_tok, idx->dim_pad, kOverlapBoxRows)) != FS_OK) return r;
+    }
     const int grid_limit = idx->grid_limit > 0 ? idx->grid_limit : idx->sm_count;
     const int slot = static_cast<int>(idx->ev_count % kTimingRing);
     FS_CUDA_CHECK(cudaEventRecord(idx->ev_start[slot], st));

@@ -136,6 +136,13 @@ struct DistParams {
     unsigned long long* counters;  // [FS_CNT_COUNT]
     float* dump;              // optional dense dump [n_fan_tok, dump_ld]
     int64_t dump_ld;
+    // fused gather (128-column kernel only): the fan tile is fetched by TMA tile::gather4 straight from the
+    // operand-row table [table | script extras | this batch's extras] by token id -- the fan operand matrix is
+    // never materialised.  Ids outside [0, n_valid_rows) fetch row n_table_rows, which lies outside the
+    // tensor map and arrives as zeros (what gather_kernel writes for unknown ids).
+    const int32_t* fan_tok;   // [n_fan_tok] row ids, or nullptr: the fan tile comes from the materialised matrix
+    int32_t n_valid_rows;
+    int32_t n_table_rows;
 };
 
 
@@ -232,6 +239,7 @@ struct GatherSources {
     int64_t n_fx;
 };
 
+bool distance_uses_n128(const DistParams& p);  // the 128-column kernel (the only one with the fused gather)
 int make_token_map(CUtensorMap* map, const void* base, int64_t rows, int32_t dim_pad, int32_t box_rows);
 int launch_distance(const CUtensorMap& map_fan, const CUtensorMap& map_fan32, const CUtensorMap& map_script,
                     const CUtensorMap& map_script128, const CUtensorMap& map_script64, const DistParams& p,
@@ -244,6 +252,9 @@ int launch_rownorm_max(const float* src, int64_t n_rows, int32_t dim, unsigned i
 int launch_absmax(const float* src, int64_t n, unsigned int* out, cudaStream_t stream);
 int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, int32_t dim_pad,
                   __half* emb, float4* tok_sq, int sm_count, cudaStream_t stream);
+// tok_sq only (fused gather: the operand rows stay in the table)
+int launch_gather_sq(const int32_t* tok, int64_t n_tok, const GatherSources& src, float4* tok_sq, int sm_count,
+                     cudaStream_t stream);
 int launch_window_norm(const float4* tok_sq, int64_t n_tok, const int64_t* off, int32_t n_rows,
                        int32_t window, float coef, bool script_side, float2* out, float4* out_plain,
                        int64_t n_pad, unsigned long long* window_counter, cudaStream_t stream);
@@ -483,6 +494,19 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         " [%0], [%1, {%3, %4}], [%2];"
         :
         : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_addr(bar)), "r"(col), "r"(row)
+        : "memory");
+}
+// Four rows of a 2-D tensor, picked by index, land as four consecutive 128-byte rows at dst (SWIZZLE_128B is
+// applied by shared-memory row as for a tiled box; rows outside the tensor arrive as zeros); issued by either
+// CTA of the pair, bytes accounted on the LEADER's mbarrier.  The tensor map's box is {64 columns, 1 row}.
+__device__ __forceinline__ void tma_gather4_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t col,
+                                                 int32_t r0, int32_t r1, int32_t r2, int32_t r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_addr(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2),
+          "r"(r3)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t cols) {

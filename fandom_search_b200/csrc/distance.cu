@@ -1328,6 +1328,8 @@ static int launch_distance_t(const CUtensorMap& map_fan, const CUtensorMap& map_
 // depth can only grow by narrowing the tile: two independent pipelines of 128-column tiles per SM
 // keep four accumulator stages in flight on the same tensor pipe.
 // =============================================================================================
+static bool n128_applies(const DistParams& p);
+
 namespace n128 {
 constexpr int kBN = 128;                      // script windows per tile (UMMA N)
 constexpr int kEpi = 8;                       // epilogue warps: 4 TMEM lane quarters x 2 groups of 64 columns
@@ -1401,7 +1403,23 @@ distance_kernel_n128(const __grid_constant__ CUtensorMap map_fan32, const __grid
         while (walk.next(tile)) {
             if (tile.fan_first) {
                 mbar_wait_warp(aempty_bar, a_phase ^ 1u, 64);
-                if (elect_one()) {
+                if (p.fan_tok != nullptr) {
+                    // fused gather: map_fan32 is the operand-row TABLE; every lane fetches four rows of the
+                    // tile by token id (lane -> quarter lane / 8, rows 4 (lane % 8) .. + 3 of its 32-row box)
+                    const int q = lane >> 3, g = lane & 7;
+                    const int64_t t0 = static_cast<int64_t>(tile.m0) + q * kQuarterRows6 + 4 * g;
+                    int32_t id[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int32_t v = (t0 + k < p.n_fan_tok) ? __ldg(p.fan_tok + t0 + k) : -1;
+                        id[k] = (v >= 0 && v < p.n_valid_rows) ? v : p.n_table_rows;  // outside the map: zeros
+                    }
+                    if (lane == 0 && leader) mbar_expect_tx(afull_bar, 2 * chunks * kABytes);
+                    __syncwarp();
+                    for (int c = 0; c < chunks; ++c)
+                        tma_gather4_pair(smem_a + c * kABytes + q * (kOverlapBoxRows * 128) + g * (4 * 128), &map_fan32,
+                                         afull_bar, c * kChunkK, id[0], id[1], id[2], id[3]);
+                } else if (elect_one()) {
                     if (leader) mbar_expect_tx(afull_bar, 2 * chunks * kABytes);
                     for (int c = 0; c < chunks; ++c)
                         for (int q = 0; q < 4; ++q)
@@ -1570,6 +1588,8 @@ distance_kernel_n128(const __grid_constant__ CUtensorMap map_fan32, const __grid
 
 // usable when: fp8/fp16 operands in CTA pairs, E = 6 with the fp16x2 one-pass epilogue, resident fan
 // tile, operand rows of at most two 128-byte chunks, candidate search (no dense dump)
+bool distance_uses_n128(const DistParams& p) { return n128_applies(p); }
+
 static bool n128_applies(const DistParams& p) {
     return p.pair && p.ares && p.diag == 6 && p.pack == 2 && !p.dump && (p.group & 5) == 5 && (p.group & 64) != 0 &&
            p.chunks <= n128::kMaxChunks && p.window == 6;

@@ -180,6 +180,25 @@ gather_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSource
     }
 }
 
+// Fused-gather path: only the per-token squares are gathered (16 B per token from L2-resident tables); the
+// operand rows are fetched from the table by the distance kernel itself (TMA tile::gather4).
+__global__ void __launch_bounds__(256)
+gather_sq_kernel(const int32_t* __restrict__ tok, int64_t n_tok, const GatherSources src,
+                 float4* __restrict__ tok_sq) {
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n_tok;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        int64_t id = __ldg(tok + t);
+        float4 sq = make_float4(0.f, 0.f, 0.f, 0.f);  // unknown ids embed as the zero vector
+        if (id >= 0 && id < src.n_base)
+            sq = __ldg(src.base_sq + id);
+        else if ((id -= src.n_base) >= 0 && id < src.n_sx)
+            sq = __ldg(src.sx_sq + id);
+        else if ((id -= src.n_sx) >= 0 && id < src.n_fx)
+            sq = __ldg(src.fx_sq + id);
+        tok_sq[t] = sq;
+    }
+}
+
 // Per window start t, with n = sqrt(sum_{k<w} tok_sq[t+k].x) (norm of the scaled fp32 window),
 // e = sqrt(sum tok_sq[t+k].y) (norm of the rounding error of its operand rows) and g = sqrt(sum
 // tok_sq[t+k].z) (norm of the elements the operand rows drop):
@@ -317,6 +336,18 @@ int launch_gather(const int32_t* tok, int64_t n_tok, const GatherSources& src, i
     if (blocks > max_blocks) blocks = max_blocks;
     gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         tok, n_tok, src, chunks16, reinterpret_cast<int4*>(emb), tok_sq);
+    FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
+int launch_gather_sq(const int32_t* tok, int64_t n_tok, const GatherSources& src, float4* tok_sq, int sm_count,
+                     cudaStream_t stream) {
+    if (n_tok <= 0) return FS_OK;
+    const int threads = 256;
+    int64_t blocks = (n_tok + threads - 1) / threads;
+    const int64_t max_blocks = static_cast<int64_t>(sm_count) * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    gather_sq_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(tok, n_tok, src, tok_sq);
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }

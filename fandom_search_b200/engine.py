@@ -60,6 +60,7 @@ class DeviceIndex:
                          ("FANDOM_SEARCH_PACKED_SHUFFLE", nt.FS_OPT_PACKED_SHUFFLE),
                          ("FANDOM_SEARCH_OPERAND_BITS", nt.FS_OPT_OPERAND_BITS),
                          ("FANDOM_SEARCH_PREFILTER_DIMS", nt.FS_OPT_PREFILTER_DIMS),
+                         ("FANDOM_SEARCH_FUSED_GATHER", nt.FS_OPT_FUSED_GATHER),
                          ("FANDOM_SEARCH_TILE_GROUP", nt.FS_OPT_TILE_GROUP)):
             v = os.environ.get(env)
             if v not in (None, ""):

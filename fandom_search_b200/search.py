@@ -834,9 +834,13 @@ def analyze(args,
             for k, (i, fan_cluster) in enumerate(mine):
                 print('Processing cluster {} ({}-{})'.format(i, chunk_size * i, chunk_size * (i + 1)))
                 prep = pending.result()
+                if k == 0:
+                    ANALYZE_STATS['first_prepared'] = time.perf_counter()
                 pending = prep_pool.submit(ann_index.prepare, mine[k + 1][1]) if k + 1 < len(mine) else None
                 # the GPU always holds the next cluster: submit this one BEFORE waiting for the previous
                 on_gpu.append((i, prep, ann_index.submit_prepared(prep, rows=True)))
+                if k == 0:
+                    ANALYZE_STATS['first_submitted'] = time.perf_counter()
                 del prep
                 if len(on_gpu) == 2:
                     collect_oldest()

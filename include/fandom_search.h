@@ -151,6 +151,13 @@ enum {
                                     window holds in the dropped columns enters its pre-filter threshold as
                                     |f_drop| |s_drop|, so the candidates stay a guaranteed superset and the
                                     float64 decision is unchanged.  Re-converts the index.             */
+    FS_OPT_FUSED_GATHER = 12,    /* 1 (default): the distance kernel fetches the fan rows of its tile straight from
+                                    the operand-row table by token id (TMA tile::gather4; search.py:65-84's
+                                    mk_vectors never materialises a fan matrix) -- applies to the default
+                                    128-column kernel (fs_index_get_info 15) and batches with at most 65536 extra
+                                    rows; 0: the fan operand matrix is written by gather_kernel first.
+                                    fs_index_get_info(16) tells which one the last search used.  Results are
+                                    identical (the same bytes reach the tensor cores).                   */
     FS_OPT_DIAG = 4              /* 1 (dense), 2, 3 or 6: the tensor cores accumulate window/E shifts
                                     and the epilogue adds E diagonal neighbours (same products,
                                     E-fold fewer tensor-core flops)                            */
@@ -193,7 +200,8 @@ int fs_index_set_lsh(fs_index* idx, const double* normals, int32_t n_tables, int
 /* what = 0: script windows, 1: dim_pad, 2: SM count, 3: candidate capacity, 4: shifts per stage,
  * 5: diagonal factor, 6: CTA pair, 7: A-resident, 8: pack level, 11: operand bits, 12: tile-group bits,
  * 13: embedding columns kept by the pre-filter, 14: share of the table's energy they hold (ppm),
- * 15: 1 when the 128-column kernel runs the current configuration */
+ * 15: 1 when the 128-column kernel runs the current configuration,
+ * 16: 1 when the last search fetched its fan rows by fused gather (FS_OPT_FUSED_GATHER) */
 int64_t fs_index_get_info(const fs_index* idx, int32_t what);
 
 /*

@@ -825,6 +825,43 @@ def test_prefilter_columns_are_the_high_energy_ones_and_bounds_measure_the_rest(
     idx.close()
 
 
+def test_fused_gather_equals_the_materialised_fan_matrix():
+    """FS_OPT_FUSED_GATHER: the default kernel fetches its fan rows from the operand-row table by token id
+    (TMA tile::gather4) -- candidates, matches and counters are those of the run that writes the fan
+    operand matrix first; batches with extra rows, ragged works and a batch after a larger one (stale rows
+    in the table's tail) included."""
+    import torch
+    table, sx, fx, script, tok, off = _case(31, works=(700, 3, 0, 6, 2397, 150, 40))
+    table2, _, fx2, _, tok2, off2 = _case(32, works=(64, 64), n_extra_f=2)
+    no_extra = np.where(tok < table.shape[0] + len(sx), tok, 0).astype(np.int32)
+    idx = _device_index(table, script, extra=sx, bits=None)      # library defaults: fp8, E = 6, 128-column kernel
+    assert idx.info(15) == 1
+    runs = {}
+    for fused in (1, 0, 1):
+        idx.set_option(nt.FS_OPT_FUSED_GATHER, fused)
+        got = [idx.search_host(tok, off, fx)]
+        assert idx.info(16) == fused
+        got.append(idx.search_host(tok2, off2, fx2))
+        got.append(idx.search_host(no_extra, off))
+        tok_t, off_t, fx_t = idx.to_device(tok, off, fx)
+        cand, cnt = idx.stage_candidates(tok_t, off_t, fx_t)
+        torch.cuda.synchronize()
+        pairs = set(map(tuple, cand.cpu().numpy()[:int(cnt.cpu()[nt.FS_CNT_CANDIDATES])].tolist()))
+        if fused in runs:                                        # a path is reproducible
+            assert runs[('cand', fused)] == pairs
+        runs[fused], runs[('cand', fused)] = got, pairs
+    for (m0, c0), (m1, c1) in zip(runs[0], runs[1]):
+        assert np.array_equal(np.sort(m0, order=['fan_pos', 'script_pos']), np.sort(m1, order=['fan_pos', 'script_pos']))
+        assert np.array_equal(c0, c1)
+    assert runs[('cand', 0)] == runs[('cand', 1)] and len(runs[('cand', 0)]) > 0
+    assert len(runs[0][0][0]) > 0
+    # other configurations fall back to the materialised matrix by themselves
+    idx.set_option(nt.FS_OPT_DIAG, 3)
+    idx.search_host(tok, off, fx)
+    assert idx.info(16) == 0
+    idx.close()
+
+
 def test_two_batches_in_flight_equal_the_blocking_call():
     """fs_search_submit / fs_search_collect: two clusters queued back to back, collected in either
     order, give the matches and counters of fs_search_csr_host; a third submit is refused."""
