@@ -12,4 +12,5 @@ python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; tail -1 gpur
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_ncu_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pipeline --distinct 2 > gpurun_out/${TAG}_ncu_a.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:distance_kernel -s 3 -c 1 -o gpurun_out/${TAG}_prof -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pipeline --distinct 2 > gpurun_out/${TAG}_ncu_b.log 2>&1
 ncu -i gpurun_out/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_distance_kernel_ncu_raw.csv 2>/dev/null
+python tools/ncu_summary.py gpurun_out/${TAG}_distance_kernel_ncu_raw.csv "ncu --set full --clock-control none, bench.py --steps 2 --warmup 3, 4th launch" > gpurun_out/${TAG}_distance_kernel_ncu_summary.json 2>/dev/null
 ls -la gpurun_out/${TAG}_prof.ncu-rep
