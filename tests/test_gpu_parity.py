@@ -862,6 +862,30 @@ def test_fused_gather_equals_the_materialised_fan_matrix():
     idx.close()
 
 
+def test_fused_gather_falls_back_when_a_batch_has_too_many_extra_rows():
+    """More out-of-vocabulary rows than the table's tail holds (65536): the batch is searched through the
+    materialised fan matrix, with the same result as a batch that fits."""
+    table, sx, _, script, tok, off = _case(33, dim=64, works=(300, 200), n_extra_f=0)
+    rng = np.random.default_rng(5)
+    n_fixed = table.shape[0] + len(sx)
+    few = np.zeros((8, 64), np.float32)
+    few[np.arange(8), rng.integers(0, 64, 8)] = 1.0
+    many = np.zeros((70000, 64), np.float32)
+    many[:8] = few
+    tok = tok.copy()
+    tok[10:18] = n_fixed + np.arange(8)                          # both batches use the same eight extra rows
+    idx = _device_index(table, script, extra=sx, bits=None)
+    if idx.info(15) != 1:
+        pytest.skip("the 128-column kernel does not run this configuration")
+    a, ca = idx.search_host(tok, off, few)
+    assert idx.info(16) == 1
+    b, cb = idx.search_host(tok, off, many)
+    assert idx.info(16) == 0
+    assert np.array_equal(np.sort(a, order=['fan_pos', 'script_pos']), np.sort(b, order=['fan_pos', 'script_pos']))
+    assert np.array_equal(ca, cb)
+    idx.close()
+
+
 def test_two_batches_in_flight_equal_the_blocking_call():
     """fs_search_submit / fs_search_collect: two clusters queued back to back, collected in either
     order, give the matches and counters of fs_search_csr_host; a third submit is refused."""
