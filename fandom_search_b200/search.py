@@ -729,6 +729,48 @@ def _dist_env():
     return rank, world
 
 
+def _concatenate_files(target, header, parts, threads=4):
+    """target = header + the bytes of every file of `parts`, in order (search.py:367, 388: the dated
+    aggregate is the header row and the rows of every cluster).  The pieces are copied inside the kernel
+    (os.copy_file_range: page cache to page cache, no pass through Python buffers) by a few threads, each
+    into its own byte range of the pre-sized target: the aggregate of a million works is gigabytes, and
+    rank 0 writes it while every other rank waits."""
+    sizes = [os.stat(p).st_size for p in parts]            # FileNotFoundError names the missing piece
+    offsets = [len(header)]
+    for n in sizes:
+        offsets.append(offsets[-1] + n)
+    with open(target, 'wb') as out:
+        out.write(header)
+        out.truncate(offsets[-1])
+        out.flush()
+        dst = out.fileno()
+
+        def copy(k):
+            with open(parts[k], 'rb') as src:
+                done, fd = 0, src.fileno()
+                while done < sizes[k]:
+                    n = 0
+                    if hasattr(os, 'copy_file_range'):
+                        try:
+                            n = os.copy_file_range(fd, dst, sizes[k] - done, done, offsets[k] + done)
+                        except OSError:                     # another file system, an old kernel: plain copy
+                            n = 0
+                    if n == 0:
+                        buf = os.pread(fd, min(sizes[k] - done, 1 << 22), done)
+                        if not buf:
+                            raise IOError("%s shrank while it was being copied" % parts[k])
+                        n = os.pwrite(dst, buf, offsets[k] + done)
+                    done += n
+
+        if threads > 1 and len(parts) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                list(pool.map(copy, range(len(parts))))
+        else:
+            for k in range(len(parts)):
+                copy(k)
+
+
 def analyze(args,
             window_size=6,
             number_of_hashes=15,
@@ -890,17 +932,13 @@ def analyze(args,
         hist_name = reuse_histogram if isinstance(reuse_histogram, str) and reuse_histogram not in ('1', 'true', 'True') \
             else name_check[:-4] + '-reuse.csv'
         hist.write_csv(hist_name, ann_index.word_lowercase)
-    import shutil
-    with open(name_check, 'wb') as out:
-        out.write(format_records([new_record_structure['fields']]).encode('utf-8'))
-        for ci in range(start, start + len(fan_clusters)):
-            try:
-                part = open(batch_filename.format(ci), 'rb')
-            except FileNotFoundError:
-                raise RuntimeError(
-                    "%s is missing: under torchrun every rank writes the batch files of its clusters into "
-                    "the CURRENT DIRECTORY and rank 0 assembles the aggregate from them -- all ranks must "
-                    "run on one node (or share that directory)" % batch_filename.format(ci)) from None
-            with part:
-                shutil.copyfileobj(part, out, 1 << 22)
+    header = format_records([new_record_structure['fields']]).encode('utf-8')
+    parts = [batch_filename.format(ci) for ci in range(start, start + len(fan_clusters))]
+    try:
+        _concatenate_files(name_check, header, parts)
+    except FileNotFoundError as exc:
+        raise RuntimeError(
+            "%s is missing: under torchrun every rank writes the batch files of its clusters into "
+            "the CURRENT DIRECTORY and rank 0 assembles the aggregate from them -- all ranks must "
+            "run on one node (or share that directory)" % exc.filename) from None
     ANALYZE_STATS['end'] = time.perf_counter()
