@@ -862,6 +862,34 @@ def test_fused_gather_equals_the_materialised_fan_matrix():
     idx.close()
 
 
+def test_fused_gather_on_ragged_shapes_around_the_tile_steps():
+    """Batches whose token counts straddle the fan-tile step (108 rows, pairs of tiles: 216) and the
+    gather granularity (4 rows), with and without extra rows: fused and materialised runs agree."""
+    table, sx, fx, script, _, _ = _case(34, works=(50,))
+    rng = np.random.default_rng(34)
+    n_ids = table.shape[0] + len(sx) + len(fx)
+    idx = _device_index(table, script, extra=sx, bits=None)
+    assert idx.info(15) == 1
+    total = 0
+    for n_tok in (6, 7, 105, 107, 108, 109, 111, 113, 215, 216, 217, 323, 324, 325, 431, 432, 433, 1000, 2701):
+        cuts = np.sort(rng.choice(np.arange(1, n_tok), size=min(3, n_tok - 1), replace=False)) if n_tok > 6 else []
+        off = np.concatenate([[0], cuts, [n_tok]]).astype(np.int64)
+        tok = rng.integers(0, n_ids, n_tok).astype(np.int32)
+        src = int(rng.integers(0, len(script) - 40))
+        ln = min(n_tok, 30)
+        tok[:ln] = script[src:src + ln]                      # some reuse in every batch
+        res = []
+        for fused in (1, 0):
+            idx.set_option(nt.FS_OPT_FUSED_GATHER, fused)
+            m, c = idx.search_host(tok, off, fx)
+            assert idx.info(16) == fused
+            res.append((np.sort(m, order=['fan_pos', 'script_pos']), c))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]), n_tok
+        total += len(res[0][0])
+    assert total > 50
+    idx.close()
+
+
 def test_fused_gather_falls_back_when_a_batch_has_too_many_extra_rows():
     """More out-of-vocabulary rows than the table's tail holds (65536): the batch is searched through the
     materialised fan matrix, with the same result as a batch that fits."""
