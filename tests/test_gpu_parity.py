@@ -491,6 +491,29 @@ def test_hash_join_with_heavy_collisions(window):
     idx.close()
 
 
+@pytest.mark.parametrize("n_script", [40000, 140000])
+def test_hash_join_with_a_long_script(n_script):
+    """Scripts of 40 k / 140 k tokens: the probe's filter takes 64 KB / 128 KB of shared memory (opt-in
+    above 48 KB, fewer resident blocks); pairs equal the dictionary join."""
+    rng = np.random.default_rng(n_script)
+    table = rng.standard_normal((2000, 32)).astype(np.float32)
+    script = rng.integers(0, 2000, n_script).astype(np.int32)
+    works = (3000, 1, 2500)
+    off = np.concatenate([[0], np.cumsum(works)]).astype(np.int64)
+    tok = rng.integers(0, 2000, int(off[-1])).astype(np.int32)
+    for k in range(40):                                         # planted quotes, some across the end of a work
+        src = int(rng.integers(0, n_script - 30))
+        dst = int(rng.integers(0, len(tok) - 30))
+        tok[dst:dst + 20] = script[src:src + 20]
+    ref = NumpyIndex(table, script)
+    want, _ = ref.exact_join_host(tok, off)
+    idx = _device_index(table, script)
+    got, cnt = idx.exact_join_host(tok, off)
+    assert cnt[nt.FS_CNT_EXACT] == len(want) > 300
+    assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
+    idx.close()
+
+
 def test_ragged_and_empty_batches():
     table, sx, fx, script, _, _ = _case(9)
     idx = _device_index(table, script, extra=sx)
