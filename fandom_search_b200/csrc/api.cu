@@ -845,8 +845,9 @@ int run_pipeline(fs_index* idx, cudaStream_t st, const BatchArgs& a, Mode mode, 
     p.group = idx->tile_group;
     {
         // 2: every lane of an epilogue warp waits on the accumulator barrier itself (try_wait with a
-        // suspend hint) -- 11 % faster than one polling lane + __syncwarp (profiles/r02_sweep_wait_modes.jsonl)
-        static const int wait_mode = getenv("FS_DEBUG_WAIT") ? atoi(getenv("FS_DEBUG_WAIT")) : 2;
+        // suspend hint) -- 11 % faster than one polling lane + __syncwarp (profiles/r02_sweep_wait_modes.jsonl);
+        // 6 (default): the same after one 200 ns sleep when the first check fails (common.cuh, mbar_wait_mode)
+        static const int wait_mode = getenv("FS_DEBUG_WAIT") ? atoi(getenv("FS_DEBUG_WAIT")) : 6;
         p.wait_mode = wait_mode;
     }
     p.tiles_m = tiles_m;
